@@ -1,0 +1,827 @@
+// capi.cu — the C-ABI shim (include/mtscomp_b200.h) over the sm_100a kernels.  Host-side orchestration only: table
+// building, scratch management, launches on one stream, copies.  No codec arithmetic happens on the host.
+#include "../../include/mtscomp_b200.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "deflate.cuh"
+#include "inflate.cuh"
+#include "transform.cuh"
+
+using namespace mts;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+  bool host = false;
+  int ensure(size_t n) {
+    if (n <= cap) return 0;
+    release();
+    size_t want = n + n / 8 + 4096;
+    cudaError_t e = host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+    if (e != cudaSuccess) { p = nullptr; cap = 0; cudaGetLastError(); return -1; }
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) { if (host) cudaFreeHost(p); else cudaFree(p); }
+    p = nullptr; cap = 0;
+  }
+};
+
+static const uint32_t INDEX_MAGIC = 0x4253544Du;   // "MTSB"
+static const int INDEX_TAIL = 16;
+
+}  // namespace
+
+struct mtsb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  std::string err;
+  // params
+  long long seg_bytes = 262144, batch_bytes = 2ll << 30, write_index = 1;
+  LzParams lz{48, 258, 1024, 8192, 32768, 1};
+  // device scratch
+  Buf d_raw, d_T, d_tok, d_hist, d_codes, d_hdrs, d_tab, d_so, d_seg_adler, d_chunk_adler, d_chunk_off, d_out,
+      d_partial, d_comp, d_status, d_tadler, d_gather;
+  Buf h_tab, h_small;
+  // timings
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Span { int stage; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  float last_ms[8] = {0};
+  long long launches = 0;
+  bool attr_set = false;
+
+  mtsb_ctx() { h_tab.host = true; h_small.host = true; }
+  cudaEvent_t ev() {
+    if (ev_used == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
+    return ev_pool[ev_used++];
+  }
+  void begin(int stage) { Span s{stage, ev(), nullptr}; cudaEventRecord(s.a, stream); spans.push_back(s); }
+  void end() { spans.back().b = ev(); cudaEventRecord(spans.back().b, stream); }
+  void reset_timing() { ev_used = 0; spans.clear(); launches = 0; for (float& f : last_ms) f = 0; }
+  void collect_timing() {
+    for (auto& s : spans) {
+      float ms = 0;
+      if (s.b && cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) last_ms[s.stage] += ms;
+    }
+    float tot = 0;
+    for (int i = 0; i < 7; i++) tot += last_ms[i];
+    last_ms[7] = tot;
+  }
+};
+
+namespace {
+
+int fail(mtsb_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess) return fail(c, MTSB_E_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+#define CKL()                                                                                                  \
+  do {                                                                                                         \
+    cudaError_t e__ = cudaGetLastError();                                                                      \
+    if (e__ != cudaSuccess) return fail(c, MTSB_E_CUDA, "kernel launch (%s:%d): %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+  } while (0)
+#define NEED(buf, n)                                                                       \
+  do {                                                                                     \
+    if ((buf).ensure(n)) return fail(c, MTSB_E_NOMEM, "cannot allocate %zu bytes for " #buf, (size_t)(n)); \
+  } while (0)
+
+int tile_rows(int nc, int isz, int extra_rows) {
+  long long P = isz == 1 ? tile_pitch<uint8_t>(nc) : isz == 2 ? tile_pitch<uint16_t>(nc) : (nc | 1);
+  long long tt = 98304 / (P * isz) - extra_rows;
+  return (int)std::min<long long>(64, tt);
+}
+size_t tile_smem(int nc, int isz, int rows) {
+  long long P = isz == 1 ? tile_pitch<uint8_t>(nc) : isz == 2 ? tile_pitch<uint16_t>(nc) : (nc | 1);
+  return (size_t)(P * isz * rows);
+}
+
+int set_attrs(mtsb_ctx* c) {
+  if (c->attr_set) return 0;
+  CK(cudaFuncSetAttribute(fwd_transform_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+  CK(cudaFuncSetAttribute(fwd_transform_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+  CK(cudaFuncSetAttribute(fwd_transform_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+  CK(cudaFuncSetAttribute(fwd_transform_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+  CK(cudaFuncSetAttribute(inv_apply_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+  CK(cudaFuncSetAttribute(inv_apply_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+  CK(cudaFuncSetAttribute(inv_apply_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+  CK(cudaFuncSetAttribute(inv_apply_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+  CK(cudaFuncSetAttribute(lz77_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LzSmem<1>::total));
+  CK(cudaFuncSetAttribute(lz77_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LzSmem<2>::total));
+  c->attr_set = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------- launches shared by several entry points
+template <class T>
+int launch_fwd_t(mtsb_ctx* c, const void* raw, void* tbuf, const ChunkDesc* d_cd, int n_chunks, int max_ns, int nc,
+                 int flags) {
+  int TT = tile_rows(nc, sizeof(T), 1);
+  if (TT < 1) return fail(c, MTSB_E_ARG, "n_channels=%d too large for the transform tile", nc);
+  dim3 grid((max_ns + TT - 1) / TT, n_chunks);
+  auto k = fwd_transform_kernel<T>;
+  MTS_LAUNCH(k, grid, dim3(512), tile_smem(nc, sizeof(T), TT + 1), c->stream, (const T*)raw, (T*)tbuf, d_cd, nc, TT, flags);
+  c->launches++;
+  CKL();
+  return 0;
+}
+int launch_fwd(mtsb_ctx* c, int isz, const void* raw, void* tbuf, const ChunkDesc* d_cd, int n_chunks, int max_ns,
+               int nc, int flags) {
+  switch (isz) {
+    case 1: return launch_fwd_t<uint8_t>(c, raw, tbuf, d_cd, n_chunks, max_ns, nc, flags);
+    case 2: return launch_fwd_t<uint16_t>(c, raw, tbuf, d_cd, n_chunks, max_ns, nc, flags);
+    case 4: return launch_fwd_t<uint32_t>(c, raw, tbuf, d_cd, n_chunks, max_ns, nc, flags);
+    case 8: return launch_fwd_t<uint64_t>(c, raw, tbuf, d_cd, n_chunks, max_ns, nc, flags);
+  }
+  return fail(c, MTSB_E_ARG, "itemsize %d not supported (1, 2, 4, 8)", isz);
+}
+
+template <class T>
+int launch_inv_t(mtsb_ctx* c, const void* tbuf, void* out, const ChunkDesc* d_cd, int n_chunks, int max_ns, int nc,
+                 int flags) {
+  int TT = tile_rows(nc, sizeof(T), 0);
+  if (TT < 1) return fail(c, MTSB_E_ARG, "n_channels=%d too large for the transform tile", nc);
+  int max_tiles = (max_ns + TT - 1) / TT;
+  dim3 grid(max_tiles, n_chunks);
+  T* partial = nullptr;
+  if (flags & FLAG_TIME_DIFF) {
+    NEED(c->d_partial, (size_t)n_chunks * max_tiles * nc * sizeof(T));
+    partial = (T*)c->d_partial.p;
+    auto k1 = inv_tile_sums_kernel<T>;
+    MTS_LAUNCH(k1, grid, dim3(512), 0, c->stream, (const T*)tbuf, partial, d_cd, nc, TT, max_tiles, flags);
+    CKL();
+    auto k2 = inv_tile_scan_kernel<T>;
+    MTS_LAUNCH(k2, dim3((nc + 255) / 256, n_chunks), dim3(256), 0, c->stream, partial, d_cd, nc, TT, max_tiles);
+    CKL();
+    c->launches += 2;
+  }
+  auto k3 = inv_apply_kernel<T>;
+  MTS_LAUNCH(k3, grid, dim3(512), tile_smem(nc, sizeof(T), TT), c->stream, (const T*)tbuf, (T*)out, (const T*)partial, d_cd, nc, TT, max_tiles, flags);
+  c->launches++;
+  CKL();
+  return 0;
+}
+int launch_inv(mtsb_ctx* c, int isz, const void* tbuf, void* out, const ChunkDesc* d_cd, int n_chunks, int max_ns,
+               int nc, int flags) {
+  switch (isz) {
+    case 1: return launch_inv_t<uint8_t>(c, tbuf, out, d_cd, n_chunks, max_ns, nc, flags);
+    case 2: return launch_inv_t<uint16_t>(c, tbuf, out, d_cd, n_chunks, max_ns, nc, flags);
+    case 4: return launch_inv_t<uint32_t>(c, tbuf, out, d_cd, n_chunks, max_ns, nc, flags);
+    case 8: return launch_inv_t<uint64_t>(c, tbuf, out, d_cd, n_chunks, max_ns, nc, flags);
+  }
+  return fail(c, MTSB_E_ARG, "itemsize %d not supported (1, 2, 4, 8)", isz);
+}
+
+long long seg_size_for(const mtsb_ctx* c, long long ns, int itemsize, int flags) {
+  // prefer whole channel runs ('F' order) so that segment boundaries coincide with the rows' seeds
+  long long target = std::max<long long>(c->seg_bytes, 4096);
+  long long run = ns * itemsize;
+  long long s = target;
+  if (!(flags & FLAG_ORDER_C) && run > 0 && run <= target) s = std::max<long long>(1, target / run) * run;
+  return std::min<long long>(s, 1ll << 30);
+}
+long long stored_bound(long long m) { return m + 5 * ((m + 65534) / 65535); }
+long long chunk_bound(const mtsb_ctx* c, long long raw, long long seg) {
+  long long k = (raw + seg - 1) / seg, full = raw / seg, rem = raw - full * seg;
+  long long b = 2 + full * stored_bound(seg) + (rem ? stored_bound(rem) : 0) + 6;
+  if (c->write_index) b += 4 * k + INDEX_TAIL;
+  return b;
+}
+
+bool valid_common(mtsb_ctx* c, int n_chunks, const long long* rows, int nc, int isz) {
+  if (!c || n_chunks < 1 || !rows || nc < 1 || rows[0] != 0) return false;
+  if (isz != 1 && isz != 2 && isz != 4 && isz != 8) return false;
+  for (int i = 0; i < n_chunks; i++) {
+    long long ns = rows[i + 1] - rows[i];
+    if (ns < 1 || ns * nc * isz > 0x7fffffffll || ns > 0x7fffffffll) return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+// =============================================================================================== basic API
+extern "C" {
+
+int mtsb_version(void) { return 100; }
+
+int mtsb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+mtsb_ctx* mtsb_create(int device_id, void* stream) {
+  int n = mtsb_device_count();
+  if (device_id < 0 || device_id >= n) { fail(nullptr, MTSB_E_CUDA, "no CUDA device %d (found %d)", device_id, n); return nullptr; }
+  if (cudaSetDevice(device_id) != cudaSuccess) { fail(nullptr, MTSB_E_CUDA, "cudaSetDevice(%d) failed", device_id); return nullptr; }
+  mtsb_ctx* c = new mtsb_ctx();
+  c->device = device_id;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+  else {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      fail(nullptr, MTSB_E_CUDA, "cudaStreamCreate failed"); delete c; return nullptr;
+    }
+    c->own_stream = true;
+  }
+  if (set_attrs(c)) { g_err = c->err; mtsb_destroy(c); return nullptr; }
+  return c;
+}
+
+void mtsb_destroy(mtsb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  Buf* bufs[] = {&c->d_raw, &c->d_T, &c->d_tok, &c->d_hist, &c->d_codes, &c->d_hdrs, &c->d_tab, &c->d_so,
+                 &c->d_seg_adler, &c->d_chunk_adler, &c->d_chunk_off, &c->d_out, &c->d_partial, &c->d_comp,
+                 &c->d_status, &c->d_tadler, &c->d_gather, &c->h_tab, &c->h_small};
+  for (Buf* b : bufs) b->release();
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* mtsb_last_error(mtsb_ctx* c) { return c ? c->err.c_str() : g_err.c_str(); }
+
+int mtsb_sync(mtsb_ctx* c) {
+  if (!c) return MTSB_E_ARG;
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int mtsb_set_param(mtsb_ctx* c, const char* name, long long v) {
+  if (!c || !name) return MTSB_E_ARG;
+  std::string s(name);
+  if (s == "seg_bytes") { if (v < 4096 || v > (1ll << 30)) return fail(c, MTSB_E_ARG, "seg_bytes out of range"); c->seg_bytes = v; }
+  else if (s == "batch_bytes") { if (v < (1 << 20)) return fail(c, MTSB_E_ARG, "batch_bytes too small"); c->batch_bytes = v; }
+  else if (s == "write_index") c->write_index = v ? 1 : 0;
+  else if (s == "max_chain") c->lz.max_chain = (int)std::max<long long>(1, v);
+  else if (s == "nice_len") c->lz.nice_len = (int)std::min<long long>(258, std::max<long long>(4, v));
+  else if (s == "far4") c->lz.far4 = (int)v;
+  else if (s == "far5") c->lz.far5 = (int)v;
+  else if (s == "far6") c->lz.far6 = (int)v;
+  else if (s == "lazy") c->lz.lazy = v ? 1 : 0;
+  else return fail(c, MTSB_E_ARG, "unknown parameter %s", name);
+  return 0;
+}
+
+long long mtsb_get_param(mtsb_ctx* c, const char* name) {
+  if (!c || !name) return MTSB_E_ARG;
+  std::string s(name);
+  if (s == "seg_bytes") return c->seg_bytes;
+  if (s == "batch_bytes") return c->batch_bytes;
+  if (s == "write_index") return c->write_index;
+  if (s == "max_chain") return c->lz.max_chain;
+  if (s == "nice_len") return c->lz.nice_len;
+  if (s == "far4") return c->lz.far4;
+  if (s == "far5") return c->lz.far5;
+  if (s == "far6") return c->lz.far6;
+  if (s == "lazy") return c->lz.lazy;
+  if (s == "sm_count") return c->sm_count;
+  return MTSB_E_ARG;
+}
+
+long long mtsb_compress_bound(mtsb_ctx* c, long long raw_bytes, long long ns, int nc, int itemsize, int flags) {
+  if (!c || raw_bytes < 0) return MTSB_E_ARG;
+  (void)nc;
+  return chunk_bound(c, raw_bytes, seg_size_for(c, ns, itemsize, flags));
+}
+
+int mtsb_last_timings(mtsb_ctx* c, float* out, int n) {
+  if (!c || !out) return 0;
+  int k = std::min(n, 8);
+  for (int i = 0; i < k; i++) out[i] = c->last_ms[i];
+  return k;
+}
+long long mtsb_last_launches(mtsb_ctx* c) { return c ? c->launches : 0; }
+
+void* mtsb_host_alloc(long long bytes) {
+  void* p = nullptr;
+  if (bytes <= 0 || cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void mtsb_host_free(void* p) { if (p) cudaFreeHost(p); }
+void* mtsb_device_alloc(mtsb_ctx* c, long long bytes) {
+  void* p = nullptr;
+  if (!c || bytes <= 0) return nullptr;
+  cudaSetDevice(c->device);
+  if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void mtsb_device_free(mtsb_ctx* c, void* p) { if (c && p) { cudaSetDevice(c->device); cudaFree(p); } }
+int mtsb_memcpy(mtsb_ctx* c, void* dst, const void* src, long long bytes, int kind) {
+  if (!c || !dst || !src || bytes < 0) return MTSB_E_ARG;
+  cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  CK(cudaMemcpyAsync(dst, src, (size_t)bytes, k, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// =============================================================================================== transforms
+static int single_chunk_desc(mtsb_ctx* c, long long ns) {
+  NEED(c->h_tab, 4096);
+  NEED(c->d_tab, 4096);
+  ChunkDesc cd{0, (int)ns, 0, 0, 0};
+  memcpy(c->h_tab.p, &cd, sizeof cd);
+  CK(cudaMemcpyAsync(c->d_tab.p, c->h_tab.p, sizeof cd, cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+
+int mtsb_delta_transform(mtsb_ctx* c, const void* src, int src_is_device, long long ns, int nc, int itemsize,
+                         int flags, void* dst, int dst_is_device) {
+  long long rows[2] = {0, ns};
+  if (!valid_common(c, 1, rows, nc, itemsize) || !src || !dst) return fail(c, MTSB_E_ARG, "delta_transform: bad arguments");
+  cudaSetDevice(c->device);
+  c->reset_timing();
+  size_t bytes = (size_t)ns * nc * itemsize;
+  int r = single_chunk_desc(c, ns);
+  if (r) return r;
+  const void* raw = src;
+  if (!src_is_device) { NEED(c->d_raw, bytes + 256); CK(cudaMemcpyAsync(c->d_raw.p, src, bytes, cudaMemcpyHostToDevice, c->stream)); raw = c->d_raw.p; }
+  void* t = dst;
+  if (!dst_is_device) { NEED(c->d_T, bytes + 8192); t = c->d_T.p; }
+  r = launch_fwd(c, itemsize, raw, t, (const ChunkDesc*)c->d_tab.p, 1, (int)ns, nc, flags);
+  if (r) return r;
+  if (!dst_is_device) CK(cudaMemcpyAsync(dst, t, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int mtsb_inverse_transform(mtsb_ctx* c, const void* src, int src_is_device, long long ns, int nc, int itemsize,
+                           int flags, void* dst, int dst_is_device, uint32_t* adler32_out) {
+  long long rows[2] = {0, ns};
+  if (!valid_common(c, 1, rows, nc, itemsize) || !src || !dst) return fail(c, MTSB_E_ARG, "inverse_transform: bad arguments");
+  cudaSetDevice(c->device);
+  c->reset_timing();
+  size_t bytes = (size_t)ns * nc * itemsize;
+  const int ASEG = 1 << 16;
+  int nas = (int)((bytes + ASEG - 1) / ASEG);
+  size_t tab_bytes = 256 + (size_t)nas * sizeof(AdlerSeg) + 64;
+  NEED(c->h_tab, tab_bytes);
+  NEED(c->d_tab, tab_bytes);
+  char* h = (char*)c->h_tab.p;
+  ChunkDesc cd{0, (int)ns, 0, 0, 0};
+  memcpy(h, &cd, sizeof cd);
+  int firsts[2] = {0, nas};
+  memcpy(h + 64, firsts, sizeof firsts);
+  AdlerSeg* as = (AdlerSeg*)(h + 256);
+  for (int i = 0; i < nas; i++) { as[i].off = (long long)i * ASEG; as[i].len = (int)std::min<size_t>(ASEG, bytes - (size_t)i * ASEG); as[i].pad_ = 0; }
+  CK(cudaMemcpyAsync(c->d_tab.p, h, tab_bytes, cudaMemcpyHostToDevice, c->stream));
+  const void* t = src;
+  if (!src_is_device) { NEED(c->d_T, bytes + 8192); CK(cudaMemcpyAsync(c->d_T.p, src, bytes, cudaMemcpyHostToDevice, c->stream)); t = c->d_T.p; }
+  void* o = dst;
+  if (!dst_is_device) { NEED(c->d_out, bytes + 256); o = c->d_out.p; }
+  char* d = (char*)c->d_tab.p;
+  if (adler32_out) {
+    NEED(c->d_seg_adler, (size_t)nas * 4);
+    NEED(c->d_chunk_adler, 64);
+    MTS_LAUNCH(adler_partial_kernel, dim3(nas), dim3(256), 0, c->stream, (const uint8_t*)t, (const AdlerSeg*)(d + 256), (uint32_t*)c->d_seg_adler.p);
+    CKL();
+    MTS_LAUNCH(adler_combine_kernel, dim3(1), dim3(32), 0, c->stream, (const AdlerSeg*)(d + 256), (const uint32_t*)c->d_seg_adler.p, (const int*)(d + 64), 1, (uint32_t*)c->d_chunk_adler.p);
+    CKL();
+    c->launches += 2;
+    CK(cudaMemcpyAsync(adler32_out, c->d_chunk_adler.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  int r = launch_inv(c, itemsize, t, o, (const ChunkDesc*)d, 1, (int)ns, nc, flags);
+  if (r) return r;
+  if (!dst_is_device) CK(cudaMemcpyAsync(dst, o, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// =============================================================================================== compress
+int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_chunks, const long long* chunk_rows,
+                         int nc, int itemsize, int flags, void* dst, int dst_is_device, long long dst_capacity,
+                         long long* out_offsets) {
+  if (!valid_common(c, n_chunks, chunk_rows, nc, itemsize) || !src || !dst || !out_offsets)
+    return fail(c, MTSB_E_ARG, "compress_chunks: bad arguments");
+  cudaSetDevice(c->device);
+  c->reset_timing();
+  const long long row_bytes = (long long)nc * itemsize;
+  // capacity check against the worst case
+  long long need = 0;
+  for (int i = 0; i < n_chunks; i++) {
+    long long ns = chunk_rows[i + 1] - chunk_rows[i];
+    need += chunk_bound(c, ns * row_bytes, seg_size_for(c, ns, itemsize, flags));
+  }
+  if (dst_capacity < need) return fail(c, MTSB_E_CAPACITY, "dst_capacity %lld < bound %lld", dst_capacity, need);
+
+  out_offsets[0] = 0;
+  long long total_out = 0;
+  int c0 = 0;
+  while (c0 < n_chunks) {
+    // ---- sub-batch [c0, c1)
+    int c1 = c0;
+    long long bbytes = 0;
+    while (c1 < n_chunks && c1 - c0 < 60000) {
+      long long cb = (chunk_rows[c1 + 1] - chunk_rows[c1]) * row_bytes;
+      if (c1 > c0 && bbytes + cb > c->batch_bytes) break;
+      bbytes += cb; c1++;
+    }
+    const int nb = c1 - c0;
+    const long long row0 = chunk_rows[c0];
+    // tables
+    std::vector<ChunkDesc> cds(nb);
+    std::vector<DeflateSeg> segs;
+    std::vector<int> first(nb + 1);
+    int max_ns = 0;
+    long long bound = 0;
+    for (int i = 0; i < nb; i++) {
+      long long ns = chunk_rows[c0 + i + 1] - chunk_rows[c0 + i];
+      long long raw = ns * row_bytes;
+      long long seg = seg_size_for(c, ns, itemsize, flags);
+      int k = (int)((raw + seg - 1) / seg);
+      cds[i].elem_off = (chunk_rows[c0 + i] - row0) * nc;
+      cds[i].ns = (int)ns;
+      cds[i].first_seg = (int)segs.size();
+      cds[i].n_seg = k;
+      cds[i].pad_ = (int)seg;
+      first[i] = (int)segs.size();
+      max_ns = std::max(max_ns, (int)ns);
+      long long base = cds[i].elem_off * itemsize;
+      for (int j = 0; j < k; j++) {
+        DeflateSeg s;
+        s.in_off = base + (long long)j * seg;
+        s.tok_off = s.in_off;
+        s.in_len = (int)std::min<long long>(seg, raw - (long long)j * seg);
+        s.chunk = i;
+        s.flags = (j == 0 ? SEG_FIRST : 0) | (j == k - 1 ? SEG_LAST : 0);
+        s.pad_ = 0;
+        segs.push_back(s);
+      }
+      bound += chunk_bound(c, raw, seg);
+    }
+    first[nb] = (int)segs.size();
+    const int n_segs = (int)segs.size();
+    // table blob: [ChunkDesc nb][DeflateSeg n_segs][AdlerSeg n_segs][first nb+1]
+    size_t o_cd = 0, o_seg = (o_cd + nb * sizeof(ChunkDesc) + 255) & ~(size_t)255;
+    size_t o_as = (o_seg + n_segs * sizeof(DeflateSeg) + 255) & ~(size_t)255;
+    size_t o_first = (o_as + n_segs * sizeof(AdlerSeg) + 255) & ~(size_t)255;
+    size_t tab_bytes = o_first + (nb + 1) * sizeof(int);
+    NEED(c->h_tab, tab_bytes);
+    NEED(c->d_tab, tab_bytes);
+    char* h = (char*)c->h_tab.p;
+    memcpy(h + o_cd, cds.data(), nb * sizeof(ChunkDesc));
+    memcpy(h + o_seg, segs.data(), n_segs * sizeof(DeflateSeg));
+    AdlerSeg* as = (AdlerSeg*)(h + o_as);
+    for (int i = 0; i < n_segs; i++) { as[i].off = segs[i].in_off; as[i].len = segs[i].in_len; as[i].pad_ = 0; }
+    memcpy(h + o_first, first.data(), (nb + 1) * sizeof(int));
+    // scratch
+    NEED(c->d_T, (size_t)bbytes + 16384);
+    NEED(c->d_tok, (size_t)bbytes * 2 + 4096);
+    NEED(c->d_hist, (size_t)n_segs * HIST_STRIDE * 4);
+    NEED(c->d_codes, (size_t)n_segs * CODE_STRIDE * 4);
+    NEED(c->d_hdrs, (size_t)n_segs * HDR_WORDS * 4);
+    NEED(c->d_so, (size_t)n_segs * sizeof(DeflateSegOut));
+    NEED(c->d_seg_adler, (size_t)n_segs * 4);
+    NEED(c->d_chunk_adler, (size_t)nb * 4);
+    NEED(c->d_chunk_off, (size_t)(nb + 1) * 8);
+    NEED(c->h_small, (size_t)(nb + 1) * 8);
+    const char* d = (const char*)c->d_tab.p;
+    const ChunkDesc* d_cd = (const ChunkDesc*)(d + o_cd);
+    const DeflateSeg* d_seg = (const DeflateSeg*)(d + o_seg);
+    const AdlerSeg* d_as = (const AdlerSeg*)(d + o_as);
+    const int* d_first = (const int*)(d + o_first);
+
+    c->begin(0);
+    CK(cudaMemcpyAsync(c->d_tab.p, h, tab_bytes, cudaMemcpyHostToDevice, c->stream));
+    const void* raw = (const char*)src + row0 * row_bytes;
+    if (!src_is_device) {
+      NEED(c->d_raw, (size_t)bbytes + 256);
+      CK(cudaMemcpyAsync(c->d_raw.p, raw, (size_t)bbytes, cudaMemcpyHostToDevice, c->stream));
+      raw = c->d_raw.p;
+    }
+    c->end();
+    unsigned char* outp;
+    if (dst_is_device) outp = (unsigned char*)dst + total_out;
+    else { NEED(c->d_out, (size_t)bound + 256); outp = (unsigned char*)c->d_out.p; }
+
+    c->begin(1);
+    int r = launch_fwd(c, itemsize, raw, c->d_T.p, d_cd, nb, max_ns, nc, flags);
+    if (r) return r;
+    c->end();
+    c->begin(2);
+    MTS_LAUNCH(adler_partial_kernel, dim3(n_segs), dim3(256), 0, c->stream, (const uint8_t*)c->d_T.p, d_as, (uint32_t*)c->d_seg_adler.p);
+    CKL();
+    MTS_LAUNCH(adler_combine_kernel, dim3((nb + 127) / 128), dim3(128), 0, c->stream, d_as, (const uint32_t*)c->d_seg_adler.p, d_first, nb, (uint32_t*)c->d_chunk_adler.p);
+    CKL();
+    c->launches += 2;
+    c->end();
+    c->begin(3);
+    {
+      int grid = std::min(n_segs, c->sm_count);
+      if (itemsize == 2) {
+        auto k = lz77_kernel<2>;
+        MTS_LAUNCH(k, dim3(grid), dim3(LZ_THREADS), LzSmem<2>::total, c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p, c->lz);
+      } else {
+        auto k = lz77_kernel<1>;
+        MTS_LAUNCH(k, dim3(grid), dim3(LZ_THREADS), LzSmem<1>::total, c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p, c->lz);
+      }
+      CKL();
+      c->launches++;
+    }
+    c->end();
+    c->begin(4);
+    MTS_LAUNCH(huff_kernel, dim3(n_segs), dim3(32), 0, c->stream, d_seg, n_segs, (unsigned*)c->d_hist.p, (unsigned*)c->d_codes.p, (unsigned*)c->d_hdrs.p, (DeflateSegOut*)c->d_so.p);
+    CKL();
+    MTS_LAUNCH(scan_kernel, dim3(1), dim3(1024), 0, c->stream, d_seg, n_segs, (DeflateSegOut*)c->d_so.p, (long long*)c->d_chunk_off.p, nb, d_cd, (int)c->write_index);
+    CKL();
+    c->launches += 2;
+    c->end();
+    c->begin(5);
+    MTS_LAUNCH(encode_kernel, dim3(n_segs), dim3(ENC_THREADS), 0, c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (const unsigned short*)c->d_tok.p, (const unsigned*)c->d_codes.p, (const unsigned*)c->d_hdrs.p, (const DeflateSegOut*)c->d_so.p, (const unsigned*)c->d_chunk_adler.p, outp, d_cd, (int)c->write_index);
+    CKL();
+    c->launches++;
+    c->end();
+    CK(cudaMemcpyAsync(c->h_small.p, c->d_chunk_off.p, (size_t)(nb + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const long long* co = (const long long*)c->h_small.p;
+    if (co[nb] > bound) return fail(c, MTSB_E_CAPACITY, "internal: sub-batch output %lld exceeds bound %lld", co[nb], bound);
+    for (int i = 0; i < nb; i++) out_offsets[c0 + i + 1] = total_out + co[i + 1];
+    if (!dst_is_device) {
+      c->begin(6);
+      CK(cudaMemcpyAsync((char*)dst + total_out, outp, (size_t)co[nb], cudaMemcpyDeviceToHost, c->stream));
+      c->end();
+      CK(cudaStreamSynchronize(c->stream));
+    }
+    total_out += co[nb];
+    c0 = c1;
+  }
+  c->collect_timing();
+  return 0;
+}
+
+// =============================================================================================== decompress
+__global__ void gather_bytes_kernel(const unsigned char* __restrict__ base, const long long* __restrict__ src_off,
+                                    const int* __restrict__ len, const long long* __restrict__ dst_off,
+                                    unsigned char* __restrict__ dst) {
+  const long long so = src_off[blockIdx.x], dof = dst_off[blockIdx.x];
+  const int n = len[blockIdx.x];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[dof + i] = base[so + i];
+}
+
+// Fetch `n` ranges of the compressed buffer to host memory (direct reads for host buffers, one gather kernel + one
+// copy for device buffers).
+static int fetch_ranges(mtsb_ctx* c, const unsigned char* comp, int comp_is_device, const std::vector<long long>& off,
+                        const std::vector<int>& len, std::vector<unsigned char>& out, std::vector<long long>& dpos) {
+  size_t n = off.size(), total = 0;
+  dpos.resize(n);
+  for (size_t i = 0; i < n; i++) { dpos[i] = (long long)total; total += (size_t)len[i]; }
+  out.resize(total);
+  if (!total) return 0;
+  if (!comp_is_device) {
+    for (size_t i = 0; i < n; i++) memcpy(out.data() + dpos[i], comp + off[i], (size_t)len[i]);
+    return 0;
+  }
+  size_t tb = n * 20 + 64;
+  NEED(c->h_tab, tb + total);
+  NEED(c->d_tab, tb);
+  NEED(c->d_gather, total);
+  char* h = (char*)c->h_tab.p;
+  size_t o1 = n * 8, o2 = n * 16;
+  memcpy(h, off.data(), n * 8);
+  memcpy(h + o1, dpos.data(), n * 8);
+  memcpy(h + o2, len.data(), n * 4);
+  CK(cudaMemcpyAsync(c->d_tab.p, h, tb, cudaMemcpyHostToDevice, c->stream));
+  const char* d = (const char*)c->d_tab.p;
+  MTS_LAUNCH(gather_bytes_kernel, dim3((unsigned)n), dim3(128), 0, c->stream, comp, (const long long*)d, (const int*)(d + o2), (const long long*)(d + o1), (unsigned char*)c->d_gather.p);
+  CKL();
+  c->launches++;
+  CK(cudaMemcpyAsync(h + tb, c->d_gather.p, total, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  memcpy(out.data(), h + tb, total);
+  return 0;
+}
+
+static uint32_t rd32(const unsigned char* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, const long long* comp_offsets,
+                           int n_chunks, const long long* chunk_rows, int nc, int itemsize, int flags, void* dst,
+                           int dst_is_device, int* chunk_status) {
+  if (!valid_common(c, n_chunks, chunk_rows, nc, itemsize) || !comp_ || !comp_offsets || !dst)
+    return fail(c, MTSB_E_ARG, "decompress_chunks: bad arguments");
+  for (int i = 0; i < n_chunks; i++) {
+    long long l = comp_offsets[i + 1] - comp_offsets[i];
+    if (l < 1 || l > 0x7fffffffll) return fail(c, MTSB_E_ARG, "decompress_chunks: bad compressed length of chunk %d", i);
+  }
+  cudaSetDevice(c->device);
+  c->reset_timing();
+  const unsigned char* comp = (const unsigned char*)comp_;
+  const long long row_bytes = (long long)nc * itemsize;
+
+  // ---- plan: look for the segment index after each chunk's zlib stream
+  c->begin(1);
+  std::vector<int> nseg(n_chunks, 0);
+  std::vector<long long> segb(n_chunks, 0);
+  std::vector<unsigned char> tails, idx;
+  std::vector<long long> tpos, ipos;
+  {
+    std::vector<long long> off;
+    std::vector<int> len;
+    std::vector<int> who;
+    for (int i = 0; i < n_chunks; i++) {
+      long long l = comp_offsets[i + 1] - comp_offsets[i];
+      if (l >= 2 + 6 + 4 + INDEX_TAIL) { off.push_back(comp_offsets[i + 1] - INDEX_TAIL); len.push_back(INDEX_TAIL); who.push_back(i); }
+    }
+    int r = fetch_ranges(c, comp, comp_is_device, off, len, tails, tpos);
+    if (r) return r;
+    std::vector<long long> off2, tail_by_chunk(n_chunks, -1);
+    std::vector<int> len2;
+    std::vector<int> who2;
+    for (size_t j = 0; j < who.size(); j++) {
+      const unsigned char* t = tails.data() + tpos[j];
+      int i = who[j];
+      tail_by_chunk[i] = tpos[j];
+      long long l = comp_offsets[i + 1] - comp_offsets[i];
+      long long raw = (chunk_rows[i + 1] - chunk_rows[i]) * row_bytes;
+      uint32_t sb = rd32(t), k = rd32(t + 4), magic = rd32(t + 8);
+      if (magic != INDEX_MAGIC || sb == 0 || k == 0) continue;
+      if ((long long)k != (raw + sb - 1) / sb) continue;
+      if (8 + 4ll * k + INDEX_TAIL >= l) continue;
+      nseg[i] = (int)k; segb[i] = sb;
+      off2.push_back(comp_offsets[i + 1] - INDEX_TAIL - 4ll * k - 4);   // adler32 + k lengths
+      len2.push_back((int)(4 * k + 4));
+      who2.push_back(i);
+    }
+    r = fetch_ranges(c, comp, comp_is_device, off2, len2, idx, ipos);
+    if (r) return r;
+    // validate: lengths must tile the stream body exactly, and match the checksum word
+    std::vector<long long> ipos_by_chunk(n_chunks, -1);
+    for (size_t j = 0; j < who2.size(); j++) {
+      int i = who2[j];
+      const unsigned char* p = idx.data() + ipos[j];
+      const unsigned char* t = tails.data() + tail_by_chunk[i];
+      long long l = comp_offsets[i + 1] - comp_offsets[i];
+      unsigned long long sum = 0;
+      bool ok = true;
+      for (int q = 0; q < nseg[i]; q++) { uint32_t v = rd32(p + 4 + 4 * q); if (v == 0) ok = false; sum += v; }
+      if (!ok || (long long)sum != l - 8 - 4ll * nseg[i] - INDEX_TAIL || (uint32_t)sum != rd32(t + 12)) { nseg[i] = 0; continue; }
+      ipos_by_chunk[i] = ipos[j];
+    }
+    for (int i = 0; i < n_chunks; i++) if (nseg[i] && ipos_by_chunk[i] < 0) nseg[i] = 0;
+    tpos.assign(ipos_by_chunk.begin(), ipos_by_chunk.end());   // reuse: tpos[i] = position of chunk i's index in idx
+  }
+  c->end();
+
+  if (chunk_status) for (int i = 0; i < n_chunks; i++) chunk_status[i] = 0;
+  bool any_bad = false;
+  int c0 = 0;
+  while (c0 < n_chunks) {
+    int c1 = c0;
+    long long bbytes = 0;
+    while (c1 < n_chunks && c1 - c0 < 60000) {
+      long long cb = (chunk_rows[c1 + 1] - chunk_rows[c1]) * row_bytes;
+      if (c1 > c0 && bbytes + cb > c->batch_bytes) break;
+      bbytes += cb; c1++;
+    }
+    const int nb = c1 - c0;
+    const long long row0 = chunk_rows[c0];
+    const long long comp0 = comp_offsets[c0], comp_bytes = comp_offsets[c1] - comp0;
+    std::vector<ChunkDesc> cds(nb);
+    std::vector<InflateSeg> segs;
+    std::vector<AdlerSeg> as;
+    std::vector<int> first(nb + 1), first_inf(nb + 1);
+    std::vector<uint32_t> want_adler(nb, 0);
+    int max_ns = 0;
+    const int ASEG = 1 << 16;
+    for (int i = 0; i < nb; i++) {
+      int g = c0 + i;
+      long long ns = chunk_rows[g + 1] - chunk_rows[g], raw = ns * row_bytes;
+      cds[i].elem_off = (chunk_rows[g] - row0) * nc;
+      cds[i].ns = (int)ns; cds[i].first_seg = 0; cds[i].n_seg = 0; cds[i].pad_ = 0;
+      max_ns = std::max(max_ns, (int)ns);
+      long long tbase = cds[i].elem_off * itemsize;
+      long long cbase = comp_offsets[g] - comp0, clen = comp_offsets[g + 1] - comp_offsets[g];
+      first_inf[i] = (int)segs.size();
+      if (nseg[g]) {
+        const unsigned char* p = idx.data() + tpos[g];
+        want_adler[i] = ((uint32_t)p[0] << 24) | (p[1] << 16) | (p[2] << 8) | p[3];
+        long long pos = cbase + 2;
+        for (int j = 0; j < nseg[g]; j++) {
+          InflateSeg s;
+          s.in_off = pos; s.in_len = (int)rd32(p + 4 + 4 * j);
+          s.out_off = tbase + (long long)j * segb[g];
+          s.out_len = (int)std::min<long long>(segb[g], raw - (long long)j * segb[g]);
+          s.flags = 0; s.pad_ = 0;
+          pos += s.in_len;
+          segs.push_back(s);
+        }
+      } else {
+        InflateSeg s;
+        s.in_off = cbase; s.in_len = (int)clen; s.out_off = tbase; s.out_len = (int)raw; s.flags = INF_ZLIB; s.pad_ = 0;
+        segs.push_back(s);
+      }
+      first[i] = (int)as.size();
+      for (long long o = 0; o < raw; o += ASEG) as.push_back(AdlerSeg{tbase + o, (int)std::min<long long>(ASEG, raw - o), 0});
+    }
+    first[nb] = (int)as.size();
+    first_inf[nb] = (int)segs.size();
+    const int n_segs = (int)segs.size(), n_as = (int)as.size();
+    size_t o_cd = 0, o_seg = (o_cd + nb * sizeof(ChunkDesc) + 255) & ~(size_t)255;
+    size_t o_as = (o_seg + n_segs * sizeof(InflateSeg) + 255) & ~(size_t)255;
+    size_t o_first = (o_as + n_as * sizeof(AdlerSeg) + 255) & ~(size_t)255;
+    size_t tab_bytes = o_first + (nb + 1) * sizeof(int);
+    NEED(c->h_tab, tab_bytes);
+    NEED(c->d_tab, tab_bytes);
+    char* h = (char*)c->h_tab.p;
+    memcpy(h + o_cd, cds.data(), nb * sizeof(ChunkDesc));
+    memcpy(h + o_seg, segs.data(), n_segs * sizeof(InflateSeg));
+    memcpy(h + o_as, as.data(), n_as * sizeof(AdlerSeg));
+    memcpy(h + o_first, first.data(), (nb + 1) * sizeof(int));
+    NEED(c->d_T, (size_t)bbytes + 16384);
+    NEED(c->d_status, (size_t)n_segs * 4);
+    NEED(c->d_tadler, (size_t)n_segs * 4);
+    NEED(c->d_seg_adler, (size_t)n_as * 4);
+    NEED(c->d_chunk_adler, (size_t)nb * 4);
+    NEED(c->h_small, (size_t)n_segs * 8 + (size_t)nb * 4 + 64);
+    const char* d = (const char*)c->d_tab.p;
+    const ChunkDesc* d_cd = (const ChunkDesc*)(d + o_cd);
+
+    c->begin(0);
+    CK(cudaMemcpyAsync(c->d_tab.p, h, tab_bytes, cudaMemcpyHostToDevice, c->stream));
+    const unsigned char* dcomp = comp + comp0;
+    if (!comp_is_device) {
+      NEED(c->d_comp, (size_t)comp_bytes + 256);
+      CK(cudaMemcpyAsync(c->d_comp.p, comp + comp0, (size_t)comp_bytes, cudaMemcpyHostToDevice, c->stream));
+      dcomp = (const unsigned char*)c->d_comp.p;
+    }
+    c->end();
+    c->begin(2);
+    MTS_LAUNCH(inflate_kernel, dim3((n_segs + INF_WARPS - 1) / INF_WARPS), dim3(INF_WARPS * 32), 0, c->stream, dcomp, (const InflateSeg*)(d + o_seg), n_segs, (unsigned char*)c->d_T.p, (int*)c->d_status.p, (unsigned*)c->d_tadler.p);
+    CKL();
+    c->launches++;
+    c->end();
+    c->begin(3);
+    MTS_LAUNCH(adler_partial_kernel, dim3(n_as), dim3(256), 0, c->stream, (const uint8_t*)c->d_T.p, (const AdlerSeg*)(d + o_as), (uint32_t*)c->d_seg_adler.p);
+    CKL();
+    MTS_LAUNCH(adler_combine_kernel, dim3((nb + 127) / 128), dim3(128), 0, c->stream, (const AdlerSeg*)(d + o_as), (const uint32_t*)c->d_seg_adler.p, (const int*)(d + o_first), nb, (uint32_t*)c->d_chunk_adler.p);
+    CKL();
+    c->launches += 2;
+    c->end();
+    void* outp;
+    if (dst_is_device) outp = (char*)dst + row0 * row_bytes;
+    else { NEED(c->d_out, (size_t)bbytes + 256); outp = c->d_out.p; }
+    c->begin(4);
+    int r = launch_inv(c, itemsize, c->d_T.p, outp, d_cd, nb, max_ns, nc, flags);
+    if (r) return r;
+    c->end();
+    char* hs = (char*)c->h_small.p;
+    CK(cudaMemcpyAsync(hs, c->d_status.p, (size_t)n_segs * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(hs + (size_t)n_segs * 4, c->d_tadler.p, (size_t)n_segs * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(hs + (size_t)n_segs * 8, c->d_chunk_adler.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (!dst_is_device) {
+      c->begin(5);
+      CK(cudaMemcpyAsync((char*)dst + row0 * row_bytes, outp, (size_t)bbytes, cudaMemcpyDeviceToHost, c->stream));
+      c->end();
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    const int* st = (const int*)hs;
+    const uint32_t* ta = (const uint32_t*)(hs + (size_t)n_segs * 4);
+    const uint32_t* ca = (const uint32_t*)(hs + (size_t)n_segs * 8);
+    for (int i = 0; i < nb; i++) {
+      int s = 0;
+      for (int j = first_inf[i]; j < first_inf[i + 1] && !s; j++) s = st[j];
+      if (!s) {
+        uint32_t want = nseg[c0 + i] ? want_adler[i] : ta[first_inf[i]];
+        if (want != ca[i]) s = INF_BAD_ADLER;
+      }
+      if (s) any_bad = true;
+      if (chunk_status) chunk_status[c0 + i] = s;
+    }
+    c0 = c1;
+  }
+  c->collect_timing();
+  if (any_bad) return fail(c, MTSB_E_CORRUPT, "at least one compressed chunk is corrupted");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,782 @@
+// deflate.cuh — K2: parallel DEFLATE encoder (RFC 1951) producing one valid zlib stream (RFC 1950) per chunk.
+//
+// Replaces `zlib.compress(chunkd.tobytes(order))` at mtscomp.py:394.  The reference Reader only requires that
+// zlib.decompress() accepts the stream and returns the transformed bytes (mtscomp.py:619), so the encoder
+// is free to pick its own parse; the contract is decodability + size <= 1.031x zlib level 6 (north star).
+//
+// Each chunk's transformed bytes are cut into independent "segments" (fresh 32 KB window, own dynamic-Huffman block,
+// closed by an empty stored block so the next segment starts byte-aligned).  Four kernels, split by parallelism shape:
+//   lz77_kernel     one CTA / segment : shared-memory hash-chain match finder over a 64 KB data ring, every position
+//                                       matched in parallel, lazy parse by pointer doubling, token + histogram output
+//   huff_kernel     one warp / segment: length-limited Huffman codes (<=15 / <=7 bits), RLE'd dynamic header, sizes
+//   scan_kernel     one CTA           : exclusive prefix of segment byte sizes -> final offsets (packed .cbin layout)
+//   encode_kernel   one CTA / segment : code lookup, prefix-sum bit offsets, bit-pack straight into the final stream,
+//                                       zlib header / stored fallback / final block / adler32 trailer
+#pragma once
+#include "common.cuh"
+
+namespace mts {
+
+// ------------------------------------------------------------------------------------------------ tables
+struct DeflateSeg {
+  long long in_off;     // byte offset of the segment's input in the transformed buffer
+  long long tok_off;    // element offset of the segment's token area (capacity = in_len u16 elements)
+  int in_len;           // input bytes (> 0)
+  int chunk;            // owning chunk (index within the batch)
+  int flags;            // SEG_FIRST | SEG_LAST
+  int pad_;
+};
+enum { SEG_FIRST = 1, SEG_LAST = 2 };
+enum { MODE_STORED = 0, MODE_DYNAMIC = 1, MODE_FIXED = 2 };
+
+struct DeflateSegOut {   // written by huff_kernel / scan_kernel, read by encode_kernel
+  unsigned n_tok;        // u16 token elements produced by lz77_kernel
+  unsigned hdr_bits;     // dynamic header length in bits
+  unsigned mode;
+  unsigned body_bytes;   // bytes of this segment's deflate data (without zlib header/trailer)
+  long long out_off;     // byte offset in the packed output
+};
+
+static const int LL_SYMS = 286, D_SYMS = 30, BL_SYMS = 19;
+static const int HIST_STRIDE = 320;          // u32 per segment: [0,286) lit/len, [288,318) dist
+static const int HDR_WORDS = 192;            // dynamic header capacity (u32) per segment
+static const int CODE_STRIDE = 320;          // u32 per segment: code | len<<16, same layout as the histogram
+
+struct LzParams {
+  int max_chain;    // candidates examined per position
+  int nice_len;     // stop searching at this length
+  int far4;         // a 4-byte match is accepted only if dist <= far4
+  int far5;         // a 5-byte match is accepted only if dist <= far5
+  int far6;         // a 6-byte match is accepted only if dist <= far6
+  int lazy;         // 1: defer to a longer match at the next position
+};
+
+__device__ __forceinline__ void len_symbol(unsigned len, unsigned& sym, unsigned& nb, unsigned& ev) {
+  unsigned l = len - 3;
+  if (l < 8) { sym = 257 + l; nb = 0; ev = 0; }
+  else if (len == 258) { sym = 285; nb = 0; ev = 0; }
+  else { nb = 29 - __clz((int)l); sym = 261 + 4 * nb + ((l >> nb) & 3); ev = l & ((1u << nb) - 1); }
+}
+__device__ __forceinline__ void dist_symbol(unsigned dist, unsigned& sym, unsigned& nb, unsigned& ev) {
+  unsigned d = dist - 1;
+  if (d < 4) { sym = d; nb = 0; ev = 0; }
+  else { nb = 30 - __clz((int)d); sym = 2 * nb + 2 + ((d >> nb) & 1); ev = d & ((1u << nb) - 1); }
+}
+__device__ __forceinline__ unsigned ll_extra_bits(unsigned sym) {   // sym in [0,286)
+  if (sym < 265 || sym == 285) return 0;
+  return (sym - 261) >> 2;
+}
+__device__ __forceinline__ unsigned d_extra_bits(unsigned sym) { return sym < 4 ? 0 : (sym >> 1) - 1; }
+
+// ------------------------------------------------------------------------------------------------ lz77_kernel
+// Shared memory (STRIDE = bytes between indexed positions: 2 for int16 streams, 1 generic):
+//   ring  64 KB  data ring, ring coordinate = position + (input address & 15) so global uint4 loads land aligned
+//   head  64 KB  2^15 x u16  most recent indexed unit (biased by 32768) per hash
+//   prev  32/64 KB  u16 per unit in the window: previous unit with the same hash
+//   mlen/mdist/jump 3 x 4 KB + reach 2 KB  per-position match, parse links
+static const int LZ_SEG = 2048;               // bytes parsed per step
+static const int LZ_THREADS = 1024;
+static const int LZ_RING = 65536;
+static const int LZ_HASH_BITS = 15;
+static const unsigned LZ_BIAS = 32768;
+
+template <int STRIDE> struct LzSmem {
+  static const int PREV_N = 32768 / STRIDE;
+  static const int MAXD_UNITS = (32768 - LZ_SEG) / STRIDE;   // prev[] entries older than this may be recycled
+  static const size_t ring_off = 0;
+  static const size_t head_off = LZ_RING;
+  static const size_t prev_off = head_off + (size_t)(1 << LZ_HASH_BITS) * 2;
+  static const size_t mlen_off = prev_off + (size_t)PREV_N * 2;
+  static const size_t mdist_off = mlen_off + (size_t)(LZ_SEG + 2) * 2;
+  static const size_t jump_off = mdist_off + (size_t)(LZ_SEG + 2) * 2;
+  static const size_t jump2_off = jump_off + (size_t)(LZ_SEG + 2) * 2;
+  static const size_t reach_off = jump2_off + (size_t)(LZ_SEG + 2) * 2;
+  static const size_t hist_off = (reach_off + LZ_SEG + 2 + 15) & ~(size_t)15;
+  static const size_t misc_off = hist_off + (size_t)HIST_STRIDE * 4;
+  static const size_t total = misc_off + 256;
+};
+
+__device__ __forceinline__ unsigned ring_load4(const unsigned char* ring, unsigned r) {
+  unsigned a = r & 0xfffcu;
+  unsigned lo = *(const unsigned*)(ring + a);
+  unsigned hi = *(const unsigned*)(ring + ((a + 4) & 0xffffu));
+  return __funnelshift_r(lo, hi, (r & 3) * 8);
+}
+__device__ __forceinline__ unsigned lz_hash(unsigned w) { return (w * 0x9E3779B1u) >> (32 - LZ_HASH_BITS); }
+
+template <int STRIDE>
+__global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char* __restrict__ tbuf,
+                                                             const DeflateSeg* __restrict__ segs, int n_segs,
+                                                             unsigned short* __restrict__ tokens,
+                                                             unsigned* __restrict__ hist, DeflateSegOut* __restrict__ so,
+                                                             LzParams prm) {
+  typedef LzSmem<STRIDE> L;
+  MTS_DYN_SMEM(sm);
+  unsigned char* ring = sm + L::ring_off;
+  unsigned short* head = (unsigned short*)(sm + L::head_off);
+  unsigned short* prev = (unsigned short*)(sm + L::prev_off);
+  unsigned short* mlen = (unsigned short*)(sm + L::mlen_off);
+  unsigned short* mdist = (unsigned short*)(sm + L::mdist_off);
+  unsigned short* jump = (unsigned short*)(sm + L::jump_off);
+  unsigned short* jump2 = (unsigned short*)(sm + L::jump2_off);
+  unsigned char* reach = sm + L::reach_off;
+  unsigned* shist = (unsigned*)(sm + L::hist_off);
+  unsigned* misc = (unsigned*)(sm + L::misc_off);   // [0..31] warp totals, [32] running token count, [33] carry
+  const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned PM = L::PREV_N - 1;
+
+  for (int sidx = blockIdx.x; sidx < n_segs; sidx += gridDim.x) {
+    const DeflateSeg sg = segs[sidx];
+    const unsigned n = (unsigned)sg.in_len;
+    const unsigned char* in = tbuf + sg.in_off;
+    const unsigned off0 = (unsigned)((uintptr_t)in & 15);
+    const uint4* in16 = (const uint4*)(in - off0);
+    unsigned short* tok = tokens + sg.tok_off;
+    const unsigned n_ring = n + off0;                    // ring coordinates [off0, n_ring) are real input
+
+    // reset tables
+    for (unsigned i = tid; i < (1u << LZ_HASH_BITS) / 2; i += LZ_THREADS) ((unsigned*)head)[i] = 0;
+    for (unsigned i = tid; i < HIST_STRIDE; i += LZ_THREADS) shist[i] = 0;
+    if (tid == 0) { misc[32] = 0; misc[33] = 0; }
+    // initial load: ring coordinates [0, 2*SEG)
+    for (unsigned v = tid; v < 2 * LZ_SEG / 16; v += LZ_THREADS)
+      if (v * 16 < n_ring) *(uint4*)(ring + v * 16) = in16[v];
+    __syncthreads();
+
+    const unsigned n_steps = (n + LZ_SEG - 1) / LZ_SEG;
+    for (unsigned step = 0; step < n_steps; step++) {
+      const unsigned s0 = step * LZ_SEG;                 // first position of this step
+      const unsigned slen = min((unsigned)LZ_SEG, n - s0);
+
+      // ---- (A) insert this step's units into the hash chains (warp 0, in position order), while the other warps
+      //          prefetch the data the NEXT step will need: ring coordinates [(step+2)*SEG, (step+3)*SEG)
+      if (wid == 0) {
+        const unsigned units = (slen + STRIDE - 1) / STRIDE;
+        for (unsigned b = 0; b < units; b += 32) {
+          unsigned u = s0 / STRIDE + b + lane;           // unit index within the segment
+          unsigned p = u * STRIDE;
+          bool valid = (b + lane < units) && (p + 4 <= n);
+          unsigned h = valid ? lz_hash(ring_load4(ring, p + off0)) : (0x10000u + lane);
+          unsigned grp = __match_any_sync(0xffffffffu, h);
+          if (valid) {
+            unsigned lower = grp & ((1u << lane) - 1);
+            unsigned short pv = lower ? (unsigned short)(u - lane + (31 - __clz((int)lower)) + LZ_BIAS) : head[h];
+            prev[u & PM] = pv;
+          }
+          __syncwarp();
+          if (valid && (grp >> lane) == 1u) head[h] = (unsigned short)(u + LZ_BIAS);
+          __syncwarp();
+        }
+      } else {
+        const unsigned base = (step + 2) * LZ_SEG;
+        for (unsigned v = tid - 32; v < LZ_SEG / 16; v += LZ_THREADS - 32) {
+          unsigned rc = base + v * 16;
+          if (rc < n_ring) *(uint4*)(ring + (rc & 0xffffu)) = in16[rc >> 4];
+        }
+      }
+      __syncthreads();
+
+      // ---- (B) match search: every indexed position of the step, one chain walk per thread
+      for (unsigned k = 0; k < (LZ_SEG / STRIDE) / LZ_THREADS + ((LZ_SEG / STRIDE) % LZ_THREADS ? 1 : 0); k++) {
+        unsigned li = (k * LZ_THREADS + tid) * STRIDE;    // local position in the step
+        if (li >= LZ_SEG) break;
+        unsigned p = s0 + li;
+        unsigned best = 3, bdist = 0;
+        if (li < slen && p + 4 <= n) {
+          const unsigned u = p / STRIDE;
+          const unsigned lim = min(258u, n - p);
+          const unsigned pr = p + off0;
+          unsigned wq = ring_load4(ring, pr);
+          unsigned short cand = prev[u & PM];
+          unsigned lastd = 0;
+          const unsigned ub = (u + LZ_BIAS) & 0xffffu;
+          for (int depth = prm.max_chain; depth > 0; depth--) {
+            unsigned du = (ub - cand) & 0xffffu;
+            if (du - 1 >= (unsigned)L::MAXD_UNITS || du <= lastd || du > u) break;
+            lastd = du;
+            const unsigned dist = du * STRIDE;
+            const unsigned qr = pr - dist;
+            if (ring_load4(ring, qr + best - 3) == wq) {
+              unsigned len = 0;
+              while (len < lim) {
+                unsigned x = ring_load4(ring, pr + len) ^ ring_load4(ring, qr + len);
+                if (x) { len += (unsigned)(__ffs((int)x) - 1) >> 3; break; }
+                len += 4;
+              }
+              len = min(len, lim);
+              if (len > best) {
+                bool ok = (len > 6) || (len == 6 && dist <= (unsigned)prm.far6) ||
+                          (len == 5 && dist <= (unsigned)prm.far5) || (len == 4 && dist <= (unsigned)prm.far4);
+                if (ok) {
+                  best = len; bdist = dist;
+                  if (len >= (unsigned)prm.nice_len || len >= lim) break;
+                  wq = ring_load4(ring, pr + best - 3);
+                }
+              }
+            }
+            cand = prev[(cand - LZ_BIAS) & PM];
+          }
+        }
+        mlen[li] = (unsigned short)(bdist ? best : 0);
+        mdist[li] = (unsigned short)bdist;
+      }
+      __syncthreads();
+
+      // ---- (C) STRIDE > 1: positions between indexed ones inherit the next indexed match, extended backwards
+      if (STRIDE > 1) {
+        for (unsigned li = tid; li < LZ_SEG; li += LZ_THREADS) {
+          if (li % STRIDE == 0) continue;
+          unsigned nx = li + (STRIDE - li % STRIDE);       // next indexed local position
+          unsigned ml = 0, md = 0;
+          if (nx < slen && li < slen) {
+            unsigned l2 = mlen[nx], d2 = mdist[nx];
+            unsigned back = nx - li, p = s0 + li;
+            if (l2 && l2 + back <= 258 && p >= d2) {
+              bool eq = true;
+              for (unsigned j = 0; j < back; j++)
+                eq = eq && (ring[(p + j + off0) & 0xffffu] == ring[(p + j + off0 - d2) & 0xffffu]);
+              if (eq) { ml = l2 + back; md = d2; }
+            }
+          }
+          mlen[li] = (unsigned short)ml;
+          mdist[li] = (unsigned short)md;
+        }
+        __syncthreads();
+      }
+
+      // ---- (D) parse: next[] per position (lazy-1 rule), reachability from the carried start by pointer doubling
+      const unsigned start = misc[33];                    // local start position (< slen unless the carry skips it)
+      __syncthreads();
+      if (start < slen) {
+        for (unsigned li = tid; li <= LZ_SEG; li += LZ_THREADS) {
+          unsigned nx = slen;
+          if (li < slen) {
+            unsigned l = mlen[li];
+            if (l && prm.lazy && li + 1 < slen && mlen[li + 1] > l) l = 0;
+            nx = min(li + (l ? l : 1u), slen);
+            if (l == 0) jump2[li] = 0; else jump2[li] = (unsigned short)l;   // jump2 doubles as "chosen length"
+          }
+          jump[li] = (unsigned short)nx;
+          if (li < LZ_SEG + 1) reach[li] = (li == start);
+        }
+        __syncthreads();
+        // chosen lengths are needed after the doubling destroys jump[]: keep them in mlen (0 = literal)
+        for (unsigned li = tid; li < slen; li += LZ_THREADS) mlen[li] = jump2[li];
+        __syncthreads();
+        for (;;) {
+          bool done = (jump[start] >= slen);
+          unsigned j2[(LZ_SEG + LZ_THREADS) / LZ_THREADS];
+          unsigned kk = 0;
+          for (unsigned li = tid; li < slen; li += LZ_THREADS, kk++) {
+            unsigned j = jump[li];
+            if (reach[li] && j < slen) reach[j] = 1;
+            j2[kk] = (j < slen) ? jump[j] : slen;
+          }
+          __syncthreads();
+          if (done) break;
+          kk = 0;
+          for (unsigned li = tid; li < slen; li += LZ_THREADS, kk++) jump[li] = (unsigned short)j2[kk];
+          __syncthreads();
+        }
+
+        // ---- (E) emit tokens of reachable positions, in order (block-wide exclusive scan of element counts)
+        unsigned cnt[LZ_SEG / LZ_THREADS], mine = 0;
+        // thread owns CONSECUTIVE positions so that its elements are consecutive in the token stream
+        const unsigned per = LZ_SEG / LZ_THREADS;
+        for (unsigned j = 0; j < per; j++) {
+          unsigned li = tid * per + j;
+          unsigned c = 0;
+          if (li < slen && reach[li]) c = mlen[li] ? 2 : 1;
+          cnt[j] = c; mine += c;
+        }
+        unsigned incl = warp_incl_scan(mine);
+        if (lane == 31) misc[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+          unsigned t = misc[lane];
+          unsigned ti = warp_incl_scan(t);
+          misc[lane] = ti - t;
+          if (lane == 31) misc[34] = ti;                  // elements emitted by this step
+        }
+        __syncthreads();
+        unsigned pos = misc[32] + misc[wid] + incl - mine;
+        for (unsigned j = 0; j < per; j++) {
+          unsigned li = tid * per + j;
+          if (!cnt[j]) continue;
+          unsigned l = mlen[li];
+          if (l) {
+            unsigned d = mdist[li];
+            tok[pos] = (unsigned short)(0x8000u | l);
+            tok[pos + 1] = (unsigned short)(d - 1);
+            unsigned sym, nb, ev;
+            len_symbol(l, sym, nb, ev);
+            atomicAdd(&shist[sym], 1u);
+            dist_symbol(d, sym, nb, ev);
+            atomicAdd(&shist[288 + sym], 1u);
+            if (li + l >= slen) misc[33] = li + l - slen;   // the one reachable position that leaves the step
+            pos += 2;
+          } else {
+            unsigned b = ring[(s0 + li + off0) & 0xffffu];
+            tok[pos] = (unsigned short)b;
+            atomicAdd(&shist[b], 1u);
+            if (li + 1 >= slen) misc[33] = 0;
+            pos += 1;
+          }
+        }
+        __syncthreads();
+        if (tid == 0) misc[32] += misc[34];
+      } else {
+        if (tid == 0) misc[33] = start - slen;
+      }
+      __syncthreads();
+    }
+
+    // ---- segment done: publish histogram + token count
+    for (unsigned i = tid; i < HIST_STRIDE; i += LZ_THREADS) hist[(size_t)sidx * HIST_STRIDE + i] = shist[i];
+    if (tid == 0) so[sidx].n_tok = misc[32];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ huff_kernel
+// One warp per segment.  Package: sort used symbols by frequency (rank sort across lanes), two-queue Huffman merge,
+// depth count, zlib-style overflow repair to the length limit, canonical codes (bit-reversed for LSB-first packing).
+struct HuffScratch {
+  unsigned weight[2 * LL_SYMS];
+  unsigned short parent[2 * LL_SYMS];
+  unsigned short sorted[LL_SYMS];
+  unsigned char depth[2 * LL_SYMS];
+  unsigned char lens[LL_SYMS + D_SYMS + 8];
+  unsigned char rle_sym[LL_SYMS + D_SYMS + 8];
+  unsigned char rle_ext[LL_SYMS + D_SYMS + 8];
+  unsigned bl_freq[BL_SYMS];
+  unsigned bl_code[BL_SYMS];
+  unsigned bl_count[16];
+  unsigned next_code[16];
+  unsigned hdr[HDR_WORDS];
+};
+
+// Builds code lengths for `nsym` symbols with frequencies f[] (u32, >= 2 non-zero entries) limited to maxbits, then
+// canonical bit-reversed codes: out[s] = code | len << 16.  All lanes call; lane 0 does the serial parts.
+__device__ void build_codes(const unsigned* f, int nsym, int maxbits, unsigned* out, unsigned char* lens_out,
+                            HuffScratch* S) {
+  const unsigned lane = lane_id();
+  // rank sort of used symbols by (freq, symbol)
+  int nused = 0;
+  for (int s0 = 0; s0 < nsym; s0 += 32) {
+    int s = s0 + lane;
+    bool used = s < nsym && f[s] > 0;
+    nused += __popc(__ballot_sync(0xffffffffu, used));
+  }
+  for (int s = lane; s < nsym; s += 32) {
+    unsigned fs = f[s];
+    lens_out[s] = 0;
+    if (!fs) continue;
+    int rank = 0;
+    for (int t = 0; t < nsym; t++) {
+      unsigned ft = f[t];
+      rank += (ft > 0) && (ft < fs || (ft == fs && t < s));
+    }
+    S->sorted[rank] = (unsigned short)s;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    const int n = nused;
+    for (int i = 0; i < n; i++) S->weight[i] = f[S->sorted[i]];
+    // two-queue merge: leaves [0,n), internal nodes [n, 2n-1)
+    int a = 0, b = n, e = n;
+    for (; e < 2 * n - 1; e++) {
+      unsigned w = 0;
+      for (int k = 0; k < 2; k++) {
+        int pick;
+        if (a < n && (b >= e || S->weight[a] <= S->weight[b])) pick = a++; else pick = b++;
+        w += S->weight[pick];
+        S->parent[pick] = (unsigned short)e;
+      }
+      S->weight[e] = w;
+    }
+    for (int i = 0; i <= maxbits; i++) S->bl_count[i] = 0;
+    const int root = 2 * n - 2;
+    S->depth[root] = 0;
+    for (int i = root - 1; i >= 0; i--) {
+      int d = S->depth[S->parent[i]] + 1;
+      if (i < n) S->bl_count[min(d, maxbits)]++;
+      S->depth[i] = (unsigned char)min(d, 255);
+    }
+    // length limiting: clamping deep leaves to maxbits over-subscribes the code by `excess` units of 2^-maxbits;
+    // each zlib-style move (one leaf one level down, one clamped leaf becomes its sibling) removes exactly one unit
+    long long excess = -(1ll << maxbits);
+    for (int b = 1; b <= maxbits; b++) excess += (long long)S->bl_count[b] << (maxbits - b);
+    while (excess > 0) {
+      int bits = maxbits - 1;
+      while (S->bl_count[bits] == 0) bits--;
+      S->bl_count[bits]--;
+      S->bl_count[bits + 1] += 2;
+      S->bl_count[maxbits]--;
+      excess--;
+    }
+    // least frequent symbols take the longest codes
+    int i = 0;
+    for (int bits = maxbits; bits >= 1; bits--)
+      for (unsigned k = 0; k < S->bl_count[bits]; k++) lens_out[S->sorted[i++]] = (unsigned char)bits;
+    unsigned code = 0;
+    S->bl_count[0] = 0;
+    for (int bits = 1; bits <= maxbits; bits++) {
+      code = (code + S->bl_count[bits - 1]) << 1;
+      S->next_code[bits] = code;
+    }
+    for (int s = 0; s < nsym; s++) {
+      unsigned l = lens_out[s];
+      unsigned c = 0;
+      if (l) c = __brev(S->next_code[l]++) >> (32 - l);
+      out[s] = c | (l << 16);
+    }
+  }
+  __syncwarp();
+}
+
+struct BitW {   // serial LSB-first bit writer (lane 0 of huff_kernel)
+  unsigned* w;
+  unsigned nbits;
+  __device__ void put(unsigned v, unsigned n) {
+    if (!n) return;
+    unsigned i = nbits >> 5, sh = nbits & 31;
+    w[i] |= v << sh;
+    if (sh + n > 32) w[i + 1] |= v >> (32 - sh);
+    nbits += n;
+  }
+};
+
+__global__ void __launch_bounds__(32) huff_kernel(const DeflateSeg* __restrict__ segs, int n_segs,
+                                                  unsigned* __restrict__ hist, unsigned* __restrict__ codes,
+                                                  unsigned* __restrict__ hdrs, DeflateSegOut* __restrict__ so) {
+  __shared__ HuffScratch S;
+  __shared__ unsigned f[HIST_STRIDE];
+  __shared__ unsigned c[CODE_STRIDE];
+  __shared__ unsigned char bl_len_sh[BL_SYMS + 5];
+  __shared__ int sh_nr, sh_hlit, sh_hdist;
+  const int sidx = blockIdx.x;
+  if (sidx >= n_segs) return;
+  const unsigned lane = lane_id();
+  for (int i = lane; i < HIST_STRIDE; i += 32) f[i] = hist[(size_t)sidx * HIST_STRIDE + i];
+  for (int i = lane; i < HDR_WORDS; i += 32) S.hdr[i] = 0;
+  __syncwarp();
+  if (lane == 0) {
+    f[256] += 1;                                          // end-of-block
+    // at least two used symbols per tree (zlib does the same so that every tree is complete)
+    int used = 0;
+    for (int i = 0; i < LL_SYMS; i++) used += f[i] > 0;
+    for (int i = 0; used < 2; i++) if (!f[i]) { f[i] = 1; used++; }
+    used = 0;
+    for (int i = 0; i < D_SYMS; i++) used += f[288 + i] > 0;
+    for (int i = 0; used < 2; i++) if (!f[288 + i]) { f[288 + i] = 1; used++; }
+  }
+  __syncwarp();
+  build_codes(f, LL_SYMS, 15, c, S.lens, &S);
+  build_codes(f + 288, D_SYMS, 15, c + 288, S.lens + LL_SYMS, &S);
+
+  // body size in bits under the dynamic codes
+  unsigned long long bits = 0;
+  for (int s = lane; s < LL_SYMS; s += 32) bits += (unsigned long long)hist[(size_t)sidx * HIST_STRIDE + s] * ((c[s] >> 16) + ll_extra_bits(s));
+  for (int s = lane; s < D_SYMS; s += 32) bits += (unsigned long long)hist[(size_t)sidx * HIST_STRIDE + 288 + s] * ((c[288 + s] >> 16) + d_extra_bits(s));
+  bits = warp_sum(bits);
+  bits += c[256] >> 16;
+
+  if (lane == 0) {
+    int hlit = LL_SYMS, hdist = D_SYMS;
+    while (hlit > 257 && S.lens[hlit - 1] == 0) hlit--;
+    while (hdist > 1 && S.lens[LL_SYMS + hdist - 1] == 0) hdist--;
+    // concatenated length sequence, run-length coded with symbols 16/17/18 (RFC 1951 3.2.7)
+    unsigned char seq[LL_SYMS + D_SYMS];
+    int nseq = 0;
+    for (int i = 0; i < hlit; i++) seq[nseq++] = S.lens[i];
+    for (int i = 0; i < hdist; i++) seq[nseq++] = S.lens[LL_SYMS + i];
+    for (int i = 0; i < BL_SYMS; i++) S.bl_freq[i] = 0;
+    int nr = 0;
+    for (int i = 0; i < nseq;) {
+      int v = seq[i], run = 1;
+      while (i + run < nseq && seq[i + run] == v) run++;
+      i += run;
+      if (v == 0) {
+        while (run >= 11) { int r = min(run, 138); S.rle_sym[nr] = 18; S.rle_ext[nr++] = (unsigned char)(r - 11); run -= r; }
+        if (run >= 3) { S.rle_sym[nr] = 17; S.rle_ext[nr++] = (unsigned char)(run - 3); run = 0; }
+        while (run-- > 0) { S.rle_sym[nr] = 0; S.rle_ext[nr++] = 0; }
+      } else {
+        S.rle_sym[nr] = (unsigned char)v; S.rle_ext[nr++] = 0; run--;
+        while (run >= 3) { int r = min(run, 6); S.rle_sym[nr] = 16; S.rle_ext[nr++] = (unsigned char)(r - 3); run -= r; }
+        while (run-- > 0) { S.rle_sym[nr] = (unsigned char)v; S.rle_ext[nr++] = 0; }
+      }
+    }
+    for (int i = 0; i < nr; i++) S.bl_freq[S.rle_sym[i]]++;
+    int used = 0;
+    for (int i = 0; i < BL_SYMS; i++) used += S.bl_freq[i] > 0;
+    for (int i = 0; used < 2; i++) if (!S.bl_freq[i]) { S.bl_freq[i] = 1; used++; }
+    sh_nr = nr; sh_hlit = hlit; sh_hdist = hdist;
+  }
+  __syncwarp();
+  const int nr = sh_nr, hlit = sh_hlit, hdist = sh_hdist;
+  build_codes(S.bl_freq, BL_SYMS, 7, S.bl_code, bl_len_sh, &S);
+
+  if (lane == 0) {
+    static const unsigned char order[BL_SYMS] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    int hclen = BL_SYMS;
+    while (hclen > 4 && bl_len_sh[order[hclen - 1]] == 0) hclen--;
+    BitW bw{S.hdr, 0};
+    bw.put(0, 1);             // BFINAL = 0 (the stream is closed by a separate empty final block)
+    bw.put(2, 2);             // BTYPE = 10 dynamic
+    bw.put((unsigned)(hlit - 257), 5);
+    bw.put((unsigned)(hdist - 1), 5);
+    bw.put((unsigned)(hclen - 4), 4);
+    for (int i = 0; i < hclen; i++) bw.put(bl_len_sh[order[i]], 3);
+    for (int i = 0; i < nr; i++) {
+      unsigned s = S.rle_sym[i];
+      bw.put(S.bl_code[s] & 0xffff, S.bl_code[s] >> 16);
+      if (s == 16) bw.put(S.rle_ext[i], 2);
+      else if (s == 17) bw.put(S.rle_ext[i], 3);
+      else if (s == 18) bw.put(S.rle_ext[i], 7);
+    }
+    const unsigned n = (unsigned)segs[sidx].in_len;
+    unsigned long long dyn_bits = bw.nbits + bits;
+    // + empty stored block that byte-aligns the next segment: 3 header bits, pad, 00 00 FF FF
+    unsigned dyn_bytes = (unsigned)((dyn_bits + 3 + 7) >> 3) + 4;
+    unsigned stored_bytes = n + 5 * ((n + 65534) / 65535);
+    DeflateSegOut o = so[sidx];
+    o.hdr_bits = bw.nbits;
+    if (dyn_bytes < stored_bytes) { o.mode = MODE_DYNAMIC; o.body_bytes = dyn_bytes; }
+    else { o.mode = MODE_STORED; o.body_bytes = stored_bytes; }
+    so[sidx] = o;
+  }
+  __syncwarp();
+  for (int i = lane; i < CODE_STRIDE; i += 32) codes[(size_t)sidx * CODE_STRIDE + i] = c[i];
+  for (int i = lane; i < HDR_WORDS; i += 32) hdrs[(size_t)sidx * HDR_WORDS + i] = S.hdr[i];
+}
+
+// ------------------------------------------------------------------------------------------------ scan_kernel
+// Single CTA: exclusive prefix of (zlib header + body + trailer) sizes over all segments of the batch, in order.
+// Segments of a chunk are contiguous, so chunk_off[] (n_chunks + 1 entries) falls out of the same scan.
+__global__ void __launch_bounds__(1024) scan_kernel(const DeflateSeg* __restrict__ segs, int n_segs,
+                                                    DeflateSegOut* __restrict__ so, long long* __restrict__ chunk_off,
+                                                    int n_chunks, const ChunkDesc* __restrict__ chunks,
+                                                    int write_index) {
+  __shared__ unsigned long long wsum[32];
+  __shared__ unsigned long long carry, tile_total;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_segs; base += 1024) {
+    int i = base + threadIdx.x;
+    unsigned long long sz = 0;
+    int fl = 0;
+    if (i < n_segs) {
+      fl = segs[i].flags;
+      sz = so[i].body_bytes + ((fl & SEG_FIRST) ? 2 : 0) + ((fl & SEG_LAST) ? 6 : 0);
+      if ((fl & SEG_LAST) && write_index) sz += 4ull * (unsigned)chunks[segs[i].chunk].n_seg + 16;
+    }
+    unsigned long long incl = warp_incl_scan(sz);
+    if (lane_id() == 31) wsum[warp_id()] = incl;
+    __syncthreads();
+    if (warp_id() == 0) {
+      unsigned long long t = wsum[lane_id()];
+      unsigned long long ti = warp_incl_scan(t);
+      wsum[lane_id()] = ti - t;
+      if (lane_id() == 31) tile_total = ti;
+    }
+    __syncthreads();
+    unsigned long long excl = carry + wsum[warp_id()] + incl - sz;
+    if (i < n_segs) {
+      so[i].out_off = (long long)excl;
+      if (fl & SEG_FIRST) chunk_off[segs[i].chunk] = (long long)excl;
+      if (i == n_segs - 1) chunk_off[n_chunks] = (long long)(excl + sz);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry += tile_total;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ encode_kernel
+static const int ENC_THREADS = 256;
+static const int ENC_PER = 8;                              // token elements per thread per tile
+static const int ENC_TILE = ENC_THREADS * ENC_PER;
+static const int ENC_STAGE_WORDS = ENC_TILE + 64;          // >= tile * 28 bits / 32 + header slack
+
+__device__ __forceinline__ void stage_or(unsigned* stage, unsigned bitpos, unsigned v, unsigned n) {
+  if (!n) return;
+  unsigned i = bitpos >> 5, sh = bitpos & 31;
+  atomicOr(&stage[i], v << sh);
+  if (sh + n > 32) atomicOr(&stage[i + 1], v >> (32 - sh));
+}
+
+// Flush stage words [0, nwords) to global memory starting at the 4-byte aligned address `gw`; bytes before
+// `lo_byte` (absolute address) or at/after `hi_byte` are not touched (they belong to neighbouring segments).
+__device__ __forceinline__ void stage_flush(const unsigned* stage, unsigned nwords, unsigned char* gw,
+                                            const unsigned char* lo_byte, const unsigned char* hi_byte) {
+  for (unsigned i = threadIdx.x; i < nwords; i += blockDim.x) {
+    unsigned char* a = gw + 4 * (size_t)i;
+    unsigned v = stage[i];
+    if (a >= lo_byte && a + 4 <= hi_byte) *(unsigned*)a = v;
+    else
+      for (int b = 0; b < 4; b++)
+        if (a + b >= lo_byte && a + b < hi_byte) a[b] = (unsigned char)(v >> (8 * b));
+  }
+}
+
+__global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char* __restrict__ tbuf,
+                                                             const DeflateSeg* __restrict__ segs, int n_segs,
+                                                             const unsigned short* __restrict__ tokens,
+                                                             const unsigned* __restrict__ codes,
+                                                             const unsigned* __restrict__ hdrs,
+                                                             const DeflateSegOut* __restrict__ so,
+                                                             const unsigned* __restrict__ chunk_adler,
+                                                             unsigned char* __restrict__ dst,
+                                                             const ChunkDesc* __restrict__ chunks, int write_index) {
+  __shared__ unsigned stage[ENC_STAGE_WORDS];
+  __shared__ unsigned code[CODE_STRIDE];
+  __shared__ unsigned wtot[ENC_THREADS / 32];
+  __shared__ unsigned tile_bits;
+  const int sidx = blockIdx.x;
+  if (sidx >= n_segs) return;
+  const DeflateSeg sg = segs[sidx];
+  const DeflateSegOut o = so[sidx];
+  const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  unsigned char* out = dst + o.out_off;
+  const unsigned total = o.body_bytes + ((sg.flags & SEG_FIRST) ? 2 : 0) + ((sg.flags & SEG_LAST) ? 6 : 0);
+  unsigned char* const out_end = out + total;   // end of the zlib stream part written by this CTA
+  if (sg.flags & SEG_FIRST) {
+    if (tid == 0) { out[0] = 0x78; out[1] = 0x9c; }
+    out += 2;
+  }
+  unsigned char* body_end = out + o.body_bytes;
+  if ((sg.flags & SEG_LAST) && tid < 6) {
+    // empty final fixed-Huffman block (03 00) + adler32 of the whole transformed chunk, big-endian
+    unsigned a = chunk_adler[sg.chunk];
+    unsigned char t[6] = {0x03, 0x00, (unsigned char)(a >> 24), (unsigned char)(a >> 16), (unsigned char)(a >> 8), (unsigned char)a};
+    body_end[tid] = t[tid];
+  }
+  if ((sg.flags & SEG_LAST) && write_index) {
+    // segment index after the zlib stream (zlib.decompress ignores trailing bytes): k compressed segment
+    // lengths, then {segment bytes, k, magic "MTSB", sum of the lengths}, all little-endian u32
+    const ChunkDesc cd = chunks[sg.chunk];
+    unsigned char* ix = body_end + 6;
+    const unsigned k = (unsigned)cd.n_seg;
+    unsigned sum = 0;
+    for (unsigned j = tid; j < k; j += blockDim.x) {
+      unsigned v = so[cd.first_seg + j].body_bytes;
+      for (int b = 0; b < 4; b++) ix[4 * j + b] = (unsigned char)(v >> (8 * b));
+    }
+    if (tid == 0) {
+      for (unsigned j = 0; j < k; j++) sum += so[cd.first_seg + j].body_bytes;
+      unsigned tail[4] = {(unsigned)cd.pad_, k, 0x4253544Du, sum};
+      for (int q = 0; q < 4; q++)
+        for (int b = 0; b < 4; b++) ix[4 * k + 4 * q + b] = (unsigned char)(tail[q] >> (8 * b));
+    }
+  }
+  const unsigned char* in = tbuf + sg.in_off;
+  if (o.mode == MODE_STORED) {
+    unsigned n = (unsigned)sg.in_len;
+    for (unsigned b0 = 0, k = 0; b0 < n; b0 += 65535, k++) {
+      unsigned len = min(65535u, n - b0);
+      unsigned char* q = out + b0 + 5 * (size_t)k;
+      if (tid == 0) { q[0] = 0; q[1] = (unsigned char)len; q[2] = (unsigned char)(len >> 8); q[3] = (unsigned char)~len; q[4] = (unsigned char)(~len >> 8); }
+      for (unsigned i = tid; i < len; i += blockDim.x) q[5 + i] = in[b0 + i];
+    }
+    return;
+  }
+  // ---- dynamic block
+  for (unsigned i = tid; i < CODE_STRIDE; i += blockDim.x) code[i] = codes[(size_t)sidx * CODE_STRIDE + i];
+  for (unsigned i = tid; i < ENC_STAGE_WORDS; i += blockDim.x) stage[i] = 0;
+  __syncthreads();
+  unsigned char* gw = (unsigned char*)((uintptr_t)out & ~(uintptr_t)3);   // global address of stage word 0
+  unsigned cur = 8 * (unsigned)((uintptr_t)out & 3);                       // bit cursor inside the stage
+  // header
+  {
+    const unsigned* h = hdrs + (size_t)sidx * HDR_WORDS;
+    const unsigned hb = o.hdr_bits;
+    for (unsigned j = tid; j * 32 < hb; j += blockDim.x) stage_or(stage, cur + 32 * j, h[j], min(32u, hb - 32 * j));
+    __syncthreads();
+    cur += hb;
+    unsigned nw = cur >> 5;
+    stage_flush(stage, nw, gw, out, out_end);
+    __syncthreads();
+    unsigned keep = stage[nw];
+    __syncthreads();
+    for (unsigned i = tid; i <= nw; i += blockDim.x) stage[i] = 0;
+    __syncthreads();
+    if (tid == 0) stage[0] = keep;
+    gw += 4 * (size_t)nw;
+    cur &= 31;
+    __syncthreads();
+  }
+  const unsigned short* tok = tokens + sg.tok_off;
+  const unsigned ntok = o.n_tok;
+  for (unsigned base = 0; base < ntok; base += ENC_TILE) {
+    unsigned v[ENC_PER], nb[ENC_PER], mine = 0;
+    unsigned i0 = base + tid * ENC_PER;
+    unsigned prev_el = (i0 > 0 && i0 <= ntok) ? tok[i0 - 1] : 0;
+    for (int j = 0; j < ENC_PER; j++) {
+      unsigned i = i0 + j;
+      v[j] = 0; nb[j] = 0;
+      if (i < ntok) {
+        unsigned e = tok[i];
+        if (prev_el & 0x8000u) {            // distance element (follows a length element)
+          unsigned sym, xb, ev;
+          dist_symbol(e + 1, sym, xb, ev);
+          unsigned c = code[288 + sym];
+          v[j] = (c & 0xffff) | (ev << (c >> 16));
+          nb[j] = (c >> 16) + xb;
+          prev_el = 0;
+        } else if (e & 0x8000u) {           // length element
+          unsigned sym, xb, ev;
+          len_symbol(e & 0x1ff, sym, xb, ev);
+          unsigned c = code[sym];
+          v[j] = (c & 0xffff) | (ev << (c >> 16));
+          nb[j] = (c >> 16) + xb;
+          prev_el = e;
+        } else {                            // literal
+          unsigned c = code[e];
+          v[j] = c & 0xffff;
+          nb[j] = c >> 16;
+          prev_el = e;
+        }
+        mine += nb[j];
+      }
+    }
+    unsigned incl = warp_incl_scan(mine);
+    if (lane == 31) wtot[wid] = incl;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned run = 0;
+      for (int w = 0; w < ENC_THREADS / 32; w++) { unsigned t = wtot[w]; wtot[w] = run; run += t; }
+      tile_bits = run;
+    }
+    __syncthreads();
+    unsigned bp = cur + wtot[wid] + incl - mine;
+    for (int j = 0; j < ENC_PER; j++) { stage_or(stage, bp, v[j], nb[j]); bp += nb[j]; }
+    __syncthreads();
+    cur += tile_bits;
+    unsigned nw = cur >> 5;
+    stage_flush(stage, nw, gw, out, out_end);
+    __syncthreads();
+    unsigned keep = stage[nw];
+    __syncthreads();
+    for (unsigned i = tid; i <= nw + 1; i += blockDim.x) stage[i] = 0;
+    __syncthreads();
+    if (tid == 0) stage[0] = keep;
+    gw += 4 * (size_t)nw;
+    cur &= 31;
+    __syncthreads();
+  }
+  // end-of-block, then the empty stored block: 3 zero bits, pad to a byte boundary, 00 00 FF FF
+  if (tid == 0) {
+    unsigned c = code[256];
+    stage_or(stage, cur, c & 0xffff, c >> 16);
+    unsigned e = cur + (c >> 16) + 3;
+    e = (e + 7) & ~7u;
+    stage_or(stage, e + 16, 0xffffu, 16);
+    tile_bits = e + 32;
+  }
+  __syncthreads();
+  unsigned endbits = tile_bits;
+  stage_flush(stage, (endbits + 31) >> 5, gw, out, body_end);
+}
+
+}  // namespace mts

@@ -1,0 +1,269 @@
+// transform.cuh — K1 (delta transform + demultiplex) and K4 (inverse: cumulative sums + re-multiplex) kernels,
+// plus the adler32 partial/combine kernels that both directions share.
+//
+// Replaces, bit-exactly for integer dtypes (arithmetic is modular in the element width):
+//   encode  mtscomp.py:381-394  diff_along_axis(axis=0) -> diff_along_axis(axis=1) -> tobytes(order=chunk_order)
+//   decode  mtscomp.py:622-635  frombuffer -> reshape(order) -> cumsum(axis=1) -> cumsum(axis=0) -> ascontiguousarray
+// Time and spatial operators act on different axes and commute exactly in modular arithmetic, so the kernels apply
+// them in whichever order is cheapest.
+//
+// HBM layout: raw chunk = row-major (ns, nc) elements; transformed chunk = the deflate input, either channel-major
+// ('F': nc runs of ns elements) or row-major ('C'), at the same element offset as the raw chunk.
+// Every CTA works on a full-width tile of TT consecutive rows, which is one contiguous span of the row-major side.
+#pragma once
+#include "common.cuh"
+
+namespace mts {
+
+// Shared-memory row pitch (elements): chosen so a column walk (lane = row) hits 32 distinct banks.
+template <class T> __host__ __device__ inline int tile_pitch(int nc) {
+  if (sizeof(T) == 1) { int p = (nc + 3) & ~3; if ((p & 4) == 0) p += 4; return p; }
+  if (sizeof(T) == 2) { int p = (nc + 1) & ~1; if ((p & 2) == 0) p += 2; return p; }
+  return nc | 1;
+}
+
+// ------------------------------------------------------------------------------------------------ K1 forward
+// Algorithmic traffic: read sizeof(T) + write sizeof(T) per element (the halo row is re-read once per tile: +1/TT).
+template <class T>
+__global__ void __launch_bounds__(512) fwd_transform_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                            const ChunkDesc* __restrict__ chunks, int nc, int TT,
+                                                            int flags) {
+  MTS_DYN_SMEM(smem_raw);
+  T* s = (T*)smem_raw;
+  const ChunkDesc cd = chunks[blockIdx.y];
+  const int ns = cd.ns;
+  const int t0 = blockIdx.x * TT;
+  if (t0 >= ns) return;
+  const int rows = min(TT, ns - t0);
+  const int P = tile_pitch<T>(nc);
+  const T* x = src + cd.elem_off;
+  T* y = dst + cd.elem_off;
+  const bool td = (flags & FLAG_TIME_DIFF) != 0, sd = (flags & FLAG_SPATIAL_DIFF) != 0;
+
+  // smem row r holds sample t0-1+r; row 0 is zero for the chunk's first tile, so "x[t]-x[t-1]" keeps row 0 as is.
+  const long long base = (long long)(t0 - 1) * nc;
+  const int n_el = (rows + 1) * nc;
+  for (int e = threadIdx.x; e < n_el; e += blockDim.x) {
+    int r = e / nc, c = e - r * nc;
+    T v = 0;
+    if (t0 > 0 || r > 0) v = x[base + e];
+    s[r * P + c] = v;
+  }
+  __syncthreads();
+
+  if (flags & FLAG_ORDER_C) {
+    for (int e = threadIdx.x; e < rows * nc; e += blockDim.x) {
+      int r = e / nc, c = e - r * nc;
+      const T* p = s + (r + 1) * P + c;
+      T v = p[0];
+      if (td) v = (T)(v - p[-P]);
+      if (sd && c > 0) { T w = p[-1]; if (td) w = (T)(w - p[-P - 1]); v = (T)(v - w); }
+      y[(long long)t0 * nc + e] = v;
+    }
+  } else {
+    const int nw = blockDim.x >> 5;
+    for (int c = warp_id(); c < nc; c += nw) {
+      for (int r = lane_id(); r < rows; r += 32) {
+        const T* p = s + (r + 1) * P + c;
+        T v = p[0];
+        if (td) v = (T)(v - p[-P]);
+        if (sd && c > 0) { T w = p[-1]; if (td) w = (T)(w - p[-P - 1]); v = (T)(v - w); }
+        y[(long long)c * ns + t0 + r] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K4 inverse
+// Pass 1: per (tile, channel) sums of the time-diffed stream.  partial[(chunk*max_tiles + tile)*nc + c].
+template <class T>
+__global__ void __launch_bounds__(512) inv_tile_sums_kernel(const T* __restrict__ in, T* __restrict__ partial,
+                                                            const ChunkDesc* __restrict__ chunks, int nc, int TT,
+                                                            int max_tiles, int flags) {
+  const ChunkDesc cd = chunks[blockIdx.y];
+  const int ns = cd.ns;
+  const int t0 = blockIdx.x * TT;
+  if (t0 >= ns) return;
+  const int rows = min(TT, ns - t0);
+  const T* x = in + cd.elem_off;
+  T* out = partial + ((long long)blockIdx.y * max_tiles + blockIdx.x) * nc;
+  if (flags & FLAG_ORDER_C) {
+    for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+      T acc = 0;
+      for (int r = 0; r < rows; r++) acc = (T)(acc + x[(long long)(t0 + r) * nc + c]);
+      out[c] = acc;
+    }
+  } else {
+    const int nw = blockDim.x >> 5;
+    for (int c = warp_id(); c < nc; c += nw) {
+      unsigned acc = 0;
+      for (int r = lane_id(); r < rows; r += 32) acc += (unsigned)x[(long long)c * ns + t0 + r];
+      if (sizeof(T) <= 4) {
+        acc = warp_sum(acc);
+        if (lane_id() == 0) out[c] = (T)acc;
+      }
+    }
+  }
+}
+// 64-bit elements need a 64-bit accumulator in the F-order branch above.
+template <>
+__global__ void __launch_bounds__(512) inv_tile_sums_kernel<uint64_t>(const uint64_t* __restrict__ in,
+                                                                      uint64_t* __restrict__ partial,
+                                                                      const ChunkDesc* __restrict__ chunks, int nc,
+                                                                      int TT, int max_tiles, int flags) {
+  const ChunkDesc cd = chunks[blockIdx.y];
+  const int ns = cd.ns;
+  const int t0 = blockIdx.x * TT;
+  if (t0 >= ns) return;
+  const int rows = min(TT, ns - t0);
+  const uint64_t* x = in + cd.elem_off;
+  uint64_t* out = partial + ((long long)blockIdx.y * max_tiles + blockIdx.x) * nc;
+  for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+    uint64_t acc = 0;
+    for (int r = 0; r < rows; r++)
+      acc += (flags & FLAG_ORDER_C) ? x[(long long)(t0 + r) * nc + c] : x[(long long)c * ns + t0 + r];
+    out[c] = acc;
+  }
+}
+
+// Pass 2: exclusive scan of the tile sums along time, per channel (tiny).
+template <class T>
+__global__ void inv_tile_scan_kernel(T* __restrict__ partial, const ChunkDesc* __restrict__ chunks, int nc, int TT,
+                                     int max_tiles) {
+  const ChunkDesc cd = chunks[blockIdx.y];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int ntiles = (cd.ns + TT - 1) / TT;
+  T* p = partial + (long long)blockIdx.y * max_tiles * nc + c;
+  T run = 0;
+  for (int j = 0; j < ntiles; j++) {
+    T v = p[(long long)j * nc];
+    p[(long long)j * nc] = run;
+    run = (T)(run + v);
+  }
+}
+
+// Pass 3: tile -> smem, per-channel running sum seeded by the scanned tile sums, optional per-row (spatial) running
+// sum, contiguous row-major write.  Traffic: read + write sizeof(T) per element.
+template <class T>
+__global__ void __launch_bounds__(512) inv_apply_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                        const T* __restrict__ partial,
+                                                        const ChunkDesc* __restrict__ chunks, int nc, int TT,
+                                                        int max_tiles, int flags) {
+  MTS_DYN_SMEM(smem_raw);
+  T* s = (T*)smem_raw;
+  const ChunkDesc cd = chunks[blockIdx.y];
+  const int ns = cd.ns;
+  const int t0 = blockIdx.x * TT;
+  if (t0 >= ns) return;
+  const int rows = min(TT, ns - t0);
+  const int P = tile_pitch<T>(nc);
+  const T* x = in + cd.elem_off;
+  T* y = out + cd.elem_off;
+  const int nw = blockDim.x >> 5;
+
+  if (flags & FLAG_ORDER_C) {
+    for (int e = threadIdx.x; e < rows * nc; e += blockDim.x) {
+      int r = e / nc, c = e - r * nc;
+      s[r * P + c] = x[(long long)t0 * nc + e];
+    }
+  } else {
+    for (int c = warp_id(); c < nc; c += nw)
+      for (int r = lane_id(); r < rows; r += 32) s[r * P + c] = x[(long long)c * ns + t0 + r];
+  }
+  __syncthreads();
+  if (flags & FLAG_TIME_DIFF) {
+    const T* seed = partial + ((long long)blockIdx.y * max_tiles + blockIdx.x) * nc;
+    for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+      T run = seed[c];
+      for (int r = 0; r < rows; r++) {
+        run = (T)(run + s[r * P + c]);
+        s[r * P + c] = run;
+      }
+    }
+    __syncthreads();
+  }
+  if (flags & FLAG_SPATIAL_DIFF) {
+    for (int r = warp_id(); r < rows; r += nw) {
+      T carry = 0;
+      for (int c0 = 0; c0 < nc; c0 += 32) {
+        int c = c0 + lane_id();
+        T v = (c < nc) ? s[r * P + c] : (T)0;
+        v = (T)(warp_incl_scan(v) + carry);
+        if (c < nc) s[r * P + c] = v;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+      }
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < rows * nc; e += blockDim.x) {
+    int r = e / nc, c = e - r * nc;
+    y[(long long)t0 * nc + e] = s[r * P + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ adler32
+// One CTA per segment: standalone adler32 of bytes [off, off+len) (i.e. starting from adler = 1).  Segments are
+// folded per chunk with zlib's adler32_combine rule by adler_combine_kernel / the deflate scan.
+struct AdlerSeg {
+  long long off;
+  int len;
+  int pad_;
+};
+
+__global__ void __launch_bounds__(256) adler_partial_kernel(const uint8_t* __restrict__ data,
+                                                            const AdlerSeg* __restrict__ segs,
+                                                            uint32_t* __restrict__ seg_adler) {
+  __shared__ unsigned long long sh_a[8], sh_b[8];
+  const AdlerSeg sg = segs[blockIdx.x];
+  const uint8_t* p = data + sg.off;
+  const unsigned n = (unsigned)sg.len;
+  unsigned long long a = 0, b = 0;  // a = sum b_i ; b = sum (n - i) * b_i
+  // head bytes up to 4-byte alignment, aligned words, tail bytes
+  unsigned head = (unsigned)((4 - ((uintptr_t)p & 3)) & 3);
+  if (head > n) head = n;
+  const unsigned nwords = (n - head) >> 2;
+  const unsigned tail0 = head + (nwords << 2);
+  if (threadIdx.x < head) { unsigned v = p[threadIdx.x]; a += v; b += (unsigned long long)(n - threadIdx.x) * v; }
+  const uint32_t* w = (const uint32_t*)(p + head);
+  for (unsigned i = threadIdx.x; i < nwords; i += blockDim.x) {
+    uint32_t v = w[i];
+    unsigned b0 = v & 255, b1 = (v >> 8) & 255, b2 = (v >> 16) & 255, b3 = v >> 24;
+    unsigned pos = head + (i << 2);
+    unsigned sum = b0 + b1 + b2 + b3;
+    a += sum;
+    b += (unsigned long long)(n - pos) * sum - (b1 + 2 * b2 + 3 * b3);
+  }
+  if (tail0 + threadIdx.x < n) { unsigned v = p[tail0 + threadIdx.x]; a += v; b += (unsigned long long)(n - tail0 - threadIdx.x) * v; }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane_id() == 0) { sh_a[warp_id()] = a; sh_b[warp_id()] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long ta = 0, tb = 0;
+    for (unsigned i = 0; i < (blockDim.x >> 5); i++) { ta += sh_a[i]; tb += sh_b[i] % ADLER_BASE; }
+    uint32_t s1 = (uint32_t)((1 + ta) % ADLER_BASE);
+    uint32_t s2 = (uint32_t)((n % ADLER_BASE + tb) % ADLER_BASE);
+    seg_adler[blockIdx.x] = (s2 << 16) | s1;
+  }
+}
+
+__device__ __forceinline__ uint32_t adler_combine(uint32_t a1, uint32_t a2, unsigned len2) {
+  uint32_t s1a = a1 & 0xffff, s2a = a1 >> 16, s1b = a2 & 0xffff, s2b = a2 >> 16;
+  uint32_t s1 = (s1a + s1b + ADLER_BASE - 1) % ADLER_BASE;
+  unsigned long long t = (unsigned long long)(len2 % ADLER_BASE) * ((s1a + ADLER_BASE - 1) % ADLER_BASE);
+  uint32_t s2 = (uint32_t)((s2a + s2b + t) % ADLER_BASE);
+  return (s2 << 16) | s1;
+}
+
+// One thread per chunk: fold the chunk's segment adlers in order.  seg ranges come from first[i] .. first[i+1].
+__global__ void adler_combine_kernel(const AdlerSeg* __restrict__ segs, const uint32_t* __restrict__ seg_adler,
+                                     const int* __restrict__ first, int n_chunks, uint32_t* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_chunks) return;
+  uint32_t a = 1;
+  for (int s = first[i]; s < first[i + 1]; s++) a = adler_combine(a, seg_adler[s], (unsigned)segs[s].len);
+  out[i] = a;
+}
+
+}  // namespace mts
