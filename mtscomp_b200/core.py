@@ -1,0 +1,543 @@
+# -*- coding: utf-8 -*-
+"""Writer / Reader / compress / decompress / check with mtscomp's API and file format, on the B200 codec.
+
+Behavioural mirror of the reference's low- and high-level API (mtscomp.py:216-997): same constructor options,
+attributes, return values, file layout (.cbin = concatenated per-chunk zlib streams, .ch = sorted indented JSON with the
+same keys) and error behaviour.  The per-chunk codec — `Writer._compress_chunk` (mtscomp.py:375-397) and
+`Reader.read_chunk` (mtscomp.py:602-635) — does not run NumPy/zlib here: whole batches of chunks go through the C ABI
+(`_native.Codec`) to the sm_100a kernels.  There is no CPU codec path.
+
+Differences that do not change results: a batch is one GPU call instead of `n_threads` zlib threads; the thread-pool
+methods are kept as no-op compatible shims; GPU-written chunks carry a small segment index after each zlib stream (zlib
+ignores trailing bytes), which lets the GPU Reader decode a chunk's segments in parallel.
+"""
+
+import bisect
+from functools import lru_cache
+import hashlib
+import json
+import os
+import os.path as op
+from pathlib import Path
+from threading import Lock
+
+import numpy as np
+from tqdm import tqdm
+
+from . import _native
+from .config import Bunch, CHECK_ATOL, FORMAT_VERSION, clip, logger, read_config
+from .rawio import load_raw_data
+
+_seek_lock = Lock()
+CRITICAL_ERROR_URL = "https://github.com/int-brain-lab/mtscomp/issues/new?title=Critical+error"
+GPU_BATCH_CHUNKS = 64  # chunks handed to the GPU per call by Writer.write / Reader.tofile
+
+
+def _require_integer_dtype(dtype):
+    dtype = np.dtype(dtype)
+    if not np.issubdtype(dtype, np.integer) or dtype.itemsize not in (1, 2, 4, 8):
+        raise NotImplementedError(
+            "mtscomp_b200 implements the integer codec path (int8..int64, modular arithmetic); dtype %s is not "
+            "supported and there is no CPU fallback." % dtype)
+    return dtype
+
+
+def _codec_for(config):
+    dev = config.get('device', None)
+    return _native.default_codec(dev)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Standalone transforms (reference mtscomp.py:143-169), executed by the K1 / K4 kernels
+# ------------------------------------------------------------------------------------------------------------------
+
+def diff_along_axis(chunk, axis=None):
+    """np.diff along `axis` keeping the first row/column (reference mtscomp.py:143-159), on the GPU."""
+    if axis is None:
+        return chunk
+    assert 0 <= axis < chunk.ndim
+    dtype = _require_integer_dtype(chunk.dtype)
+    flags = (_native.TIME_DIFF if axis == 0 else _native.SPATIAL_DIFF) | _native.ORDER_C
+    out = _native.default_codec().delta_transform(np.ascontiguousarray(chunk), flags)
+    return out.view(dtype).reshape(chunk.shape)
+
+
+def cumsum_along_axis(chunk, axis=None):
+    """np.cumsum along `axis` in the array's own dtype (reference mtscomp.py:162-169), on the GPU."""
+    if axis is None:
+        return chunk
+    assert 0 <= axis < chunk.ndim
+    dtype = _require_integer_dtype(chunk.dtype)
+    flags = (_native.TIME_DIFF if axis == 0 else _native.SPATIAL_DIFF) | _native.ORDER_C
+    c = np.ascontiguousarray(chunk)
+    return _native.default_codec().inverse_transform(c.tobytes(), c.shape[0], c.shape[1], dtype, flags)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Writer
+# ------------------------------------------------------------------------------------------------------------------
+
+class Writer:
+    """Compress a raw (memory-mapped) recording into `.cbin` + `.ch` (reference mtscomp.py:216-511).
+
+    Options: chunk_duration, algorithm ('zlib'), comp_level (recorded only, as in the reference: SURVEY G1),
+    do_time_diff, do_spatial_diff, chunk_order, n_threads (batch size attribute), check_after_compress,
+    before_check (callback), quiet; plus `device` (CUDA device index).
+    """
+
+    def __init__(self, before_check=None, **kwargs):
+        self.pool = None
+        self.quiet = kwargs.pop('quiet', False)
+        cfg = read_config(**kwargs)
+        self.config = cfg
+        assert cfg.algorithm == 'zlib', "Only zlib is currently supported."
+        for key in ('chunk_duration', 'algorithm', 'comp_level', 'do_time_diff', 'do_spatial_diff', 'n_threads',
+                    'check_after_compress', 'chunk_order'):
+            setattr(self, key, cfg[key])
+        self.before_check = before_check or (lambda x: None)
+
+    # -- opening --------------------------------------------------------------------------------------------------
+    def open(self, data_path, sample_rate=None, n_channels=None, dtype=None, offset=None, mmap=True):
+        """Open the raw file (flat binary or .npy) and compute the chunk layout (reference mtscomp.py:257-339)."""
+        self.data_path = Path(data_path)
+        sample_rate = sample_rate or self.config.get('sample_rate', None)
+        if not sample_rate:
+            raise ValueError("Please provide a sample rate (-s option in the command-line).")
+        if str(data_path).endswith('.npy'):
+            self.data = np.load(data_path, mmap_mode='r')
+            self.shape = self.data.shape
+            if self.data.ndim >= 3:
+                self.data = np.reshape(self.data, (-1, self.data.shape[-1]))
+            self.dtype = dtype = self.data.dtype
+            self.n_channels = n_channels = self.data.shape[1]
+        else:
+            n_channels = n_channels or self.config.get('n_channels', None)
+            if not n_channels:
+                raise ValueError("Please provide n_channels (-n option in the command-line).")
+            dtype = dtype or self.config.get('dtype', None)
+            if not dtype:
+                raise ValueError("Please provide a dtype (-d option in the command-line).")
+            self.dtype = np.dtype(dtype)
+            self.data = load_raw_data(data_path, n_channels=n_channels, dtype=self.dtype)
+            self.shape = self.data.shape
+        self.sample_rate = float(sample_rate)
+        assert sample_rate > 0
+        assert n_channels > 0
+        self.file_size = self.data.size * self.data.itemsize
+        assert self.data.ndim == 2
+        self.n_samples, self.n_channels = self.data.shape
+        assert self.n_samples > 0
+        assert self.n_channels > 0
+        assert n_channels == self.n_channels
+        logger.info("Opening %s, duration %.1fs, %d channels.", data_path,
+                    self.n_samples / self.sample_rate, self.n_channels)
+        self._compute_chunk_bounds()
+        self.sha1_compressed = hashlib.sha1()
+        self.sha1_uncompressed = hashlib.sha1()
+
+    def _compute_chunk_bounds(self):
+        chunk_size = int(np.round(self.chunk_duration * self.sample_rate))
+        bounds = list(range(0, self.n_samples, chunk_size))
+        if bounds[-1] < self.n_samples:
+            bounds.append(self.n_samples)
+        self.chunk_bounds = bounds
+        self.n_chunks = len(bounds) - 1
+        assert bounds[0] == 0 and bounds[-1] == self.n_samples
+        self.batch_size = self.n_threads
+        self.n_batches = int(np.ceil(self.n_chunks / self.batch_size))
+
+    def get_cmeta(self):
+        """Contents of the `.ch` file (reference mtscomp.py:341-358)."""
+        return {
+            'version': FORMAT_VERSION,
+            'algorithm': self.algorithm,
+            'comp_level': self.comp_level,
+            'do_time_diff': self.do_time_diff,
+            'do_spatial_diff': self.do_spatial_diff,
+            'dtype': str(np.dtype(self.dtype)),
+            'n_channels': self.n_channels,
+            'sample_rate': self.sample_rate,
+            'chunk_bounds': self.chunk_bounds,
+            'chunk_offsets': self.chunk_offsets,
+            'chunk_order': self.chunk_order,
+            'sha1_compressed': self.sha1_compressed.hexdigest(),
+            'sha1_uncompressed': self.sha1_uncompressed.hexdigest(),
+            'shape': self.shape,
+        }
+
+    def get_chunk(self, chunk_idx):
+        assert 0 <= chunk_idx <= self.n_chunks - 1
+        return self.data[self.chunk_bounds[chunk_idx]:self.chunk_bounds[chunk_idx + 1], :]
+
+    # -- the codec seam ---------------------------------------------------------------------------------------------
+    def _flags(self):
+        return _native.flags_of(self.do_time_diff, self.do_spatial_diff, self.chunk_order)
+
+    def compress_batch(self, first_chunk, last_chunk):
+        """{chunk_idx: (uncompressed_chunk, compressed_bytes)} for chunks [first_chunk, last_chunk)
+        (reference mtscomp.py:399-423); one batched GPU call instead of pool.map(_compress_chunk)."""
+        assert 0 <= first_chunk < last_chunk <= self.n_chunks
+        _require_integer_dtype(self.dtype)
+        b = self.chunk_bounds
+        block = np.ascontiguousarray(self.data[b[first_chunk]:b[last_chunk], :])
+        rows = np.asarray(b[first_chunk:last_chunk + 1], dtype=np.int64) - b[first_chunk]
+        comp, offs = _codec_for(self.config).compress(block, rows, self._flags())
+        out = {}
+        for k, idx in enumerate(range(first_chunk, last_chunk)):
+            raw = block[rows[k]:rows[k + 1]]
+            cbytes = comp[offs[k]:offs[k + 1]].tobytes()
+            logger.debug("Chunk %d/%d: -%.3f%%.", idx + 1, self.n_chunks, 100 - 100 * len(cbytes) / max(raw.nbytes, 1))
+            out[idx] = (raw, cbytes)
+        return out
+
+    def _compress_chunk(self, chunk_idx):
+        """Single-chunk form of the seam, same return shape as the reference's (mtscomp.py:375-397)."""
+        return chunk_idx, self.compress_batch(chunk_idx, chunk_idx + 1)[chunk_idx]
+
+    def write(self, out, outmeta):
+        """Write `.cbin` and `.ch`; returns csize / raw size (reference mtscomp.py:425-507)."""
+        if not out:
+            out = self.data_path.with_suffix('.c' + self.data_path.suffix[1:])
+        if not outmeta:
+            outmeta = self.data_path.with_suffix('.ch')
+        Path(out).parent.mkdir(exist_ok=True, parents=True)
+        offset = 0
+        self.chunk_offsets = [0]
+        logger.info("Starting compression on the GPU.")
+        step = max(int(self.batch_size), GPU_BATCH_CHUNKS)
+        with open(out, 'wb') as fb:
+            for first in tqdm(range(0, self.n_chunks, step), desc='Compressing', disable=self.quiet):
+                last = min(first + step, self.n_chunks)
+                batch = self.compress_batch(first, last)
+                assert set(batch.keys()) <= set(range(first, last))
+                for idx in sorted(batch.keys()):
+                    raw, cbytes = batch[idx]
+                    fb.write(cbytes)
+                    offset += len(cbytes)
+                    self.chunk_offsets.append(offset)
+                    self.sha1_uncompressed.update(raw)
+                    self.sha1_compressed.update(cbytes)
+            csize = fb.tell()
+        assert self.chunk_offsets[-1] == csize
+        ratio = csize / self.file_size
+        logger.info("Wrote %s (%.1f GB, -%.3f%%).", out, csize / 1024 ** 3, 100 - 100 * ratio)
+        with open(outmeta, 'w') as f:
+            json.dump(self.get_cmeta(), f, indent=2, sort_keys=True)
+        if self.check_after_compress:
+            self.before_check(self)
+            try:
+                check(self.data, out, outmeta)
+            except AssertionError:
+                raise RuntimeError(
+                    "CRITICAL ERROR: automatic check failed when compressing the data. "
+                    "Report immediately to " + CRITICAL_ERROR_URL)
+            logger.debug("Automatic integrity check after compression PASSED.")
+        return ratio
+
+    def close(self):
+        mm = getattr(self.data, '_mmap', None)
+        if mm is not None:
+            mm.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Reader
+# ------------------------------------------------------------------------------------------------------------------
+
+class _SerialPool:
+    """Stand-in returned by Reader.start_thread_pool(): the GPU call is already batched."""
+
+    def map(self, fn, it):
+        return [fn(x) for x in it]
+
+    def close(self):
+        pass
+
+    def join(self):
+        pass
+
+
+class Reader:
+    """Random-access reader of `.cbin` + `.ch` (reference mtscomp.py:514-859), decoding on the GPU."""
+
+    def __init__(self, **kwargs):
+        self.pool = None
+        self.cdata = None
+        self.quiet = kwargs.pop('quiet', False)
+        self.config = read_config(**kwargs)
+        self.cache_size = self.config.cache_size
+        self.check_after_decompress = self.config.check_after_decompress
+
+    def open(self, cdata, cmeta=None):
+        if cmeta is None:
+            cmeta = Path(cdata).with_suffix('.ch')
+        if not isinstance(cmeta, dict):
+            with open(cmeta, 'r') as f:
+                cmeta = json.load(f)
+        assert isinstance(cmeta, dict)
+        self.cmeta = Bunch(cmeta)
+        m = self.cmeta
+        self.n_channels = m.n_channels
+        self.sample_rate = m.sample_rate
+        self.dtype = np.dtype(m.dtype)
+        self.chunk_offsets = m.chunk_offsets
+        self.chunk_bounds = m.chunk_bounds
+        self.chunk_order = m.chunk_order
+        self.n_samples = self.chunk_bounds[-1]
+        self.n_chunks = len(self.chunk_bounds) - 1
+        self.shape = (self.n_samples, self.n_channels)
+        self.ndim = 2
+        self.batch_size = self.config.n_threads
+        self.n_batches = int(np.ceil(self.n_chunks / self.batch_size))
+        if isinstance(cdata, (str, Path)):
+            if Path(cdata).suffix in ('.bin', '.dat'):  # pragma: no cover
+                logger.error("File to decompress has unexpected extension %s.", Path(cdata).suffix)
+            cdata = open(cdata, 'rb')
+        self.cdata = cdata
+        self.set_cache_size()
+
+    def set_cache_size(self, cache_size=None):
+        """(Re)wrap read_chunk in an LRU cache (reference mtscomp.py:582-588)."""
+        if cache_size != self.cache_size:
+            cache_size = cache_size or self.cache_size
+            assert cache_size > 0
+            self.read_chunk = lru_cache(maxsize=cache_size)(self.read_chunk)
+            self.cache_size = cache_size
+
+    def iter_chunks(self, first_chunk=0, last_chunk=None):
+        """Yield (chunk_idx, chunk_start, chunk_length) (reference mtscomp.py:590-600)."""
+        last_chunk = last_chunk if last_chunk is not None else self.n_chunks - 1
+        offs = self.chunk_offsets
+        for idx in range(first_chunk, last_chunk + 1):
+            yield idx, offs[idx], offs[idx + 1] - offs[idx]
+
+    # -- the codec seam ---------------------------------------------------------------------------------------------
+    def _flags(self):
+        return _native.flags_of(self.cmeta.do_time_diff, self.cmeta.do_spatial_diff, self.chunk_order)
+
+    def _pread(self, length, start):
+        if hasattr(os, 'pread'):
+            buf = os.pread(self.cdata.fileno(), length, start)
+        else:  # pragma: no cover
+            with _seek_lock:
+                self.cdata.seek(start)
+                buf = self.cdata.read(length)
+        assert len(buf) == length
+        return buf
+
+    def _decode(self, chunk_ids, spans):
+        """Decode several chunks in one GPU call.  spans: [(start, length)] in the .cbin."""
+        _require_integer_dtype(self.dtype)
+        bufs = [self._pread(length, start) for start, length in spans]
+        offs = np.concatenate(([0], np.cumsum([len(b) for b in bufs]))).astype(np.int64)
+        sizes = [self.chunk_bounds[i + 1] - self.chunk_bounds[i] for i in chunk_ids]
+        rows = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
+        out, status = _codec_for(self.config).decompress(
+            b''.join(bufs), offs, rows, self.n_channels, self.dtype, self._flags())
+        bad = np.flatnonzero(status)
+        if len(bad):
+            raise IOError("Compressed chunk #%d is corrupted." % chunk_ids[int(bad[0])])
+        return [out[rows[k]:rows[k + 1]] for k in range(len(chunk_ids))]
+
+    def read_chunk(self, chunk_idx, chunk_start, chunk_length):
+        """Read + decode one chunk -> C-contiguous (n_samples_chunk, n_channels) (reference mtscomp.py:602-635)."""
+        logger.debug("Reading compressed chunk %d, %d, %d", chunk_idx, chunk_start, chunk_length)
+        chunk = self._decode([chunk_idx], [(chunk_start, chunk_length)])[0]
+        i0, i1 = self.chunk_bounds[chunk_idx:chunk_idx + 2]
+        assert chunk.shape == (i1 - i0, self.n_channels) and chunk.dtype == self.dtype
+        return np.ascontiguousarray(chunk)
+
+    def _decompress_chunk(self, chunk_idx):
+        assert 0 <= chunk_idx <= self.n_chunks - 1
+        start = self.chunk_offsets[chunk_idx]
+        return chunk_idx, self.read_chunk(chunk_idx, start, self.chunk_offsets[chunk_idx + 1] - start)
+
+    def decompress_chunks(self, chunk_ids, pool=None):
+        """{chunk_idx: array} for `chunk_ids` (reference mtscomp.py:645-650), as one batched GPU call."""
+        ids = list(chunk_ids)
+        spans = [(self.chunk_offsets[i], self.chunk_offsets[i + 1] - self.chunk_offsets[i]) for i in ids]
+        for i in ids:
+            assert 0 <= i <= self.n_chunks - 1
+        out = dict(zip(ids, self._decode(ids, spans))) if ids else {}
+        assert set(out.keys()) == set(ids)
+        return out
+
+    def start_thread_pool(self):
+        if not self.pool:
+            self.pool = _SerialPool()
+        return self.pool
+
+    def stop_thread_pool(self):
+        self.pool = None
+
+    # -- indexing ---------------------------------------------------------------------------------------------------
+    def _validate_index(self, i, value_for_none=0):
+        if i is None:
+            i = value_for_none
+        elif i < 0:
+            i += self.n_samples
+        return int(clip(i, 0, self.n_samples))
+
+    def _chunks_for_interval(self, i0, i1):
+        """First and last chunk needed for samples [i0, i1] (reference mtscomp.py:661-684, pinned by its tests)."""
+        i0 = clip(i0, 0, self.n_samples - 1)
+        i1 = clip(i1, i0, self.n_samples - 1)
+        first = clip(bisect.bisect_right(self.chunk_bounds, i0) - 1, 0, self.n_chunks - 1)
+        last = clip(bisect.bisect_right(self.chunk_bounds, i1, lo=first) - 1, 0, self.n_chunks - 1)
+        assert self.chunk_bounds[first] <= i0 < self.chunk_bounds[first + 1]
+        assert self.chunk_bounds[last] <= i1 <= self.chunk_bounds[last + 1]
+        assert 0 <= first <= last <= self.n_chunks - 1
+        return first, last
+
+    def __getitem__(self, item):
+        """NumPy-style slicing returning in-memory arrays (reference mtscomp.py:798-856)."""
+        empty = np.zeros((0, self.n_channels), dtype=self.dtype)
+        if isinstance(item, slice):
+            i0 = self._validate_index(item.start, 0)
+            i1 = self._validate_index(item.stop, self.n_samples)
+            if i1 <= i0:
+                return empty
+            first, last = self._chunks_for_interval(i0, i1)
+            chunks = [self.read_chunk(idx, start, length) for idx, start, length in self.iter_chunks(first, last)]
+            if not chunks:  # pragma: no cover
+                return empty
+            arr = chunks[0] if len(chunks) == 1 else np.concatenate(chunks)
+            assert arr.shape == (self.chunk_bounds[last + 1] - self.chunk_bounds[first], self.n_channels)
+            a, b = i0 - self.chunk_bounds[first], i1 - self.chunk_bounds[first]
+            assert 0 <= a <= b <= arr.shape[0]
+            out = arr[a:b:item.step, :]
+            assert out.shape[0] == len(range(i0, i1, item.step or 1))
+            return out
+        if isinstance(item, tuple):
+            if len(item) == 1:
+                return self[item[0]]
+            if len(item) == 2 and np.isscalar(item[0]):
+                return self[item[0]][item[1]]
+            if len(item) == 2:
+                return self[item[0]][:, item[1]]
+        elif isinstance(item, (int, np.integer)):
+            item = int(item)
+            if item < 0:
+                item += self.n_samples * -int(np.floor(item / self.n_samples))
+                assert 0 <= item < self.n_samples
+            if not 0 <= item < self.n_samples:  # pragma: no cover
+                raise IndexError(
+                    "index %d is out of bounds for axis 0 with size %d" % (item, self.n_samples))
+            return self[item:item + 1][0]
+        elif isinstance(item, (list, np.ndarray)):  # pragma: no cover
+            raise NotImplementedError("Indexing with multiple values is currently unsupported.")
+        return empty  # pragma: no cover
+
+    # -- whole-file operations --------------------------------------------------------------------------------------
+    def tofile(self, out, overwrite=False):
+        """Write the decompressed array to `out` (reference mtscomp.py:701-743)."""
+        if out is None:
+            out = Path(self.cdata.name).with_suffix('.bin')
+        out = Path(out)
+        if not overwrite and out.exists():  # pragma: no cover
+            raise ValueError(
+                "The output file %s already exists, use --overwrite or specify another output path." % out)
+        elif overwrite and out.exists():
+            out.unlink()
+        step = max(int(self.batch_size), GPU_BATCH_CHUNKS)
+        with open(out, 'wb') as fb:
+            for first in tqdm(range(0, self.n_chunks, step), desc='Decompressing', disable=self.quiet):
+                last = min(first + step, self.n_chunks)
+                chunks = self.decompress_chunks(range(first, last))
+                for idx in sorted(chunks.keys()):
+                    fb.write(chunks[idx])
+            dsize = fb.tell()
+        assert dsize == self.chunk_bounds[-1] * self.n_channels * self.dtype.itemsize
+        logger.info("Wrote %s (%.1f GB).", out, dsize / 1024 ** 3)
+        if self.check_after_decompress:
+            decompressed = load_raw_data(out, n_channels=self.n_channels, dtype=self.dtype)
+            check(decompressed, self.cdata, self.cmeta)
+            logger.debug("Automatic integrity check after decompression PASSED.")
+
+    def close(self):
+        if self.cdata:
+            self.cdata.close()
+
+    def chop(self, n_chunks, out=None):
+        """Copy the first `n_chunks` compressed chunks into a new .cbin/.ch pair (reference mtscomp.py:750-796)."""
+        assert n_chunks > 0
+        if n_chunks >= self.n_chunks:  # pragma: no cover
+            logger.warning("Cannot chop more chunks than there are in the original file.")
+            return
+        assert out is not None, "The output path must be specified."
+        out = Path(out)
+        assert out.suffix == '.cbin'
+        if out.exists():  # pragma: no cover
+            raise IOError("File %s already exists." % out)
+        out.parent.mkdir(exist_ok=True, parents=True)
+        end = self.chunk_offsets[n_chunks]
+        with open(out, 'wb') as f:
+            for i in tqdm(range(n_chunks), desc='Chopping %d chunks' % n_chunks):
+                start = self.chunk_offsets[i]
+                f.write(self._pread(self.chunk_offsets[i + 1] - start, start))
+            assert f.tell() == end
+        outmeta = out.with_suffix('.ch')
+        if outmeta.exists():  # pragma: no cover
+            raise IOError("File %s already exists." % out)
+        cmeta = Bunch(self.cmeta.copy())
+        cmeta['chunk_bounds'] = cmeta['chunk_bounds'][:n_chunks + 1]
+        cmeta['chunk_offsets'] = cmeta['chunk_offsets'][:n_chunks + 1]
+        cmeta['sha1_compressed'] = None
+        cmeta['sha1_uncompressed'] = None
+        cmeta['chopped'] = True
+        with open(outmeta, 'w') as f:
+            json.dump(cmeta, f, indent=2, sort_keys=True)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pragma: no cover
+            pass
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# High-level API
+# ------------------------------------------------------------------------------------------------------------------
+
+def check(data, out, outmeta):
+    """Decode every chunk and compare with `data` (reference mtscomp.py:866-888); AssertionError on mismatch."""
+    unc = decompress(out, outmeta)
+    try:
+        step = GPU_BATCH_CHUNKS
+        for first in tqdm(range(0, unc.n_chunks, step), desc='Checking'):
+            last = min(first + step, unc.n_chunks)
+            chunks = unc.decompress_chunks(range(first, last))
+            for idx in range(first, last):
+                i0, i1 = unc.chunk_bounds[idx], unc.chunk_bounds[idx + 1]
+                expected = data[i0:i1]
+                chunk = chunks[idx]
+                assert chunk.dtype == expected.dtype
+                assert chunk.shape == expected.shape
+                if np.issubdtype(chunk.dtype, np.integer):
+                    assert np.array_equal(chunk, expected)
+                else:  # pragma: no cover
+                    assert np.allclose(chunk, expected, atol=CHECK_ATOL)
+    finally:
+        unc.close()
+
+
+def compress(path, out=None, outmeta=None, sample_rate=None, n_channels=None, dtype=None, **kwargs):
+    """Compress a raw binary file into `out` (.cbin) + `outmeta` (.ch); returns compressed/raw size ratio
+    (reference mtscomp.py:891-958)."""
+    w = Writer(**kwargs)
+    w.open(path, sample_rate=sample_rate, n_channels=n_channels, dtype=dtype)
+    ratio = w.write(out, outmeta)
+    w.close()
+    return ratio
+
+
+def decompress(cdata, cmeta=None, out=None, write_output=False, overwrite=False, **kwargs):
+    """Open a compressed dataset, optionally writing the decompressed file; returns the Reader
+    (reference mtscomp.py:961-997)."""
+    if out:
+        write_output = True
+    r = Reader(**kwargs)
+    r.open(cdata, cmeta)
+    if write_output:
+        r.tofile(out, overwrite=overwrite)
+    return r

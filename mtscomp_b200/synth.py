@@ -39,7 +39,7 @@ def ap_chunk(ns=30000, nc=385, sample_rate=30000., seed=1234, rms=9.0, t0=0):
             c0, c1 = max(c - 4, 0), min(c + 5, nc)
             prof = np.exp(-0.5 * ((np.arange(c0, c1) - c) / 1.5) ** 2).astype(np.float32)
             x[t:t + tl, c0:c1] += a * templ[:, None] * prof[None, :]
-    out = np.clip(np.rint(x), -512, 511).astype(np.int16)
+    out = np.ascontiguousarray(np.clip(np.rint(x), -512, 511).astype(np.int16))
     out[:, nc - 1] = _sync_channel(ns, sample_rate, t0)
     return out
 
@@ -58,7 +58,7 @@ def lfp_chunk(ns=2500, nc=385, sample_rate=2500., seed=4321, t0=0):
     x = src @ prof
     x *= 60.0 / max(float(np.sqrt(np.mean(x * x))), 1e-9)
     x += 6.0 * rng.standard_normal((ns, nc), dtype=np.float32)
-    out = np.clip(np.rint(x), -512, 511).astype(np.int16)
+    out = np.ascontiguousarray(np.clip(np.rint(x), -512, 511).astype(np.int16))
     out[:, nc - 1] = _sync_channel(ns, sample_rate, t0)
     return out
 

@@ -1,0 +1,57 @@
+"""CPU: kernel LOGIC through the host emulation build (csrc/emu/cuda_emu.h) against the oracle and the golden files.
+
+This is a development aid that lets the CPU-only container exercise the exact kernel sources; it is not a product
+path (mtscomp_b200/_native.py never loads the emulation library) and it says nothing about the GPU memory model —
+the `-m gpu` tests do that on a B200."""
+import json
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import codec as ora
+
+
+@pytest.fixture(scope='module')
+def emu():
+    from mtscomp_b200 import _native, build
+    return _native.Codec(0, lib=_native.load_library(build.build_emulation()))
+
+
+def _flags(ch):
+    from mtscomp_b200 import _native
+    return _native.flags_of(ch['do_time_diff'], ch['do_spatial_diff'], ch['chunk_order'])
+
+
+@pytest.mark.parametrize('name', ['lfp_spatial', 'order_c', 'fullrange', 'wrap_edges', 'tiny_1x1', 'tiny_chunks',
+                                  'zeros_runs', 'spatial_only', 'nodiff', 'one_channel'])
+def test_emulated_kernels_on_golden(emu, name):
+    m = json.loads((GOLDEN / 'manifest.json').read_text())['cases'][name]
+    ch = json.loads((GOLDEN / (name + '.ch')).read_text())
+    raw = np.fromfile(GOLDEN / (name + '.bin'), dtype=m['dtype']).reshape(m['shape'])
+    cbin = (GOLDEN / (name + '.cbin')).read_bytes()
+    fl = _flags(ch)
+    b, o = ch['chunk_bounds'], ch['chunk_offsets']
+    # K1 vs the bytes the reference handed to zlib
+    assert emu.delta_transform(raw[b[0]:b[1]], fl).tobytes() == (GOLDEN / (name + '.tr')).read_bytes()
+    # decoder on the reference-written file
+    out, st = emu.decompress(cbin, o, b, ch['n_channels'], ch['dtype'], fl)
+    assert not st.any() and np.array_equal(out, raw)
+    # encoder: zlib must accept every chunk and return the reference's transform bytes
+    comp, offs = emu.compress(raw, b, fl)
+    kw = dict(do_time_diff=ch['do_time_diff'], do_spatial_diff=ch['do_spatial_diff'], chunk_order=ch['chunk_order'])
+    for i in range(len(b) - 1):
+        assert zlib.decompress(bytes(comp[offs[i]:offs[i + 1]])) == ora.transform_chunk(raw[b[i]:b[i + 1]], **kw)
+    out2, st2 = emu.decompress(comp, offs, b, ch['n_channels'], ch['dtype'], fl)
+    assert not st2.any() and np.array_equal(out2, raw)
+
+
+def test_emulated_corruption_is_reported(emu):
+    ch = json.loads((GOLDEN / 'nodiff.ch').read_text())
+    cbin = bytearray((GOLDEN / 'nodiff.cbin').read_bytes())
+    o = ch['chunk_offsets']
+    cbin[o[2] - 1] ^= 0x40          # adler32 of chunk 1
+    cbin[o[2] + 40] ^= 0x10         # payload of chunk 2
+    _, st = emu.decompress(bytes(cbin), o, ch['chunk_bounds'], ch['n_channels'], ch['dtype'], _flags(ch))
+    assert st[0] == 0 and st[1] == 9 and st[2] != 0

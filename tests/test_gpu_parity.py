@@ -1,0 +1,206 @@
+"""GPU: parity of the sm_100a kernels against the oracle and the reference-written golden files, through the C ABI.
+
+Bit-exact everywhere (integer / byte work): K1 output == the bytes the reference hands to zlib; zlib (the reference
+Reader's decoder) accepts every GPU-written chunk and returns those bytes; the GPU decoder returns exactly what the
+reference Reader returns for reference-written chunks.  Compression ratio: GPU bytes <= 1.031 x zlib level 6 (north
+star: ratio >= 0.97 x the reference's)."""
+import hashlib
+import json
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import codec as ora
+
+pytestmark = pytest.mark.gpu
+
+MANIFEST = json.loads((GOLDEN / 'manifest.json').read_text())
+CASES = sorted(MANIFEST['cases'])
+
+
+def F(td=True, sd=False, order='F'):
+    from mtscomp_b200 import _native
+    return _native.flags_of(td, sd, order)
+
+
+def load_case(name):
+    m = MANIFEST['cases'][name]
+    ch = json.loads((GOLDEN / (name + '.ch')).read_text())
+    raw = np.fromfile(GOLDEN / (name + '.bin'), dtype=m['dtype']).reshape(m['shape'])
+    return m, ch, raw, (GOLDEN / (name + '.cbin')).read_bytes()
+
+
+def kw_of(ch):
+    return dict(do_time_diff=ch['do_time_diff'], do_spatial_diff=ch['do_spatial_diff'], chunk_order=ch['chunk_order'])
+
+
+def test_native_library_is_the_cuda_build(codec):
+    from mtscomp_b200 import _native
+    assert str(_native.LIB_PATH).endswith('libmtscomp_b200.so')
+    assert codec.lib.mtsb_device_count() >= 1
+    assert codec.get_param('sm_count') > 100
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_golden_reference_files(codec, name):
+    m, ch, raw, cbin = load_case(name)
+    fl = F(**{'td': ch['do_time_diff'], 'sd': ch['do_spatial_diff'], 'order': ch['chunk_order']})
+    b, o = ch['chunk_bounds'], ch['chunk_offsets']
+    # K1 == reference transform bytes
+    assert codec.delta_transform(raw[b[0]:b[1]], fl).tobytes() == (GOLDEN / (name + '.tr')).read_bytes()
+    # K3+K4 on the reference-written .cbin == reference Reader output
+    out, st = codec.decompress(cbin, o, b, ch['n_channels'], ch['dtype'], fl)
+    assert not st.any()
+    assert hashlib.sha1(out.tobytes()).hexdigest() == m['sha1_decoded']
+    # K1+K2: zlib accepts each chunk and yields the reference's transform bytes
+    comp, offs = codec.compress(raw, b, fl)
+    for i in range(len(b) - 1):
+        assert zlib.decompress(bytes(comp[offs[i]:offs[i + 1]])) == ora.transform_chunk(raw[b[i]:b[i + 1]], **kw_of(ch))
+    out2, st2 = codec.decompress(comp, offs, b, ch['n_channels'], ch['dtype'], fl)
+    assert not st2.any() and np.array_equal(out2, raw)
+
+
+@pytest.mark.parametrize('dtype', ['uint8', 'int8', 'uint16', 'int16', 'int32', 'uint32', 'int64'])
+@pytest.mark.parametrize('shape', [(1, 1), (7, 3), (64, 19), (65, 385), (257, 384), (130, 33), (3, 1000)])
+def test_transform_all_flag_combinations(codec, dtype, shape):
+    rng = np.random.default_rng(hash((dtype, shape)) % 2 ** 32)
+    info = np.iinfo(dtype)
+    x = rng.integers(info.min, info.max, shape, dtype=dtype, endpoint=True)
+    for td in (True, False):
+        for sd in (True, False):
+            for order in 'FC':
+                want = ora.transform_chunk(x, td, sd, order)
+                assert codec.delta_transform(x, F(td, sd, order)).tobytes() == want
+                back, ad = codec.inverse_transform(want, shape[0], shape[1], dtype, F(td, sd, order), want_adler=True)
+                assert np.array_equal(back, x)
+                assert ad == zlib.adler32(want)
+
+
+@pytest.mark.parametrize('td,sd,order', [(True, False, 'F'), (True, True, 'F'), (True, False, 'C'), (False, False, 'F')])
+def test_codec_ap_small_chunks(codec, td, sd, order):
+    from mtscomp_b200 import synth
+    x = synth.ap_chunk(ns=4000, nc=96, seed=31)
+    rows = [0, 1500, 3000, 4000]
+    fl = F(td, sd, order)
+    comp, offs = codec.compress(x, rows, fl)
+    for i in range(3):
+        want = ora.transform_chunk(x[rows[i]:rows[i + 1]], td, sd, order)
+        assert zlib.decompress(bytes(comp[offs[i]:offs[i + 1]])) == want
+    out, st = codec.decompress(comp, offs, rows, 96, np.int16, fl)
+    assert not st.any() and np.array_equal(out, x)
+    # same chunks written by zlib (what the reference Writer produces) through the GPU decoder
+    parts = [ora.encode_chunk(x[rows[i]:rows[i + 1]], td, sd, order) for i in range(3)]
+    roffs = np.concatenate(([0], np.cumsum([len(p) for p in parts])))
+    out2, st2 = codec.decompress(b''.join(parts), roffs, rows, 96, np.int16, fl)
+    assert not st2.any() and np.array_equal(out2, x)
+
+
+def test_full_size_ap_chunk_ratio_and_cross_compat(codec):
+    """BASELINE config 1 chunk shape (30000 x 385): exact both ways + the north star's ratio bound."""
+    from mtscomp_b200 import synth
+    x = synth.ap_chunk(ns=30000, nc=385, seed=1234)
+    want = ora.transform_chunk(x)
+    comp, offs = codec.compress(x, [0, 30000], F())
+    assert zlib.decompress(bytes(comp)) == want
+    ref = zlib.compress(want)
+    assert len(comp) <= 1.031 * len(ref), (len(comp), len(ref))
+    out, st = codec.decompress(ref, [0, len(ref)], [0, 30000], 385, np.int16, F())
+    assert not st.any() and np.array_equal(out, x)
+    out2, st2 = codec.decompress(comp, offs, [0, 30000], 385, np.int16, F())
+    assert not st2.any() and np.array_equal(out2, x)
+
+
+def test_lfp_spatial_ratio(codec):
+    from mtscomp_b200 import synth
+    x = np.concatenate([synth.lfp_chunk(ns=2500, nc=385, seed=50 + i) for i in range(4)])
+    rows = [0, 2500, 5000, 7500, 10000]
+    comp, offs = codec.compress(x, rows, F(True, True))
+    ref = sum(len(ora.encode_chunk(x[rows[i]:rows[i + 1]], True, True)) for i in range(4))
+    assert len(comp) <= 1.031 * ref, (len(comp), ref)
+    out, st = codec.decompress(comp, offs, rows, 385, np.int16, F(True, True))
+    assert not st.any() and np.array_equal(out, x)
+
+
+def test_many_chunks_batch_properties(codec):
+    """Size-independent properties at a multi-sub-batch size: offsets monotone, every chunk independently decodable
+    in any order (chunks are independent streams), deterministic bytes (reference tests.py:489-492 relies on it)."""
+    from mtscomp_b200 import synth
+    base = [synth.ap_chunk(ns=3000, nc=385, seed=70 + i) for i in range(3)]
+    n = 40
+    x = np.concatenate([base[i % 3] for i in range(n)])
+    rows = np.arange(n + 1) * 3000
+    codec.set_param('batch_bytes', 16 << 20)      # force several internal sub-batches
+    try:
+        comp, offs = codec.compress(x, rows, F())
+        comp_b, offs_b = codec.compress(x, rows, F())
+    finally:
+        codec.set_param('batch_bytes', 2 << 30)
+    assert np.array_equal(offs, offs_b) and np.array_equal(comp, comp_b)
+    assert (np.diff(offs) > 0).all()
+    # compressing the first 7 chunks alone gives the same bytes as the first 7 chunks of the big batch (chop-ability)
+    comp7, offs7 = codec.compress(x[:7 * 3000], rows[:8], F())
+    assert bytes(comp7) == bytes(comp[:offs[7]])
+    # decode a permuted subset
+    ids = [17, 3, 39, 0, 22]
+    sub = b''.join(bytes(comp[offs[i]:offs[i + 1]]) for i in ids)
+    soffs = np.concatenate(([0], np.cumsum([offs[i + 1] - offs[i] for i in ids])))
+    out, st = codec.decompress(sub, soffs, np.arange(len(ids) + 1) * 3000, 385, np.int16, F())
+    assert not st.any()
+    for k, i in enumerate(ids):
+        assert np.array_equal(out[k * 3000:(k + 1) * 3000], x[i * 3000:(i + 1) * 3000])
+
+
+def test_incompressible_and_runs(codec):
+    rng = np.random.default_rng(9)
+    x = rng.integers(-32768, 32767, (5000, 64), dtype=np.int64).astype(np.int16)
+    comp, offs = codec.compress(x, [0, 5000], F())
+    assert len(comp) <= codec.compress_bound(5000, 64, 2, F())
+    assert zlib.decompress(bytes(comp)) == ora.transform_chunk(x)
+    z = np.zeros((30000, 8), np.int16)
+    z[:, 7] = (np.arange(30000) // 15000) * 64
+    comp, offs = codec.compress(z, [0, 30000], F())
+    assert zlib.decompress(bytes(comp)) == ora.transform_chunk(z)
+    assert len(comp) < 4000
+    out, st = codec.decompress(comp, offs, [0, 30000], 8, np.int16, F())
+    assert not st.any() and np.array_equal(out, z)
+
+
+def test_corruption_is_detected_per_chunk(codec):
+    _, ch, raw, cbin = load_case('nodiff')
+    o = ch['chunk_offsets']
+    bad = bytearray(cbin)
+    bad[o[2] - 1] ^= 0x40       # adler32 trailer of chunk 1
+    bad[o[2] + 40] ^= 0x10      # payload of chunk 2
+    fl = F(ch['do_time_diff'], ch['do_spatial_diff'], ch['chunk_order'])
+    _, st = codec.decompress(bytes(bad), o, ch['chunk_bounds'], ch['n_channels'], ch['dtype'], fl)
+    assert st[0] == 0 and st[1] == 9 and st[2] != 0
+    with pytest.raises(zlib.error):
+        zlib.decompress(bytes(bad[o[1]:o[2]]))      # the reference rejects the same chunk
+    # truncated stream and garbage
+    _, st = codec.decompress(bytes(cbin[:o[1] - 9]), [0, o[1] - 9], ch['chunk_bounds'][:2], ch['n_channels'], ch['dtype'], fl)
+    assert st[0] != 0
+    junk = np.random.default_rng(1).integers(0, 256, 500, dtype=np.uint8).tobytes()
+    _, st = codec.decompress(junk, [0, 500], ch['chunk_bounds'][:2], ch['n_channels'], ch['dtype'], fl)
+    assert st[0] != 0
+
+
+def test_zlib_variants_accepted(codec):
+    """stored blocks, fixed-Huffman blocks, smaller declared windows, trailing bytes, multi-block streams."""
+    from mtscomp_b200 import synth
+    x = synth.ap_chunk(ns=2000, nc=32, seed=77)
+    want = ora.transform_chunk(x)
+    variants = []
+    for level, wbits, strategy in [(0, 15, 0), (1, 15, 0), (9, 15, 0), (6, 9, 0), (6, 12, 0), (6, 15, zlib.Z_FIXED),
+                                   (6, 15, zlib.Z_HUFFMAN_ONLY), (6, 15, zlib.Z_RLE)]:
+        c = zlib.compressobj(level, zlib.DEFLATED, wbits, 8, strategy)
+        variants.append(c.compress(want) + c.flush())
+    c = zlib.compressobj(6)
+    parts = b''.join(c.compress(want[i:i + 9000]) + c.flush(zlib.Z_SYNC_FLUSH) for i in range(0, len(want), 9000))
+    variants.append(parts + c.flush())
+    variants.append(zlib.compress(want) + b'\x00\x01\x02\x03')
+    for v in variants:
+        assert zlib.decompress(v) == want
+        out, st = codec.decompress(v, [0, len(v)], [0, 2000], 32, np.int16, F())
+        assert not st.any() and np.array_equal(out, x)

@@ -1,0 +1,68 @@
+"""CPU, build container only: files written through this package's Writer (kernels emulated on the host) must open in
+the UNMODIFIED reference Reader, and reference-written files must open in this package's Reader, byte for byte.
+Skipped where /root/reference does not exist (the GPU box); the committed golden files cover that side there."""
+import importlib.util
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+REF = Path('/root/reference/mtscomp.py')
+pytestmark = pytest.mark.skipif(not REF.exists(), reason='reference tree not present')
+
+
+@pytest.fixture(scope='module')
+def ref():
+    spec = importlib.util.spec_from_file_location('mtscomp_reference', str(REF))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    m.CONFIG_PATH = Path('/nonexistent/.mtscomp')
+    return m
+
+
+@pytest.fixture(scope='module')
+def emulated_default_codec():
+    from mtscomp_b200 import _native, build
+    emu = _native.Codec(0, lib=_native.load_library(build.build_emulation()))
+    saved = dict(_native._default)
+    _native._default.clear()
+    _native._default[0] = emu
+    yield emu
+    _native._default.clear()
+    _native._default.update(saved)
+
+
+@pytest.mark.parametrize('kw', [{}, dict(do_spatial_diff=True), dict(chunk_order='C'), dict(do_time_diff=False),
+                                dict(chunk_duration=0.25)])
+def test_cross_compatibility(ref, emulated_default_codec, tmp_path, kw):
+    import mtscomp_b200 as M
+    from mtscomp_b200 import synth
+    M.CONFIG_PATH = tmp_path / '.mtscomp'
+    arr = synth.ap_chunk(ns=2600, nc=50, sample_rate=30000., seed=3)
+    raw = tmp_path / 'data.bin'
+    arr.tofile(raw)
+    # ours -> reference Reader
+    M.compress(raw, tmp_path / 'g.cbin', tmp_path / 'g.ch', sample_rate=1000., n_channels=50, dtype='int16', quiet=True, **kw)
+    r = ref.decompress(tmp_path / 'g.cbin', tmp_path / 'g.ch')
+    assert np.array_equal(r[:], arr)
+    assert np.array_equal(r[1234:2345:7, 3:40], arr[1234:2345:7, 3:40])
+    ref.decompress(tmp_path / 'g.cbin', tmp_path / 'g.ch', tmp_path / 'g_back.bin', quiet=True).close()
+    assert (tmp_path / 'g_back.bin').read_bytes() == raw.read_bytes()
+    r.close()
+    # reference -> ours
+    ref.compress(raw, tmp_path / 'r.cbin', tmp_path / 'r.ch', sample_rate=1000., n_channels=50, dtype='int16',
+                 quiet=True, n_threads=1, **kw)
+    g = M.decompress(tmp_path / 'r.cbin', tmp_path / 'r.ch')
+    assert np.array_equal(g[:], arr)
+    g.close()
+    M.decompress(tmp_path / 'r.cbin', tmp_path / 'r.ch', tmp_path / 'r_back.bin', quiet=True).close()
+    assert (tmp_path / 'r_back.bin').read_bytes() == raw.read_bytes()
+    # same metadata keys / values apart from offsets and hashes
+    mg, mr = json.loads((tmp_path / 'g.ch').read_text()), json.loads((tmp_path / 'r.ch').read_text())
+    assert set(mg) == set(mr)
+    for k in mg:
+        if k not in ('chunk_offsets', 'sha1_compressed'):
+            assert mg[k] == mr[k], k
+    # ratio: within the north star's 3 % of the reference's zlib
+    assert (tmp_path / 'g.cbin').stat().st_size <= 1.031 * (tmp_path / 'r.cbin').stat().st_size + 64 * len(mg['chunk_bounds'])
