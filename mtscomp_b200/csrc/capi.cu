@@ -52,7 +52,7 @@ struct mtsb_ctx {
   std::string err;
   // params
   long long seg_bytes = 262144, batch_bytes = 2ll << 30, write_index = 1;
-  LzParams lz{48, 258, 1024, 8192, 32768, 1};
+  LzParams lz{16, 258, 32768, 32768, 32768, 0};   // greedy, every match >= 4 bytes accepted: tuned on synthetic AP/LFP
   // device scratch
   Buf d_raw, d_T, d_tok, d_hist, d_codes, d_hdrs, d_tab, d_so, d_seg_adler, d_chunk_adler, d_chunk_off, d_out,
       d_partial, d_comp, d_status, d_tadler, d_gather;
@@ -776,7 +776,7 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
     }
     c->end();
     c->begin(2);
-    MTS_LAUNCH(inflate_kernel, dim3((n_segs + INF_WARPS - 1) / INF_WARPS), dim3(INF_WARPS * 32), 0, c->stream, dcomp, (const InflateSeg*)(d + o_seg), n_segs, (unsigned char*)c->d_T.p, (int*)c->d_status.p, (unsigned*)c->d_tadler.p);
+    MTS_LAUNCH(inflate_kernel, dim3(n_segs), dim3(32), 0, c->stream, dcomp, (const InflateSeg*)(d + o_seg), n_segs, (unsigned char*)c->d_T.p, (int*)c->d_status.p, (unsigned*)c->d_tadler.p);
     CKL();
     c->launches++;
     c->end();

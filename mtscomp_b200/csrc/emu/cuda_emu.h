@@ -29,7 +29,7 @@
 #define __shared__ static thread_local
 #define __constant__ static const
 #define __launch_bounds__(...)
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 
 struct uint3 { unsigned x, y, z; };
 struct dim3 {

@@ -31,7 +31,6 @@ enum {
   INF_BAD_SIZE = 6, INF_INPUT_OVERRUN = 7, INF_BAD_STORED = 8, INF_BAD_ADLER = 9
 };
 
-static const int INF_WARPS = 4;
 static const int INF_LBITS = 10, INF_DBITS = 8;
 
 struct InflateWarpSmem {
@@ -133,20 +132,45 @@ __device__ __forceinline__ void fixed_lengths(unsigned char* lens, unsigned lane
   if (lane < 32) lens[288 + lane] = (lane < 30) ? 5 : 0;
 }
 
-__global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const unsigned char* __restrict__ comp,
-                                                                 const InflateSeg* __restrict__ segs, int n_segs,
-                                                                 unsigned char* out_base, int* __restrict__ status,
-                                                                 unsigned* __restrict__ trailer_adler) {
-  __shared__ InflateWarpSmem sm_all[INF_WARPS];
+// Output window: the last 32 KB of output plus the batch being produced live in a shared-memory ring, so that
+// back-references never touch global memory; finished bytes are streamed to HBM as aligned 32-bit words.
+static const unsigned INF_RING = 40960;        // 32768 history + up to 8192 bytes of the batch in flight
+static const unsigned INF_BATCH_BYTES = 8192 - 258;
+
+__device__ __forceinline__ unsigned ring_wrap(unsigned i) { return i >= INF_RING ? i - INF_RING : i; }
+
+// Stream bytes [from, to) of the output (ring -> global).  a0 = (address of out) & 3; ring index of position p is
+// (p + a0) mod INF_RING with INF_RING % 4 == 0, so aligned words of the ring are aligned words of the output.
+__device__ __forceinline__ void inflate_flush(const unsigned char* ring, unsigned char* out, unsigned a0, unsigned from,
+                                              unsigned to, unsigned lane) {
+  if (to <= from) return;
+  unsigned g0 = from + a0, g1 = to + a0;                 // coordinates relative to the aligned word base of out
+  unsigned w0 = (g0 + 3) & ~3u, w1 = g1 & ~3u;
+  unsigned char* gb = out - a0;
+  if (w0 >= w1) {                                        // no full word: bytes only
+    for (unsigned g = g0 + lane; g < g1; g += 32) gb[g] = ring[g % INF_RING];
+    return;
+  }
+  if (lane < w0 - g0) gb[g0 + lane] = ring[(g0 + lane) % INF_RING];
+  for (unsigned g = w0 + 4 * lane; g < w1; g += 128) *(unsigned*)(gb + g) = *(const unsigned*)(ring + g % INF_RING);
+  if (lane < g1 - w1) gb[w1 + lane] = ring[(w1 + lane) % INF_RING];
+}
+
+__global__ void __launch_bounds__(32) inflate_kernel(const unsigned char* __restrict__ comp,
+                                                     const InflateSeg* __restrict__ segs, int n_segs,
+                                                     unsigned char* out_base, int* __restrict__ status,
+                                                     unsigned* __restrict__ trailer_adler) {
+  __shared__ InflateWarpSmem S;
+  __shared__ __align__(16) unsigned char ring[INF_RING];
   const unsigned lane = lane_id();
-  const int sidx = blockIdx.x * INF_WARPS + (int)warp_id();
+  const int sidx = blockIdx.x;
   if (sidx >= n_segs) return;
-  InflateWarpSmem& S = sm_all[warp_id()];
   const InflateSeg sg = segs[sidx];
   unsigned char* out = out_base + sg.out_off;
   const unsigned out_len = (unsigned)sg.out_len;
   const unsigned char* in = comp + sg.in_off;
   const unsigned in_len = (unsigned)sg.in_len;
+  const unsigned a0 = (unsigned)((uintptr_t)out & 3);
 
   BitR br;
   br.mis = (unsigned)((uintptr_t)in & 3);
@@ -154,7 +178,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const unsigned 
   br.kmax = (br.mis + in_len - 1) >> 2;
   br.bb = 0; br.bc = 0; br.ip = 0;
   int err = INF_OK;
-  unsigned opos = 0;
+  unsigned opos = 0;            // bytes produced so far (all flushed at batch boundaries)
   unsigned adler = 0;
 
   if (sg.flags & INF_ZLIB) {
@@ -172,7 +196,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const unsigned 
     last = br.get(1) != 0;
     unsigned type = br.get(2);
     if (type == 0) {
-      // stored: skip to the byte boundary, LEN / NLEN, raw copy
+      // stored: skip to the byte boundary, LEN / NLEN, raw copy through the ring (later blocks may reference it)
       br.drop(br.bc & 7);
       br.refill();
       unsigned len = br.get(16);
@@ -182,10 +206,15 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const unsigned 
       unsigned src = br.byte_pos();
       if (src + len > in_len) { err = INF_INPUT_OVERRUN; break; }
       if (opos + len > out_len) { err = INF_BAD_SIZE; break; }
-      for (unsigned i = lane; i < len; i += 32) out[opos + i] = in[src + i];
-      opos += len;
+      for (unsigned b0 = 0; b0 < len; b0 += 4096) {
+        unsigned m = min(4096u, len - b0);
+        for (unsigned i = lane; i < m; i += 32) ring[(opos + a0 + i) % INF_RING] = in[src + b0 + i];
+        __syncwarp();
+        inflate_flush(ring, out, a0, opos, opos + m, lane);
+        __syncwarp();
+        opos += m;
+      }
       br.ip = src + len; br.bb = 0; br.bc = 0;
-      __syncwarp();
       continue;
     }
     if (type == 3) { err = INF_BAD_BLOCK; break; }
@@ -225,7 +254,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const unsigned 
         } else if (sym == 17) { val = 0; rep = 3 + br.get(3); }
         else if (sym == 18) { val = 0; rep = 11 + br.get(7); }
         if (idx + (int)rep > nl + nd) { err = INF_BAD_LENGTHS; break; }
-        if (lane == 0) for (unsigned k = 0; k < rep; k++) S.lens[24 + idx + k] = (unsigned char)val;
+        for (unsigned k = lane; k < rep; k += 32) S.lens[24 + idx + k] = (unsigned char)val;
         idx += (int)rep;
         prev_len = val;
       }
@@ -241,13 +270,13 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const unsigned 
     if (!inflate_build(dl, nd, S.dtab, INF_DBITS, S.dsorted, S.dcount, S.run)) { err = INF_BAD_LENGTHS; break; }
     __syncwarp();
 
-    // ---- symbol loop: batches of up to 32 symbols
+    // ---- symbol loop: batches of up to 32 symbols / INF_BATCH_BYTES output bytes
     bool eob = false;
     while (!eob && !err) {
       unsigned my_pos = 0, my_len = 0, my_dist = 0, my_lit = 0;
       unsigned bpos = opos;
       int k = 0;
-      for (; k < 32; k++) {
+      for (; k < 32 && bpos - opos < INF_BATCH_BYTES; k++) {
         br.refill();
         unsigned e = S.ltab[br.peek(INF_LBITS)];
         unsigned sym;
@@ -283,29 +312,38 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const unsigned 
       }
       if (err) break;
       if (br.byte_pos() > in_len + 8) { err = INF_INPUT_OVERRUN; break; }
-      // literals in parallel, then matches in stream order
       const bool have = lane < (unsigned)k;
-      if (have && my_len == 0) out[my_pos] = (unsigned char)my_lit;
+      const bool is_match = have && my_len != 0;
+      // a match is independent of this batch's other symbols if everything it reads was produced before the batch
+      const bool indep = is_match && (my_pos - my_dist + min(my_len, my_dist) <= opos);
+      const unsigned rp = (my_pos + a0) % INF_RING;
+      if (have && my_len == 0) ring[rp] = (unsigned char)my_lit;
+      if (indep) {
+        unsigned rs = rp >= my_dist ? rp - my_dist : rp + INF_RING - my_dist;
+        for (unsigned i = 0; i < my_len; i++) ring[ring_wrap(rp + i)] = ring[ring_wrap(rs + i)];
+      }
       __syncwarp();
-      unsigned mm = __ballot_sync(0xffffffffu, have && my_len != 0);
+      unsigned mm = __ballot_sync(0xffffffffu, is_match && !indep);
       while (mm) {
         int src_lane = __ffs((int)mm) - 1;
         mm &= mm - 1;
-        unsigned p = __shfl_sync(0xffffffffu, my_pos, src_lane);
+        unsigned p = __shfl_sync(0xffffffffu, rp, src_lane);
         unsigned l = __shfl_sync(0xffffffffu, my_len, src_lane);
         unsigned d = __shfl_sync(0xffffffffu, my_dist, src_lane);
-        const unsigned char* s = out + p - d;
-        if (d >= l) { for (unsigned i = lane; i < l; i += 32) out[p + i] = s[i]; }
+        unsigned s = p >= d ? p - d : p + INF_RING - d;
+        if (d >= l) { for (unsigned i = lane; i < l; i += 32) ring[ring_wrap(p + i)] = ring[ring_wrap(s + i)]; }
         else if (d >= 32) {
           // overlapping copy with period d >= 32: rounds of 32 bytes never read what the same round writes
           for (unsigned i0 = 0; i0 < l; i0 += 32) {
             unsigned i = i0 + lane;
-            if (i < l) out[p + i] = s[i];
+            if (i < l) ring[ring_wrap(p + i)] = ring[ring_wrap(s + i)];
             __syncwarp();
           }
-        } else { for (unsigned i = lane; i < l; i += 32) out[p + i] = s[i % d]; }
+        } else { for (unsigned i = lane; i < l; i += 32) ring[ring_wrap(p + i)] = ring[ring_wrap(s + i % d)]; }
         __syncwarp();
       }
+      inflate_flush(ring, out, a0, opos, bpos, lane);
+      __syncwarp();
       opos = bpos;
     }
   }
