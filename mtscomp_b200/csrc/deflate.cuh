@@ -69,29 +69,36 @@ __device__ __forceinline__ unsigned ll_extra_bits(unsigned sym) {   // sym in [0
 __device__ __forceinline__ unsigned d_extra_bits(unsigned sym) { return sym < 4 ? 0 : (sym >> 1) - 1; }
 
 // ------------------------------------------------------------------------------------------------ lz77_kernel
-// Shared memory (STRIDE = bytes between indexed positions: 2 for int16 streams, 1 generic):
-//   ring  64 KB  data ring, ring coordinate = position + (input address & 15) so global uint4 loads land aligned
-//   head  64 KB  2^15 x u16  most recent indexed unit (biased by 32768) per hash
-//   prev  32/64 KB  u16 per unit in the window: previous unit with the same hash
-//   mlen/mdist/jump 3 x 4 KB + reach 2 KB  per-position match, parse links
-static const int LZ_SEG = 2048;               // bytes parsed per step
+// One persistent CTA (1024 threads, 1 per SM) per segment.  STRIDE = bytes between indexed positions: 2 for int16
+// streams (matches are searched at sample boundaries, the byte in between inherits the next sample's match extended
+// backwards), 1 generic.  Shared memory:
+//   ring  64 KB     data ring; ring coordinate = position + (input address & 15), so global uint4 loads land aligned
+//   head  64 KB     2^15 x u16: most recent indexed unit (biased by 32768) per 4-byte hash
+//   prev  32/64 KB  u16 per unit of the window: previous unit with the same hash (the chain)
+//   mlen / mdist / jump / jump2 / reach: per-position match and parse links of the step in flight
+// The segment is processed in steps of 992 units.  Warp 0 is the INSERTER: it prefetches input and threads the units of
+// step s+1 into the hash chains (in position order) while warps 1..31 SEARCH step s, one chain walk per thread.  Then
+// all warps parse the step (greedy, pointer doubling) and emit tokens + histogram counts.
 static const int LZ_THREADS = 1024;
+static const int LZ_UNITS = 992;              // units searched per step = 31 searcher warps x 32 lanes
 static const int LZ_RING = 65536;
 static const int LZ_HASH_BITS = 15;
 static const unsigned LZ_BIAS = 32768;
 
 template <int STRIDE> struct LzSmem {
+  static const int SEG = LZ_UNITS * STRIDE;   // bytes per step
   static const int PREV_N = 32768 / STRIDE;
-  static const int MAXD_UNITS = (32768 - LZ_SEG) / STRIDE;   // prev[] entries older than this may be recycled
+  // the inserter runs one step ahead, so chain entries older than PREV_N - 2 steps may already be recycled
+  static const int MAXD_UNITS = PREV_N - 2 * LZ_UNITS - 8;
   static const size_t ring_off = 0;
   static const size_t head_off = LZ_RING;
   static const size_t prev_off = head_off + (size_t)(1 << LZ_HASH_BITS) * 2;
   static const size_t mlen_off = prev_off + (size_t)PREV_N * 2;
-  static const size_t mdist_off = mlen_off + (size_t)(LZ_SEG + 2) * 2;
-  static const size_t jump_off = mdist_off + (size_t)(LZ_SEG + 2) * 2;
-  static const size_t jump2_off = jump_off + (size_t)(LZ_SEG + 2) * 2;
-  static const size_t reach_off = jump2_off + (size_t)(LZ_SEG + 2) * 2;
-  static const size_t hist_off = (reach_off + LZ_SEG + 2 + 15) & ~(size_t)15;
+  static const size_t mdist_off = mlen_off + (size_t)(SEG + 8) * 2;
+  static const size_t jump_off = mdist_off + (size_t)(SEG + 8) * 2;
+  static const size_t jump2_off = jump_off + (size_t)(SEG + 8) * 2;
+  static const size_t reach_off = jump2_off + (size_t)(SEG + 8) * 2;
+  static const size_t hist_off = (reach_off + SEG + 8 + 15) & ~(size_t)15;
   static const size_t misc_off = hist_off + (size_t)HIST_STRIDE * 4;
   static const size_t total = misc_off + 256;
 };
@@ -104,6 +111,37 @@ __device__ __forceinline__ unsigned ring_load4(const unsigned char* ring, unsign
 }
 __device__ __forceinline__ unsigned lz_hash(unsigned w) { return (w * 0x9E3779B1u) >> (32 - LZ_HASH_BITS); }
 
+// Thread `units` consecutive units starting at unit u0 into the hash chains, in position order (one warp).
+template <int STRIDE>
+__device__ __forceinline__ void lz_insert_step(const unsigned char* ring, unsigned short* head, unsigned short* prev,
+                                               unsigned u0, unsigned units, unsigned n, unsigned off0, unsigned lane) {
+  const unsigned PM = LzSmem<STRIDE>::PREV_N - 1;
+  for (unsigned b = 0; b < units; b += 32) {
+    const unsigned u = u0 + b + lane;
+    const unsigned p = u * STRIDE;
+    const bool valid = (b + lane < units) && (p + 4 <= n);
+    const unsigned short ub = (unsigned short)(u + LZ_BIAS);
+    unsigned h = 0;
+    unsigned short old = 0;
+    if (valid) { h = lz_hash(ring_load4(ring, p + off0)); old = head[h]; }
+    __syncwarp();
+    if (valid) head[h] = ub;                         // same-hash lanes collide: an arbitrary one wins for now
+    __syncwarp();
+    const bool clash = valid && head[h] != ub;
+    unsigned short pv = old;
+    if (__any_sync(0xffffffffu, clash)) {
+      // rare (runs, repeated samples inside 32 units): order the colliding lanes explicitly
+      const unsigned grp = __match_any_sync(0xffffffffu, valid ? h : (0x10000u + lane));
+      const unsigned lower = grp & ((1u << lane) - 1);
+      if (lower) pv = (unsigned short)(u - lane + (31 - __clz((int)lower)) + LZ_BIAS);
+      __syncwarp();
+      if (valid && (grp >> lane) == 1u) head[h] = ub;   // the last unit of each group is the new head
+    }
+    if (valid) prev[u & PM] = pv;
+    __syncwarp();
+  }
+}
+
 template <int STRIDE>
 __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char* __restrict__ tbuf,
                                                              const DeflateSeg* __restrict__ segs, int n_segs,
@@ -111,6 +149,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
                                                              unsigned* __restrict__ hist, DeflateSegOut* __restrict__ so,
                                                              LzParams prm) {
   typedef LzSmem<STRIDE> L;
+  const unsigned SEG = L::SEG;
   MTS_DYN_SMEM(sm);
   unsigned char* ring = sm + L::ring_off;
   unsigned short* head = (unsigned short*)(sm + L::head_off);
@@ -134,97 +173,92 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
     unsigned short* tok = tokens + sg.tok_off;
     const unsigned n_ring = n + off0;                    // ring coordinates [off0, n_ring) are real input
 
-    // reset tables
+    // reset tables; initial load: ring coordinates [0, 3*SEG)
     for (unsigned i = tid; i < (1u << LZ_HASH_BITS) / 2; i += LZ_THREADS) ((unsigned*)head)[i] = 0;
     for (unsigned i = tid; i < HIST_STRIDE; i += LZ_THREADS) shist[i] = 0;
     if (tid == 0) { misc[32] = 0; misc[33] = 0; }
-    // initial load: ring coordinates [0, 2*SEG)
-    for (unsigned v = tid; v < 2 * LZ_SEG / 16; v += LZ_THREADS)
+    for (unsigned v = tid; v * 16 < 3 * SEG; v += LZ_THREADS)
       if (v * 16 < n_ring) *(uint4*)(ring + v * 16) = in16[v];
     __syncthreads();
+    if (wid == 0) lz_insert_step<STRIDE>(ring, head, prev, 0, min((unsigned)LZ_UNITS, (n + STRIDE - 1) / STRIDE), n, off0, lane);
+    __syncthreads();
 
-    const unsigned n_steps = (n + LZ_SEG - 1) / LZ_SEG;
+    const unsigned n_steps = (n + SEG - 1) / SEG;
     for (unsigned step = 0; step < n_steps; step++) {
-      const unsigned s0 = step * LZ_SEG;                 // first position of this step
-      const unsigned slen = min((unsigned)LZ_SEG, n - s0);
+      const unsigned s0 = step * SEG;                    // first position of this step
+      const unsigned slen = min(SEG, n - s0);
 
-      // ---- (A) insert this step's units into the hash chains (warp 0, in position order), while the other warps
-      //          prefetch the data the NEXT step will need: ring coordinates [(step+2)*SEG, (step+3)*SEG)
       if (wid == 0) {
-        const unsigned units = (slen + STRIDE - 1) / STRIDE;
-        for (unsigned b = 0; b < units; b += 32) {
-          unsigned u = s0 / STRIDE + b + lane;           // unit index within the segment
-          unsigned p = u * STRIDE;
-          bool valid = (b + lane < units) && (p + 4 <= n);
-          unsigned h = valid ? lz_hash(ring_load4(ring, p + off0)) : (0x10000u + lane);
-          unsigned grp = __match_any_sync(0xffffffffu, h);
-          if (valid) {
-            unsigned lower = grp & ((1u << lane) - 1);
-            unsigned short pv = lower ? (unsigned short)(u - lane + (31 - __clz((int)lower)) + LZ_BIAS) : head[h];
-            prev[u & PM] = pv;
-          }
-          __syncwarp();
-          if (valid && (grp >> lane) == 1u) head[h] = (unsigned short)(u + LZ_BIAS);
-          __syncwarp();
-        }
-      } else {
-        const unsigned base = (step + 2) * LZ_SEG;
-        for (unsigned v = tid - 32; v < LZ_SEG / 16; v += LZ_THREADS - 32) {
+        // ---- (A) inserter: prefetch ring coordinates [(step+3)*SEG, (step+4)*SEG), then insert step+1's units
+        const unsigned base = (step + 3) * SEG;
+        for (unsigned v = lane; v * 16 < SEG; v += 32) {
           unsigned rc = base + v * 16;
           if (rc < n_ring) *(uint4*)(ring + (rc & 0xffffu)) = in16[rc >> 4];
         }
-      }
-      __syncthreads();
-
-      // ---- (B) match search: every indexed position of the step, one chain walk per thread
-      for (unsigned k = 0; k < (LZ_SEG / STRIDE) / LZ_THREADS + ((LZ_SEG / STRIDE) % LZ_THREADS ? 1 : 0); k++) {
-        unsigned li = (k * LZ_THREADS + tid) * STRIDE;    // local position in the step
-        if (li >= LZ_SEG) break;
-        unsigned p = s0 + li;
+        const unsigned s1 = s0 + SEG;
+        if (s1 < n) {
+          const unsigned units1 = (min(SEG, n - s1) + STRIDE - 1) / STRIDE;
+          lz_insert_step<STRIDE>(ring, head, prev, s1 / STRIDE, units1, n, off0, lane);
+        }
+      } else {
+        // ---- (B) searchers: one chain walk per indexed position of this step
+        const unsigned li = (tid - 32) * STRIDE;          // local position in the step
+        const unsigned p = s0 + li;
         unsigned best = 3, bdist = 0;
         if (li < slen && p + 4 <= n) {
           const unsigned u = p / STRIDE;
           const unsigned lim = min(258u, n - p);
           const unsigned pr = p + off0;
-          unsigned wq = ring_load4(ring, pr);
+          // the first 16 bytes at p stay in registers
+          unsigned w0, w1, w2, w3;
+          {
+            const unsigned a = pr & 0xfffcu, sh = (pr & 3) * 8;
+            unsigned t0 = *(const unsigned*)(ring + a), t1 = *(const unsigned*)(ring + ((a + 4) & 0xffffu)),
+                     t2 = *(const unsigned*)(ring + ((a + 8) & 0xffffu)), t3 = *(const unsigned*)(ring + ((a + 12) & 0xffffu)),
+                     t4 = *(const unsigned*)(ring + ((a + 16) & 0xffffu));
+            w0 = __funnelshift_r(t0, t1, sh); w1 = __funnelshift_r(t1, t2, sh);
+            w2 = __funnelshift_r(t2, t3, sh); w3 = __funnelshift_r(t3, t4, sh);
+          }
+          unsigned wq = w0;                               // bytes [best-3, best] of p: what a longer match must equal
           unsigned short cand = prev[u & PM];
           unsigned lastd = 0;
           const unsigned ub = (u + LZ_BIAS) & 0xffffu;
           for (int depth = prm.max_chain; depth > 0; depth--) {
-            unsigned du = (ub - cand) & 0xffffu;
+            const unsigned du = (ub - cand) & 0xffffu;
             if (du - 1 >= (unsigned)L::MAXD_UNITS || du <= lastd || du > u) break;
             lastd = du;
             const unsigned dist = du * STRIDE;
             const unsigned qr = pr - dist;
-            if (ring_load4(ring, qr + best - 3) == wq) {
-              unsigned len = 0;
-              while (len < lim) {
-                unsigned x = ring_load4(ring, pr + len) ^ ring_load4(ring, qr + len);
-                if (x) { len += (unsigned)(__ffs((int)x) - 1) >> 3; break; }
-                len += 4;
-              }
-              len = min(len, lim);
-              if (len > best) {
-                bool ok = (len > 6) || (len == 6 && dist <= (unsigned)prm.far6) ||
-                          (len == 5 && dist <= (unsigned)prm.far5) || (len == 4 && dist <= (unsigned)prm.far4);
-                if (ok) {
-                  best = len; bdist = dist;
-                  if (len >= (unsigned)prm.nice_len || len >= lim) break;
-                  wq = ring_load4(ring, pr + best - 3);
-                }
-              }
-            }
             cand = prev[(cand - LZ_BIAS) & PM];
+            if (ring_load4(ring, qr + best - 3) != wq) continue;
+            unsigned len, x;
+            if (best == 3) { len = 4; x = 0; }            // the check above compared bytes 0..3
+            else { len = 0; x = ring_load4(ring, qr) ^ w0; if (!x) len = 4; }
+            if (!x) { x = ring_load4(ring, qr + 4) ^ w1;
+              if (!x) { len = 8; x = ring_load4(ring, qr + 8) ^ w2;
+                if (!x) { len = 12; x = ring_load4(ring, qr + 12) ^ w3;
+                  if (!x) { len = 16;
+                    while (len < lim) {
+                      x = ring_load4(ring, pr + len) ^ ring_load4(ring, qr + len);
+                      if (x) break;
+                      len += 4;
+                    } } } } }
+            if (x) len += (unsigned)(__ffs((int)x) - 1) >> 3;
+            len = min(len, lim);
+            if (len > best) {
+              best = len; bdist = dist;
+              if (len >= (unsigned)prm.nice_len || len >= lim) break;
+              wq = ring_load4(ring, pr + best - 3);
+            }
           }
         }
-        mlen[li] = (unsigned short)(bdist ? best : 0);
-        mdist[li] = (unsigned short)bdist;
+        if (li < SEG) { mlen[li] = (unsigned short)(bdist ? best : 0); mdist[li] = (unsigned short)bdist; }
       }
       __syncthreads();
 
       // ---- (C) STRIDE > 1: positions between indexed ones inherit the next indexed match, extended backwards
       if (STRIDE > 1) {
-        for (unsigned li = tid; li < LZ_SEG; li += LZ_THREADS) {
+        for (unsigned li = tid; li < SEG; li += LZ_THREADS) {
           if (li % STRIDE == 0) continue;
           unsigned nx = li + (STRIDE - li % STRIDE);       // next indexed local position
           unsigned ml = 0, md = 0;
@@ -244,28 +278,27 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
         __syncthreads();
       }
 
-      // ---- (D) parse: next[] per position (lazy-1 rule), reachability from the carried start by pointer doubling
+      // ---- (D) parse: next[] per position, reachability from the carried start by pointer doubling
       const unsigned start = misc[33];                    // local start position (< slen unless the carry skips it)
       __syncthreads();
       if (start < slen) {
-        for (unsigned li = tid; li <= LZ_SEG; li += LZ_THREADS) {
+        for (unsigned li = tid; li <= SEG; li += LZ_THREADS) {
           unsigned nx = slen;
           if (li < slen) {
             unsigned l = mlen[li];
             if (l && prm.lazy && li + 1 < slen && mlen[li + 1] > l) l = 0;
             nx = min(li + (l ? l : 1u), slen);
-            if (l == 0) jump2[li] = 0; else jump2[li] = (unsigned short)l;   // jump2 doubles as "chosen length"
+            jump2[li] = (unsigned short)l;                 // jump2 doubles as "chosen length" (0 = literal)
           }
           jump[li] = (unsigned short)nx;
-          if (li < LZ_SEG + 1) reach[li] = (li == start);
+          reach[li] = (li == start);
         }
         __syncthreads();
-        // chosen lengths are needed after the doubling destroys jump[]: keep them in mlen (0 = literal)
         for (unsigned li = tid; li < slen; li += LZ_THREADS) mlen[li] = jump2[li];
         __syncthreads();
         for (;;) {
           bool done = (jump[start] >= slen);
-          unsigned j2[(LZ_SEG + LZ_THREADS) / LZ_THREADS];
+          unsigned j2[(L::SEG + LZ_THREADS) / LZ_THREADS];
           unsigned kk = 0;
           for (unsigned li = tid; li < slen; li += LZ_THREADS, kk++) {
             unsigned j = jump[li];
@@ -280,10 +313,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
         }
 
         // ---- (E) emit tokens of reachable positions, in order (block-wide exclusive scan of element counts)
-        unsigned cnt[LZ_SEG / LZ_THREADS], mine = 0;
-        // thread owns CONSECUTIVE positions so that its elements are consecutive in the token stream
-        const unsigned per = LZ_SEG / LZ_THREADS;
-        for (unsigned j = 0; j < per; j++) {
+        const unsigned per = (L::SEG + LZ_THREADS - 1) / LZ_THREADS;
+        unsigned cnt[(L::SEG + LZ_THREADS - 1) / LZ_THREADS], mine = 0;
+        for (unsigned j = 0; j < per; j++) {               // a thread owns CONSECUTIVE positions
           unsigned li = tid * per + j;
           unsigned c = 0;
           if (li < slen && reach[li]) c = mlen[li] ? 2 : 1;
