@@ -52,7 +52,7 @@ struct mtsb_ctx {
   std::string err;
   // params
   long long seg_bytes = 262144, batch_bytes = 2ll << 30, write_index = 1;
-  LzParams lz{16, 8, 32768, 32768, 32768, 0};   // greedy, every match >= 4 bytes accepted: tuned on synthetic AP/LFP
+  LzParams lz{4, 16, 32768, 32768, 32768, 0};   // greedy, every match >= 4 bytes accepted: tuned on synthetic AP/LFP
   // device scratch
   Buf d_raw, d_T, d_tok, d_hist, d_codes, d_hdrs, d_tab, d_so, d_seg_adler, d_chunk_adler, d_chunk_off, d_out,
       d_partial, d_comp, d_status, d_tadler, d_gather;

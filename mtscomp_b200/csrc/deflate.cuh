@@ -71,29 +71,31 @@ __device__ __forceinline__ unsigned d_extra_bits(unsigned sym) { return sym < 4 
 // ------------------------------------------------------------------------------------------------ lz77_kernel
 // One persistent CTA (1024 threads, 1 per SM) per segment.  STRIDE = bytes between indexed positions: 2 for int16
 // streams (matches are searched at sample boundaries, the byte in between inherits the next sample's match extended
-// backwards), 1 generic.  Shared memory:
-//   ring  64 KB     data ring; ring coordinate = position + (input address & 15), so global uint4 loads land aligned
-//   head  64 KB     2^15 x u16: most recent indexed unit (biased by 32768) per 4-byte hash
-//   prev  32/64 KB  u16 per unit of the window: previous unit with the same hash (the chain)
-//   mlen / mdist / jump / jump2 / reach: per-position match and parse links of the step in flight
-// The segment is processed in steps of 992 units.  Warp 0 is the INSERTER: it prefetches input and threads the units of
-// step s+1 into the hash chains (in position order) while warps 1..31 SEARCH step s, one chain walk per thread.  Then
-// all warps parse the step (greedy, pointer doubling) and emit tokens + histogram counts.
+// backwards), 1 generic.  Two match finders share the 64 KB data ring:
+//   L ("long")   hash of the 6 bytes at a unit -> headL (2^15 x u16) + prevL chain over the whole window; the searcher
+//                walks up to max_chain candidates and keeps the longest match (>= 6 bytes)
+//   S ("short")  hash of the 4 bytes at a unit -> headS (2^14 x u16); only the NEAREST previous unit with the same 4
+//                bytes is kept (prevS, two steps deep) and is used when L finds nothing
+// The segment is processed in steps of 960 units.  Warps 0 and 1 are the INSERTERS (S resp. L table; warp 0 also
+// prefetches input): they thread the units of step s+1 into the tables, in position order, while warps 2..31 SEARCH
+// step s, one unit per thread.  Then all warps parse the step (greedy, pointer doubling) and emit tokens + histogram.
 static const int LZ_THREADS = 1024;
-static const int LZ_UNITS = 992;              // units searched per step = 31 searcher warps x 32 lanes
+static const int LZ_UNITS = 960;              // units searched per step = 30 searcher warps x 32 lanes
 static const int LZ_RING = 65536;
-static const int LZ_HASH_BITS = 15;
+static const int LZ_HASHL_BITS = 15, LZ_HASHS_BITS = 14;
 static const unsigned LZ_BIAS = 32768;
 
 template <int STRIDE> struct LzSmem {
   static const int SEG = LZ_UNITS * STRIDE;   // bytes per step
   static const int PREV_N = 32768 / STRIDE;
-  // the inserter runs one step ahead, so chain entries older than PREV_N - 2 steps may already be recycled
+  // the inserters run one step ahead, so chain entries older than PREV_N - 2 steps may already be recycled
   static const int MAXD_UNITS = PREV_N - 2 * LZ_UNITS - 8;
   static const size_t ring_off = 0;
-  static const size_t head_off = LZ_RING;
-  static const size_t prev_off = head_off + (size_t)(1 << LZ_HASH_BITS) * 2;
-  static const size_t mlen_off = prev_off + (size_t)PREV_N * 2;
+  static const size_t headl_off = LZ_RING;
+  static const size_t heads_off = headl_off + (size_t)(1 << LZ_HASHL_BITS) * 2;
+  static const size_t prevl_off = heads_off + (size_t)(1 << LZ_HASHS_BITS) * 2;
+  static const size_t prevs_off = prevl_off + (size_t)PREV_N * 2;
+  static const size_t mlen_off = prevs_off + (size_t)(2 * LZ_UNITS) * 2;
   static const size_t mdist_off = mlen_off + (size_t)(SEG + 8) * 2;
   static const size_t jump_off = mdist_off + (size_t)(SEG + 8) * 2;
   static const size_t jump2_off = jump_off + (size_t)(SEG + 8) * 2;
@@ -109,21 +111,31 @@ __device__ __forceinline__ unsigned ring_load4(const unsigned char* ring, unsign
   unsigned hi = *(const unsigned*)(ring + ((a + 4) & 0xffffu));
   return __funnelshift_r(lo, hi, (r & 3) * 8);
 }
-__device__ __forceinline__ unsigned lz_hash(unsigned w) { return (w * 0x9E3779B1u) >> (32 - LZ_HASH_BITS); }
+__device__ __forceinline__ unsigned lz_hash4(unsigned w) { return (w * 0x9E3779B1u) >> (32 - LZ_HASHS_BITS); }
+__device__ __forceinline__ unsigned lz_hash6(unsigned w0, unsigned w1) {
+  return ((w0 * 0x9E3779B1u) ^ ((w1 & 0xffffu) * 0x85EBCA6Bu)) >> (32 - LZ_HASHL_BITS);
+}
 
-// Thread `units` consecutive units starting at unit u0 into the hash chains, in position order (one warp).
-template <int STRIDE>
+// Thread `units` consecutive units starting at unit u0 into one hash table, in position order (one warp).
+// LONG: key = 6 bytes, links go to the prev ring (index u & pmask); otherwise key = 4 bytes, links go to a two-step
+// array (index u % (2 * LZ_UNITS)).
+template <int STRIDE, bool LONG>
 __device__ __forceinline__ void lz_insert_step(const unsigned char* ring, unsigned short* head, unsigned short* prev,
                                                unsigned u0, unsigned units, unsigned n, unsigned off0, unsigned lane) {
   const unsigned PM = LzSmem<STRIDE>::PREV_N - 1;
+  const unsigned KEY = LONG ? 6 : 4;
   for (unsigned b = 0; b < units; b += 32) {
     const unsigned u = u0 + b + lane;
     const unsigned p = u * STRIDE;
-    const bool valid = (b + lane < units) && (p + 4 <= n);
+    const bool valid = (b + lane < units) && (p + KEY <= n);
     const unsigned short ub = (unsigned short)(u + LZ_BIAS);
     unsigned h = 0;
     unsigned short old = 0;
-    if (valid) { h = lz_hash(ring_load4(ring, p + off0)); old = head[h]; }
+    if (valid) {
+      unsigned w0 = ring_load4(ring, p + off0);
+      h = LONG ? lz_hash6(w0, ring_load4(ring, p + off0 + 4)) : lz_hash4(w0);
+      old = head[h];
+    }
     __syncwarp();
     if (valid) head[h] = ub;                         // same-hash lanes collide: an arbitrary one wins for now
     __syncwarp();
@@ -137,9 +149,27 @@ __device__ __forceinline__ void lz_insert_step(const unsigned char* ring, unsign
       __syncwarp();
       if (valid && (grp >> lane) == 1u) head[h] = ub;   // the last unit of each group is the new head
     }
-    if (valid) prev[u & PM] = pv;
+    if (b + lane < units) prev[LONG ? (u & PM) : (u % (2 * LZ_UNITS))] = valid ? pv : (unsigned short)ub;
     __syncwarp();
   }
+}
+
+// Length of the match between ring positions pr (whose first 16 bytes are w0..w3) and qr, up to lim.
+__device__ __forceinline__ unsigned lz_match_len(const unsigned char* ring, unsigned pr, unsigned qr, unsigned lim,
+                                                 unsigned w0, unsigned w1, unsigned w2, unsigned w3) {
+  unsigned len = 0;
+  unsigned x = ring_load4(ring, qr) ^ w0;
+  if (!x) { len = 4; x = ring_load4(ring, qr + 4) ^ w1;
+    if (!x) { len = 8; x = ring_load4(ring, qr + 8) ^ w2;
+      if (!x) { len = 12; x = ring_load4(ring, qr + 12) ^ w3;
+        if (!x) { len = 16;
+          while (len < lim) {
+            x = ring_load4(ring, pr + len) ^ ring_load4(ring, qr + len);
+            if (x) break;
+            len += 4;
+          } } } } }
+  if (x) len += (unsigned)(__ffs((int)x) - 1) >> 3;
+  return min(len, lim);
 }
 
 template <int STRIDE>
@@ -152,8 +182,10 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
   const unsigned SEG = L::SEG;
   MTS_DYN_SMEM(sm);
   unsigned char* ring = sm + L::ring_off;
-  unsigned short* head = (unsigned short*)(sm + L::head_off);
-  unsigned short* prev = (unsigned short*)(sm + L::prev_off);
+  unsigned short* headL = (unsigned short*)(sm + L::headl_off);
+  unsigned short* headS = (unsigned short*)(sm + L::heads_off);
+  unsigned short* prevL = (unsigned short*)(sm + L::prevl_off);
+  unsigned short* prevS = (unsigned short*)(sm + L::prevs_off);
   unsigned short* mlen = (unsigned short*)(sm + L::mlen_off);
   unsigned short* mdist = (unsigned short*)(sm + L::mdist_off);
   unsigned short* jump = (unsigned short*)(sm + L::jump_off);
@@ -173,14 +205,18 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
     unsigned short* tok = tokens + sg.tok_off;
     const unsigned n_ring = n + off0;                    // ring coordinates [off0, n_ring) are real input
 
-    // reset tables; initial load: ring coordinates [0, 3*SEG)
-    for (unsigned i = tid; i < (1u << LZ_HASH_BITS) / 2; i += LZ_THREADS) ((unsigned*)head)[i] = 0;
+    // reset tables (headL and headS are contiguous); initial load: ring coordinates [0, 3*SEG)
+    for (unsigned i = tid; i < ((1u << LZ_HASHL_BITS) + (1u << LZ_HASHS_BITS)) / 2; i += LZ_THREADS) ((unsigned*)headL)[i] = 0;
     for (unsigned i = tid; i < HIST_STRIDE; i += LZ_THREADS) shist[i] = 0;
     if (tid == 0) { misc[32] = 0; misc[33] = 0; }
     for (unsigned v = tid; v * 16 < 3 * SEG; v += LZ_THREADS)
       if (v * 16 < n_ring) *(uint4*)(ring + v * 16) = in16[v];
     __syncthreads();
-    if (wid == 0) lz_insert_step<STRIDE>(ring, head, prev, 0, min((unsigned)LZ_UNITS, (n + STRIDE - 1) / STRIDE), n, off0, lane);
+    {
+      const unsigned units0 = min((unsigned)LZ_UNITS, (n + STRIDE - 1) / STRIDE);
+      if (wid == 0) lz_insert_step<STRIDE, false>(ring, headS, prevS, 0, units0, n, off0, lane);
+      if (wid == 1) lz_insert_step<STRIDE, true>(ring, headL, prevL, 0, units0, n, off0, lane);
+    }
     __syncthreads();
 
     const unsigned n_steps = (n + SEG - 1) / SEG;
@@ -188,29 +224,31 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
       const unsigned s0 = step * SEG;                    // first position of this step
       const unsigned slen = min(SEG, n - s0);
 
-      if (wid == 0) {
-        // ---- (A) inserter: prefetch ring coordinates [(step+3)*SEG, (step+4)*SEG), then insert step+1's units
-        const unsigned base = (step + 3) * SEG;
-        for (unsigned v = lane; v * 16 < SEG; v += 32) {
-          unsigned rc = base + v * 16;
-          if (rc < n_ring) *(uint4*)(ring + (rc & 0xffffu)) = in16[rc >> 4];
+      if (wid < 2) {
+        // ---- (A) inserters: prefetch ring coordinates [(step+3)*SEG, (step+4)*SEG), insert step+1's units
+        if (wid == 0) {
+          const unsigned base = (step + 3) * SEG;
+          for (unsigned v = lane; v * 16 < SEG; v += 32) {
+            unsigned rc = base + v * 16;
+            if (rc < n_ring) *(uint4*)(ring + (rc & 0xffffu)) = in16[rc >> 4];
+          }
         }
         const unsigned s1 = s0 + SEG;
         if (s1 < n) {
           const unsigned units1 = (min(SEG, n - s1) + STRIDE - 1) / STRIDE;
-          lz_insert_step<STRIDE>(ring, head, prev, s1 / STRIDE, units1, n, off0, lane);
+          if (wid == 0) lz_insert_step<STRIDE, false>(ring, headS, prevS, s1 / STRIDE, units1, n, off0, lane);
+          else lz_insert_step<STRIDE, true>(ring, headL, prevL, s1 / STRIDE, units1, n, off0, lane);
         }
       } else {
-        // ---- (B) searchers: one chain walk per indexed position of this step
-        const unsigned li = (tid - 32) * STRIDE;          // local position in the step
+        // ---- (B) searchers: one unit per thread
+        const unsigned li = (tid - 64) * STRIDE;          // local position in the step
         const unsigned p = s0 + li;
-        unsigned best = 3, bdist = 0;
+        unsigned best = 0, bdist = 0;
         if (li < slen && p + 4 <= n) {
           const unsigned u = p / STRIDE;
           const unsigned lim = min(258u, n - p);
           const unsigned pr = p + off0;
-          // the first 16 bytes at p stay in registers
-          unsigned w0, w1, w2, w3;
+          unsigned w0, w1, w2, w3;                        // the first 16 bytes at p stay in registers
           {
             const unsigned a = pr & 0xfffcu, sh = (pr & 3) * 8;
             unsigned t0 = *(const unsigned*)(ring + a), t1 = *(const unsigned*)(ring + ((a + 4) & 0xffffu)),
@@ -219,36 +257,37 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
             w0 = __funnelshift_r(t0, t1, sh); w1 = __funnelshift_r(t1, t2, sh);
             w2 = __funnelshift_r(t2, t3, sh); w3 = __funnelshift_r(t3, t4, sh);
           }
-          unsigned wq = w0;                               // bytes [best-3, best] of p: what a longer match must equal
-          unsigned short cand = prev[u & PM];
-          unsigned lastd = 0;
           const unsigned ub = (u + LZ_BIAS) & 0xffffu;
-          for (int depth = prm.max_chain; depth > 0; depth--) {
-            const unsigned du = (ub - cand) & 0xffffu;
-            if (du - 1 >= (unsigned)L::MAXD_UNITS || du <= lastd || du > u) break;
-            lastd = du;
-            const unsigned dist = du * STRIDE;
-            const unsigned qr = pr - dist;
-            cand = prev[(cand - LZ_BIAS) & PM];
-            if (ring_load4(ring, qr + best - 3) != wq) continue;
-            unsigned len, x;
-            if (best == 3) { len = 4; x = 0; }            // the check above compared bytes 0..3
-            else { len = 0; x = ring_load4(ring, qr) ^ w0; if (!x) len = 4; }
-            if (!x) { x = ring_load4(ring, qr + 4) ^ w1;
-              if (!x) { len = 8; x = ring_load4(ring, qr + 8) ^ w2;
-                if (!x) { len = 12; x = ring_load4(ring, qr + 12) ^ w3;
-                  if (!x) { len = 16;
-                    while (len < lim) {
-                      x = ring_load4(ring, pr + len) ^ ring_load4(ring, qr + len);
-                      if (x) break;
-                      len += 4;
-                    } } } } }
-            if (x) len += (unsigned)(__ffs((int)x) - 1) >> 3;
-            len = min(len, lim);
-            if (len > best) {
-              best = len; bdist = dist;
-              if (len >= (unsigned)prm.nice_len || len >= lim) break;
-              wq = ring_load4(ring, pr + best - 3);
+          if (lim >= 6) {
+            // L chain: candidates share (the hash of) 6 bytes; keep the longest
+            best = 5;
+            unsigned wq = __funnelshift_r(w0, w1, 16);     // bytes [best-3, best] of p
+            unsigned short cand = prevL[u & PM];
+            unsigned lastd = 0;
+            for (int depth = prm.max_chain; depth > 0; depth--) {
+              const unsigned du = (ub - cand) & 0xffffu;
+              if (du - 1 >= (unsigned)L::MAXD_UNITS || du <= lastd || du > u) break;
+              lastd = du;
+              const unsigned dist = du * STRIDE;
+              const unsigned qr = pr - dist;
+              cand = prevL[(cand - LZ_BIAS) & PM];
+              if (ring_load4(ring, qr + best - 3) != wq) continue;
+              const unsigned len = lz_match_len(ring, pr, qr, lim, w0, w1, w2, w3);
+              if (len > best) {
+                best = len; bdist = dist;
+                if (len >= (unsigned)prm.nice_len || len >= lim) break;
+                wq = ring_load4(ring, pr + best - 3);
+              }
+            }
+          }
+          if (!bdist) {
+            // S: the nearest previous unit with the same 4 bytes
+            best = 0;
+            const unsigned du = (ub - prevS[u % (2 * LZ_UNITS)]) & 0xffffu;
+            if (du - 1 < (unsigned)L::MAXD_UNITS && du <= u) {
+              const unsigned dist = du * STRIDE;
+              const unsigned len = lz_match_len(ring, pr, pr - dist, lim, w0, w1, w2, w3);
+              if (len >= 4) { best = len; bdist = dist; }
             }
           }
         }

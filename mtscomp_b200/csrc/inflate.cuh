@@ -6,11 +6,14 @@
 // pass computes over the inflated bytes (a mismatch surfaces as the reference's "Compressed chunk #i is corrupted").
 //
 // A "stream" is either a whole chunk (reference-written files: strictly serial, block boundaries are only known by
-// decoding) or one encoder segment of a GPU-written file (byte-aligned start, fresh window, listed in the side index).
+// decoding) or one encoder segment of a GPU-written file (byte-aligned start, fresh window, listed in the in-band index).
 //
 // Warp organisation: all 32 lanes run the Huffman decode loop redundantly (uniform control flow, broadcast loads), lane
-// k keeps the k-th symbol of a batch of 32; literals are then stored in parallel and matches are copied cooperatively in
-// stream order.  Back-references read the output buffer itself (the 32 KB window lives in L1/L2).
+// k keeps the k-th symbol of a batch of 32.  Literals are then stored in parallel, matches that only read bytes produced
+// before the batch are copied one per lane, the (few) others cooperatively in stream order.  The last 32 KB of output
+// plus the batch in flight live in a shared-memory ring, finished bytes are streamed to HBM as aligned 32-bit words.
+// The decode tables hold fully decoded entries (code length, extra-bit count, base value, kind) so the symbol loop has
+// no per-symbol arithmetic on symbol numbers.
 #pragma once
 #include "common.cuh"
 
@@ -32,31 +35,64 @@ enum {
 };
 
 static const int INF_LBITS = 10, INF_DBITS = 8;
+static const unsigned INF_RING = 41216;        // 32768 history + 32 x 258 bytes of the batch in flight (+ slack), % 16 == 0
+
+// Table entry: bits 0-3 code length (0 = not in the fast table), 4-7 extra-bit count, 8-23 base value, 24-25 kind.
+enum { K_LIT = 0, K_LEN = 1, K_EOB = 2, K_BAD = 3 };
+__device__ __forceinline__ unsigned ll_entry(unsigned s, unsigned l) {
+  if (s < 256) return l | (s << 8) | (K_LIT << 24);
+  if (s == 256) return l | (K_EOB << 24);
+  if (s < 265) return l | ((s - 254) << 8) | (K_LEN << 24);
+  if (s < 285) { unsigned nb = (s - 261) >> 2; return l | (nb << 4) | ((3 + ((4 + ((s - 257) & 3)) << nb)) << 8) | (K_LEN << 24); }
+  if (s == 285) return l | (258u << 8) | (K_LEN << 24);
+  return l | (K_BAD << 24);
+}
+__device__ __forceinline__ unsigned d_entry(unsigned s, unsigned l) {
+  if (s < 4) return l | ((s + 1) << 8);
+  if (s < 30) { unsigned nb = (s >> 1) - 1; return l | (nb << 4) | ((1 + ((2 + (s & 1)) << nb)) << 8); }
+  return l | (K_BAD << 24);
+}
+__device__ __forceinline__ unsigned cl_entry(unsigned s, unsigned l) { return l | (s << 8); }
 
 struct InflateWarpSmem {
-  unsigned short ltab[1 << INF_LBITS];   // sym << 4 | len, 0 = not in the fast table
-  unsigned short dtab[1 << INF_DBITS];
+  unsigned ltab[1 << INF_LBITS];
+  unsigned dtab[1 << INF_DBITS];
   unsigned short lsorted[288];           // symbols in canonical order (slow path for codes longer than the table)
   unsigned short dsorted[32];
   unsigned short lcount[16], dcount[16];
   unsigned short run[16];
-  unsigned char lens[352];             // [0,19) code-length code, [24, 24+316) literal/length + distance lengths
+  unsigned char lens[352];               // [0,19) code-length code, [24, 24+316) literal/length + distance lengths
 };
 
 struct BitR {
-  const unsigned* w;     // 4-byte aligned base
-  unsigned mis;          // byte offset of the stream inside w
-  unsigned kmax;         // last valid word index
-  unsigned long long bb; // bit buffer
-  unsigned bc;           // valid bits in bb
-  unsigned ip;           // next unread byte of the stream
-  __device__ __forceinline__ unsigned load32(unsigned byte_idx) const {
-    unsigned a = byte_idx + mis, k = a >> 2;
-    unsigned lo = w[min(k, kmax)], hi = w[min(k + 1, kmax)];
-    return __funnelshift_r(lo, hi, (a & 3) * 8);
+  const unsigned* w;      // 4-byte aligned base
+  unsigned sh;            // 8 * (address & 3)
+  unsigned kmax;          // last valid word index
+  unsigned k;             // index of the next word to fetch
+  unsigned nextw;         // w[k - 1], already fetched
+  unsigned long long bb;  // bit buffer
+  unsigned bc;            // valid bits in bb
+  unsigned ip;            // stream bytes fetched into bb so far (relative to the stream start)
+  // start reading at `p` (= stream start + ip0) with `avail` bytes left
+  __device__ __forceinline__ void init(const unsigned char* p, unsigned avail, unsigned ip0) {
+    unsigned mis = (unsigned)((uintptr_t)p & 3);
+    w = (const unsigned*)(p - mis);
+    sh = mis * 8;
+    kmax = (mis + max(avail, 1u) - 1) >> 2;
+    nextw = w[0];
+    k = 1;
+    bb = 0; bc = 0; ip = ip0;
   }
   __device__ __forceinline__ void refill() {
-    if (bc <= 32) { bb |= (unsigned long long)load32(ip) << bc; ip += 4; bc += 32; }
+    if (bc <= 32) {
+      unsigned hi = w[min(k, kmax)];
+      unsigned v = __funnelshift_r(nextw, hi, sh);
+      nextw = hi;
+      k++;
+      bb |= (unsigned long long)v << bc;
+      ip += 4;
+      bc += 32;
+    }
   }
   __device__ __forceinline__ unsigned peek(unsigned n) const { return (unsigned)bb & ((1u << n) - 1); }
   __device__ __forceinline__ void drop(unsigned n) { bb >>= n; bc -= n; }
@@ -65,8 +101,10 @@ struct BitR {
 };
 
 // Build one decoding table from code lengths lens[0..n): fast table of `tb` bits + canonical arrays for longer codes.
-// Returns false if the lengths are over-subscribed.  All lanes participate.
-__device__ bool inflate_build(const unsigned char* lens, int n, unsigned short* tab, int tb, unsigned short* sorted,
+// KIND selects the entry encoder (0 code-length code, 1 literal/length, 2 distance).  Returns false if the lengths are
+// over-subscribed.  All lanes participate.
+template <int KIND>
+__device__ bool inflate_build(const unsigned char* lens, int n, unsigned* tab, int tb, unsigned short* sorted,
                               unsigned short* count, unsigned short* run) {
   const unsigned lane = lane_id();
   if (lane < 16) { count[lane] = 0; run[lane] = 0; }
@@ -101,7 +139,7 @@ __device__ bool inflate_build(const unsigned char* lens, int n, unsigned short* 
       sorted[offs[l] + rank] = (unsigned short)s;
       if ((int)l <= tb) {
         unsigned r = __brev(first[l] + rank) >> (32 - l);
-        unsigned short e = (unsigned short)((s << 4) | l);
+        unsigned e = KIND == 1 ? ll_entry((unsigned)s, l) : KIND == 2 ? d_entry((unsigned)s, l) : cl_entry((unsigned)s, l);
         for (unsigned k = r; k < (1u << tb); k += 1u << l) tab[k] = e;
       }
     }
@@ -112,14 +150,19 @@ __device__ bool inflate_build(const unsigned char* lens, int n, unsigned short* 
   return true;
 }
 
-// Slow path: canonical decode of a code longer than the fast table (puff-style, one bit at a time).
-__device__ __forceinline__ int inflate_slow(BitR& br, const unsigned short* count, const unsigned short* sorted,
-                                            unsigned& sym) {
+// Slow path: canonical decode of a code longer than the fast table (puff-style, one bit at a time); returns the
+// symbol's table entry, 0 if no code matches.
+template <int KIND>
+__device__ __noinline__ unsigned inflate_slow(unsigned long long bb, const unsigned short* count,
+                                              const unsigned short* sorted) {
   unsigned code = 0, first = 0, index = 0;
   for (int l = 1; l <= 15; l++) {
-    code |= (unsigned)(br.bb >> (l - 1)) & 1;
+    code |= (unsigned)(bb >> (l - 1)) & 1;
     unsigned c = count[l];
-    if (code - first < c) { sym = sorted[index + (code - first)]; br.drop(l); return l; }
+    if (code - first < c) {
+      unsigned s = sorted[index + (code - first)];
+      return KIND == 1 ? ll_entry(s, (unsigned)l) : d_entry(s, (unsigned)l);
+    }
     index += c;
     first = (first + c) << 1;
     code <<= 1;
@@ -129,13 +172,8 @@ __device__ __forceinline__ int inflate_slow(BitR& br, const unsigned short* coun
 
 __device__ __forceinline__ void fixed_lengths(unsigned char* lens, unsigned lane) {
   for (int s = lane; s < 288; s += 32) lens[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8;
-  if (lane < 32) lens[288 + lane] = (lane < 30) ? 5 : 0;
+  lens[288 + lane] = (lane < 30) ? 5 : 0;
 }
-
-// Output window: the last 32 KB of output plus the batch being produced live in a shared-memory ring, so that
-// back-references never touch global memory; finished bytes are streamed to HBM as aligned 32-bit words.
-static const unsigned INF_RING = 40960;        // 32768 history + up to 8192 bytes of the batch in flight
-static const unsigned INF_BATCH_BYTES = 8192 - 258;
 
 __device__ __forceinline__ unsigned ring_wrap(unsigned i) { return i >= INF_RING ? i - INF_RING : i; }
 
@@ -152,7 +190,11 @@ __device__ __forceinline__ void inflate_flush(const unsigned char* ring, unsigne
     return;
   }
   if (lane < w0 - g0) gb[g0 + lane] = ring[(g0 + lane) % INF_RING];
-  for (unsigned g = w0 + 4 * lane; g < w1; g += 128) *(unsigned*)(gb + g) = *(const unsigned*)(ring + g % INF_RING);
+  unsigned r = (w0 + 4 * lane) % INF_RING;
+  for (unsigned g = w0 + 4 * lane; g < w1; g += 128) {
+    *(unsigned*)(gb + g) = *(const unsigned*)(ring + r);
+    r = ring_wrap(r + 128);
+  }
   if (lane < g1 - w1) gb[w1 + lane] = ring[(w1 + lane) % INF_RING];
 }
 
@@ -173,10 +215,7 @@ __global__ void __launch_bounds__(32) inflate_kernel(const unsigned char* __rest
   const unsigned a0 = (unsigned)((uintptr_t)out & 3);
 
   BitR br;
-  br.mis = (unsigned)((uintptr_t)in & 3);
-  br.w = (const unsigned*)(in - br.mis);
-  br.kmax = (br.mis + in_len - 1) >> 2;
-  br.bb = 0; br.bc = 0; br.ip = 0;
+  br.init(in, in_len, 0);
   int err = INF_OK;
   unsigned opos = 0;            // bytes produced so far (all flushed at batch boundaries)
   unsigned adler = 0;
@@ -214,7 +253,7 @@ __global__ void __launch_bounds__(32) inflate_kernel(const unsigned char* __rest
         __syncwarp();
         opos += m;
       }
-      br.ip = src + len; br.bb = 0; br.bc = 0;
+      br.init(in + src + len, in_len - (src + len), src + len);   // restart the bit reader after the stored bytes
       continue;
     }
     if (type == 3) { err = INF_BAD_BLOCK; break; }
@@ -237,7 +276,7 @@ __global__ void __launch_bounds__(32) inflate_kernel(const unsigned char* __rest
       }
       __syncwarp();
       // the code-length code is decoded with the distance-table slots (7-bit table)
-      if (!inflate_build(S.lens, 19, S.dtab, 7, S.dsorted, S.dcount, S.run)) { err = INF_BAD_LENGTHS; break; }
+      if (!inflate_build<0>(S.lens, 19, S.dtab, 7, S.dsorted, S.dcount, S.run)) { err = INF_BAD_LENGTHS; break; }
       __syncwarp();
       int idx = 0;
       unsigned prev_len = 0;
@@ -246,7 +285,7 @@ __global__ void __launch_bounds__(32) inflate_kernel(const unsigned char* __rest
         unsigned e = S.dtab[br.peek(7)];
         if (!e) { err = INF_BAD_LENGTHS; break; }
         br.drop(e & 15);
-        unsigned sym = e >> 4;
+        unsigned sym = e >> 8;
         unsigned rep = 1, val = sym;
         if (sym == 16) {
           if (idx == 0) { err = INF_BAD_LENGTHS; break; }
@@ -265,62 +304,67 @@ __global__ void __launch_bounds__(32) inflate_kernel(const unsigned char* __rest
     __syncwarp();
     const unsigned char* ll = (type == 1) ? S.lens : S.lens + 24;
     const unsigned char* dl = (type == 1) ? S.lens + 288 : S.lens + 24 + nl;
-    if (!inflate_build(ll, nl, S.ltab, INF_LBITS, S.lsorted, S.lcount, S.run)) { err = INF_BAD_LENGTHS; break; }
+    if (!inflate_build<1>(ll, nl, S.ltab, INF_LBITS, S.lsorted, S.lcount, S.run)) { err = INF_BAD_LENGTHS; break; }
     __syncwarp();
-    if (!inflate_build(dl, nd, S.dtab, INF_DBITS, S.dsorted, S.dcount, S.run)) { err = INF_BAD_LENGTHS; break; }
+    if (!inflate_build<2>(dl, nd, S.dtab, INF_DBITS, S.dsorted, S.dcount, S.run)) { err = INF_BAD_LENGTHS; break; }
     __syncwarp();
 
-    // ---- symbol loop: batches of up to 32 symbols / INF_BATCH_BYTES output bytes
+    // ---- symbol loop: batches of up to 32 symbols (<= 32 * 258 output bytes, which the ring has room for)
     bool eob = false;
     while (!eob && !err) {
-      unsigned my_pos = 0, my_len = 0, my_dist = 0, my_lit = 0;
+      unsigned my_pos = 0, my_tok = 0;          // my_tok: literal byte, or len << 16 | dist
       unsigned bpos = opos;
+      unsigned bad = 0;                          // deferred checks (distance too far / invalid symbol)
       int k = 0;
-      for (; k < 32 && bpos - opos < INF_BATCH_BYTES; k++) {
+      for (; k < 32; k++) {
         br.refill();
         unsigned e = S.ltab[br.peek(INF_LBITS)];
-        unsigned sym;
-        if (e) { br.drop(e & 15); sym = e >> 4; }
-        else if (!inflate_slow(br, S.lcount, S.lsorted, sym)) { err = INF_BAD_CODE; break; }
-        if (sym < 256) {
-          if (lane == (unsigned)k) { my_pos = bpos; my_lit = sym; my_len = 0; }
+        if ((e & 15) == 0) { e = inflate_slow<1>(br.bb, S.lcount, S.lsorted); if (!e) { err = INF_BAD_CODE; break; } }
+        br.drop(e & 15);
+        const unsigned kind = e >> 24;
+        unsigned val = (e >> 8) & 0xffff;
+        if (kind == K_LIT) {
+          if (lane == (unsigned)k) { my_pos = bpos; my_tok = val; }
           bpos += 1;
-        } else if (sym == 256) {
-          eob = true;
-          break;
-        } else {
-          sym -= 257;
-          if (sym >= 29) { err = INF_BAD_CODE; break; }
-          unsigned len;
-          if (sym < 8) len = sym + 3;
-          else if (sym == 28) len = 258;
-          else { unsigned nb = (sym - 4) >> 2; len = 3 + ((4 + (sym & 3)) << nb) + br.get(nb); }
-          br.refill();
-          unsigned e2 = S.dtab[br.peek(INF_DBITS)];
-          unsigned ds;
-          if (e2) { br.drop(e2 & 15); ds = e2 >> 4; }
-          else if (!inflate_slow(br, S.dcount, S.dsorted, ds)) { err = INF_BAD_CODE; break; }
-          if (ds >= 30) { err = INF_BAD_CODE; break; }
-          unsigned dist;
-          if (ds < 4) dist = ds + 1;
-          else { unsigned nb = (ds >> 1) - 1; br.refill(); dist = 1 + ((2 + (ds & 1)) << nb) + br.get(nb); }
-          if (dist > bpos) { err = INF_BAD_DISTANCE; break; }
-          if (lane == (unsigned)k) { my_pos = bpos; my_len = len; my_dist = dist; }
-          bpos += len;
+          continue;
         }
-        if (bpos > out_len) { err = INF_BAD_SIZE; break; }
+        if (kind != K_LEN) {
+          if (kind == K_EOB) eob = true; else err = INF_BAD_CODE;
+          break;
+        }
+        const unsigned xb = (e >> 4) & 15;
+        val += br.peek(xb);
+        br.drop(xb);
+        br.refill();
+        unsigned e2 = S.dtab[br.peek(INF_DBITS)];
+        if ((e2 & 15) == 0) { e2 = inflate_slow<2>(br.bb, S.dcount, S.dsorted); if (!e2) { err = INF_BAD_CODE; break; } }
+        br.drop(e2 & 15);
+        const unsigned xb2 = (e2 >> 4) & 15;
+        const unsigned dist = ((e2 >> 8) & 0xffff) + br.peek(xb2);
+        br.drop(xb2);
+        bad |= (e2 >> 24) | (unsigned)(dist > bpos);
+        if (lane == (unsigned)k) { my_pos = bpos; my_tok = (val << 16) | dist; }
+        bpos += val;
       }
       if (err) break;
+      if (bad) { err = (bad & 2) ? INF_BAD_CODE : INF_BAD_DISTANCE; break; }
+      if (bpos > out_len) { err = INF_BAD_SIZE; break; }
       if (br.byte_pos() > in_len + 8) { err = INF_INPUT_OVERRUN; break; }
       const bool have = lane < (unsigned)k;
+      const unsigned my_len = my_tok >> 16, my_dist = my_tok & 0xffff;
       const bool is_match = have && my_len != 0;
       // a match is independent of this batch's other symbols if everything it reads was produced before the batch
       const bool indep = is_match && (my_pos - my_dist + min(my_len, my_dist) <= opos);
       const unsigned rp = (my_pos + a0) % INF_RING;
-      if (have && my_len == 0) ring[rp] = (unsigned char)my_lit;
+      if (have && my_len == 0) ring[rp] = (unsigned char)my_tok;
       if (indep) {
         unsigned rs = rp >= my_dist ? rp - my_dist : rp + INF_RING - my_dist;
-        for (unsigned i = 0; i < my_len; i++) ring[ring_wrap(rp + i)] = ring[ring_wrap(rs + i)];
+        unsigned rd = rp;
+        for (unsigned i = 0; i < my_len; i++) {
+          ring[rd] = ring[rs];
+          rd = ring_wrap(rd + 1);
+          rs = ring_wrap(rs + 1);
+        }
       }
       __syncwarp();
       unsigned mm = __ballot_sync(0xffffffffu, is_match && !indep);
@@ -328,8 +372,8 @@ __global__ void __launch_bounds__(32) inflate_kernel(const unsigned char* __rest
         int src_lane = __ffs((int)mm) - 1;
         mm &= mm - 1;
         unsigned p = __shfl_sync(0xffffffffu, rp, src_lane);
-        unsigned l = __shfl_sync(0xffffffffu, my_len, src_lane);
-        unsigned d = __shfl_sync(0xffffffffu, my_dist, src_lane);
+        unsigned t = __shfl_sync(0xffffffffu, my_tok, src_lane);
+        unsigned l = t >> 16, d = t & 0xffff;
         unsigned s = p >= d ? p - d : p + INF_RING - d;
         if (d >= l) { for (unsigned i = lane; i < l; i += 32) ring[ring_wrap(p + i)] = ring[ring_wrap(s + i)]; }
         else if (d >= 32) {
