@@ -51,10 +51,12 @@ struct mtsb_ctx {
   int sm_count = 148;
   std::string err;
   // params
-  long long seg_bytes = 262144, batch_bytes = 2ll << 30, write_index = 1;
+  long long seg_bytes = 262144, batch_bytes = 2ll << 30, host_batch_bytes = 256ll << 20, write_index = 1;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of the host-buffer paths
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_done = nullptr;
   LzParams lz{4, 16, 32768, 32768, 32768, 0};   // greedy, every match >= 4 bytes accepted: tuned on synthetic AP/LFP
   // device scratch
-  Buf d_raw, d_T, d_tok, d_hist, d_codes, d_hdrs, d_tab, d_so, d_seg_adler, d_chunk_adler, d_chunk_off, d_out,
+  Buf d_raw, d_raw2, d_out2, d_comp2, d_T, d_tok, d_hist, d_codes, d_hdrs, d_tab, d_so, d_seg_adler, d_chunk_adler, d_chunk_off, d_out,
       d_partial, d_comp, d_status, d_tadler, d_gather;
   Buf h_tab, h_small;
   // timings
@@ -122,6 +124,8 @@ size_t tile_smem(int nc, int isz, int rows) {
   long long P = isz == 1 ? tile_pitch<uint8_t>(nc) : isz == 2 ? tile_pitch<uint16_t>(nc) : (nc | 1);
   return (size_t)(P * isz * rows);
 }
+
+static_assert(LzSmem<1>::total <= 232448 && LzSmem<2>::total <= 232448, "lz77_kernel exceeds the 227 KB opt-in shared memory of sm_100");
 
 int set_attrs(mtsb_ctx* c) {
   if (c->attr_set) return 0;
@@ -253,6 +257,15 @@ mtsb_ctx* mtsb_create(int device_id, void* stream) {
     }
     c->own_stream = true;
   }
+  if (cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking) != cudaSuccess) {
+    fail(nullptr, MTSB_E_CUDA, "cudaStreamCreate failed"); mtsb_destroy(c); return nullptr;
+  }
+  for (int i = 0; i < 2; i++) {
+    cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming);
+  }
+  cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming);
   if (set_attrs(c)) { g_err = c->err; mtsb_destroy(c); return nullptr; }
   return c;
 }
@@ -261,11 +274,15 @@ void mtsb_destroy(mtsb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  Buf* bufs[] = {&c->d_raw, &c->d_T, &c->d_tok, &c->d_hist, &c->d_codes, &c->d_hdrs, &c->d_tab, &c->d_so,
+  Buf* bufs[] = {&c->d_raw, &c->d_raw2, &c->d_out2, &c->d_comp2, &c->d_T, &c->d_tok, &c->d_hist, &c->d_codes, &c->d_hdrs, &c->d_tab, &c->d_so,
                  &c->d_seg_adler, &c->d_chunk_adler, &c->d_chunk_off, &c->d_out, &c->d_partial, &c->d_comp,
                  &c->d_status, &c->d_tadler, &c->d_gather, &c->h_tab, &c->h_small};
   for (Buf* b : bufs) b->release();
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  for (int i = 0; i < 2; i++) { if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]); if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]); }
+  if (c->ev_done) cudaEventDestroy(c->ev_done);
+  if (c->copy_in) cudaStreamDestroy(c->copy_in);
+  if (c->copy_out) cudaStreamDestroy(c->copy_out);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -283,6 +300,7 @@ int mtsb_set_param(mtsb_ctx* c, const char* name, long long v) {
   std::string s(name);
   if (s == "seg_bytes") { if (v < 4096 || v > (1ll << 30)) return fail(c, MTSB_E_ARG, "seg_bytes out of range"); c->seg_bytes = v; }
   else if (s == "batch_bytes") { if (v < (1 << 20)) return fail(c, MTSB_E_ARG, "batch_bytes too small"); c->batch_bytes = v; }
+  else if (s == "host_batch_bytes") { if (v < (1 << 20)) return fail(c, MTSB_E_ARG, "host_batch_bytes too small"); c->host_batch_bytes = v; }
   else if (s == "write_index") c->write_index = v ? 1 : 0;
   else if (s == "max_chain") c->lz.max_chain = (int)std::max<long long>(1, v);
   else if (s == "nice_len") c->lz.nice_len = (int)std::min<long long>(258, std::max<long long>(4, v));
@@ -299,6 +317,7 @@ long long mtsb_get_param(mtsb_ctx* c, const char* name) {
   std::string s(name);
   if (s == "seg_bytes") return c->seg_bytes;
   if (s == "batch_bytes") return c->batch_bytes;
+  if (s == "host_batch_bytes") return c->host_batch_bytes;
   if (s == "write_index") return c->write_index;
   if (s == "max_chain") return c->lz.max_chain;
   if (s == "nice_len") return c->lz.nice_len;
@@ -437,15 +456,46 @@ int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_
 
   out_offsets[0] = 0;
   long long total_out = 0;
-  int c0 = 0;
-  while (c0 < n_chunks) {
-    // ---- sub-batch [c0, c1)
-    int c1 = c0;
-    long long bbytes = 0;
-    while (c1 < n_chunks && c1 - c0 < 60000) {
-      long long cb = (chunk_rows[c1 + 1] - chunk_rows[c1]) * row_bytes;
-      if (c1 > c0 && bbytes + cb > c->batch_bytes) break;
-      bbytes += cb; c1++;
+  // sub-batches: bounded by batch_bytes; smaller when a host buffer is involved so that copies pipeline with kernels
+  const bool host_io = !src_is_device || !dst_is_device;
+  const long long sb_limit = host_io ? std::min(c->batch_bytes, c->host_batch_bytes) : c->batch_bytes;
+  std::vector<int> sb_first;
+  long long max_sb_bytes = 0, max_sb_bound = 0;
+  for (int a = 0; a < n_chunks;) {
+    sb_first.push_back(a);
+    int b = a;
+    long long bb = 0, bd = 0;
+    while (b < n_chunks && b - a < 60000) {
+      long long ns = chunk_rows[b + 1] - chunk_rows[b], cb = ns * row_bytes;
+      if (b > a && bb + cb > sb_limit) break;
+      bb += cb; bd += chunk_bound(c, cb, seg_size_for(c, ns, itemsize, flags)); b++;
+    }
+    max_sb_bytes = std::max(max_sb_bytes, bb);
+    max_sb_bound = std::max(max_sb_bound, bd);
+    a = b;
+  }
+  sb_first.push_back(n_chunks);
+  const int n_sb = (int)sb_first.size() - 1;
+  Buf* raw_buf[2] = {&c->d_raw, &c->d_raw2};
+  Buf* out_buf[2] = {&c->d_out, &c->d_out2};
+  if (!src_is_device) { NEED(c->d_raw, (size_t)max_sb_bytes + 256); if (n_sb > 1) NEED(c->d_raw2, (size_t)max_sb_bytes + 256); }
+  if (!dst_is_device) { NEED(c->d_out, (size_t)max_sb_bound + 256); if (n_sb > 1) NEED(c->d_out2, (size_t)max_sb_bound + 256); }
+  auto sb_bytes = [&](int k) { return (chunk_rows[sb_first[k + 1]] - chunk_rows[sb_first[k]]) * row_bytes; };
+  if (!src_is_device) {
+    // the copy-in stream must not start before work already queued on the caller's stream (e.g. producing `src`)
+    CK(cudaEventRecord(c->ev_done, c->stream));
+    CK(cudaStreamWaitEvent(c->copy_in, c->ev_done, 0));
+    CK(cudaMemcpyAsync(raw_buf[0]->p, (const char*)src, (size_t)sb_bytes(0), cudaMemcpyHostToDevice, c->copy_in));
+    CK(cudaEventRecord(c->ev_in[0], c->copy_in));
+  }
+  for (int k = 0; k < n_sb; k++) {
+    const int c0 = sb_first[k], c1 = sb_first[k + 1];
+    const long long bbytes = sb_bytes(k);
+    if (!src_is_device && k + 1 < n_sb) {
+      // prefetch the next sub-batch while this one is compressed (its buffer was last read by sub-batch k-1, done)
+      CK(cudaMemcpyAsync(raw_buf[(k + 1) & 1]->p, (const char*)src + chunk_rows[sb_first[k + 1]] * row_bytes,
+                         (size_t)sb_bytes(k + 1), cudaMemcpyHostToDevice, c->copy_in));
+      CK(cudaEventRecord(c->ev_in[(k + 1) & 1], c->copy_in));
     }
     const int nb = c1 - c0;
     const long long row0 = chunk_rows[c0];
@@ -516,14 +566,16 @@ int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_
     CK(cudaMemcpyAsync(c->d_tab.p, h, tab_bytes, cudaMemcpyHostToDevice, c->stream));
     const void* raw = (const char*)src + row0 * row_bytes;
     if (!src_is_device) {
-      NEED(c->d_raw, (size_t)bbytes + 256);
-      CK(cudaMemcpyAsync(c->d_raw.p, raw, (size_t)bbytes, cudaMemcpyHostToDevice, c->stream));
-      raw = c->d_raw.p;
+      CK(cudaStreamWaitEvent(c->stream, c->ev_in[k & 1], 0));
+      raw = raw_buf[k & 1]->p;
     }
     c->end();
     unsigned char* outp;
     if (dst_is_device) outp = (unsigned char*)dst + total_out;
-    else { NEED(c->d_out, (size_t)bound + 256); outp = (unsigned char*)c->d_out.p; }
+    else {
+      if (k >= 2) CK(cudaStreamWaitEvent(c->stream, c->ev_out[k & 1], 0));   // D2H of sub-batch k-2 has drained it
+      outp = (unsigned char*)out_buf[k & 1]->p;
+    }
 
     c->begin(1);
     int r = launch_fwd(c, itemsize, raw, c->d_T.p, d_cd, nb, max_ns, nc, flags);
@@ -568,14 +620,13 @@ int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_
     if (co[nb] > bound) return fail(c, MTSB_E_CAPACITY, "internal: sub-batch output %lld exceeds bound %lld", co[nb], bound);
     for (int i = 0; i < nb; i++) out_offsets[c0 + i + 1] = total_out + co[i + 1];
     if (!dst_is_device) {
-      c->begin(6);
-      CK(cudaMemcpyAsync((char*)dst + total_out, outp, (size_t)co[nb], cudaMemcpyDeviceToHost, c->stream));
-      c->end();
-      CK(cudaStreamSynchronize(c->stream));
+      // the kernels of this sub-batch are complete (synchronised above): drain it on the copy-out stream
+      CK(cudaMemcpyAsync((char*)dst + total_out, outp, (size_t)co[nb], cudaMemcpyDeviceToHost, c->copy_out));
+      CK(cudaEventRecord(c->ev_out[k & 1], c->copy_out));
     }
     total_out += co[nb];
-    c0 = c1;
   }
+  if (!dst_is_device) CK(cudaStreamSynchronize(c->copy_out));
   c->collect_timing();
   return 0;
 }
@@ -694,14 +745,44 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
 
   if (chunk_status) for (int i = 0; i < n_chunks; i++) chunk_status[i] = 0;
   bool any_bad = false;
-  int c0 = 0;
-  while (c0 < n_chunks) {
-    int c1 = c0;
-    long long bbytes = 0;
-    while (c1 < n_chunks && c1 - c0 < 60000) {
-      long long cb = (chunk_rows[c1 + 1] - chunk_rows[c1]) * row_bytes;
-      if (c1 > c0 && bbytes + cb > c->batch_bytes) break;
-      bbytes += cb; c1++;
+  const bool host_io = !comp_is_device || !dst_is_device;
+  const long long sb_limit = host_io ? std::min(c->batch_bytes, c->host_batch_bytes) : c->batch_bytes;
+  std::vector<int> sb_first;
+  long long max_sb_bytes = 0, max_sb_comp = 0;
+  for (int a = 0; a < n_chunks;) {
+    sb_first.push_back(a);
+    int b = a;
+    long long bb = 0;
+    while (b < n_chunks && b - a < 60000) {
+      long long cb = (chunk_rows[b + 1] - chunk_rows[b]) * row_bytes;
+      if (b > a && bb + cb > sb_limit) break;
+      bb += cb; b++;
+    }
+    max_sb_bytes = std::max(max_sb_bytes, bb);
+    max_sb_comp = std::max(max_sb_comp, comp_offsets[b] - comp_offsets[a]);
+    a = b;
+  }
+  sb_first.push_back(n_chunks);
+  const int n_sb = (int)sb_first.size() - 1;
+  Buf* comp_buf[2] = {&c->d_comp, &c->d_comp2};
+  Buf* out_buf[2] = {&c->d_out, &c->d_out2};
+  if (!comp_is_device) { NEED(c->d_comp, (size_t)max_sb_comp + 256); if (n_sb > 1) NEED(c->d_comp2, (size_t)max_sb_comp + 256); }
+  if (!dst_is_device) { NEED(c->d_out, (size_t)max_sb_bytes + 256); if (n_sb > 1) NEED(c->d_out2, (size_t)max_sb_bytes + 256); }
+  if (!comp_is_device) {
+    CK(cudaEventRecord(c->ev_done, c->stream));
+    CK(cudaStreamWaitEvent(c->copy_in, c->ev_done, 0));
+    CK(cudaMemcpyAsync(comp_buf[0]->p, comp + comp_offsets[0], (size_t)(comp_offsets[sb_first[1]] - comp_offsets[0]),
+                       cudaMemcpyHostToDevice, c->copy_in));
+    CK(cudaEventRecord(c->ev_in[0], c->copy_in));
+  }
+  for (int k = 0; k < n_sb; k++) {
+    const int c0 = sb_first[k], c1 = sb_first[k + 1];
+    const long long bbytes = (chunk_rows[c1] - chunk_rows[c0]) * row_bytes;
+    if (!comp_is_device && k + 1 < n_sb) {
+      const int a = sb_first[k + 1], b = sb_first[k + 2];
+      CK(cudaMemcpyAsync(comp_buf[(k + 1) & 1]->p, comp + comp_offsets[a], (size_t)(comp_offsets[b] - comp_offsets[a]),
+                         cudaMemcpyHostToDevice, c->copy_in));
+      CK(cudaEventRecord(c->ev_in[(k + 1) & 1], c->copy_in));
     }
     const int nb = c1 - c0;
     const long long row0 = chunk_rows[c0];
@@ -770,9 +851,8 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
     CK(cudaMemcpyAsync(c->d_tab.p, h, tab_bytes, cudaMemcpyHostToDevice, c->stream));
     const unsigned char* dcomp = comp + comp0;
     if (!comp_is_device) {
-      NEED(c->d_comp, (size_t)comp_bytes + 256);
-      CK(cudaMemcpyAsync(c->d_comp.p, comp + comp0, (size_t)comp_bytes, cudaMemcpyHostToDevice, c->stream));
-      dcomp = (const unsigned char*)c->d_comp.p;
+      CK(cudaStreamWaitEvent(c->stream, c->ev_in[k & 1], 0));
+      dcomp = (const unsigned char*)comp_buf[k & 1]->p;
     }
     c->end();
     c->begin(2);
@@ -789,7 +869,10 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
     c->end();
     void* outp;
     if (dst_is_device) outp = (char*)dst + row0 * row_bytes;
-    else { NEED(c->d_out, (size_t)bbytes + 256); outp = c->d_out.p; }
+    else {
+      if (k >= 2) CK(cudaStreamWaitEvent(c->stream, c->ev_out[k & 1], 0));   // D2H of sub-batch k-2 has drained it
+      outp = out_buf[k & 1]->p;
+    }
     c->begin(4);
     int r = launch_inv(c, itemsize, c->d_T.p, outp, d_cd, nb, max_ns, nc, flags);
     if (r) return r;
@@ -798,12 +881,11 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
     CK(cudaMemcpyAsync(hs, c->d_status.p, (size_t)n_segs * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(hs + (size_t)n_segs * 4, c->d_tadler.p, (size_t)n_segs * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(hs + (size_t)n_segs * 8, c->d_chunk_adler.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (!dst_is_device) {
-      c->begin(5);
-      CK(cudaMemcpyAsync((char*)dst + row0 * row_bytes, outp, (size_t)bbytes, cudaMemcpyDeviceToHost, c->stream));
-      c->end();
-    }
     CK(cudaStreamSynchronize(c->stream));
+    if (!dst_is_device) {
+      CK(cudaMemcpyAsync((char*)dst + row0 * row_bytes, outp, (size_t)bbytes, cudaMemcpyDeviceToHost, c->copy_out));
+      CK(cudaEventRecord(c->ev_out[k & 1], c->copy_out));
+    }
     const int* st = (const int*)hs;
     const uint32_t* ta = (const uint32_t*)(hs + (size_t)n_segs * 4);
     const uint32_t* ca = (const uint32_t*)(hs + (size_t)n_segs * 8);
@@ -817,8 +899,8 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
       if (s) any_bad = true;
       if (chunk_status) chunk_status[c0 + i] = s;
     }
-    c0 = c1;
   }
+  if (!dst_is_device) CK(cudaStreamSynchronize(c->copy_out));
   c->collect_timing();
   if (any_bad) return fail(c, MTSB_E_CORRUPT, "at least one compressed chunk is corrupted");
   return 0;

@@ -82,17 +82,18 @@ __device__ __forceinline__ unsigned d_extra_bits(unsigned sym) { return sym < 4 
 static const int LZ_THREADS = 1024;
 static const int LZ_UNITS = 960;              // units searched per step = 30 searcher warps x 32 lanes
 static const int LZ_RING = 65536;
-static const int LZ_HASHL_BITS = 15, LZ_HASHS_BITS = 14;
+static const int LZ_HASHS_BITS = 14;
 static const unsigned LZ_BIAS = 32768;
 
 template <int STRIDE> struct LzSmem {
   static const int SEG = LZ_UNITS * STRIDE;   // bytes per step
   static const int PREV_N = 32768 / STRIDE;
+  static const int HL_BITS = STRIDE == 1 ? 14 : 15;   // headL size: what still fits next to the 64 KB prev ring of STRIDE 1
   // the inserters run one step ahead, so chain entries older than PREV_N - 2 steps may already be recycled
   static const int MAXD_UNITS = PREV_N - 2 * LZ_UNITS - 8;
   static const size_t ring_off = 0;
   static const size_t headl_off = LZ_RING;
-  static const size_t heads_off = headl_off + (size_t)(1 << LZ_HASHL_BITS) * 2;
+  static const size_t heads_off = headl_off + (size_t)(1 << HL_BITS) * 2;
   static const size_t prevl_off = heads_off + (size_t)(1 << LZ_HASHS_BITS) * 2;
   static const size_t prevs_off = prevl_off + (size_t)PREV_N * 2;
   static const size_t mlen_off = prevs_off + (size_t)(2 * LZ_UNITS) * 2;
@@ -112,8 +113,8 @@ __device__ __forceinline__ unsigned ring_load4(const unsigned char* ring, unsign
   return __funnelshift_r(lo, hi, (r & 3) * 8);
 }
 __device__ __forceinline__ unsigned lz_hash4(unsigned w) { return (w * 0x9E3779B1u) >> (32 - LZ_HASHS_BITS); }
-__device__ __forceinline__ unsigned lz_hash6(unsigned w0, unsigned w1) {
-  return ((w0 * 0x9E3779B1u) ^ ((w1 & 0xffffu) * 0x85EBCA6Bu)) >> (32 - LZ_HASHL_BITS);
+template <int BITS> __device__ __forceinline__ unsigned lz_hash6(unsigned w0, unsigned w1) {
+  return ((w0 * 0x9E3779B1u) ^ ((w1 & 0xffffu) * 0x85EBCA6Bu)) >> (32 - BITS);
 }
 
 // Thread `units` consecutive units starting at unit u0 into one hash table, in position order (one warp).
@@ -133,7 +134,7 @@ __device__ __forceinline__ void lz_insert_step(const unsigned char* ring, unsign
     unsigned short old = 0;
     if (valid) {
       unsigned w0 = ring_load4(ring, p + off0);
-      h = LONG ? lz_hash6(w0, ring_load4(ring, p + off0 + 4)) : lz_hash4(w0);
+      h = LONG ? lz_hash6<LzSmem<STRIDE>::HL_BITS>(w0, ring_load4(ring, p + off0 + 4)) : lz_hash4(w0);
       old = head[h];
     }
     __syncwarp();
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
     const unsigned n_ring = n + off0;                    // ring coordinates [off0, n_ring) are real input
 
     // reset tables (headL and headS are contiguous); initial load: ring coordinates [0, 3*SEG)
-    for (unsigned i = tid; i < ((1u << LZ_HASHL_BITS) + (1u << LZ_HASHS_BITS)) / 2; i += LZ_THREADS) ((unsigned*)headL)[i] = 0;
+    for (unsigned i = tid; i < ((1u << L::HL_BITS) + (1u << LZ_HASHS_BITS)) / 2; i += LZ_THREADS) ((unsigned*)headL)[i] = 0;
     for (unsigned i = tid; i < HIST_STRIDE; i += LZ_THREADS) shist[i] = 0;
     if (tid == 0) { misc[32] = 0; misc[33] = 0; }
     for (unsigned v = tid; v * 16 < 3 * SEG; v += LZ_THREADS)

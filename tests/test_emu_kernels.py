@@ -55,3 +55,21 @@ def test_emulated_corruption_is_reported(emu):
     cbin[o[2] + 40] ^= 0x10         # payload of chunk 2
     _, st = emu.decompress(bytes(cbin), o, ch['chunk_bounds'], ch['n_channels'], ch['dtype'], _flags(ch))
     assert st[0] == 0 and st[1] == 9 and st[2] != 0
+
+
+def test_emulated_host_pipeline_many_sub_batches(emu):
+    """Host-buffer path with several double-buffered sub-batches (H2D / kernels / D2H on separate streams)."""
+    from mtscomp_b200 import synth, _native
+    x = np.concatenate([synth.ap_chunk(ns=1500, nc=96, seed=80 + i) for i in range(3)] * 3)
+    rows = np.arange(10) * 1500
+    emu.set_param('host_batch_bytes', 1 << 20)
+    emu.set_param('batch_bytes', 1 << 20)
+    try:
+        comp, offs = emu.compress(x, rows, _native.TIME_DIFF)
+        for i in range(9):
+            assert zlib.decompress(bytes(comp[offs[i]:offs[i + 1]])) == ora.transform_chunk(x[rows[i]:rows[i + 1]])
+        out, st = emu.decompress(comp, offs, rows, 96, np.int16, _native.TIME_DIFF)
+        assert not st.any() and np.array_equal(out, x)
+    finally:
+        emu.set_param('host_batch_bytes', 256 << 20)
+        emu.set_param('batch_bytes', 2 << 30)
