@@ -147,6 +147,16 @@ int set_attrs(mtsb_ctx* c) {
 template <class T>
 int launch_fwd_t(mtsb_ctx* c, const void* raw, void* tbuf, const ChunkDesc* d_cd, int n_chunks, int max_ns, int nc,
                  int flags) {
+  if (!(flags & (FLAG_ORDER_C | FLAG_SPATIAL_DIFF))) {
+    // default layout: register-only kernel, one 32-byte channel run per thread
+    const int R = ColRun<T>::R;
+    dim3 grid((nc + 31) / 32, (max_ns + 4 * R - 1) / (4 * R), n_chunks);
+    auto k = fwd_cols_kernel<T>;
+    MTS_LAUNCH(k, grid, dim3(128), 0, c->stream, (const T*)raw, (T*)tbuf, d_cd, nc, flags);
+    c->launches++;
+    CKL();
+    return 0;
+  }
   int TT = tile_rows(nc, sizeof(T), 1);
   if (TT < 1) return fail(c, MTSB_E_ARG, "n_channels=%d too large for the transform tile", nc);
   dim3 grid((max_ns + TT - 1) / TT, n_chunks);
@@ -170,7 +180,8 @@ int launch_fwd(mtsb_ctx* c, int isz, const void* raw, void* tbuf, const ChunkDes
 template <class T>
 int launch_inv_t(mtsb_ctx* c, const void* tbuf, void* out, const ChunkDesc* d_cd, int n_chunks, int max_ns, int nc,
                  int flags) {
-  int TT = tile_rows(nc, sizeof(T), 0);
+  const bool fast = !(flags & (FLAG_ORDER_C | FLAG_SPATIAL_DIFF));
+  int TT = fast ? 256 : tile_rows(nc, sizeof(T), 0);
   if (TT < 1) return fail(c, MTSB_E_ARG, "n_channels=%d too large for the transform tile", nc);
   int max_tiles = (max_ns + TT - 1) / TT;
   dim3 grid(max_tiles, n_chunks);
@@ -186,8 +197,13 @@ int launch_inv_t(mtsb_ctx* c, const void* tbuf, void* out, const ChunkDesc* d_cd
     CKL();
     c->launches += 2;
   }
-  auto k3 = inv_apply_kernel<T>;
-  MTS_LAUNCH(k3, grid, dim3(512), tile_smem(nc, sizeof(T), TT), c->stream, (const T*)tbuf, (T*)out, (const T*)partial, d_cd, nc, TT, max_tiles, flags);
+  if (fast) {
+    auto k3 = inv_cols_kernel<T>;
+    MTS_LAUNCH(k3, dim3((nc + 127) / 128, max_tiles, n_chunks), dim3(128), 0, c->stream, (const T*)tbuf, (T*)out, (const T*)partial, d_cd, nc, TT, max_tiles, flags);
+  } else {
+    auto k3 = inv_apply_kernel<T>;
+    MTS_LAUNCH(k3, grid, dim3(512), tile_smem(nc, sizeof(T), TT), c->stream, (const T*)tbuf, (T*)out, (const T*)partial, d_cd, nc, TT, max_tiles, flags);
+  }
   c->launches++;
   CKL();
   return 0;

@@ -100,10 +100,9 @@ template <int STRIDE> struct LzSmem {
   static const size_t mdist_off = mlen_off + (size_t)(SEG + 8) * 2;
   static const size_t jump_off = mdist_off + (size_t)(SEG + 8) * 2;
   static const size_t jump2_off = jump_off + (size_t)(SEG + 8) * 2;
-  static const size_t reach_off = jump2_off + (size_t)(SEG + 8) * 2;
-  static const size_t hist_off = (reach_off + SEG + 8 + 15) & ~(size_t)15;
+  static const size_t hist_off = (jump2_off + (size_t)(SEG + 8) * 2 + 15) & ~(size_t)15;
   static const size_t misc_off = hist_off + (size_t)HIST_STRIDE * 4;
-  static const size_t total = misc_off + 256;
+  static const size_t total = misc_off + 512;
 };
 
 __device__ __forceinline__ unsigned ring_load4(const unsigned char* ring, unsigned r) {
@@ -181,6 +180,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
                                                              LzParams prm) {
   typedef LzSmem<STRIDE> L;
   const unsigned SEG = L::SEG;
+  const unsigned NSW = 30;                          // searcher / parser warps; warps 30 and 31 are the inserters
+  const unsigned STRETCH = L::SEG / 30;             // positions parsed per warp (64 for STRIDE 2, 32 for STRIDE 1)
+  const unsigned PER_LANE = STRETCH / 32;
   MTS_DYN_SMEM(sm);
   unsigned char* ring = sm + L::ring_off;
   unsigned short* headL = (unsigned short*)(sm + L::headl_off);
@@ -189,11 +191,11 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
   unsigned short* prevS = (unsigned short*)(sm + L::prevs_off);
   unsigned short* mlen = (unsigned short*)(sm + L::mlen_off);
   unsigned short* mdist = (unsigned short*)(sm + L::mdist_off);
-  unsigned short* jump = (unsigned short*)(sm + L::jump_off);
-  unsigned short* jump2 = (unsigned short*)(sm + L::jump2_off);
-  unsigned char* reach = sm + L::reach_off;
+  unsigned short* nxt = (unsigned short*)(sm + L::jump_off);     // next token position per position
+  unsigned short* ex = (unsigned short*)(sm + L::jump2_off);     // stage 1: stretch exit; stage 3: token list
   unsigned* shist = (unsigned*)(sm + L::hist_off);
-  unsigned* misc = (unsigned*)(sm + L::misc_off);   // [0..31] warp totals, [32] running token count, [33] carry
+  unsigned* misc = (unsigned*)(sm + L::misc_off);   // [0..29] per-warp element counts / bases, [33],[34] carry, [36..] entries
+  unsigned* ent = misc + 36;                         // [0..29] parse entry position of each stretch, [30..59] token counts
   const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned PM = L::PREV_N - 1;
 
@@ -205,18 +207,19 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
     const uint4* in16 = (const uint4*)(in - off0);
     unsigned short* tok = tokens + sg.tok_off;
     const unsigned n_ring = n + off0;                    // ring coordinates [off0, n_ring) are real input
+    unsigned run_tok = 0;                                // token elements emitted so far (uniform across threads)
 
     // reset tables (headL and headS are contiguous); initial load: ring coordinates [0, 3*SEG)
     for (unsigned i = tid; i < ((1u << L::HL_BITS) + (1u << LZ_HASHS_BITS)) / 2; i += LZ_THREADS) ((unsigned*)headL)[i] = 0;
     for (unsigned i = tid; i < HIST_STRIDE; i += LZ_THREADS) shist[i] = 0;
-    if (tid == 0) { misc[32] = 0; misc[33] = 0; }
+    if (tid == 0) { misc[33] = 0; misc[34] = 0; }
     for (unsigned v = tid; v * 16 < 3 * SEG; v += LZ_THREADS)
       if (v * 16 < n_ring) *(uint4*)(ring + v * 16) = in16[v];
     __syncthreads();
     {
       const unsigned units0 = min((unsigned)LZ_UNITS, (n + STRIDE - 1) / STRIDE);
-      if (wid == 0) lz_insert_step<STRIDE, false>(ring, headS, prevS, 0, units0, n, off0, lane);
-      if (wid == 1) lz_insert_step<STRIDE, true>(ring, headL, prevL, 0, units0, n, off0, lane);
+      if (wid == 30) lz_insert_step<STRIDE, false>(ring, headS, prevS, 0, units0, n, off0, lane);
+      if (wid == 31) lz_insert_step<STRIDE, true>(ring, headL, prevL, 0, units0, n, off0, lane);
     }
     __syncthreads();
 
@@ -225,9 +228,10 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
       const unsigned s0 = step * SEG;                    // first position of this step
       const unsigned slen = min(SEG, n - s0);
 
-      if (wid < 2) {
-        // ---- (A) inserters: prefetch ring coordinates [(step+3)*SEG, (step+4)*SEG), insert step+1's units
-        if (wid == 0) {
+      if (wid >= NSW) {
+        // ---- (A) inserters (the two highest warp ids: the issue arbiter favours them over the searchers): prefetch
+        //          ring coordinates [(step+3)*SEG, (step+4)*SEG) and thread step+1's units into the tables
+        if (wid == 30) {
           const unsigned base = (step + 3) * SEG;
           for (unsigned v = lane; v * 16 < SEG; v += 32) {
             unsigned rc = base + v * 16;
@@ -237,12 +241,12 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
         const unsigned s1 = s0 + SEG;
         if (s1 < n) {
           const unsigned units1 = (min(SEG, n - s1) + STRIDE - 1) / STRIDE;
-          if (wid == 0) lz_insert_step<STRIDE, false>(ring, headS, prevS, s1 / STRIDE, units1, n, off0, lane);
+          if (wid == 30) lz_insert_step<STRIDE, false>(ring, headS, prevS, s1 / STRIDE, units1, n, off0, lane);
           else lz_insert_step<STRIDE, true>(ring, headL, prevL, s1 / STRIDE, units1, n, off0, lane);
         }
       } else {
         // ---- (B) searchers: one unit per thread
-        const unsigned li = (tid - 64) * STRIDE;          // local position in the step
+        const unsigned li = tid * STRIDE;                 // local position in the step
         const unsigned p = s0 + li;
         unsigned best = 0, bdist = 0;
         if (li < slen && p + 4 <= n) {
@@ -292,120 +296,114 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
             }
           }
         }
-        if (li < SEG) { mlen[li] = (unsigned short)(bdist ? best : 0); mdist[li] = (unsigned short)bdist; }
-      }
-      __syncthreads();
-
-      // ---- (C) STRIDE > 1: positions between indexed ones inherit the next indexed match, extended backwards
-      if (STRIDE > 1) {
-        for (unsigned li = tid; li < SEG; li += LZ_THREADS) {
-          if (li % STRIDE == 0) continue;
-          unsigned nx = li + (STRIDE - li % STRIDE);       // next indexed local position
-          unsigned ml = 0, md = 0;
-          if (nx < slen && li < slen) {
-            unsigned l2 = mlen[nx], d2 = mdist[nx];
-            unsigned back = nx - li, p = s0 + li;
-            if (l2 && l2 + back <= 258 && p >= d2) {
-              bool eq = true;
-              for (unsigned j = 0; j < back; j++)
-                eq = eq && (ring[(p + j + off0) & 0xffffu] == ring[(p + j + off0 - d2) & 0xffffu]);
-              if (eq) { ml = l2 + back; md = d2; }
-            }
+        mlen[li] = (unsigned short)(bdist ? best : 0);
+        mdist[li] = (unsigned short)bdist;
+        if (STRIDE > 1) {
+          // the bytes between this unit and the previous one inherit this match, extended backwards while they agree
+          unsigned l2 = bdist ? best : 0;
+          for (unsigned back = 1; back < (unsigned)STRIDE && back <= li; back++) {
+            const unsigned q = p - back;
+            if (l2 && l2 < 258 && q >= bdist &&
+                ring[(q + off0) & 0xffffu] == ring[(q + off0 - bdist) & 0xffffu]) l2++;
+            else l2 = 0;
+            mlen[li - back] = (unsigned short)l2;
+            mdist[li - back] = (unsigned short)(l2 ? bdist : 0);
           }
-          mlen[li] = (unsigned short)ml;
-          mdist[li] = (unsigned short)md;
+          if (tid == LZ_UNITS - 1)
+            for (unsigned j = 1; j < (unsigned)STRIDE; j++) { mlen[li + j] = 0; mdist[li + j] = 0; }
         }
-        __syncthreads();
       }
-
-      // ---- (D) parse: next[] per position, reachability from the carried start by pointer doubling
-      const unsigned start = misc[33];                    // local start position (< slen unless the carry skips it)
       __syncthreads();
+
+      // ---- (C) greedy parse, hierarchical: per-warp stretches resolved by pointer doubling, chained by one thread
+      const unsigned start = misc[33 + (step & 1)];       // local start position carried from the previous step
       if (start < slen) {
-        for (unsigned li = tid; li <= SEG; li += LZ_THREADS) {
-          unsigned nx = slen;
-          if (li < slen) {
-            unsigned l = mlen[li];
-            if (l && prm.lazy && li + 1 < slen && mlen[li + 1] > l) l = 0;
-            nx = min(li + (l ? l : 1u), slen);
-            jump2[li] = (unsigned short)l;                 // jump2 doubles as "chosen length" (0 = literal)
+        if (wid < NSW) {
+          const unsigned e = min((wid + 1) * STRETCH, slen);
+          unsigned j[PER_LANE];
+          for (unsigned k = 0; k < PER_LANE; k++) {
+            const unsigned i = wid * STRETCH + lane * PER_LANE + k;
+            unsigned nx = i + 1;
+            if (i < e) { unsigned l = mlen[i]; nx = i + (l ? l : 1u); nxt[i] = (unsigned short)nx; }
+            j[k] = nx;
+            ex[i] = (unsigned short)nx;
           }
-          jump[li] = (unsigned short)nx;
-          reach[li] = (li == start);
+          __syncwarp();
+          for (unsigned r = 1; r < STRETCH; r <<= 1) {
+            for (unsigned k = 0; k < PER_LANE; k++) if (j[k] < e) j[k] = ex[j[k]];
+            __syncwarp();
+            for (unsigned k = 0; k < PER_LANE; k++) ex[wid * STRETCH + lane * PER_LANE + k] = (unsigned short)j[k];
+            __syncwarp();
+          }
         }
         __syncthreads();
-        for (unsigned li = tid; li < slen; li += LZ_THREADS) mlen[li] = jump2[li];
-        __syncthreads();
-        for (;;) {
-          bool done = (jump[start] >= slen);
-          unsigned j2[(L::SEG + LZ_THREADS) / LZ_THREADS];
-          unsigned kk = 0;
-          for (unsigned li = tid; li < slen; li += LZ_THREADS, kk++) {
-            unsigned j = jump[li];
-            if (reach[li] && j < slen) reach[j] = 1;
-            j2[kk] = (j < slen) ? jump[j] : slen;
+        if (tid == 0) {
+          unsigned p = start;
+          for (unsigned w = 0; w < NSW; w++) {
+            ent[w] = p;
+            if (p < min((w + 1) * STRETCH, slen)) p = ex[p];
           }
-          __syncthreads();
-          if (done) break;
-          kk = 0;
-          for (unsigned li = tid; li < slen; li += LZ_THREADS, kk++) jump[li] = (unsigned short)j2[kk];
-          __syncthreads();
+          misc[33 + ((step + 1) & 1)] = p - slen;          // p >= slen: where the last token of this step ends
         }
-
-        // ---- (E) emit tokens of reachable positions, in order (block-wide exclusive scan of element counts)
-        const unsigned per = (L::SEG + LZ_THREADS - 1) / LZ_THREADS;
-        unsigned cnt[(L::SEG + LZ_THREADS - 1) / LZ_THREADS], mine = 0;
-        for (unsigned j = 0; j < per; j++) {               // a thread owns CONSECUTIVE positions
-          unsigned li = tid * per + j;
-          unsigned c = 0;
-          if (li < slen && reach[li]) c = mlen[li] ? 2 : 1;
-          cnt[j] = c; mine += c;
+        __syncthreads();
+        // token list of each stretch (lane 0 walks it) + element counts
+        if (wid < NSW && lane == 0) {
+          const unsigned e = min((wid + 1) * STRETCH, slen);
+          unsigned p = ent[wid], nt = 0, el = 0;
+          while (p < e) {
+            const unsigned nx = nxt[p];
+            ex[wid * STRETCH + nt] = (unsigned short)p;
+            nt++;
+            el += (nx - p > 1) ? 2 : 1;
+            p = nx;
+          }
+          ent[30 + wid] = nt;
+          misc[wid] = el;
         }
-        unsigned incl = warp_incl_scan(mine);
-        if (lane == 31) misc[wid] = incl;
         __syncthreads();
         if (wid == 0) {
-          unsigned t = misc[lane];
+          unsigned t = lane < NSW ? misc[lane] : 0;
           unsigned ti = warp_incl_scan(t);
-          misc[lane] = ti - t;
-          if (lane == 31) misc[34] = ti;                  // elements emitted by this step
+          if (lane < NSW) misc[lane] = ti - t;
+          if (lane == 31) misc[35] = ti;                   // elements emitted by this step
         }
         __syncthreads();
-        unsigned pos = misc[32] + misc[wid] + incl - mine;
-        for (unsigned j = 0; j < per; j++) {
-          unsigned li = tid * per + j;
-          if (!cnt[j]) continue;
-          unsigned l = mlen[li];
-          if (l) {
-            unsigned d = mdist[li];
-            tok[pos] = (unsigned short)(0x8000u | l);
-            tok[pos + 1] = (unsigned short)(d - 1);
-            unsigned sym, nb, ev;
-            len_symbol(l, sym, nb, ev);
-            atomicAdd(&shist[sym], 1u);
-            dist_symbol(d, sym, nb, ev);
-            atomicAdd(&shist[288 + sym], 1u);
-            if (li + l >= slen) misc[33] = li + l - slen;   // the one reachable position that leaves the step
-            pos += 2;
-          } else {
-            unsigned b = ring[(s0 + li + off0) & 0xffffu];
-            tok[pos] = (unsigned short)b;
-            atomicAdd(&shist[b], 1u);
-            if (li + 1 >= slen) misc[33] = 0;
-            pos += 1;
+        if (wid < NSW) {
+          const unsigned nt = ent[30 + wid];
+          unsigned base = run_tok + misc[wid];
+          for (unsigned k0 = 0; k0 < nt; k0 += 32) {
+            const unsigned k = k0 + lane;
+            unsigned li = 0, l = 0, cnt = 0;
+            if (k < nt) { li = ex[wid * STRETCH + k]; l = mlen[li]; cnt = l ? 2 : 1; }
+            const unsigned incl = warp_incl_scan(cnt);
+            const unsigned pos = base + incl - cnt;
+            if (cnt == 2) {
+              const unsigned d = mdist[li];
+              tok[pos] = (unsigned short)(0x8000u | l);
+              tok[pos + 1] = (unsigned short)(d - 1);
+              unsigned sym, nb, ev;
+              len_symbol(l, sym, nb, ev);
+              atomicAdd(&shist[sym], 1u);
+              dist_symbol(d, sym, nb, ev);
+              atomicAdd(&shist[288 + sym], 1u);
+            } else if (cnt == 1) {
+              const unsigned b = ring[(s0 + li + off0) & 0xffffu];
+              tok[pos] = (unsigned short)b;
+              atomicAdd(&shist[b], 1u);
+            }
+            base += __shfl_sync(0xffffffffu, incl, 31);
           }
         }
-        __syncthreads();
-        if (tid == 0) misc[32] += misc[34];
+        run_tok += misc[35];
       } else {
-        if (tid == 0) misc[33] = start - slen;
+        if (tid == 0) misc[33 + ((step + 1) & 1)] = start - slen;
       }
       __syncthreads();
     }
 
     // ---- segment done: publish histogram + token count
     for (unsigned i = tid; i < HIST_STRIDE; i += LZ_THREADS) hist[(size_t)sidx * HIST_STRIDE + i] = shist[i];
-    if (tid == 0) so[sidx].n_tok = misc[32];
+    if (tid == 0) so[sidx].n_tok = run_tok;
     __syncthreads();
   }
 }

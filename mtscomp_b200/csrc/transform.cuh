@@ -202,6 +202,79 @@ __global__ void __launch_bounds__(512) inv_apply_kernel(const T* __restrict__ in
   }
 }
 
+// ------------------------------------------------------------------------------------------------ fast paths
+// Default layout ('F' order, time diff only, the reference's defaults): no shared memory at all.  A thread owns one
+// channel and a run of R = 32 / sizeof(T) consecutive samples, i.e. one 32-byte sector of the channel-major side.
+// On the row-major side the 32 lanes of a warp touch 32 consecutive channels of a row (contiguous bytes).
+template <class T> struct ColRun { static const int R = 32 / sizeof(T); };
+
+template <class T>
+__global__ void __launch_bounds__(128) fwd_cols_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                       const ChunkDesc* __restrict__ chunks, int nc, int flags) {
+  const int R = ColRun<T>::R;
+  const ChunkDesc cd = chunks[blockIdx.z];
+  const int ns = cd.ns;
+  const int c = blockIdx.x * 32 + (int)lane_id();
+  const int t0 = (blockIdx.y * 4 + (int)warp_id()) * R;
+  if (t0 >= ns || c >= nc) return;
+  const T* x = src + cd.elem_off;
+  T* y = dst + cd.elem_off + (long long)c * ns + t0;
+  const bool td = (flags & FLAG_TIME_DIFF) != 0;
+  const int rows = min(R, ns - t0);
+  T v[R];
+  T prev = (td && t0 > 0) ? x[(long long)(t0 - 1) * nc + c] : (T)0;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    T cur = (r < rows) ? x[(long long)(t0 + r) * nc + c] : (T)0;
+    v[r] = td ? (T)(cur - prev) : cur;
+    prev = cur;
+  }
+  if (rows == R && ((uintptr_t)y & 15) == 0) {
+    uint4 a, b;
+    memcpy(&a, &v[0], 16);
+    memcpy(&b, &v[R / 2], 16);
+    ((uint4*)y)[0] = a;
+    ((uint4*)y)[1] = b;
+  } else {
+    for (int r = 0; r < rows; r++) y[r] = v[r];
+  }
+}
+
+// Inverse of the above: per-channel running sum seeded by the scanned tile sums (tile = TT rows, TT % R == 0).
+template <class T>
+__global__ void __launch_bounds__(128) inv_cols_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                       const T* __restrict__ partial,
+                                                       const ChunkDesc* __restrict__ chunks, int nc, int TT,
+                                                       int max_tiles, int flags) {
+  const int R = ColRun<T>::R;
+  const ChunkDesc cd = chunks[blockIdx.z];
+  const int ns = cd.ns;
+  const int c = blockIdx.x * 128 + (int)threadIdx.x;
+  const int t0 = blockIdx.y * TT;
+  if (t0 >= ns || c >= nc) return;
+  const T* x = in + cd.elem_off + (long long)c * ns;
+  T* y = out + cd.elem_off;
+  const bool td = (flags & FLAG_TIME_DIFF) != 0;
+  T run = td ? partial[((long long)blockIdx.z * max_tiles + blockIdx.y) * nc + c] : (T)0;
+  const int tend = min(t0 + TT, ns);
+  for (int t = t0; t < tend; t += R) {
+    const int rows = min(R, tend - t);
+    T v[R];
+    if (rows == R && ((uintptr_t)(x + t) & 15) == 0) {
+      uint4 a = ((const uint4*)(x + t))[0], b = ((const uint4*)(x + t))[1];
+      memcpy(&v[0], &a, 16);
+      memcpy(&v[R / 2], &b, 16);
+    } else {
+      for (int r = 0; r < R; r++) v[r] = (r < rows) ? x[t + r] : (T)0;
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      if (td) { run = (T)(run + v[r]); v[r] = run; }
+      if (r < rows) y[(long long)(t + r) * nc + c] = v[r];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ adler32
 // One CTA per segment: standalone adler32 of bytes [off, off+len) (i.e. starting from adler = 1).  Segments are
 // folded per chunk with zlib's adler32_combine rule by adler_combine_kernel / the deflate scan.
