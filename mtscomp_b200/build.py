@@ -31,6 +31,8 @@ def build_native(force=False, verbose=False):
            '-Xcompiler', '-fPIC', '-shared', '-o', str(LIB)] + [str(CSRC / s) for s in SOURCES]
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
+    if os.environ.get('MTS_LZ_PROFILE'):
+        cmd.insert(1, '-DMTS_LZ_PROFILE')
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)

@@ -323,7 +323,7 @@ int mtsb_set_param(mtsb_ctx* c, const char* name, long long v) {
   else if (s == "far4") c->lz.far4 = (int)v;
   else if (s == "far5") c->lz.far5 = (int)v;
   else if (s == "far6") c->lz.far6 = (int)v;
-  else if (s == "lazy") c->lz.lazy = v ? 1 : 0;
+  else if (s == "lazy") c->lz.lazy = (int)v;
   else return fail(c, MTSB_E_ARG, "unknown parameter %s", name);
   return 0;
 }
@@ -350,6 +350,17 @@ long long mtsb_compress_bound(mtsb_ctx* c, long long raw_bytes, long long ns, in
   (void)nc;
   return chunk_bound(c, raw_bytes, seg_size_for(c, ns, itemsize, flags));
 }
+
+#if defined(MTS_LZ_PROFILE) && !defined(MTSCOMP_EMU)
+// development only (not in the public header): read and reset the lz77 phase counters
+int mtsb_debug_lz_profile(unsigned long long* out16) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out16, g_lz_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(g_lz_prof, z, sizeof z);
+  return 0;
+}
+#endif
 
 int mtsb_last_timings(mtsb_ctx* c, float* out, int n) {
   if (!c || !out) return 0;
@@ -872,7 +883,15 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
     }
     c->end();
     c->begin(2);
-    MTS_LAUNCH(inflate_kernel, dim3(n_segs), dim3(32), 0, c->stream, dcomp, (const InflateSeg*)(d + o_seg), n_segs, (unsigned char*)c->d_T.p, (int*)c->d_status.p, (unsigned*)c->d_tadler.p);
+    if (n_segs >= 6 * c->sm_count) {
+      // many short streams: global-memory window, 2 warps per CTA, up to 64 warps per SM
+      auto k = inflate_kernel<false, 2>;
+      MTS_LAUNCH(k, dim3((n_segs + 1) / 2), dim3(64), 0, c->stream, dcomp, (const InflateSeg*)(d + o_seg), n_segs, (unsigned char*)c->d_T.p, (int*)c->d_status.p, (unsigned*)c->d_tadler.p);
+    } else {
+      // few long streams: shared-memory window, one warp per CTA
+      auto k = inflate_kernel<true, 1>;
+      MTS_LAUNCH(k, dim3(n_segs), dim3(32), 0, c->stream, dcomp, (const InflateSeg*)(d + o_seg), n_segs, (unsigned char*)c->d_T.p, (int*)c->d_status.p, (unsigned*)c->d_tadler.p);
+    }
     CKL();
     c->launches++;
     c->end();

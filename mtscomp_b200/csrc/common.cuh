@@ -26,6 +26,15 @@ enum { FLAG_TIME_DIFF = 1, FLAG_SPATIAL_DIFF = 2, FLAG_ORDER_C = 4 };
 
 static const uint32_t ADLER_BASE = 65521u;
 
+// Barrier among `count` threads (a multiple of 32) of the CTA on hardware barrier `id` (1..15; 0 is __syncthreads).
+__device__ __forceinline__ void named_barrier(int id, int count) {
+#ifdef MTSCOMP_EMU
+  __emu_named_barrier(id, count);
+#else
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ unsigned warp_id() { return threadIdx.x >> 5; }
 

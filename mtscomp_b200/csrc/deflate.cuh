@@ -96,11 +96,13 @@ template <int STRIDE> struct LzSmem {
   static const size_t heads_off = headl_off + (size_t)(1 << HL_BITS) * 2;
   static const size_t prevl_off = heads_off + (size_t)(1 << LZ_HASHS_BITS) * 2;
   static const size_t prevs_off = prevl_off + (size_t)PREV_N * 2;
-  static const size_t mlen_off = prevs_off + (size_t)(2 * LZ_UNITS) * 2;
+  static const size_t hbuf_off = prevs_off + (size_t)(2 * LZ_UNITS) * 2;   // [2 steps][S,L][LZ_UNITS] u16 hashes
+  static const size_t mlen_off = hbuf_off + (size_t)(4 * LZ_UNITS) * 2;
   static const size_t mdist_off = mlen_off + (size_t)(SEG + 8) * 2;
   static const size_t jump_off = mdist_off + (size_t)(SEG + 8) * 2;
   static const size_t jump2_off = jump_off + (size_t)(SEG + 8) * 2;
-  static const size_t hist_off = (jump2_off + (size_t)(SEG + 8) * 2 + 15) & ~(size_t)15;
+  static const size_t flag_off = jump2_off + (size_t)(SEG + 8) * 2;             // reachability flags, one byte per position
+  static const size_t hist_off = (flag_off + (size_t)(SEG + 8) + 15) & ~(size_t)15;
   static const size_t misc_off = hist_off + (size_t)HIST_STRIDE * 4;
   static const size_t total = misc_off + 512;
 };
@@ -116,42 +118,67 @@ template <int BITS> __device__ __forceinline__ unsigned lz_hash6(unsigned w0, un
   return ((w0 * 0x9E3779B1u) ^ ((w1 & 0xffffu) * 0x85EBCA6Bu)) >> (32 - BITS);
 }
 
-// Thread `units` consecutive units starting at unit u0 into one hash table, in position order (one warp).
-// LONG: key = 6 bytes, links go to the prev ring (index u & pmask); otherwise key = 4 bytes, links go to a two-step
-// array (index u % (2 * LZ_UNITS)).
-template <int STRIDE, bool LONG>
-__device__ __forceinline__ void lz_insert_step(const unsigned char* ring, unsigned short* head, unsigned short* prev,
-                                               unsigned u0, unsigned units, unsigned n, unsigned off0, unsigned lane) {
-  const unsigned PM = LzSmem<STRIDE>::PREV_N - 1;
-  const unsigned KEY = LONG ? 6 : 4;
-  for (unsigned b = 0; b < units; b += 32) {
-    const unsigned u = u0 + b + lane;
-    const unsigned p = u * STRIDE;
-    const bool valid = (b + lane < units) && (p + KEY <= n);
-    const unsigned short ub = (unsigned short)(u + LZ_BIAS);
-    unsigned h = 0;
-    unsigned short old = 0;
-    if (valid) {
-      unsigned w0 = ring_load4(ring, p + off0);
-      h = LONG ? lz_hash6<LzSmem<STRIDE>::HL_BITS>(w0, ring_load4(ring, p + off0 + 4)) : lz_hash4(w0);
-      old = head[h];
-    }
-    __syncwarp();
-    if (valid) head[h] = ub;                         // same-hash lanes collide: an arbitrary one wins for now
-    __syncwarp();
-    const bool clash = valid && head[h] != ub;
-    unsigned short pv = old;
-    if (__any_sync(0xffffffffu, clash)) {
-      // rare (runs, repeated samples inside 32 units): order the colliding lanes explicitly
-      const unsigned grp = __match_any_sync(0xffffffffu, valid ? h : (0x10000u + lane));
-      const unsigned lower = grp & ((1u << lane) - 1);
-      if (lower) pv = (unsigned short)(u - lane + (31 - __clz((int)lower)) + LZ_BIAS);
-      __syncwarp();
-      if (valid && (grp >> lane) == 1u) head[h] = ub;   // the last unit of each group is the new head
-    }
-    if (b + lane < units) prev[LONG ? (u & PM) : (u % (2 * LZ_UNITS))] = valid ? pv : (unsigned short)ub;
-    __syncwarp();
+// Hashes of the unit at position p for both tables, 0xffff where the key would run past the end of the segment.
+// (Computed by the searcher threads two steps ahead of their use, so the serial inserters only touch the tables.)
+template <int STRIDE>
+__device__ __forceinline__ void lz_unit_hashes(const unsigned char* ring, unsigned p, unsigned n, unsigned off0,
+                                               unsigned short& hs, unsigned short& hl) {
+  hs = 0xffff; hl = 0xffff;
+  if (p + 4 <= n) {
+    const unsigned w0 = ring_load4(ring, p + off0);
+    hs = (unsigned short)lz_hash4(w0);
+    if (p + 6 <= n) hl = (unsigned short)lz_hash6<LzSmem<STRIDE>::HL_BITS>(w0, ring_load4(ring, p + off0 + 4));
   }
+}
+
+// Thread `units` consecutive units starting at unit u0 into one hash table (one warp), batches of 32 units in position
+// order.  Every unit links to the table head as it was BEFORE its batch (units of one batch never link to each other:
+// such matches are < 32 units away and the next batch finds them anyway), then the batch's LAST unit of each hash
+// becomes the new head: colliding lanes re-store until the highest one has won, so the result does not depend on how
+// the hardware orders same-address stores.  No __match_any_sync: it costs > 1000 cycles per call on sm_100.
+// LONG: links go to the prev ring (index u & pmask); otherwise to a two-step array.
+template <int STRIDE, bool LONG>
+__device__ __forceinline__ void lz_insert_step(const unsigned short* hbuf, unsigned short* head, unsigned short* prev,
+                                               unsigned u0, unsigned units, unsigned lane) {
+  const unsigned PM = LzSmem<STRIDE>::PREV_N - 1;
+  // Four batches per round trip.  Lookups and stores are issued back to back (shared memory is in order per warp, so
+  // batch j+1 sees batch j's stores); the read-back that settles same-hash collisions inside a batch is done once per
+  // group: a lane only re-stores while an EARLIER unit of its own batch is visible, so stores of later batches stand.
+  const unsigned pbase = LONG ? 0 : (u0 % (2 * LZ_UNITS));     // S links live in a two-step array
+  for (unsigned g = 0; g < units; g += 128) {
+    unsigned h[4];
+    unsigned short old[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const unsigned i = g + 32 * j + lane;
+      h[j] = (i < units) ? hbuf[i] : 0xffffu;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const unsigned short ub = (unsigned short)(u0 + g + 32 * j + lane + LZ_BIAS);
+      old[j] = ub;                                             // invalid units link to themselves (distance 0 = none)
+      if (h[j] != 0xffffu) { old[j] = head[h[j]]; head[h[j]] = ub; }
+      __syncwarp();
+    }
+    bool want;
+    do {
+      want = false;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const unsigned short ub = (unsigned short)(u0 + g + 32 * j + lane + LZ_BIAS);
+        const bool w = h[j] != 0xffffu && (unsigned short)(ub - head[h[j]] - 1) < 31;
+        if (w) head[h[j]] = ub;
+        want |= w;
+      }
+      __syncwarp();
+    } while (__any_sync(0xffffffffu, want));
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const unsigned i = g + 32 * j + lane;
+      if (i < units) prev[LONG ? ((u0 + i) & PM) : (pbase + i)] = old[j];
+    }
+  }
+  __syncwarp();
 }
 
 // Length of the match between ring positions pr (whose first 16 bytes are w0..w3) and qr, up to lim.
@@ -172,6 +199,17 @@ __device__ __forceinline__ unsigned lz_match_len(const unsigned char* ring, unsi
   return min(len, lim);
 }
 
+#if defined(MTS_LZ_PROFILE) && !defined(MTSCOMP_EMU)
+// development instrumentation: cycles per phase, summed over steps and CTAs
+// [0] steps [1] A/B phase (thread 0) [2] thread 0's own search [3] S inserter [4] L inserter [5] parse+emit phase
+__device__ unsigned long long g_lz_prof[16];
+#define LZ_PROF_T(var) long long var = clock64()
+#define LZ_PROF_ADD(i, v) do { if (blockIdx.x == 0) atomicAdd(&g_lz_prof[i], (unsigned long long)(v)); } while (0)
+#else
+#define LZ_PROF_T(var)
+#define LZ_PROF_ADD(i, v)
+#endif
+
 template <int STRIDE>
 __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char* __restrict__ tbuf,
                                                              const DeflateSeg* __restrict__ segs, int n_segs,
@@ -189,13 +227,15 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
   unsigned short* headS = (unsigned short*)(sm + L::heads_off);
   unsigned short* prevL = (unsigned short*)(sm + L::prevl_off);
   unsigned short* prevS = (unsigned short*)(sm + L::prevs_off);
+  unsigned short* hbuf = (unsigned short*)(sm + L::hbuf_off);   // hbuf[(step & 1) * 2 * LZ_UNITS + (LONG ? LZ_UNITS : 0) + k]
   unsigned short* mlen = (unsigned short*)(sm + L::mlen_off);
   unsigned short* mdist = (unsigned short*)(sm + L::mdist_off);
-  unsigned short* nxt = (unsigned short*)(sm + L::jump_off);     // next token position per position
-  unsigned short* ex = (unsigned short*)(sm + L::jump2_off);     // stage 1: stretch exit; stage 3: token list
+  unsigned short* ex = (unsigned short*)(sm + L::jump_off);      // stage 1: exit of the stretch; stage 3: jump pointers
+  unsigned short* ec = (unsigned short*)(sm + L::jump2_off);     // stage 1: token elements emitted up to the stretch exit
+  unsigned char* rf = sm + L::flag_off;                           // stage 3: position is a token start
   unsigned* shist = (unsigned*)(sm + L::hist_off);
-  unsigned* misc = (unsigned*)(sm + L::misc_off);   // [0..29] per-warp element counts / bases, [33],[34] carry, [36..] entries
-  unsigned* ent = misc + 36;                         // [0..29] parse entry position of each stretch, [30..59] token counts
+  unsigned* misc = (unsigned*)(sm + L::misc_off);   // [0..29] element base of each stretch, [33],[34] carry, [35] step total
+  unsigned* ent = misc + 36;                         // [0..29] parse entry position of each stretch
   const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned PM = L::PREV_N - 1;
 
@@ -209,17 +249,27 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
     const unsigned n_ring = n + off0;                    // ring coordinates [off0, n_ring) are real input
     unsigned run_tok = 0;                                // token elements emitted so far (uniform across threads)
 
-    // reset tables (headL and headS are contiguous); initial load: ring coordinates [0, 3*SEG)
+    // reset tables (headL and headS are contiguous); initial load: ring coordinates [0, 3*SEG + 32) (the hashes of
+    // step 2 read up to 3*SEG + 8 + 15)
     for (unsigned i = tid; i < ((1u << L::HL_BITS) + (1u << LZ_HASHS_BITS)) / 2; i += LZ_THREADS) ((unsigned*)headL)[i] = 0;
     for (unsigned i = tid; i < HIST_STRIDE; i += LZ_THREADS) shist[i] = 0;
     if (tid == 0) { misc[33] = 0; misc[34] = 0; }
-    for (unsigned v = tid; v * 16 < 3 * SEG; v += LZ_THREADS)
+    for (unsigned v = tid; v * 16 < 3 * SEG + 32; v += LZ_THREADS)
       if (v * 16 < n_ring) *(uint4*)(ring + v * 16) = in16[v];
+    __syncthreads();
+    // hashes of the units of steps 0 and 1 (later steps: computed two steps ahead by the searchers)
+    for (unsigned k = tid; k < 2 * LZ_UNITS; k += LZ_THREADS) {
+      unsigned short hs, hl;
+      lz_unit_hashes<STRIDE>(ring, k * STRIDE, n, off0, hs, hl);
+      const unsigned st = k / LZ_UNITS, kk = k % LZ_UNITS;
+      hbuf[st * 2 * LZ_UNITS + kk] = hs;
+      hbuf[st * 2 * LZ_UNITS + LZ_UNITS + kk] = hl;
+    }
     __syncthreads();
     {
       const unsigned units0 = min((unsigned)LZ_UNITS, (n + STRIDE - 1) / STRIDE);
-      if (wid == 30) lz_insert_step<STRIDE, false>(ring, headS, prevS, 0, units0, n, off0, lane);
-      if (wid == 31) lz_insert_step<STRIDE, true>(ring, headL, prevL, 0, units0, n, off0, lane);
+      if (wid == 30) lz_insert_step<STRIDE, false>(hbuf, headS, prevS, 0, units0, lane);
+      if (wid == 31) lz_insert_step<STRIDE, true>(hbuf + LZ_UNITS, headL, prevL, 0, units0, lane);
     }
     __syncthreads();
 
@@ -228,28 +278,29 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
       const unsigned s0 = step * SEG;                    // first position of this step
       const unsigned slen = min(SEG, n - s0);
 
+      LZ_PROF_T(t_step);
       if (wid >= NSW) {
         // ---- (A) inserters (the two highest warp ids: the issue arbiter favours them over the searchers): prefetch
         //          ring coordinates [(step+3)*SEG, (step+4)*SEG) and thread step+1's units into the tables
-        if (wid == 30) {
-          const unsigned base = (step + 3) * SEG;
-          for (unsigned v = lane; v * 16 < SEG; v += 32) {
-            unsigned rc = base + v * 16;
-            if (rc < n_ring) *(uint4*)(ring + (rc & 0xffffu)) = in16[rc >> 4];
-          }
-        }
         const unsigned s1 = s0 + SEG;
         if (s1 < n) {
           const unsigned units1 = (min(SEG, n - s1) + STRIDE - 1) / STRIDE;
-          if (wid == 30) lz_insert_step<STRIDE, false>(ring, headS, prevS, s1 / STRIDE, units1, n, off0, lane);
-          else lz_insert_step<STRIDE, true>(ring, headL, prevL, s1 / STRIDE, units1, n, off0, lane);
+          const unsigned short* hb = hbuf + ((step + 1) & 1) * 2 * LZ_UNITS;
+          if (wid == 30) lz_insert_step<STRIDE, false>(hb, headS, prevS, s1 / STRIDE, units1, lane);
+          else lz_insert_step<STRIDE, true>(hb + LZ_UNITS, headL, prevL, s1 / STRIDE, units1, lane);
         }
+        if (lane == 0) { LZ_PROF_T(t_i); LZ_PROF_ADD(wid == 30 ? 3 : 4, t_i - t_step); }
       } else {
-        // ---- (B) searchers: one unit per thread
+        // ---- (B) searchers: one unit per thread.  The first SEG/16 of them also prefetch ring coordinates
+        //      [(step+3)*SEG + 32, (step+4)*SEG + 32): load now, store after the search has hidden the latency.
         const unsigned li = tid * STRIDE;                 // local position in the step
         const unsigned p = s0 + li;
         unsigned best = 0, bdist = 0;
-        if (li < slen && p + 4 <= n) {
+        const unsigned pf_rc = (step + 3) * SEG + 32 + tid * 16;
+        const bool pf = tid * 16 < SEG && pf_rc < n_ring;
+        uint4 pf_v = make_uint4(0, 0, 0, 0);
+        if (pf) pf_v = in16[pf_rc >> 4];
+        if (li < slen && p + 4 <= n && prm.lazy != 2) {
           const unsigned u = p / STRIDE;
           const unsigned lim = min(258u, n - p);
           const unsigned pr = p + off0;
@@ -296,6 +347,16 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
             }
           }
         }
+        {
+          // hashes of this thread's unit two steps ahead (consumed by the inserters during the next step)
+          unsigned short hs, hl;
+          lz_unit_hashes<STRIDE>(ring, p + 2 * SEG, n, off0, hs, hl);
+          unsigned short* hb = hbuf + (step & 1) * 2 * LZ_UNITS;
+          hb[tid] = hs;
+          hb[LZ_UNITS + tid] = hl;
+        }
+        if (pf) *(uint4*)(ring + (pf_rc & 0xffffu)) = pf_v;
+        if (tid == 0) { LZ_PROF_T(t_s); LZ_PROF_ADD(2, t_s - t_step); }
         mlen[li] = (unsigned short)(bdist ? best : 0);
         mdist[li] = (unsigned short)bdist;
         if (STRIDE > 1) {
@@ -313,92 +374,125 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
             for (unsigned j = 1; j < (unsigned)STRIDE; j++) { mlen[li + j] = 0; mdist[li + j] = 0; }
         }
       }
-      __syncthreads();
-
-      // ---- (C) greedy parse, hierarchical: per-warp stretches resolved by pointer doubling, chained by one thread
+      // The 30 searcher warps now parse and emit the step among themselves (hardware barrier 1, 960 threads); the two
+      // inserter warps keep threading step+1 into the tables and only rejoin at the end of the step.
+      if (wid < NSW) {
+      named_barrier(1, NSW * 32);
+      // ---- (C) greedy parse, hierarchical.  Stage 1: every warp resolves its stretch by pointer doubling (for each
+      //      position: where the token chain leaves the stretch and how many token elements it emits on the way).
+      //      Stage 2: one thread chains the 30 stretches from the carried start (entry + element base per stretch).
+      //      Stage 3: every warp marks the token starts reachable from its entry (doubling again) and emits them.
       const unsigned start = misc[33 + (step & 1)];       // local start position carried from the previous step
       if (start < slen) {
+        const unsigned sb = wid * STRETCH, se = min(sb + STRETCH, slen);
+        unsigned j[PER_LANE], c[PER_LANE];
         if (wid < NSW) {
-          const unsigned e = min((wid + 1) * STRETCH, slen);
-          unsigned j[PER_LANE];
           for (unsigned k = 0; k < PER_LANE; k++) {
-            const unsigned i = wid * STRETCH + lane * PER_LANE + k;
-            unsigned nx = i + 1;
-            if (i < e) { unsigned l = mlen[i]; nx = i + (l ? l : 1u); nxt[i] = (unsigned short)nx; }
-            j[k] = nx;
-            ex[i] = (unsigned short)nx;
+            const unsigned i = sb + lane * PER_LANE + k;
+            const unsigned l = (i < se) ? mlen[i] : 0;
+            j[k] = i + (l ? l : 1u);
+            c[k] = (i < se) ? (l ? 2u : 1u) : 0u;
+            ex[i] = (unsigned short)j[k];
+            ec[i] = (unsigned short)c[k];
           }
           __syncwarp();
           for (unsigned r = 1; r < STRETCH; r <<= 1) {
-            for (unsigned k = 0; k < PER_LANE; k++) if (j[k] < e) j[k] = ex[j[k]];
+            for (unsigned k = 0; k < PER_LANE; k++)
+              if (j[k] < se) { c[k] += ec[j[k]]; j[k] = ex[j[k]]; }
             __syncwarp();
-            for (unsigned k = 0; k < PER_LANE; k++) ex[wid * STRETCH + lane * PER_LANE + k] = (unsigned short)j[k];
+            for (unsigned k = 0; k < PER_LANE; k++) {
+              const unsigned i = sb + lane * PER_LANE + k;
+              ex[i] = (unsigned short)j[k];
+              ec[i] = (unsigned short)c[k];
+            }
             __syncwarp();
           }
         }
-        __syncthreads();
+        named_barrier(1, NSW * 32);
         if (tid == 0) {
-          unsigned p = start;
+          unsigned p = start, acc = 0;
           for (unsigned w = 0; w < NSW; w++) {
             ent[w] = p;
-            if (p < min((w + 1) * STRETCH, slen)) p = ex[p];
+            misc[w] = acc;
+            if (p < min((w + 1) * STRETCH, slen)) { acc += ec[p]; p = ex[p]; }
           }
+          misc[35] = acc;                                   // elements emitted by this step
           misc[33 + ((step + 1) & 1)] = p - slen;          // p >= slen: where the last token of this step ends
         }
-        __syncthreads();
-        // token list of each stretch (lane 0 walks it) + element counts
-        if (wid < NSW && lane == 0) {
-          const unsigned e = min((wid + 1) * STRETCH, slen);
-          unsigned p = ent[wid], nt = 0, el = 0;
-          while (p < e) {
-            const unsigned nx = nxt[p];
-            ex[wid * STRETCH + nt] = (unsigned short)p;
-            nt++;
-            el += (nx - p > 1) ? 2 : 1;
-            p = nx;
-          }
-          ent[30 + wid] = nt;
-          misc[wid] = el;
-        }
-        __syncthreads();
-        if (wid == 0) {
-          unsigned t = lane < NSW ? misc[lane] : 0;
-          unsigned ti = warp_incl_scan(t);
-          if (lane < NSW) misc[lane] = ti - t;
-          if (lane == 31) misc[35] = ti;                   // elements emitted by this step
-        }
-        __syncthreads();
+        named_barrier(1, NSW * 32);
         if (wid < NSW) {
-          const unsigned nt = ent[30 + wid];
-          unsigned base = run_tok + misc[wid];
-          for (unsigned k0 = 0; k0 < nt; k0 += 32) {
-            const unsigned k = k0 + lane;
-            unsigned li = 0, l = 0, cnt = 0;
-            if (k < nt) { li = ex[wid * STRETCH + k]; l = mlen[li]; cnt = l ? 2 : 1; }
-            const unsigned incl = warp_incl_scan(cnt);
-            const unsigned pos = base + incl - cnt;
-            if (cnt == 2) {
-              const unsigned d = mdist[li];
-              tok[pos] = (unsigned short)(0x8000u | l);
-              tok[pos + 1] = (unsigned short)(d - 1);
-              unsigned sym, nb, ev;
-              len_symbol(l, sym, nb, ev);
-              atomicAdd(&shist[sym], 1u);
-              dist_symbol(d, sym, nb, ev);
-              atomicAdd(&shist[288 + sym], 1u);
-            } else if (cnt == 1) {
-              const unsigned b = ring[(s0 + li + off0) & 0xffffu];
-              tok[pos] = (unsigned short)b;
-              atomicAdd(&shist[b], 1u);
+          const unsigned entry = ent[wid];
+          if (entry < se) {                                 // warp-uniform
+            unsigned jm[PER_LANE];
+            for (unsigned k = 0; k < PER_LANE; k++) {
+              const unsigned i = sb + lane * PER_LANE + k;
+              const unsigned l = (i < se) ? mlen[i] : 0;
+              jm[k] = i + (l ? l : 1u);
+              ex[i] = (unsigned short)jm[k];
+              rf[i] = (i == entry);
             }
-            base += __shfl_sync(0xffffffffu, incl, 31);
+            __syncwarp();
+            for (unsigned r = 1; r < STRETCH; r <<= 1) {
+              unsigned jn[PER_LANE];
+              for (unsigned k = 0; k < PER_LANE; k++) {
+                const unsigned i = sb + lane * PER_LANE + k;
+                if (jm[k] < se && rf[i]) rf[jm[k]] = 1;
+                jn[k] = (jm[k] < se) ? ex[jm[k]] : jm[k];
+              }
+              __syncwarp();
+              for (unsigned k = 0; k < PER_LANE; k++) {
+                ex[sb + lane * PER_LANE + k] = (unsigned short)jn[k];
+                jm[k] = jn[k];
+              }
+              __syncwarp();
+            }
+            // emit: element offset of a token = elements of the reachable tokens before it (ballot prefix)
+            unsigned pre = run_tok + misc[wid];
+            unsigned lens[PER_LANE];
+            bool isr[PER_LANE];
+            for (unsigned k = 0; k < PER_LANE; k++) {
+              const unsigned i = sb + lane * PER_LANE + k;
+              isr[k] = (i < se) && rf[i];
+              lens[k] = isr[k] ? mlen[i] : 0;
+            }
+            unsigned mine = 0;
+            for (unsigned k = 0; k < PER_LANE; k++) mine += isr[k] ? (lens[k] ? 2u : 1u) : 0u;
+            // exclusive prefix over lanes of `mine` (0..4) from two ballots per bit plane
+            const unsigned lt = (1u << lane) - 1;
+            unsigned excl = __popc(__ballot_sync(0xffffffffu, mine & 1) & lt) +
+                            2 * __popc(__ballot_sync(0xffffffffu, mine & 2) & lt) +
+                            4 * __popc(__ballot_sync(0xffffffffu, mine & 4) & lt);
+            unsigned pos = pre + excl;
+            for (unsigned k = 0; k < PER_LANE; k++) {
+              if (!isr[k]) continue;
+              const unsigned li = sb + lane * PER_LANE + k;
+              const unsigned l = lens[k];
+              if (l) {
+                const unsigned d = mdist[li];
+                tok[pos] = (unsigned short)(0x8000u | l);
+                tok[pos + 1] = (unsigned short)(d - 1);
+                unsigned sym, nb, ev;
+                len_symbol(l, sym, nb, ev);
+                atomicAdd(&shist[sym], 1u);
+                dist_symbol(d, sym, nb, ev);
+                atomicAdd(&shist[288 + sym], 1u);
+                pos += 2;
+              } else {
+                const unsigned bt = ring[(s0 + li + off0) & 0xffffu];
+                tok[pos] = (unsigned short)bt;
+                atomicAdd(&shist[bt], 1u);
+                pos += 1;
+              }
+            }
           }
         }
         run_tok += misc[35];
       } else {
         if (tid == 0) misc[33 + ((step + 1) & 1)] = start - slen;
       }
+      }   // wid < NSW
       __syncthreads();
+      if (tid == 0) { LZ_PROF_T(t_end); LZ_PROF_ADD(5, t_end - t_step); }
     }
 
     // ---- segment done: publish histogram + token count

@@ -55,6 +55,7 @@ static void run_block(Block& b, dim3 bd, const std::function<void()>& body) {
   b.nthreads = b.alive = n;
   b.body = &body;
   b.bar_count = 0; b.bar_acc = 0; b.bar_and = 1;
+  for (int i = 0; i < 16; i++) b.nb_count[i] = 0;
   if (b.stacks.size() < n) {
     size_t old = b.stacks.size();
     b.stacks.resize(n);

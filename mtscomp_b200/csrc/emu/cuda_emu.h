@@ -65,6 +65,8 @@ struct Block {
   unsigned bar_gen = 0;
   long bar_acc = 0, bar_result = 0;
   long bar_and = 1, bar_and_result = 1;
+  int nb_count[16] = {0};
+  unsigned nb_gen[16] = {0};
   const std::function<void()>* body = nullptr;
 };
 
@@ -113,6 +115,13 @@ static inline int __syncthreads_and(int p) {
   emu::g_blk->bar_and &= (p != 0);
   __syncthreads();
   return emu::g_blk->bar_and_result != 0;
+}
+// named barrier: `count` threads of the CTA meet at barrier `id` (PTX bar.sync id, count)
+static inline void __emu_named_barrier(int id, int count) {
+  emu::Block* b = emu::g_blk;
+  unsigned g = b->nb_gen[id];
+  if (++b->nb_count[id] == count) { b->nb_count[id] = 0; b->nb_gen[id]++; }
+  else while (b->nb_gen[id] == g) emu::yield();
 }
 static inline unsigned __emu_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }
 static inline emu::Warp& __emu_warp() { return emu::g_blk->warps[__emu_tid() >> 5]; }

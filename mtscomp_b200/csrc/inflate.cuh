@@ -64,40 +64,46 @@ struct InflateWarpSmem {
   unsigned char lens[352];               // [0,19) code-length code, [24, 24+316) literal/length + distance lengths
 };
 
+// LSB-first bit reader over 32-bit words: (lo, hi) hold 64 stream bits, `pos` (< 32 after refill()) is the cursor in
+// them, so 32 bits are always available right after a refill and peek() is one funnel shift.
 struct BitR {
   const unsigned* w;      // 4-byte aligned base
   unsigned sh;            // 8 * (address & 3)
   unsigned kmax;          // last valid word index
-  unsigned k;             // index of the next word to fetch
-  unsigned nextw;         // w[k - 1], already fetched
-  unsigned long long bb;  // bit buffer
-  unsigned bc;            // valid bits in bb
-  unsigned ip;            // stream bytes fetched into bb so far (relative to the stream start)
+  unsigned k;             // index of the next raw word to fetch
+  unsigned raw;           // w[k - 1]: raw word whose upper part belongs to the next stream word
+  unsigned lo, hi;        // stream words n and n+1
+  unsigned pos;           // bit cursor inside (lo, hi)
+  unsigned ip;            // stream bytes represented by lo and everything before it, + 4 (i.e. end of lo)
+  __device__ __forceinline__ unsigned next_word() {
+    unsigned nw = w[min(k, kmax)];
+    unsigned v = __funnelshift_r(raw, nw, sh);
+    raw = nw;
+    k++;
+    return v;
+  }
   // start reading at `p` (= stream start + ip0) with `avail` bytes left
   __device__ __forceinline__ void init(const unsigned char* p, unsigned avail, unsigned ip0) {
     unsigned mis = (unsigned)((uintptr_t)p & 3);
     w = (const unsigned*)(p - mis);
     sh = mis * 8;
     kmax = (mis + max(avail, 1u) - 1) >> 2;
-    nextw = w[0];
+    raw = w[0];
     k = 1;
-    bb = 0; bc = 0; ip = ip0;
+    lo = next_word();
+    hi = next_word();
+    pos = 0;
+    ip = ip0 + 4;
   }
   __device__ __forceinline__ void refill() {
-    if (bc <= 32) {
-      unsigned hi = w[min(k, kmax)];
-      unsigned v = __funnelshift_r(nextw, hi, sh);
-      nextw = hi;
-      k++;
-      bb |= (unsigned long long)v << bc;
-      ip += 4;
-      bc += 32;
-    }
+    if (pos >= 32) { lo = hi; hi = next_word(); pos -= 32; ip += 4; }
   }
-  __device__ __forceinline__ unsigned peek(unsigned n) const { return (unsigned)bb & ((1u << n) - 1); }
-  __device__ __forceinline__ void drop(unsigned n) { bb >>= n; bc -= n; }
-  __device__ __forceinline__ unsigned get(unsigned n) { unsigned v = peek(n); drop(n); return v; }
-  __device__ __forceinline__ unsigned byte_pos() const { return ip - (bc >> 3); }   // bytes fully or partly consumed
+  __device__ __forceinline__ unsigned window() const { return __funnelshift_r(lo, hi, pos); }   // next 32 bits
+  __device__ __forceinline__ unsigned peek(unsigned n) const { return window() & ((1u << n) - 1); }
+  __device__ __forceinline__ void drop(unsigned n) { pos += n; }
+  __device__ __forceinline__ unsigned get(unsigned n) { refill(); unsigned v = peek(n); drop(n); return v; }   // n <= 32
+  __device__ __forceinline__ void align_byte() { pos = (pos + 7) & ~7u; }
+  __device__ __forceinline__ unsigned byte_pos() const { return ip - 4 + ((pos + 7) >> 3); }   // bytes consumed
 };
 
 // Build one decoding table from code lengths lens[0..n): fast table of `tb` bits + canonical arrays for longer codes.
@@ -153,11 +159,11 @@ __device__ bool inflate_build(const unsigned char* lens, int n, unsigned* tab, i
 // Slow path: canonical decode of a code longer than the fast table (puff-style, one bit at a time); returns the
 // symbol's table entry, 0 if no code matches.
 template <int KIND>
-__device__ __noinline__ unsigned inflate_slow(unsigned long long bb, const unsigned short* count,
+__device__ __noinline__ unsigned inflate_slow(unsigned bb, const unsigned short* count,
                                               const unsigned short* sorted) {
   unsigned code = 0, first = 0, index = 0;
   for (int l = 1; l <= 15; l++) {
-    code |= (unsigned)(bb >> (l - 1)) & 1;
+    code |= (bb >> (l - 1)) & 1;
     unsigned c = count[l];
     if (code - first < c) {
       unsigned s = sorted[index + (code - first)];
@@ -175,10 +181,23 @@ __device__ __forceinline__ void fixed_lengths(unsigned char* lens, unsigned lane
   lens[288 + lane] = (lane < 30) ? 5 : 0;
 }
 
+// Window policies.  SMEM: the last 32 KB of output + the batch in flight live in a shared-memory ring (index of
+// position p = (p + a0) mod INF_RING, a0 = output address & 3, so aligned ring words are aligned output words) and are
+// streamed to HBM after every batch: right for few long streams (reference-written chunks).  GLOBAL: bytes go straight
+// to the output buffer and back-references read it (L1/L2): no per-warp shared window, so 64 warps per SM can hide the
+// latency: right for many short streams (the segments of GPU-written chunks).
+template <bool SMEM> struct Win {
+  unsigned char* base;
+  __device__ __forceinline__ unsigned index(unsigned pos, unsigned a0) const { return SMEM ? (pos + a0) % INF_RING : pos; }
+  __device__ __forceinline__ unsigned wrap(unsigned i) const { return (SMEM && i >= INF_RING) ? i - INF_RING : i; }
+  __device__ __forceinline__ unsigned back(unsigned i, unsigned d) const {
+    return (SMEM && i < d) ? i + INF_RING - d : i - d;
+  }
+};
+
 __device__ __forceinline__ unsigned ring_wrap(unsigned i) { return i >= INF_RING ? i - INF_RING : i; }
 
-// Stream bytes [from, to) of the output (ring -> global).  a0 = (address of out) & 3; ring index of position p is
-// (p + a0) mod INF_RING with INF_RING % 4 == 0, so aligned words of the ring are aligned words of the output.
+// Stream bytes [from, to) of the output (ring -> global).
 __device__ __forceinline__ void inflate_flush(const unsigned char* ring, unsigned char* out, unsigned a0, unsigned from,
                                               unsigned to, unsigned lane) {
   if (to <= from) return;
@@ -198,21 +217,26 @@ __device__ __forceinline__ void inflate_flush(const unsigned char* ring, unsigne
   if (lane < g1 - w1) gb[w1 + lane] = ring[(w1 + lane) % INF_RING];
 }
 
-__global__ void __launch_bounds__(32) inflate_kernel(const unsigned char* __restrict__ comp,
-                                                     const InflateSeg* __restrict__ segs, int n_segs,
-                                                     unsigned char* out_base, int* __restrict__ status,
-                                                     unsigned* __restrict__ trailer_adler) {
-  __shared__ InflateWarpSmem S;
-  __shared__ __align__(16) unsigned char ring[INF_RING];
+template <bool SMEM, int WPC>
+__global__ void __launch_bounds__(32 * WPC) inflate_kernel(const unsigned char* __restrict__ comp,
+                                                           const InflateSeg* __restrict__ segs, int n_segs,
+                                                           unsigned char* out_base, int* __restrict__ status,
+                                                           unsigned* __restrict__ trailer_adler) {
+  __shared__ InflateWarpSmem S_all[WPC];
+  __shared__ __align__(16) unsigned char ring_all[SMEM ? INF_RING * WPC : 16];
   const unsigned lane = lane_id();
-  const int sidx = blockIdx.x;
+  const int sidx = blockIdx.x * WPC + (int)warp_id();
   if (sidx >= n_segs) return;
+  InflateWarpSmem& S = S_all[warp_id()];
   const InflateSeg sg = segs[sidx];
   unsigned char* out = out_base + sg.out_off;
   const unsigned out_len = (unsigned)sg.out_len;
   const unsigned char* in = comp + sg.in_off;
   const unsigned in_len = (unsigned)sg.in_len;
-  const unsigned a0 = (unsigned)((uintptr_t)out & 3);
+  const unsigned a0 = SMEM ? (unsigned)((uintptr_t)out & 3) : 0;
+  Win<SMEM> W;
+  W.base = SMEM ? ring_all + (SMEM ? INF_RING * warp_id() : 0) : out;
+  unsigned char* const win = W.base;
 
   BitR br;
   br.init(in, in_len, 0);
@@ -223,7 +247,6 @@ __global__ void __launch_bounds__(32) inflate_kernel(const unsigned char* __rest
   if (sg.flags & INF_ZLIB) {
     if (in_len < 8) err = INF_BAD_HEADER;
     else {
-      br.refill();
       unsigned cmf = br.get(8), flg = br.get(8);
       if ((cmf & 15) != 8 || (cmf >> 4) > 7 || ((cmf << 8) | flg) % 31 != 0 || (flg & 0x20)) err = INF_BAD_HEADER;
     }
@@ -235,8 +258,8 @@ __global__ void __launch_bounds__(32) inflate_kernel(const unsigned char* __rest
     last = br.get(1) != 0;
     unsigned type = br.get(2);
     if (type == 0) {
-      // stored: skip to the byte boundary, LEN / NLEN, raw copy through the ring (later blocks may reference it)
-      br.drop(br.bc & 7);
+      // stored: skip to the byte boundary, LEN / NLEN, raw copy through the window (later blocks may reference it)
+      br.align_byte();
       br.refill();
       unsigned len = br.get(16);
       br.refill();
@@ -247,10 +270,9 @@ __global__ void __launch_bounds__(32) inflate_kernel(const unsigned char* __rest
       if (opos + len > out_len) { err = INF_BAD_SIZE; break; }
       for (unsigned b0 = 0; b0 < len; b0 += 4096) {
         unsigned m = min(4096u, len - b0);
-        for (unsigned i = lane; i < m; i += 32) ring[(opos + a0 + i) % INF_RING] = in[src + b0 + i];
+        for (unsigned i = lane; i < m; i += 32) win[W.index(opos + i, a0)] = in[src + b0 + i];
         __syncwarp();
-        inflate_flush(ring, out, a0, opos, opos + m, lane);
-        __syncwarp();
+        if (SMEM) { inflate_flush(win, out, a0, opos, opos + m, lane); __syncwarp(); }
         opos += m;
       }
       br.init(in + src + len, in_len - (src + len), src + len);   // restart the bit reader after the stored bytes
@@ -318,30 +340,32 @@ __global__ void __launch_bounds__(32) inflate_kernel(const unsigned char* __rest
       int k = 0;
       for (; k < 32; k++) {
         br.refill();
-        unsigned e = S.ltab[br.peek(INF_LBITS)];
-        if ((e & 15) == 0) { e = inflate_slow<1>(br.bb, S.lcount, S.lsorted); if (!e) { err = INF_BAD_CODE; break; } }
-        br.drop(e & 15);
+        unsigned win32 = br.window();
+        unsigned e = S.ltab[win32 & ((1u << INF_LBITS) - 1)];
+        if ((e & 15) == 0) { e = inflate_slow<1>(win32, S.lcount, S.lsorted); if (!e) { err = INF_BAD_CODE; break; } }
         const unsigned kind = e >> 24;
         unsigned val = (e >> 8) & 0xffff;
         if (kind == K_LIT) {
+          br.drop(e & 15);
           if (lane == (unsigned)k) { my_pos = bpos; my_tok = val; }
           bpos += 1;
           continue;
         }
         if (kind != K_LEN) {
+          br.drop(e & 15);
           if (kind == K_EOB) eob = true; else err = INF_BAD_CODE;
           break;
         }
-        const unsigned xb = (e >> 4) & 15;
-        val += br.peek(xb);
-        br.drop(xb);
+        const unsigned cl = e & 15, xb = (e >> 4) & 15;
+        val += (win32 >> cl) & ((1u << xb) - 1);
+        br.drop(cl + xb);
         br.refill();
-        unsigned e2 = S.dtab[br.peek(INF_DBITS)];
-        if ((e2 & 15) == 0) { e2 = inflate_slow<2>(br.bb, S.dcount, S.dsorted); if (!e2) { err = INF_BAD_CODE; break; } }
-        br.drop(e2 & 15);
-        const unsigned xb2 = (e2 >> 4) & 15;
-        const unsigned dist = ((e2 >> 8) & 0xffff) + br.peek(xb2);
-        br.drop(xb2);
+        win32 = br.window();
+        unsigned e2 = S.dtab[win32 & ((1u << INF_DBITS) - 1)];
+        if ((e2 & 15) == 0) { e2 = inflate_slow<2>(win32, S.dcount, S.dsorted); if (!e2) { err = INF_BAD_CODE; break; } }
+        const unsigned cl2 = e2 & 15, xb2 = (e2 >> 4) & 15;
+        const unsigned dist = ((e2 >> 8) & 0xffff) + ((win32 >> cl2) & ((1u << xb2) - 1));
+        br.drop(cl2 + xb2);
         bad |= (e2 >> 24) | (unsigned)(dist > bpos);
         if (lane == (unsigned)k) { my_pos = bpos; my_tok = (val << 16) | dist; }
         bpos += val;
@@ -355,15 +379,15 @@ __global__ void __launch_bounds__(32) inflate_kernel(const unsigned char* __rest
       const bool is_match = have && my_len != 0;
       // a match is independent of this batch's other symbols if everything it reads was produced before the batch
       const bool indep = is_match && (my_pos - my_dist + min(my_len, my_dist) <= opos);
-      const unsigned rp = (my_pos + a0) % INF_RING;
-      if (have && my_len == 0) ring[rp] = (unsigned char)my_tok;
+      const unsigned rp = W.index(my_pos, a0);
+      if (have && my_len == 0) win[rp] = (unsigned char)my_tok;
       if (indep) {
-        unsigned rs = rp >= my_dist ? rp - my_dist : rp + INF_RING - my_dist;
+        unsigned rs = W.back(rp, my_dist);
         unsigned rd = rp;
         for (unsigned i = 0; i < my_len; i++) {
-          ring[rd] = ring[rs];
-          rd = ring_wrap(rd + 1);
-          rs = ring_wrap(rs + 1);
+          win[rd] = win[rs];
+          rd = W.wrap(rd + 1);
+          rs = W.wrap(rs + 1);
         }
       }
       __syncwarp();
@@ -374,27 +398,26 @@ __global__ void __launch_bounds__(32) inflate_kernel(const unsigned char* __rest
         unsigned p = __shfl_sync(0xffffffffu, rp, src_lane);
         unsigned t = __shfl_sync(0xffffffffu, my_tok, src_lane);
         unsigned l = t >> 16, d = t & 0xffff;
-        unsigned s = p >= d ? p - d : p + INF_RING - d;
-        if (d >= l) { for (unsigned i = lane; i < l; i += 32) ring[ring_wrap(p + i)] = ring[ring_wrap(s + i)]; }
+        unsigned s = W.back(p, d);
+        if (d >= l) { for (unsigned i = lane; i < l; i += 32) win[W.wrap(p + i)] = win[W.wrap(s + i)]; }
         else if (d >= 32) {
           // overlapping copy with period d >= 32: rounds of 32 bytes never read what the same round writes
           for (unsigned i0 = 0; i0 < l; i0 += 32) {
             unsigned i = i0 + lane;
-            if (i < l) ring[ring_wrap(p + i)] = ring[ring_wrap(s + i)];
+            if (i < l) win[W.wrap(p + i)] = win[W.wrap(s + i)];
             __syncwarp();
           }
-        } else { for (unsigned i = lane; i < l; i += 32) ring[ring_wrap(p + i)] = ring[ring_wrap(s + i % d)]; }
+        } else { for (unsigned i = lane; i < l; i += 32) win[W.wrap(p + i)] = win[W.wrap(s + i % d)]; }
         __syncwarp();
       }
-      inflate_flush(ring, out, a0, opos, bpos, lane);
-      __syncwarp();
+      if (SMEM) { inflate_flush(win, out, a0, opos, bpos, lane); __syncwarp(); }
       opos = bpos;
     }
   }
   if (!err) {
     if (opos != out_len) err = INF_BAD_SIZE;
     else if (sg.flags & INF_ZLIB) {
-      br.drop(br.bc & 7);
+      br.align_byte();
       unsigned a = 0;
       for (int i = 0; i < 4; i++) { br.refill(); a = (a << 8) | br.get(8); }
       adler = a;

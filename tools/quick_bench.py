@@ -44,6 +44,11 @@ def main():
         tm = cd.timings()
         print('compress  wall %.1f ms  %.2f GB/s  stages(h2d,transform,adler,lz77,huff+scan,encode,d2h,total)=%s launches=%d' % (
             dt * 1e3, raw_bytes / dt / 1e9, ['%.2f' % v for v in tm], cd.launches()), flush=True)
+    if hasattr(lib, 'mtsb_debug_lz_profile'):
+        buf = (C.c_ulonglong * 16)()
+        lib.mtsb_debug_lz_profile(buf)
+        v = list(buf); st = max(v[0], 1)
+        print('lz profile (cycles/step, block 0): steps %d  A/B(seen by inserter) %.0f  search(t0) %.0f  insS %.0f  insL %.0f  whole step %.0f' % (v[0], v[1] / st, v[2] / st, v[3] / st, v[4] / st, v[5] / st), flush=True)
     csize = int(offs[-1])
     comp = np.empty(csize, dtype=np.uint8)
     lib.mtsb_memcpy(cd.ctx, comp.ctypes.data, d_comp, csize, 2)
