@@ -518,12 +518,6 @@ int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_
   for (int k = 0; k < n_sb; k++) {
     const int c0 = sb_first[k], c1 = sb_first[k + 1];
     const long long bbytes = sb_bytes(k);
-    if (!src_is_device && k + 1 < n_sb) {
-      // prefetch the next sub-batch while this one is compressed (its buffer was last read by sub-batch k-1, done)
-      CK(cudaMemcpyAsync(raw_buf[(k + 1) & 1]->p, (const char*)src + chunk_rows[sb_first[k + 1]] * row_bytes,
-                         (size_t)sb_bytes(k + 1), cudaMemcpyHostToDevice, c->copy_in));
-      CK(cudaEventRecord(c->ev_in[(k + 1) & 1], c->copy_in));
-    }
     const int nb = c1 - c0;
     const long long row0 = chunk_rows[c0];
     // tables
@@ -591,6 +585,13 @@ int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_
 
     c->begin(0);
     CK(cudaMemcpyAsync(c->d_tab.p, h, tab_bytes, cudaMemcpyHostToDevice, c->stream));
+    // only now queue the next sub-batch's upload: the copy engine serves transfers in submission order, so the small
+    // table upload above must not sit behind it
+    if (!src_is_device && k + 1 < n_sb) {
+      CK(cudaMemcpyAsync(raw_buf[(k + 1) & 1]->p, (const char*)src + chunk_rows[sb_first[k + 1]] * row_bytes,
+                         (size_t)sb_bytes(k + 1), cudaMemcpyHostToDevice, c->copy_in));
+      CK(cudaEventRecord(c->ev_in[(k + 1) & 1], c->copy_in));
+    }
     const void* raw = (const char*)src + row0 * row_bytes;
     if (!src_is_device) {
       CK(cudaStreamWaitEvent(c->stream, c->ev_in[k & 1], 0));
@@ -774,16 +775,20 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
   bool any_bad = false;
   const bool host_io = !comp_is_device || !dst_is_device;
   const long long sb_limit = host_io ? std::min(c->batch_bytes, c->host_batch_bytes) : c->batch_bytes;
+  // a sub-batch must also hold enough independent streams to fill the GPU: chunks without a segment index (e.g.
+  // reference-written ones) are ONE serial stream each, so they are batched by count (up to 16 GiB of output)
+  const long long min_streams = 8ll * c->sm_count, hard_limit = std::max<long long>(c->batch_bytes, 16ll << 30);
   std::vector<int> sb_first;
   long long max_sb_bytes = 0, max_sb_comp = 0;
   for (int a = 0; a < n_chunks;) {
     sb_first.push_back(a);
     int b = a;
-    long long bb = 0;
+    long long bb = 0, streams = 0;
     while (b < n_chunks && b - a < 60000) {
       long long cb = (chunk_rows[b + 1] - chunk_rows[b]) * row_bytes;
-      if (b > a && bb + cb > sb_limit) break;
-      bb += cb; b++;
+      if (b > a && bb + cb > hard_limit) break;
+      if (b > a && bb + cb > sb_limit && streams >= min_streams) break;
+      bb += cb; streams += nseg[b] ? nseg[b] : 1; b++;
     }
     max_sb_bytes = std::max(max_sb_bytes, bb);
     max_sb_comp = std::max(max_sb_comp, comp_offsets[b] - comp_offsets[a]);
@@ -805,12 +810,6 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
   for (int k = 0; k < n_sb; k++) {
     const int c0 = sb_first[k], c1 = sb_first[k + 1];
     const long long bbytes = (chunk_rows[c1] - chunk_rows[c0]) * row_bytes;
-    if (!comp_is_device && k + 1 < n_sb) {
-      const int a = sb_first[k + 1], b = sb_first[k + 2];
-      CK(cudaMemcpyAsync(comp_buf[(k + 1) & 1]->p, comp + comp_offsets[a], (size_t)(comp_offsets[b] - comp_offsets[a]),
-                         cudaMemcpyHostToDevice, c->copy_in));
-      CK(cudaEventRecord(c->ev_in[(k + 1) & 1], c->copy_in));
-    }
     const int nb = c1 - c0;
     const long long row0 = chunk_rows[c0];
     const long long comp0 = comp_offsets[c0], comp_bytes = comp_offsets[c1] - comp0;
@@ -876,6 +875,12 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
 
     c->begin(0);
     CK(cudaMemcpyAsync(c->d_tab.p, h, tab_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (!comp_is_device && k + 1 < n_sb) {
+      const int a = sb_first[k + 1], b = sb_first[k + 2];
+      CK(cudaMemcpyAsync(comp_buf[(k + 1) & 1]->p, comp + comp_offsets[a], (size_t)(comp_offsets[b] - comp_offsets[a]),
+                         cudaMemcpyHostToDevice, c->copy_in));
+      CK(cudaEventRecord(c->ev_in[(k + 1) & 1], c->copy_in));
+    }
     const unsigned char* dcomp = comp + comp0;
     if (!comp_is_device) {
       CK(cudaStreamWaitEvent(c->stream, c->ev_in[k & 1], 0));

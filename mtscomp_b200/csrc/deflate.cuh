@@ -141,42 +141,30 @@ template <int STRIDE, bool LONG>
 __device__ __forceinline__ void lz_insert_step(const unsigned short* hbuf, unsigned short* head, unsigned short* prev,
                                                unsigned u0, unsigned units, unsigned lane) {
   const unsigned PM = LzSmem<STRIDE>::PREV_N - 1;
-  // Four batches per round trip.  Lookups and stores are issued back to back (shared memory is in order per warp, so
-  // batch j+1 sees batch j's stores); the read-back that settles same-hash collisions inside a batch is done once per
-  // group: a lane only re-stores while an EARLIER unit of its own batch is visible, so stores of later batches stand.
   const unsigned pbase = LONG ? 0 : (u0 % (2 * LZ_UNITS));     // S links live in a two-step array
-  for (unsigned g = 0; g < units; g += 128) {
-    unsigned h[4];
-    unsigned short old[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const unsigned i = g + 32 * j + lane;
-      h[j] = (i < units) ? hbuf[i] : 0xffffu;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const unsigned short ub = (unsigned short)(u0 + g + 32 * j + lane + LZ_BIAS);
-      old[j] = ub;                                             // invalid units link to themselves (distance 0 = none)
-      if (h[j] != 0xffffu) { old[j] = head[h[j]]; head[h[j]] = ub; }
+  // software pipeline: the next batch's head lookups are issued right after this batch's stores (shared memory is
+  // in order per warp), so the warp does not wait for the read-back that settles same-hash collisions
+  unsigned h = (lane < units) ? hbuf[lane] : 0xffffu;
+  bool valid = h != 0xffffu;
+  unsigned short old = valid ? head[h] : (unsigned short)0;
+  for (unsigned b = 0; b < units; b += 32) {
+    const unsigned i = b + lane;
+    const unsigned short ub = (unsigned short)(u0 + i + LZ_BIAS);
+    const unsigned hn = (i + 32 < units) ? hbuf[i + 32] : 0xffffu;
+    __syncwarp();
+    if (valid) head[h] = ub;
+    __syncwarp();
+    const bool validn = hn != 0xffffu;
+    const unsigned short oldn = validn ? head[hn] : (unsigned short)0;
+    // a later unit of this batch must end up as the head: re-store while an earlier one is visible
+    bool want = valid && (unsigned short)(ub - head[h] - 1) < 31;
+    while (__any_sync(0xffffffffu, want)) {
+      if (want) head[h] = ub;
       __syncwarp();
+      want = valid && (unsigned short)(ub - head[h] - 1) < 31;
     }
-    bool want;
-    do {
-      want = false;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const unsigned short ub = (unsigned short)(u0 + g + 32 * j + lane + LZ_BIAS);
-        const bool w = h[j] != 0xffffu && (unsigned short)(ub - head[h[j]] - 1) < 31;
-        if (w) head[h[j]] = ub;
-        want |= w;
-      }
-      __syncwarp();
-    } while (__any_sync(0xffffffffu, want));
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const unsigned i = g + 32 * j + lane;
-      if (i < units) prev[LONG ? ((u0 + i) & PM) : (pbase + i)] = old[j];
-    }
+    if (i < units) prev[LONG ? ((u0 + i) & PM) : (pbase + i)] = valid ? old : ub;   // invalid: distance 0 = none
+    h = hn; valid = validn; old = oldn;
   }
   __syncwarp();
 }

@@ -35,7 +35,8 @@ enum {
 };
 
 static const int INF_LBITS = 10, INF_DBITS = 8;
-static const unsigned INF_RING = 41216;        // 32768 history + 32 x 258 bytes of the batch in flight (+ slack), % 16 == 0
+static const unsigned INF_RING = 36864;        // 32768 history + the batch in flight (<= INF_BATCH_BYTES + 258), % 16 == 0
+static const unsigned INF_BATCH_BYTES = 3800;   // a batch stops early once it has produced this much (keeps 5 CTAs / SM)
 
 // Table entry: bits 0-3 code length (0 = not in the fast table), 4-7 extra-bit count, 8-23 base value, 24-25 kind.
 enum { K_LIT = 0, K_LEN = 1, K_EOB = 2, K_BAD = 3 };
@@ -331,14 +332,15 @@ __global__ void __launch_bounds__(32 * WPC) inflate_kernel(const unsigned char* 
     if (!inflate_build<2>(dl, nd, S.dtab, INF_DBITS, S.dsorted, S.dcount, S.run)) { err = INF_BAD_LENGTHS; break; }
     __syncwarp();
 
-    // ---- symbol loop: batches of up to 32 symbols (<= 32 * 258 output bytes, which the ring has room for)
+    // ---- symbol loop: batches of up to 32 symbols / INF_BATCH_BYTES + 258 output bytes (the ring has room for that)
     bool eob = false;
     while (!eob && !err) {
       unsigned my_pos = 0, my_tok = 0;          // my_tok: literal byte, or len << 16 | dist
       unsigned bpos = opos;
       unsigned bad = 0;                          // deferred checks (distance too far / invalid symbol)
       int k = 0;
-      for (; k < 32; k++) {
+      const unsigned blimit = opos + INF_BATCH_BYTES;
+      for (; k < 32 && bpos < blimit; k++) {
         br.refill();
         unsigned win32 = br.window();
         unsigned e = S.ltab[win32 & ((1u << INF_LBITS) - 1)];
