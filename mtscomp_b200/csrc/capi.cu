@@ -51,7 +51,7 @@ struct mtsb_ctx {
   int sm_count = 148;
   std::string err;
   // params
-  long long seg_bytes = 262144, batch_bytes = 2ll << 30, host_batch_bytes = 256ll << 20, write_index = 1;
+  long long seg_bytes = 262144, batch_bytes = 2ll << 30, host_batch_bytes = 512ll << 20, write_index = 1;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of the host-buffer paths
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_done = nullptr;
   LzParams lz{4, 16, 32768, 32768, 32768, 0};   // greedy, every match >= 4 bytes accepted: tuned on synthetic AP/LFP
@@ -140,6 +140,22 @@ int set_attrs(mtsb_ctx* c) {
   CK(cudaFuncSetAttribute(lz77_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LzSmem<1>::total));
   CK(cudaFuncSetAttribute(lz77_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LzSmem<2>::total));
   c->attr_set = true;
+  return 0;
+}
+
+// Small host<->device table transfers on the compute stream are done by kernels over mapped pinned memory: a
+// cudaMemcpyAsync would queue on the copy engines behind the large sub-batch transfers of the copy streams and stall
+// the kernels (measured: the table upload only ran after the NEXT sub-batch's 256 MB upload).
+__global__ void table_copy_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+int small_copy(mtsb_ctx* c, void* dst, const void* src, size_t bytes) {
+  size_t n16 = (bytes + 15) / 16;
+  if (!n16) return 0;
+  unsigned grid = (unsigned)std::min<size_t>((n16 + 255) / 256, 64);
+  MTS_LAUNCH(table_copy_kernel, dim3(grid), dim3(256), 0, c->stream, (uint4*)dst, (const uint4*)src, n16);
+  c->launches++;
+  CKL();
   return 0;
 }
 
@@ -441,7 +457,7 @@ int mtsb_inverse_transform(mtsb_ctx* c, const void* src, int src_is_device, long
   memcpy(h + 64, firsts, sizeof firsts);
   AdlerSeg* as = (AdlerSeg*)(h + 256);
   for (int i = 0; i < nas; i++) { as[i].off = (long long)i * ASEG; as[i].len = (int)std::min<size_t>(ASEG, bytes - (size_t)i * ASEG); as[i].pad_ = 0; }
-  CK(cudaMemcpyAsync(c->d_tab.p, h, tab_bytes, cudaMemcpyHostToDevice, c->stream));
+  { int rc_ = small_copy(c, c->d_tab.p, h, tab_bytes); if (rc_) return rc_; }
   const void* t = src;
   if (!src_is_device) { NEED(c->d_T, bytes + 8192); CK(cudaMemcpyAsync(c->d_T.p, src, bytes, cudaMemcpyHostToDevice, c->stream)); t = c->d_T.p; }
   void* o = dst;
@@ -584,7 +600,7 @@ int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_
     const int* d_first = (const int*)(d + o_first);
 
     c->begin(0);
-    CK(cudaMemcpyAsync(c->d_tab.p, h, tab_bytes, cudaMemcpyHostToDevice, c->stream));
+    { int rc_ = small_copy(c, c->d_tab.p, h, tab_bytes); if (rc_) return rc_; }
     // only now queue the next sub-batch's upload: the copy engine serves transfers in submission order, so the small
     // table upload above must not sit behind it
     if (!src_is_device && k + 1 < n_sb) {
@@ -642,7 +658,7 @@ int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_
     CKL();
     c->launches++;
     c->end();
-    CK(cudaMemcpyAsync(c->h_small.p, c->d_chunk_off.p, (size_t)(nb + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    { int rc_ = small_copy(c, c->h_small.p, c->d_chunk_off.p, (size_t)(nb + 1) * 8); if (rc_) return rc_; }
     CK(cudaStreamSynchronize(c->stream));
     const long long* co = (const long long*)c->h_small.p;
     if (co[nb] > bound) return fail(c, MTSB_E_CAPACITY, "internal: sub-batch output %lld exceeds bound %lld", co[nb], bound);
@@ -869,12 +885,12 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
     NEED(c->d_tadler, (size_t)n_segs * 4);
     NEED(c->d_seg_adler, (size_t)n_as * 4);
     NEED(c->d_chunk_adler, (size_t)nb * 4);
-    NEED(c->h_small, (size_t)n_segs * 8 + (size_t)nb * 4 + 64);
+    NEED(c->h_small, (size_t)n_segs * 8 + (size_t)nb * 4 + 128);
     const char* d = (const char*)c->d_tab.p;
     const ChunkDesc* d_cd = (const ChunkDesc*)(d + o_cd);
 
     c->begin(0);
-    CK(cudaMemcpyAsync(c->d_tab.p, h, tab_bytes, cudaMemcpyHostToDevice, c->stream));
+    { int rc_ = small_copy(c, c->d_tab.p, h, tab_bytes); if (rc_) return rc_; }
     if (!comp_is_device && k + 1 < n_sb) {
       const int a = sb_first[k + 1], b = sb_first[k + 2];
       CK(cudaMemcpyAsync(comp_buf[(k + 1) & 1]->p, comp + comp_offsets[a], (size_t)(comp_offsets[b] - comp_offsets[a]),
@@ -918,17 +934,18 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
     if (r) return r;
     c->end();
     char* hs = (char*)c->h_small.p;
-    CK(cudaMemcpyAsync(hs, c->d_status.p, (size_t)n_segs * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(hs + (size_t)n_segs * 4, c->d_tadler.p, (size_t)n_segs * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(hs + (size_t)n_segs * 8, c->d_chunk_adler.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, c->stream));
+    const size_t so_t = ((size_t)n_segs * 4 + 15) & ~(size_t)15, so_c = so_t + (((size_t)n_segs * 4 + 15) & ~(size_t)15);
+    { int rc_ = small_copy(c, hs, c->d_status.p, (size_t)n_segs * 4); if (rc_) return rc_; }
+    { int rc_ = small_copy(c, hs + so_t, c->d_tadler.p, (size_t)n_segs * 4); if (rc_) return rc_; }
+    { int rc_ = small_copy(c, hs + so_c, c->d_chunk_adler.p, (size_t)nb * 4); if (rc_) return rc_; }
     CK(cudaStreamSynchronize(c->stream));
     if (!dst_is_device) {
       CK(cudaMemcpyAsync((char*)dst + row0 * row_bytes, outp, (size_t)bbytes, cudaMemcpyDeviceToHost, c->copy_out));
       CK(cudaEventRecord(c->ev_out[k & 1], c->copy_out));
     }
     const int* st = (const int*)hs;
-    const uint32_t* ta = (const uint32_t*)(hs + (size_t)n_segs * 4);
-    const uint32_t* ca = (const uint32_t*)(hs + (size_t)n_segs * 8);
+    const uint32_t* ta = (const uint32_t*)(hs + so_t);
+    const uint32_t* ca = (const uint32_t*)(hs + so_c);
     for (int i = 0; i < nb; i++) {
       int s = 0;
       for (int j = first_inf[i]; j < first_inf[i + 1] && !s; j++) s = st[j];

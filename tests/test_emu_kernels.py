@@ -71,5 +71,5 @@ def test_emulated_host_pipeline_many_sub_batches(emu):
         out, st = emu.decompress(comp, offs, rows, 96, np.int16, _native.TIME_DIFF)
         assert not st.any() and np.array_equal(out, x)
     finally:
-        emu.set_param('host_batch_bytes', 256 << 20)
+        emu.set_param('host_batch_bytes', 512 << 20)
         emu.set_param('batch_bytes', 2 << 30)
