@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "deflate.cuh"
 #include "inflate.cuh"
+#include "inflate_par.cuh"
 #include "transform.cuh"
 
 using namespace mts;
@@ -51,11 +52,14 @@ struct mtsb_ctx {
   int sm_count = 148;
   std::string err;
   // params
+  long long par_inflate = 1;   // decode index-less zlib streams block-parallel (inflate_par.cuh)
+  long long par_stats[4] = {0, 0, 0, 0};   // last call: survivors, candidates, chained blocks, streams resumed
   long long seg_bytes = 262144, batch_bytes = 2ll << 30, host_batch_bytes = 512ll << 20, write_index = 1;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of the host-buffer paths
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_done = nullptr;
   LzParams lz{4, 16, 32768, 32768, 32768, 0};   // greedy, every match >= 4 bytes accepted: tuned on synthetic AP/LFP
   // device scratch
+  Buf d_pstreams, d_surv, d_cand, d_pcount, d_cells, d_ptab, d_plist, d_pbad;   // block-parallel inflate scratch
   Buf d_raw, d_raw2, d_out2, d_comp2, d_T, d_tok, d_hist, d_codes, d_hdrs, d_tab, d_so, d_seg_adler, d_chunk_adler, d_chunk_off, d_out,
       d_partial, d_comp, d_status, d_tadler, d_gather;
   Buf h_tab, h_small;
@@ -306,7 +310,8 @@ void mtsb_destroy(mtsb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  Buf* bufs[] = {&c->d_raw, &c->d_raw2, &c->d_out2, &c->d_comp2, &c->d_T, &c->d_tok, &c->d_hist, &c->d_codes, &c->d_hdrs, &c->d_tab, &c->d_so,
+  Buf* bufs[] = {&c->d_pstreams, &c->d_surv, &c->d_cand, &c->d_pcount, &c->d_cells, &c->d_ptab, &c->d_plist, &c->d_pbad,
+                 &c->d_raw, &c->d_raw2, &c->d_out2, &c->d_comp2, &c->d_T, &c->d_tok, &c->d_hist, &c->d_codes, &c->d_hdrs, &c->d_tab, &c->d_so,
                  &c->d_seg_adler, &c->d_chunk_adler, &c->d_chunk_off, &c->d_out, &c->d_partial, &c->d_comp,
                  &c->d_status, &c->d_tadler, &c->d_gather, &c->h_tab, &c->h_small};
   for (Buf* b : bufs) b->release();
@@ -334,6 +339,7 @@ int mtsb_set_param(mtsb_ctx* c, const char* name, long long v) {
   else if (s == "batch_bytes") { if (v < (1 << 20)) return fail(c, MTSB_E_ARG, "batch_bytes too small"); c->batch_bytes = v; }
   else if (s == "host_batch_bytes") { if (v < (1 << 20)) return fail(c, MTSB_E_ARG, "host_batch_bytes too small"); c->host_batch_bytes = v; }
   else if (s == "write_index") c->write_index = v ? 1 : 0;
+  else if (s == "par_inflate") c->par_inflate = v ? 1 : 0;
   else if (s == "max_chain") c->lz.max_chain = (int)std::max<long long>(1, v);
   else if (s == "nice_len") c->lz.nice_len = (int)std::min<long long>(258, std::max<long long>(4, v));
   else if (s == "far4") c->lz.far4 = (int)v;
@@ -351,6 +357,11 @@ long long mtsb_get_param(mtsb_ctx* c, const char* name) {
   if (s == "batch_bytes") return c->batch_bytes;
   if (s == "host_batch_bytes") return c->host_batch_bytes;
   if (s == "write_index") return c->write_index;
+  if (s == "par_inflate") return c->par_inflate;
+  if (s == "par_survivors") return c->par_stats[0];
+  if (s == "par_candidates") return c->par_stats[1];
+  if (s == "par_chained") return c->par_stats[2];
+  if (s == "par_resumed") return c->par_stats[3];
   if (s == "max_chain") return c->lz.max_chain;
   if (s == "nice_len") return c->lz.nice_len;
   if (s == "far4") return c->lz.far4;
@@ -719,6 +730,135 @@ static int fetch_ranges(mtsb_ctx* c, const unsigned char* comp, int comp_is_devi
 
 static uint32_t rd32(const unsigned char* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
 
+// Block-parallel decode of the whole-stream segments `whole` (indices into segs).  On success the listed segments are
+// rewritten as INF_RESUME tails; on any doubt they are left untouched (full serial decode).
+static int par_phase(mtsb_ctx* c, const unsigned char* dcomp, std::vector<InflateSeg>& segs, const std::vector<int>& whole,
+                     unsigned char* dT) {
+  const int ns = (int)whole.size();
+  std::vector<ParStream> ps(ns);
+  long long in_total = 0, out_min = (1ll << 62), out_max = 0;
+  int max_in = 0;
+  for (int i = 0; i < ns; i++) {
+    const InflateSeg& s = segs[whole[i]];
+    ps[i].in_off = s.in_off; ps[i].out_off = s.out_off; ps[i].in_len = s.in_len; ps[i].out_len = s.out_len;
+    in_total += s.in_len;
+    out_min = std::min(out_min, s.out_off);
+    out_max = std::max(out_max, s.out_off + s.out_len);
+    max_in = std::max(max_in, s.in_len);
+  }
+  const long long cells_n = out_max - out_min;
+  const size_t surv_cap = (size_t)std::max<long long>(1 << 20, in_total * 8 / 300);
+  const size_t cand_cap = (size_t)std::max<long long>(1 << 16, in_total / 4096 + 64ll * ns);
+  NEED(c->d_pstreams, (size_t)ns * sizeof(ParStream));
+  NEED(c->d_surv, surv_cap * 8);
+  NEED(c->d_cand, cand_cap * sizeof(ParCand));
+  NEED(c->d_pcount, 256);
+  NEED(c->d_pbad, (size_t)ns * 4 + 64);
+  NEED(c->h_tab, std::max((size_t)ns * sizeof(ParStream), cand_cap * sizeof(ParCand)) + 4096);
+  NEED(c->h_small, 4096 + (size_t)ns * 4);
+  memcpy(c->h_tab.p, ps.data(), (size_t)ns * sizeof(ParStream));
+  { int r = small_copy(c, c->d_pstreams.p, c->h_tab.p, (size_t)ns * sizeof(ParStream)); if (r) return r; }
+  CK(cudaMemsetAsync(c->d_pcount.p, 0, 256, c->stream));
+  CK(cudaMemsetAsync(c->d_pbad.p, 0, (size_t)ns * 4, c->stream));
+  const ParStream* d_ps = (const ParStream*)c->d_pstreams.p;
+  unsigned* d_cnt = (unsigned*)c->d_pcount.p;
+  MTS_LAUNCH(par_find_kernel, dim3((max_in + 255) / 256, ns), dim3(256), 0, c->stream, dcomp, d_ps,
+             (unsigned long long*)c->d_surv.p, (unsigned)surv_cap, d_cnt);
+  CKL();
+  c->launches++;
+  { int r = small_copy(c, c->h_small.p, c->d_pcount.p, 64); if (r) return r; }
+  CK(cudaStreamSynchronize(c->stream));
+  const unsigned n_surv = ((const unsigned*)c->h_small.p)[0];
+  c->par_stats[0] += n_surv;
+  if (n_surv == 0 || n_surv > surv_cap) return 0;
+  MTS_LAUNCH(par_validate_kernel, dim3((n_surv + 127) / 128), dim3(128), 0, c->stream, dcomp, d_ps,
+             (const unsigned long long*)c->d_surv.p, n_surv, (ParCand*)c->d_cand.p, (unsigned)cand_cap, d_cnt);
+  CKL();
+  c->launches++;
+  { int r = small_copy(c, c->h_small.p, c->d_pcount.p, 64); if (r) return r; }
+  CK(cudaStreamSynchronize(c->stream));
+  const unsigned n_cand = ((const unsigned*)c->h_small.p)[1];
+  c->par_stats[1] += n_cand;
+  if (n_cand == 0 || n_cand > cand_cap) return 0;
+  NEED(c->d_ptab, (size_t)n_cand * sizeof(ParTables));
+  NEED(c->d_cells, (size_t)cells_n * 2 + 64);
+  {
+    auto k = par_decode_kernel<0>;
+    MTS_LAUNCH(k, dim3((n_cand + 127) / 128), dim3(128), 0, c->stream, dcomp, d_ps, (ParCand*)c->d_cand.p,
+               (const unsigned*)nullptr, n_cand, (ParTables*)c->d_ptab.p, (unsigned short*)nullptr, out_min);
+    CKL();
+    c->launches++;
+  }
+  { int r = small_copy(c, c->h_tab.p, c->d_cand.p, (size_t)n_cand * sizeof(ParCand)); if (r) return r; }
+  CK(cudaStreamSynchronize(c->stream));
+  // ---- host: chain the blocks of every stream
+  ParCand* hc = (ParCand*)c->h_tab.p;
+  std::vector<std::vector<std::pair<unsigned, unsigned>>> by_stream(ns);
+  for (unsigned i = 0; i < n_cand; i++)
+    if (hc[i].state == 1 && hc[i].stream < (unsigned)ns) by_stream[hc[i].stream].push_back({hc[i].bit, i});
+  std::vector<unsigned> chain, first(ns + 1, 0);
+  std::vector<unsigned> tail_bit(ns, 16), tail_out(ns, 0);
+  std::vector<char> fin(ns, 0);
+  for (int sidx = 0; sidx < ns; sidx++) {
+    auto& v = by_stream[sidx];
+    std::sort(v.begin(), v.end());
+    first[sidx] = (unsigned)chain.size();
+    unsigned cur = 16, run = 0;
+    for (;;) {
+      auto it = std::lower_bound(v.begin(), v.end(), std::make_pair(cur, 0u));
+      if (it == v.end() || it->first != cur) break;
+      ParCand& cd = hc[it->second];
+      if ((long long)run + cd.out_len > ps[sidx].out_len || cd.end_bit <= cur) break;
+      cd.out_off = run;
+      chain.push_back(it->second);
+      run += cd.out_len;
+      cur = cd.end_bit;
+      if (cd.final_) { fin[sidx] = 1; break; }
+    }
+    tail_bit[sidx] = cur; tail_out[sidx] = run;
+  }
+  first[ns] = (unsigned)chain.size();
+  const unsigned n_chain = (unsigned)chain.size();
+  c->par_stats[2] += n_chain;
+  if (n_chain == 0) return 0;
+  // upload the candidates (now with output offsets), the chain and its per-stream ranges
+  { int r = small_copy(c, c->d_cand.p, c->h_tab.p, (size_t)n_cand * sizeof(ParCand)); if (r) return r; }
+  CK(cudaStreamSynchronize(c->stream));                       // h_tab is reused below
+  const size_t o_first = ((size_t)n_chain * 4 + 255) & ~(size_t)255;
+  NEED(c->d_plist, o_first + (size_t)(ns + 1) * 4);
+  NEED(c->h_tab, o_first + (size_t)(ns + 1) * 4 + 64);
+  memcpy(c->h_tab.p, chain.data(), (size_t)n_chain * 4);
+  memcpy((char*)c->h_tab.p + o_first, first.data(), (size_t)(ns + 1) * 4);
+  { int r = small_copy(c, c->d_plist.p, c->h_tab.p, o_first + (size_t)(ns + 1) * 4); if (r) return r; }
+  {
+    auto k = par_decode_kernel<1>;
+    MTS_LAUNCH(k, dim3((n_chain + 127) / 128), dim3(128), 0, c->stream, dcomp, d_ps, (ParCand*)c->d_cand.p,
+               (const unsigned*)c->d_plist.p, n_chain, (ParTables*)c->d_ptab.p, (unsigned short*)c->d_cells.p, out_min);
+    CKL();
+    MTS_LAUNCH(par_resolve_kernel, dim3(ns), dim3(1024), 0, c->stream, d_ps, (const ParCand*)c->d_cand.p,
+               (const unsigned*)c->d_plist.p, (const unsigned*)((const char*)c->d_plist.p + o_first),
+               (const unsigned short*)c->d_cells.p, out_min, dT, (int*)c->d_pbad.p);
+    CKL();
+    c->launches += 2;
+  }
+  CK(cudaStreamSynchronize(c->stream));                       // h_tab free again
+  { int r = small_copy(c, c->h_tab.p, c->d_cand.p, (size_t)n_cand * sizeof(ParCand)); if (r) return r; }
+  { int r = small_copy(c, c->h_small.p, c->d_pbad.p, (size_t)ns * 4); if (r) return r; }
+  CK(cudaStreamSynchronize(c->stream));
+  const int* bad = (const int*)c->h_small.p;
+  for (int sidx = 0; sidx < ns; sidx++) {
+    bool ok = !bad[sidx] && first[sidx + 1] > first[sidx];
+    for (unsigned j = first[sidx]; ok && j < first[sidx + 1]; j++) ok = hc[chain[j]].state == 1;
+    if (!ok) continue;                                         // full serial decode of this stream
+    InflateSeg& s = segs[whole[sidx]];
+    s.flags = INF_ZLIB | INF_RESUME | (fin[sidx] ? INF_NO_BLOCKS : 0);
+    s.start_bit = tail_bit[sidx];
+    s.opos0 = tail_out[sidx];
+    c->par_stats[3]++;
+  }
+  return 0;
+}
+
 int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, const long long* comp_offsets,
                            int n_chunks, const long long* chunk_rows, int nc, int itemsize, int flags, void* dst,
                            int dst_is_device, int* chunk_status) {
@@ -730,6 +870,7 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
   }
   cudaSetDevice(c->device);
   c->reset_timing();
+  for (long long& v : c->par_stats) v = 0;
   const unsigned char* comp = (const unsigned char*)comp_;
   const long long row_bytes = (long long)nc * itemsize;
 
@@ -832,7 +973,7 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
     std::vector<ChunkDesc> cds(nb);
     std::vector<InflateSeg> segs;
     std::vector<AdlerSeg> as;
-    std::vector<int> first(nb + 1), first_inf(nb + 1);
+    std::vector<int> first(nb + 1), first_inf(nb + 1), whole;
     std::vector<uint32_t> want_adler(nb, 0);
     int max_ns = 0;
     const int ASEG = 1 << 16;
@@ -854,13 +995,15 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
           s.in_off = pos; s.in_len = (int)rd32(p + 4 + 4 * j);
           s.out_off = tbase + (long long)j * segb[g];
           s.out_len = (int)std::min<long long>(segb[g], raw - (long long)j * segb[g]);
-          s.flags = 0; s.pad_ = 0;
+          s.flags = 0; s.start_bit = 0; s.opos0 = 0; s.pad_ = 0;
           pos += s.in_len;
           segs.push_back(s);
         }
       } else {
         InflateSeg s;
-        s.in_off = cbase; s.in_len = (int)clen; s.out_off = tbase; s.out_len = (int)raw; s.flags = INF_ZLIB; s.pad_ = 0;
+        s.in_off = cbase; s.in_len = (int)clen; s.out_off = tbase; s.out_len = (int)raw; s.flags = INF_ZLIB;
+        s.start_bit = 0; s.opos0 = 0; s.pad_ = 0;
+        whole.push_back((int)segs.size());
         segs.push_back(s);
       }
       first[i] = (int)as.size();
@@ -873,24 +1016,8 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
     size_t o_as = (o_seg + n_segs * sizeof(InflateSeg) + 255) & ~(size_t)255;
     size_t o_first = (o_as + n_as * sizeof(AdlerSeg) + 255) & ~(size_t)255;
     size_t tab_bytes = o_first + (nb + 1) * sizeof(int);
-    NEED(c->h_tab, tab_bytes);
-    NEED(c->d_tab, tab_bytes);
-    char* h = (char*)c->h_tab.p;
-    memcpy(h + o_cd, cds.data(), nb * sizeof(ChunkDesc));
-    memcpy(h + o_seg, segs.data(), n_segs * sizeof(InflateSeg));
-    memcpy(h + o_as, as.data(), n_as * sizeof(AdlerSeg));
-    memcpy(h + o_first, first.data(), (nb + 1) * sizeof(int));
     NEED(c->d_T, (size_t)bbytes + 16384);
-    NEED(c->d_status, (size_t)n_segs * 4);
-    NEED(c->d_tadler, (size_t)n_segs * 4);
-    NEED(c->d_seg_adler, (size_t)n_as * 4);
-    NEED(c->d_chunk_adler, (size_t)nb * 4);
-    NEED(c->h_small, (size_t)n_segs * 8 + (size_t)nb * 4 + 128);
-    const char* d = (const char*)c->d_tab.p;
-    const ChunkDesc* d_cd = (const ChunkDesc*)(d + o_cd);
-
     c->begin(0);
-    { int rc_ = small_copy(c, c->d_tab.p, h, tab_bytes); if (rc_) return rc_; }
     if (!comp_is_device && k + 1 < n_sb) {
       const int a = sb_first[k + 1], b = sb_first[k + 2];
       CK(cudaMemcpyAsync(comp_buf[(k + 1) & 1]->p, comp + comp_offsets[a], (size_t)(comp_offsets[b] - comp_offsets[a]),
@@ -904,6 +1031,26 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
     }
     c->end();
     c->begin(2);
+    if (c->par_inflate && !whole.empty()) {
+      long long whole_in = 0;
+      for (int w : whole) whole_in += segs[w].in_len;
+      if (whole_in >= 65536) { int r = par_phase(c, dcomp, segs, whole, (unsigned char*)c->d_T.p); if (r) return r; }
+    }
+    NEED(c->h_tab, tab_bytes);
+    NEED(c->d_tab, tab_bytes);
+    char* h = (char*)c->h_tab.p;
+    memcpy(h + o_cd, cds.data(), nb * sizeof(ChunkDesc));
+    memcpy(h + o_seg, segs.data(), n_segs * sizeof(InflateSeg));
+    memcpy(h + o_as, as.data(), n_as * sizeof(AdlerSeg));
+    memcpy(h + o_first, first.data(), (nb + 1) * sizeof(int));
+    NEED(c->d_status, (size_t)n_segs * 4);
+    NEED(c->d_tadler, (size_t)n_segs * 4);
+    NEED(c->d_seg_adler, (size_t)n_as * 4);
+    NEED(c->d_chunk_adler, (size_t)nb * 4);
+    NEED(c->h_small, (size_t)n_segs * 8 + (size_t)nb * 4 + 128);
+    const char* d = (const char*)c->d_tab.p;
+    const ChunkDesc* d_cd = (const ChunkDesc*)(d + o_cd);
+    { int rc_ = small_copy(c, c->d_tab.p, h, tab_bytes); if (rc_) return rc_; }
     if (n_segs >= 6 * c->sm_count) {
       // many short streams: global-memory window, 2 warps per CTA, up to 64 warps per SM
       auto k = inflate_kernel<false, 2>;

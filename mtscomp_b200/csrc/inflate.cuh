@@ -26,9 +26,11 @@ struct InflateSeg {
   int out_len;         // exact number of bytes the stream must produce
   int flags;           // INF_ZLIB: 2-byte zlib header + adler32 trailer, decode to the final block
                        // otherwise raw deflate blocks, stop once out_len bytes are produced at a block end
+  unsigned start_bit;  // INF_RESUME: bit offset (from in_off) of the block header at which decoding resumes ...
+  unsigned opos0;      // ... and the number of output bytes already produced (by the block-parallel path)
   int pad_;
 };
-enum { INF_ZLIB = 1 };
+enum { INF_ZLIB = 1, INF_RESUME = 2, INF_NO_BLOCKS = 4 };   // INF_NO_BLOCKS: the final block is already decoded
 enum {
   INF_OK = 0, INF_BAD_HEADER = 1, INF_BAD_BLOCK = 2, INF_BAD_LENGTHS = 3, INF_BAD_CODE = 4, INF_BAD_DISTANCE = 5,
   INF_BAD_SIZE = 6, INF_INPUT_OVERRUN = 7, INF_BAD_STORED = 8, INF_BAD_ADLER = 9
@@ -240,19 +242,34 @@ __global__ void __launch_bounds__(32 * WPC) inflate_kernel(const unsigned char* 
   unsigned char* const win = W.base;
 
   BitR br;
-  br.init(in, in_len, 0);
   int err = INF_OK;
   unsigned opos = 0;            // bytes produced so far (all flushed at batch boundaries)
   unsigned adler = 0;
+  bool last = false;
 
   if (sg.flags & INF_ZLIB) {
     if (in_len < 8) err = INF_BAD_HEADER;
     else {
-      unsigned cmf = br.get(8), flg = br.get(8);
+      const unsigned cmf = in[0], flg = in[1];
       if ((cmf & 15) != 8 || (cmf >> 4) > 7 || ((cmf << 8) | flg) % 31 != 0 || (flg & 0x20)) err = INF_BAD_HEADER;
     }
   }
-  bool last = false;
+  if (sg.flags & INF_RESUME) {
+    // the block-parallel path has produced out[0, opos0): continue at the block header at start_bit
+    const unsigned sb = min(sg.start_bit >> 3, in_len);
+    br.init(in + sb, in_len - sb, sb);
+    br.pos = sg.start_bit & 7;
+    opos = min(sg.opos0, out_len);
+    last = (sg.flags & INF_NO_BLOCKS) != 0;
+    if (SMEM) {
+      const unsigned hist = min(opos, 32768u);
+      for (unsigned i = lane; i < hist; i += 32) win[W.index(opos - 1 - i, a0)] = out[opos - 1 - i];
+      __syncwarp();
+    }
+  } else {
+    br.init(in, in_len, 0);
+    if (sg.flags & INF_ZLIB) br.pos = 16;
+  }
   while (!err && !last) {
     if (!(sg.flags & INF_ZLIB) && opos >= out_len) break;
     br.refill();
