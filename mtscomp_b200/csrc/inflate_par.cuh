@@ -129,7 +129,7 @@ __device__ bool par_parse_header(TBits& br, unsigned char* lens, int& nl, int& n
   if (strict && left != 0) return false;
   for (int i = 0; i < 19; i++) if (cl[i]) sorted[offs[cl[i]]++] = (unsigned char)i;
   int idx = 0;
-  unsigned prev = 0;
+  unsigned prev = 0, kl_run = 0, kd_run = 0;
   while (idx < nl + nd) {
     br.refill();
     unsigned nb;
@@ -142,6 +142,12 @@ __device__ bool par_parse_header(TBits& br, unsigned char* lens, int& nl, int& n
     else if (sym == 18) { val = 0; rep = 11 + br.get(7); }
     if (idx + (int)rep > nl + nd) return false;
     for (unsigned k = 0; k < rep; k++) lens[idx + k] = (unsigned char)val;
+    if (strict && val) {
+      // running Kraft sums (units of 2^-15): a random bit string over-subscribes one of the codes within a few dozen
+      // lengths, so false survivors are dropped long before the end of the header
+      for (unsigned k = 0; k < rep; k++) { if (idx + (int)k < nl) kl_run += 32768u >> val; else kd_run += 32768u >> val; }
+      if (kl_run > 32768u || kd_run > 32768u) return false;
+    }
     idx += (int)rep;
     prev = val;
   }
@@ -207,11 +213,19 @@ __device__ __forceinline__ unsigned par_slow(unsigned win, const unsigned short*
 }
 
 // ---------------------------------------------------------------------------------------------- kernels
-// 1. Survivors of the cheap header test: one thread per stream byte (8 bit offsets).
+// 1. Survivors of the cheap header test: one thread per stream byte (8 bit offsets).  Phase 1 tests the fixed fields of
+//    all 8 offsets (BTYPE = dynamic, HLIT <= 29, HDIST <= 29); phase 2 visits only the passing offsets and checks that the
+//    code-length code is complete: its 3-bit lengths are summed 3 at a time through a 512-entry table of 2^(7-len).
 __global__ void __launch_bounds__(256) par_find_kernel(const unsigned char* __restrict__ comp,
                                                        const ParStream* __restrict__ streams,
                                                        unsigned long long* __restrict__ surv, unsigned cap,
                                                        unsigned* __restrict__ counters) {
+  __shared__ unsigned char k9[512];
+  for (unsigned i = threadIdx.x; i < 512; i += blockDim.x) {
+    unsigned a = i & 7, b2 = (i >> 3) & 7, c2 = i >> 6;
+    k9[i] = (unsigned char)((a ? 128u >> a : 0) + (b2 ? 128u >> b2 : 0) + (c2 ? 128u >> c2 : 0));
+  }
+  __syncthreads();
   const ParStream st = streams[blockIdx.y];
   const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
   // a dynamic header is at least 17 + 12 bits + two codes: ignore the last bytes (zlib trailer + shortest block)
@@ -226,20 +240,26 @@ __global__ void __launch_bounds__(256) par_find_kernel(const unsigned char* __re
     x[0] = __funnelshift_r(r0, r1, mis * 8); x[1] = __funnelshift_r(r1, r2, mis * 8);
     x[2] = __funnelshift_r(r2, r3, mis * 8); x[3] = __funnelshift_r(r3, r4, mis * 8);
   }
+  unsigned mask = 0;
+#pragma unroll
   for (unsigned s = 0; s < 8; s++) {
     const unsigned t0 = __funnelshift_r(x[0], x[1], s);
-    if (((t0 >> 1) & 3) != 2 || ((t0 >> 3) & 31) > 29 || ((t0 >> 8) & 31) > 29) continue;
+    const bool pass = ((t0 >> 1) & 3) == 2 && ((t0 >> 3) & 31) <= 29 && ((t0 >> 8) & 31) <= 29;
+    mask |= (unsigned)pass << s;
+  }
+  while (mask) {
+    const unsigned s = (unsigned)__ffs((int)mask) - 1;
+    mask &= mask - 1;
+    const unsigned t0 = __funnelshift_r(x[0], x[1], s), t1 = __funnelshift_r(x[1], x[2], s),
+                   t2 = __funnelshift_r(x[2], x[3], s);
     const unsigned ncl = ((t0 >> 13) & 15) + 4;
-    // code-length code lengths: 3 bits each from bit 17; complete code <=> sum of 2^(7-len) == 128
-    const unsigned t1 = __funnelshift_r(x[1], x[2], s), t2 = __funnelshift_r(x[2], x[3], s);
-    const unsigned long long lo = ((unsigned long long)t1 << 32) | t0, hi = t2;
-    unsigned kraft = 0;
-    for (unsigned i = 0; i < ncl; i++) {
-      const unsigned bp = 17 + 3 * i;
-      unsigned l = bp < 61 ? (unsigned)(lo >> bp) : (unsigned)(((hi << 3) | (lo >> 61)) >> (bp - 61));
-      l &= 7;
-      if (l) kraft += 128u >> l;
-    }
+    // stream bits [17, 17 + 3 * ncl) = the code-length code lengths (<= 57 bits)
+    unsigned long long f = ((((unsigned long long)t1 << 32) | t0) >> 17) | ((unsigned long long)t2 << 47);
+    f &= (1ull << (3 * ncl)) - 1;
+    const unsigned lo = (unsigned)f, hi = (unsigned)(f >> 32);
+    const unsigned kraft = k9[lo & 511] + k9[(lo >> 9) & 511] + k9[(lo >> 18) & 511] +
+                           k9[((lo >> 27) | (hi << 5)) & 511] + k9[(hi >> 4) & 511] + k9[(hi >> 13) & 511] +
+                           k9[(hi >> 22) & 511];
     if (kraft != 128) continue;
     const unsigned at = atomicAdd(&counters[0], 1u);
     if (at < cap) surv[at] = ((unsigned long long)blockIdx.y << 32) | (b * 8 + s);
@@ -332,9 +352,22 @@ __global__ void __launch_bounds__(128) par_decode_kernel(const unsigned char* __
     br.drop(cl2 + xb2);
     if (opos + val > cap || br.bit_pos() > in_bits) { ok = false; break; }
     if (REAL) {
-      for (unsigned j = 0; j < val; j++) {
-        const int src = (int)(opos + j) - (int)dist;
-        out[opos + j] = src >= 0 ? out[src] : (unsigned short)(0x8000u | (unsigned)(32768 + src));
+      if (dist >= val && dist <= opos) {
+        // non-overlapping copy inside the block: loads first, then stores, 8 cells at a time (one memory latency)
+        const unsigned short* sp = out + (opos - dist);
+        unsigned short* dp = out + opos;
+        for (unsigned j0 = 0; j0 < val; j0 += 8) {
+          unsigned short t[8];
+#pragma unroll
+          for (unsigned j = 0; j < 8; j++) t[j] = (j0 + j < val) ? sp[j0 + j] : (unsigned short)0;
+#pragma unroll
+          for (unsigned j = 0; j < 8; j++) if (j0 + j < val) dp[j0 + j] = t[j];
+        }
+      } else {
+        for (unsigned j = 0; j < val; j++) {
+          const int src = (int)(opos + j) - (int)dist;
+          out[opos + j] = src >= 0 ? out[src] : (unsigned short)(0x8000u | (unsigned)(32768 + src));
+        }
       }
     }
     opos += val;

@@ -73,3 +73,17 @@ def test_emulated_host_pipeline_many_sub_batches(emu):
     finally:
         emu.set_param('host_batch_bytes', 512 << 20)
         emu.set_param('batch_bytes', 2 << 30)
+
+
+def test_emulated_block_parallel_inflate(emu):
+    """Kernel logic of the block-parallel decoder on a reference-style zlib stream (several deflate blocks)."""
+    from mtscomp_b200 import synth, _native
+    x = synth.ap_chunk(ns=20000, nc=16, seed=33)
+    good = ora.encode_chunk(x)
+    out, st = emu.decompress(good, [0, len(good)], [0, 20000], 16, np.int16, _native.TIME_DIFF)
+    assert not st.any() and np.array_equal(out, x)
+    assert emu.get_param('par_chained') >= 5 and emu.get_param('par_resumed') == 1
+    bad = bytearray(good)
+    bad[len(bad) // 2] ^= 0x33
+    _, st = emu.decompress(bytes(bad), [0, len(bad)], [0, 20000], 16, np.int16, _native.TIME_DIFF)
+    assert st[0] != 0

@@ -204,3 +204,41 @@ def test_zlib_variants_accepted(codec):
         assert zlib.decompress(v) == want
         out, st = codec.decompress(v, [0, len(v)], [0, 2000], 32, np.int16, F())
         assert not st.any() and np.array_equal(out, x)
+
+
+def test_block_parallel_inflate_matches_serial(codec):
+    """Index-less zlib streams (what the reference Writer emits) go through the block-parallel decoder
+    (inflate_par.cuh); it must agree with the serial warp decoder and with the oracle, and report what it did."""
+    from mtscomp_b200 import synth
+    x = np.concatenate([synth.ap_chunk(ns=30000, nc=48, seed=90 + i) for i in range(3)])
+    rows = [0, 30000, 60000, 90000]
+    parts = [ora.encode_chunk(x[rows[i]:rows[i + 1]]) for i in range(3)]
+    offs = np.concatenate(([0], np.cumsum([len(p) for p in parts])))
+    blob = b''.join(parts)
+    try:
+        codec.set_param('par_inflate', 1)
+        out1, st1 = codec.decompress(blob, offs, rows, 48, np.int16, F())
+        chained, resumed = codec.get_param('par_chained'), codec.get_param('par_resumed')
+        codec.set_param('par_inflate', 0)
+        out0, st0 = codec.decompress(blob, offs, rows, 48, np.int16, F())
+        assert codec.get_param('par_chained') == 0
+    finally:
+        codec.set_param('par_inflate', 1)
+    assert not st1.any() and not st0.any()
+    assert np.array_equal(out1, x) and np.array_equal(out0, x)
+    assert resumed == 3 and chained >= 3 * 30          # ~39 zlib blocks per 2.9 MB stream
+
+
+def test_block_parallel_inflate_reports_corruption(codec):
+    from mtscomp_b200 import synth
+    x = synth.ap_chunk(ns=30000, nc=32, seed=95)
+    good = ora.encode_chunk(x)
+    for pos in (len(good) // 3, len(good) - 2, 1):
+        bad = bytearray(good)
+        bad[pos] ^= 0x5a
+        with pytest.raises(zlib.error):
+            zlib.decompress(bytes(bad))
+        _, st = codec.decompress(bytes(bad), [0, len(bad)], [0, 30000], 32, np.int16, F())
+        assert st[0] != 0, pos
+    out, st = codec.decompress(good + b'\x00' * 7, [0, len(good) + 7], [0, 30000], 32, np.int16, F())
+    assert st[0] == 0 and np.array_equal(out, x)        # trailing bytes are ignored, as zlib does
