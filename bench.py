@@ -48,6 +48,12 @@ def parse():
     return ap.parse_args()
 
 
+def workload_config(n_chunks, n_distinct):
+    return {'workload': 'BASELINE configs[1] shape: 10 min AP, 385ch x 30kHz int16, %d chunks of 1 s (23.1 MB) '
+                        'per GPU, chunk_order F, time diff; compress AND decompress' % n_chunks,
+            'chunks_per_gpu': n_chunks, 'n_distinct_chunks': n_distinct, 'raw_bytes_per_gpu': n_chunks * CHUNK_BYTES}
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -140,8 +146,7 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': n_sample * CHUNK_BYTES / v / 1e6, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int16', 'data': 'synthetic',
-        'config': {'workload': 'AP 385ch x 30kHz int16, 1 s chunks (23.1 MB), zlib level 6, chunk_order F, time diff',
-                   'sample': sample},
+        'config': dict(workload_config(args.chunks, min(args.distinct, args.chunks)), sample=sample),
         'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample,
                          'decompress_value': float(np.mean(vals_d))},
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -201,25 +206,45 @@ def run_b200(args):
     raw_bytes = n_chunks * CHUNK_BYTES
     rows = np.arange(n_chunks + 1, dtype=np.int64) * NS
 
-    # pinned host copies (e2e path) and device-resident copies (kernel path)
-    h_raw_t = torch.empty(raw_bytes, dtype=torch.uint8, pin_memory=True)
-    h_raw = h_raw_t.numpy()
-    for i in range(n_chunks):
-        h_raw[i * CHUNK_BYTES:(i + 1) * CHUNK_BYTES] = base[i % n_distinct].reshape(-1).view(np.uint8)
+    # the end-to-end legs need pinned host buffers (raw, .cbin bound, decoded, reference .cbin: ~78 MB per chunk); they
+    # run on all the chunks unless this rank's share of the free host memory is smaller
+    n_e2e = n_chunks
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available * 0.55 / max(world, 1)
+        n_e2e = int(max(8, min(n_chunks, avail // (3.4 * CHUNK_BYTES))))
+    except Exception:
+        pass
+    e2e_bytes = n_e2e * CHUNK_BYTES
+    rows_e = rows[:n_e2e + 1]
+    # device-resident copies (kernel path): tiled on the device from the distinct chunks
     cap = n_chunks * cd.compress_bound(NS, NC, 2, fl)
+    base_dev = [torch.from_numpy(b.reshape(-1).view(np.uint8)).cuda() for b in base]
     d_raw = torch.empty(raw_bytes, dtype=torch.uint8, device='cuda')
-    d_raw.copy_(h_raw_t)
+    for i in range(n_chunks):
+        d_raw[i * CHUNK_BYTES:(i + 1) * CHUNK_BYTES].copy_(base_dev[i % n_distinct])
     d_comp = torch.empty(cap, dtype=torch.uint8, device='cuda')
     d_out = torch.empty(raw_bytes, dtype=torch.uint8, device='cuda')
-    h_comp_t = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
-    h_out_t = torch.empty(raw_bytes, dtype=torch.uint8, pin_memory=True)
     ref_sizes = [len(ref_streams[i % n_distinct]) for i in range(n_chunks)]
     ref_offs = np.concatenate(([0], np.cumsum(ref_sizes))).astype(np.int64)
-    h_ref_t = torch.empty(int(ref_offs[-1]) + 64, dtype=torch.uint8, pin_memory=True)
-    h_ref = h_ref_t.numpy()
+    ref_dev = [torch.from_numpy(np.frombuffer(r, np.uint8).copy()).cuda() for r in ref_streams]
+    d_ref = torch.empty(int(ref_offs[-1]) + 64, dtype=torch.uint8, device='cuda')
     for i in range(n_chunks):
+        d_ref[ref_offs[i]:ref_offs[i + 1]].copy_(ref_dev[i % n_distinct])
+    # pinned host copies (end-to-end path) of the first n_e2e chunks
+    cap_e = n_e2e * cd.compress_bound(NS, NC, 2, fl)
+    ref_offs_e = ref_offs[:n_e2e + 1]
+    h_raw_t = torch.empty(e2e_bytes, dtype=torch.uint8, pin_memory=True)
+    h_raw = h_raw_t.numpy()
+    for i in range(n_e2e):
+        h_raw[i * CHUNK_BYTES:(i + 1) * CHUNK_BYTES] = base[i % n_distinct].reshape(-1).view(np.uint8)
+    h_comp_t = torch.empty(cap_e, dtype=torch.uint8, pin_memory=True)
+    h_out_t = torch.empty(e2e_bytes, dtype=torch.uint8, pin_memory=True)
+    h_ref_t = torch.empty(int(ref_offs_e[-1]) + 64, dtype=torch.uint8, pin_memory=True)
+    h_ref = h_ref_t.numpy()
+    for i in range(n_e2e):
         h_ref[ref_offs[i]:ref_offs[i + 1]] = np.frombuffer(ref_streams[i % n_distinct], np.uint8)
-    d_ref = h_ref_t.cuda()
+    del base_dev, ref_dev
     torch.cuda.synchronize()
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -240,7 +265,7 @@ def run_b200(args):
         tm, ln = cd.timings(), cd.launches()
         state['offs'] = offs
         # (b) compress end to end from pinned host memory
-        ms_e, offs_e = timed(lambda: cd.compress_ptr(h_raw_t.data_ptr(), 0, rows, NC, 2, fl, h_comp_t.data_ptr(), 0, cap))
+        ms_e, offs_e = timed(lambda: cd.compress_ptr(h_raw_t.data_ptr(), 0, rows_e, NC, 2, fl, h_comp_t.data_ptr(), 0, cap_e))
         ln += cd.launches()
         # (c) decompress reference-written streams, device resident
         ms_r, st = timed(lambda: cd.decompress_ptr(d_ref.data_ptr(), 1, ref_offs, rows, NC, 2, fl, d_out.data_ptr(), 1))
@@ -253,7 +278,7 @@ def run_b200(args):
         ln += cd.launches()
         assert not st.any()
         # (e) decompress reference-written streams end to end (host .cbin bytes -> host array)
-        ms_re, st = timed(lambda: cd.decompress_ptr(h_ref_t.data_ptr(), 0, ref_offs, rows, NC, 2, fl, h_out_t.data_ptr(), 0))
+        ms_re, st = timed(lambda: cd.decompress_ptr(h_ref_t.data_ptr(), 0, ref_offs_e, rows_e, NC, 2, fl, h_out_t.data_ptr(), 0))
         ln += cd.launches()
         assert not st.any()
         if record is not None:
@@ -277,8 +302,10 @@ def run_b200(args):
     keys = ['c', 'ce', 'r', 'g', 're']
     mean_ms = np.array([np.mean([r[k] for r in rec]) for k in keys])
     mx = max_over_ranks(mean_ms)          # max over ranks of the per-step means
-    tot = world * raw_bytes
-    gbps = {k: tot / (mx[i] / 1e3) / 1e9 for i, k in enumerate(keys)}
+    gbps = {k: world * (e2e_bytes if k in ('ce', 're') else raw_bytes) / (mx[i] / 1e3) / 1e9 for i, k in enumerate(keys)}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     csize = rec[-1]['csize']
@@ -297,14 +324,13 @@ def run_b200(args):
         'metric': METRIC, 'value': gbps['c'], 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': float(mx[0]), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'int16', 'data': 'synthetic',
-        'config': {'workload': 'BASELINE configs[1] shape: 10 min AP, 385ch x 30kHz int16, %d chunks of 1 s (23.1 MB) '
-                               'per GPU, chunk_order F, time diff; compress AND decompress' % n_chunks,
-                   'chunks_per_gpu': n_chunks, 'n_distinct_chunks': n_distinct, 'raw_bytes_per_gpu': raw_bytes,
-                   'l2': 'inputs larger than L2 (%.0f MB distinct raw per GPU, %.1f GB per step)' % (
+        'config': dict(workload_config(n_chunks, n_distinct),
+                   l2='inputs larger than L2 (%.0f MB distinct raw per GPU, %.1f GB per step)' % (
                        n_distinct * CHUNK_BYTES / 1e6, raw_bytes / 1e9),
-                   'sharding': 'contiguous chunk ranges per GPU, no collective on the data path',
-                   'seg_bytes': cd.get_param('seg_bytes'), 'max_chain': cd.get_param('max_chain')},
-        'e2e': {'value': gbps['ce'], 'unit': UNIT, 'h2d_bytes_per_step': raw_bytes, 'd2h_bytes_per_step': rec[-1]['csize_e']},
+                   sharding='contiguous chunk ranges per GPU, no collective on the data path',
+                   seg_bytes=cd.get_param('seg_bytes'), max_chain=cd.get_param('max_chain'),
+                   e2e_chunks_per_gpu=n_e2e),
+        'e2e': {'value': gbps['ce'], 'unit': UNIT, 'h2d_bytes_per_step': e2e_bytes, 'd2h_bytes_per_step': rec[-1]['csize_e']},
         'decompress': {
             'reference_written': {'value': gbps['r'], 'unit': UNIT, 'e2e_value': gbps['re'], 'inflate_ms': inf_ms,
                                   'streams': n_chunks, 'note': 'index-less zlib streams (what the reference Writer emits): block-parallel decoder'},
