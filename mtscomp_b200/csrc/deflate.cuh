@@ -98,11 +98,9 @@ template <int STRIDE> struct LzSmem {
   static const size_t prevs_off = prevl_off + (size_t)PREV_N * 2;
   static const size_t hbuf_off = prevs_off + (size_t)(2 * LZ_UNITS) * 2;   // [2 steps][S,L][LZ_UNITS] u16 hashes
   static const size_t mlen_off = hbuf_off + (size_t)(4 * LZ_UNITS) * 2;
-  static const size_t mdist_off = mlen_off + (size_t)(SEG + 8) * 2;
-  static const size_t jump_off = mdist_off + (size_t)(SEG + 8) * 2;
-  static const size_t jump2_off = jump_off + (size_t)(SEG + 8) * 2;
-  static const size_t flag_off = jump2_off + (size_t)(SEG + 8) * 2;             // reachability flags, one byte per position
-  static const size_t hist_off = (flag_off + (size_t)(SEG + 8) + 15) & ~(size_t)15;
+  static const size_t mdist_off = mlen_off + (size_t)(LZ_UNITS + 8) * 2;       // per unit: match length | back-extension flag
+  static const size_t jump_off = (mdist_off + (size_t)(LZ_UNITS + 8) * 2 + 3) & ~(size_t)3;
+  static const size_t hist_off = (jump_off + (size_t)(LZ_UNITS + 8) * 4 + 15) & ~(size_t)15;
   static const size_t misc_off = hist_off + (size_t)HIST_STRIDE * 4;
   static const size_t total = misc_off + 512;
 };
@@ -131,40 +129,50 @@ __device__ __forceinline__ void lz_unit_hashes(const unsigned char* ring, unsign
   }
 }
 
-// Thread `units` consecutive units starting at unit u0 into one hash table (one warp), batches of 32 units in position
-// order.  Every unit links to the table head as it was BEFORE its batch (units of one batch never link to each other:
-// such matches are < 32 units away and the next batch finds them anyway), then the batch's LAST unit of each hash
+// Thread `units` consecutive units starting at unit u0 into one hash table (one warp), batches of 64 units (two
+// consecutive units per lane) in position order.  Every unit links to the table head as it was BEFORE its batch — or to
+// its lane's first unit when both have the same hash; units of different lanes of one batch never link to each other
+// (such matches are < 64 units away and later batches find them anyway).  Then the batch's LAST unit of each hash
 // becomes the new head: colliding lanes re-store until the highest one has won, so the result does not depend on how
-// the hardware orders same-address stores.  No __match_any_sync: it costs > 1000 cycles per call on sm_100.
+// the hardware orders same-address stores.  No __match_any_sync: it costs > 1000 cycles per call when many warps use it.
 // LONG: links go to the prev ring (index u & pmask); otherwise to a two-step array.
 template <int STRIDE, bool LONG>
 __device__ __forceinline__ void lz_insert_step(const unsigned short* hbuf, unsigned short* head, unsigned short* prev,
                                                unsigned u0, unsigned units, unsigned lane) {
   const unsigned PM = LzSmem<STRIDE>::PREV_N - 1;
   const unsigned pbase = LONG ? 0 : (u0 % (2 * LZ_UNITS));     // S links live in a two-step array
-  // software pipeline: the next batch's head lookups are issued right after this batch's stores (shared memory is
-  // in order per warp), so the warp does not wait for the read-back that settles same-hash collisions
-  unsigned h = (lane < units) ? hbuf[lane] : 0xffffu;
-  bool valid = h != 0xffffu;
-  unsigned short old = valid ? head[h] : (unsigned short)0;
-  for (unsigned b = 0; b < units; b += 32) {
-    const unsigned i = b + lane;
-    const unsigned short ub = (unsigned short)(u0 + i + LZ_BIAS);
-    const unsigned hn = (i + 32 < units) ? hbuf[i + 32] : 0xffffu;
+  // software pipeline: the next batch's hashes and head lookups are issued right after this batch's stores (shared
+  // memory is in order per warp), so the warp does not wait for the read-back that settles collisions
+  unsigned hA = (2 * lane < units) ? hbuf[2 * lane] : 0xffffu;
+  unsigned hB = (2 * lane + 1 < units) ? hbuf[2 * lane + 1] : 0xffffu;
+  unsigned short oldA = hA != 0xffffu ? head[hA] : (unsigned short)0;
+  unsigned short oldB = hB != 0xffffu ? head[hB] : (unsigned short)0;
+  for (unsigned b = 0; b < units; b += 64) {
+    const unsigned iA = b + 2 * lane, iB = iA + 1;
+    const unsigned short ubA = (unsigned short)(u0 + iA + LZ_BIAS), ubB = (unsigned short)(ubA + 1);
+    const bool vA = hA != 0xffffu, vB = hB != 0xffffu;
+    const bool same = vA && hA == hB;                          // the lane's second unit follows its first
+    const unsigned nA = (iA + 64 < units) ? hbuf[iA + 64] : 0xffffu;
+    const unsigned nB = (iB + 64 < units) ? hbuf[iB + 64] : 0xffffu;
     __syncwarp();
-    if (valid) head[h] = ub;
+    if (vA && !same) head[hA] = ubA;
+    if (vB) head[hB] = ubB;
     __syncwarp();
-    const bool validn = hn != 0xffffu;
-    const unsigned short oldn = validn ? head[hn] : (unsigned short)0;
+    const unsigned short noA = nA != 0xffffu ? head[nA] : (unsigned short)0;
+    const unsigned short noB = nB != 0xffffu ? head[nB] : (unsigned short)0;
     // a later unit of this batch must end up as the head: re-store while an earlier one is visible
-    bool want = valid && (unsigned short)(ub - head[h] - 1) < 31;
-    while (__any_sync(0xffffffffu, want)) {
-      if (want) head[h] = ub;
+    bool wA = vA && !same && (unsigned short)(ubA - head[hA] - 1) < 63;
+    bool wB = vB && (unsigned short)(ubB - head[hB] - 1) < 63;
+    while (__any_sync(0xffffffffu, wA || wB)) {
+      if (wA) head[hA] = ubA;
+      if (wB) head[hB] = ubB;
       __syncwarp();
-      want = valid && (unsigned short)(ub - head[h] - 1) < 31;
+      wA = vA && !same && (unsigned short)(ubA - head[hA] - 1) < 63;
+      wB = vB && (unsigned short)(ubB - head[hB] - 1) < 63;
     }
-    if (i < units) prev[LONG ? ((u0 + i) & PM) : (pbase + i)] = valid ? old : ub;   // invalid: distance 0 = none
-    h = hn; valid = validn; old = oldn;
+    if (iA < units) prev[LONG ? ((u0 + iA) & PM) : (pbase + iA)] = vA ? oldA : ubA;   // invalid: distance 0 = none
+    if (iB < units) prev[LONG ? ((u0 + iB) & PM) : (pbase + iB)] = vB ? (same ? ubA : oldB) : ubB;
+    hA = nA; hB = nB; oldA = noA; oldB = noB;
   }
   __syncwarp();
 }
@@ -207,8 +215,6 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
   typedef LzSmem<STRIDE> L;
   const unsigned SEG = L::SEG;
   const unsigned NSW = 30;                          // searcher / parser warps; warps 30 and 31 are the inserters
-  const unsigned STRETCH = L::SEG / 30;             // positions parsed per warp (64 for STRIDE 2, 32 for STRIDE 1)
-  const unsigned PER_LANE = STRETCH / 32;
   MTS_DYN_SMEM(sm);
   unsigned char* ring = sm + L::ring_off;
   unsigned short* headL = (unsigned short*)(sm + L::headl_off);
@@ -218,9 +224,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
   unsigned short* hbuf = (unsigned short*)(sm + L::hbuf_off);   // hbuf[(step & 1) * 2 * LZ_UNITS + (LONG ? LZ_UNITS : 0) + k]
   unsigned short* mlen = (unsigned short*)(sm + L::mlen_off);
   unsigned short* mdist = (unsigned short*)(sm + L::mdist_off);
-  unsigned short* ex = (unsigned short*)(sm + L::jump_off);      // stage 1: exit of the stretch; stage 3: jump pointers
-  unsigned short* ec = (unsigned short*)(sm + L::jump2_off);     // stage 1: token elements emitted up to the stretch exit
-  unsigned char* rf = sm + L::flag_off;                           // stage 3: position is a token start
+  unsigned* xe = (unsigned*)(sm + L::jump_off);                   // per unit: exit of its stretch | token elements << 16
   unsigned* shist = (unsigned*)(sm + L::hist_off);
   unsigned* misc = (unsigned*)(sm + L::misc_off);   // [0..29] element base of each stretch, [33],[34] carry, [35] step total
   unsigned* ent = misc + 36;                         // [0..29] parse entry position of each stretch
@@ -345,138 +349,107 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
         }
         if (pf) *(uint4*)(ring + (pf_rc & 0xffffu)) = pf_v;
         if (tid == 0) { LZ_PROF_T(t_s); LZ_PROF_ADD(2, t_s - t_step); }
-        mlen[li] = (unsigned short)(bdist ? best : 0);
-        mdist[li] = (unsigned short)bdist;
-        if (STRIDE > 1) {
-          // the bytes between this unit and the previous one inherit this match, extended backwards while they agree
-          unsigned l2 = bdist ? best : 0;
-          for (unsigned back = 1; back < (unsigned)STRIDE && back <= li; back++) {
-            const unsigned q = p - back;
-            if (l2 && l2 < 258 && q >= bdist &&
-                ring[(q + off0) & 0xffffu] == ring[(q + off0 - bdist) & 0xffffu]) l2++;
-            else l2 = 0;
-            mlen[li - back] = (unsigned short)l2;
-            mdist[li - back] = (unsigned short)(l2 ? bdist : 0);
-          }
-          if (tid == LZ_UNITS - 1)
-            for (unsigned j = 1; j < (unsigned)STRIDE; j++) { mlen[li + j] = 0; mdist[li + j] = 0; }
+        unsigned bext = 0;
+        if (STRIDE == 2 && bdist) {
+          // The parse works on units, so matches cover whole units (length truncated to even: a sample whose low byte
+          // matched nearly always matches in its high byte too).  Bit 15 = the match also covers the byte BEFORE this
+          // unit (the previous sample's high byte); used when the previous unit of the same stretch turns out to be a literal.
+          best &= ~1u;
+          const unsigned q = p - 1;
+          bext = (lane > 0 && best < 258 && q >= bdist &&
+                  ring[(q + off0) & 0xffffu] == ring[(q + off0 - bdist) & 0xffffu]) ? 0x8000u : 0u;
         }
+        mlen[tid] = (unsigned short)(bdist ? (best | bext) : 0);
+        mdist[tid] = (unsigned short)bdist;
       }
       // The 30 searcher warps now parse and emit the step among themselves (hardware barrier 1, 960 threads); the two
       // inserter warps keep threading step+1 into the tables and only rejoin at the end of the step.
       if (wid < NSW) {
       named_barrier(1, NSW * 32);
-      // ---- (C) greedy parse, hierarchical.  Stage 1: every warp resolves its stretch by pointer doubling (for each
-      //      position: where the token chain leaves the stretch and how many token elements it emits on the way).
+      LZ_PROF_T(t_p0);
+      if (tid == 0) { LZ_PROF_ADD(0, 1); LZ_PROF_ADD(1, t_p0 - t_step); }
+      // ---- (C) greedy parse over units, hierarchical; thread = unit, warp = stretch of 32 units.
+      //      Stage 1 (registers, shuffles): pointer doubling gives every unit the exit of the token chain that starts
+      //      there (where it leaves the stretch), the token elements it emits on the way and the mask of units it visits.
       //      Stage 2: one thread chains the 30 stretches from the carried start (entry + element base per stretch).
-      //      Stage 3: every warp marks the token starts reachable from its entry (doubling again) and emits them.
-      const unsigned start = misc[33 + (step & 1)];       // local start position carried from the previous step
-      if (start < slen) {
-        const unsigned sb = wid * STRETCH, se = min(sb + STRETCH, slen);
-        unsigned j[PER_LANE], c[PER_LANE];
-        if (wid < NSW) {
-          for (unsigned k = 0; k < PER_LANE; k++) {
-            const unsigned i = sb + lane * PER_LANE + k;
-            const unsigned l = (i < se) ? mlen[i] : 0;
-            j[k] = i + (l ? l : 1u);
-            c[k] = (i < se) ? (l ? 2u : 1u) : 0u;
-            ex[i] = (unsigned short)j[k];
-            ec[i] = (unsigned short)c[k];
-          }
-          __syncwarp();
-          for (unsigned r = 1; r < STRETCH; r <<= 1) {
-            for (unsigned k = 0; k < PER_LANE; k++)
-              if (j[k] < se) { c[k] += ec[j[k]]; j[k] = ex[j[k]]; }
-            __syncwarp();
-            for (unsigned k = 0; k < PER_LANE; k++) {
-              const unsigned i = sb + lane * PER_LANE + k;
-              ex[i] = (unsigned short)j[k];
-              ec[i] = (unsigned short)c[k];
-            }
-            __syncwarp();
+      //      Stage 3: the warp picks the mask of its entry unit and emits those tokens (ballot prefix -> offsets).
+      const unsigned nu = (slen + STRIDE - 1) / STRIDE;   // units in this step
+      const unsigned start = misc[33 + (step & 1)];       // local start unit carried from the previous step
+      if (start < nu) {
+        const unsigned sb = wid * 32, se = min(sb + 32, nu);
+        const unsigned sel = se > sb ? se - sb : 0;        // valid lanes of this stretch
+        const unsigned m = tid < nu ? mlen[tid] : 0;
+        const unsigned mnext = tid + 1 < nu ? mlen[tid + 1] : 0;
+        const unsigned l = m & 0x7fffu;
+        unsigned el = 0;                                   // token elements of the token starting at this unit
+        if (tid < nu) {
+          if (l) el = 2;
+          else {
+            el = (STRIDE == 2 && s0 + tid * STRIDE + 1 < n) ? 2 : 1;       // a literal per byte ...
+            if (mnext & 0x8000u) el--;                                     // ... unless the next match takes the last one
           }
         }
+        unsigned v = (lane + (l ? l / STRIDE : 1u)) | (el << 16);   // next unit (stretch-local) | elements
+        unsigned M = 1u << lane;
+        for (unsigned r = 0; r < 5; r++) {
+          const unsigned j = v & 0xffffu;
+          const unsigned tv = __shfl_sync(0xffffffffu, v, j & 31);
+          const unsigned tM = __shfl_sync(0xffffffffu, M, j & 31);
+          if (j < sel) { v = (tv & 0xffffu) | ((v & 0xffff0000u) + (tv & 0xffff0000u)); M |= tM; }
+        }
+        xe[tid] = (sb + (v & 0xffffu)) | (v & 0xffff0000u);
         named_barrier(1, NSW * 32);
+        if (tid == 0) { LZ_PROF_T(t_b); LZ_PROF_ADD(6, t_b - t_p0); }
         if (tid == 0) {
           unsigned p = start, acc = 0;
           for (unsigned w = 0; w < NSW; w++) {
             ent[w] = p;
             misc[w] = acc;
-            if (p < min((w + 1) * STRETCH, slen)) { acc += ec[p]; p = ex[p]; }
+            if (p < min((w + 1) * 32, nu)) { const unsigned t = xe[p]; acc += t >> 16; p = t & 0xffffu; }
           }
           misc[35] = acc;                                   // elements emitted by this step
-          misc[33 + ((step + 1) & 1)] = p - slen;          // p >= slen: where the last token of this step ends
+          misc[33 + ((step + 1) & 1)] = p - nu;            // p >= nu: where the last token of this step ends
         }
         named_barrier(1, NSW * 32);
-        if (wid < NSW) {
-          const unsigned entry = ent[wid];
-          if (entry < se) {                                 // warp-uniform
-            unsigned jm[PER_LANE];
-            for (unsigned k = 0; k < PER_LANE; k++) {
-              const unsigned i = sb + lane * PER_LANE + k;
-              const unsigned l = (i < se) ? mlen[i] : 0;
-              jm[k] = i + (l ? l : 1u);
-              ex[i] = (unsigned short)jm[k];
-              rf[i] = (i == entry);
-            }
-            __syncwarp();
-            for (unsigned r = 1; r < STRETCH; r <<= 1) {
-              unsigned jn[PER_LANE];
-              for (unsigned k = 0; k < PER_LANE; k++) {
-                const unsigned i = sb + lane * PER_LANE + k;
-                if (jm[k] < se && rf[i]) rf[jm[k]] = 1;
-                jn[k] = (jm[k] < se) ? ex[jm[k]] : jm[k];
-              }
-              __syncwarp();
-              for (unsigned k = 0; k < PER_LANE; k++) {
-                ex[sb + lane * PER_LANE + k] = (unsigned short)jn[k];
-                jm[k] = jn[k];
-              }
-              __syncwarp();
-            }
-            // emit: element offset of a token = elements of the reachable tokens before it (ballot prefix)
-            unsigned pre = run_tok + misc[wid];
-            unsigned lens[PER_LANE];
-            bool isr[PER_LANE];
-            for (unsigned k = 0; k < PER_LANE; k++) {
-              const unsigned i = sb + lane * PER_LANE + k;
-              isr[k] = (i < se) && rf[i];
-              lens[k] = isr[k] ? mlen[i] : 0;
-            }
-            unsigned mine = 0;
-            for (unsigned k = 0; k < PER_LANE; k++) mine += isr[k] ? (lens[k] ? 2u : 1u) : 0u;
-            // exclusive prefix over lanes of `mine` (0..4) from two ballots per bit plane
-            const unsigned lt = (1u << lane) - 1;
-            unsigned excl = __popc(__ballot_sync(0xffffffffu, mine & 1) & lt) +
-                            2 * __popc(__ballot_sync(0xffffffffu, mine & 2) & lt) +
-                            4 * __popc(__ballot_sync(0xffffffffu, mine & 4) & lt);
-            unsigned pos = pre + excl;
-            for (unsigned k = 0; k < PER_LANE; k++) {
-              if (!isr[k]) continue;
-              const unsigned li = sb + lane * PER_LANE + k;
-              const unsigned l = lens[k];
-              if (l) {
-                const unsigned d = mdist[li];
-                tok[pos] = (unsigned short)(0x8000u | l);
-                tok[pos + 1] = (unsigned short)(d - 1);
-                unsigned sym, nb, ev;
-                len_symbol(l, sym, nb, ev);
-                atomicAdd(&shist[sym], 1u);
-                dist_symbol(d, sym, nb, ev);
-                atomicAdd(&shist[288 + sym], 1u);
-                pos += 2;
-              } else {
-                const unsigned bt = ring[(s0 + li + off0) & 0xffffu];
-                tok[pos] = (unsigned short)bt;
-                atomicAdd(&shist[bt], 1u);
-                pos += 1;
+        if (tid == 0) { LZ_PROF_T(t_b); LZ_PROF_ADD(7, t_b - t_p0); }
+        const unsigned entry = ent[wid];
+        if (entry < se) {                                   // warp-uniform
+          const unsigned reach = __shfl_sync(0xffffffffu, M, entry - sb);
+          const bool isr = (reach >> lane) & 1u;
+          const unsigned mine = isr ? el : 0u;
+          const unsigned lt = (1u << lane) - 1;
+          const unsigned excl = __popc(__ballot_sync(0xffffffffu, mine & 1) & lt) +
+                                2 * __popc(__ballot_sync(0xffffffffu, mine & 2) & lt);
+          const unsigned pos = run_tok + misc[wid] + excl;
+          if (isr) {
+            if (l) {
+              const unsigned d = mdist[tid];
+              // back-extended over the last byte of the previous unit when that one is a (literal) token start
+              const unsigned le = l + ((m >> 15) & (reach >> ((lane + 31) & 31)) & 1u);
+              tok[pos] = (unsigned short)(0x8000u | le);
+              tok[pos + 1] = (unsigned short)(d - 1);
+              unsigned sym, nb, ev;
+              len_symbol(le, sym, nb, ev);
+              atomicAdd(&shist[sym], 1u);
+              dist_symbol(d, sym, nb, ev);
+              atomicAdd(&shist[288 + sym], 1u);
+            } else {
+              const unsigned r0 = s0 + tid * STRIDE + off0;
+              const unsigned b0 = ring[r0 & 0xffffu];
+              tok[pos] = (unsigned short)b0;
+              atomicAdd(&shist[b0], 1u);
+              if (mine == 2) {
+                const unsigned b1 = ring[(r0 + 1) & 0xffffu];
+                tok[pos + 1] = (unsigned short)b1;
+                atomicAdd(&shist[b1], 1u);
               }
             }
           }
         }
+        if (tid == 0) { LZ_PROF_T(t_b); LZ_PROF_ADD(8, t_b - t_p0); }
         run_tok += misc[35];
       } else {
-        if (tid == 0) misc[33 + ((step + 1) & 1)] = start - slen;
+        if (tid == 0) misc[33 + ((step + 1) & 1)] = start - nu;
       }
       }   // wid < NSW
       __syncthreads();
