@@ -53,13 +53,14 @@ struct mtsb_ctx {
   std::string err;
   // params
   long long par_inflate = 1;   // decode index-less zlib streams block-parallel (inflate_par.cuh)
+  long long par_batch_bytes = 6ll << 30;   // host-buffer sub-batch of index-less chunks (output bytes): large enough to amortise the block search
   long long par_stats[4] = {0, 0, 0, 0};   // last call: survivors, candidates, chained blocks, streams resumed
   long long seg_bytes = 262144, batch_bytes = 2ll << 30, host_batch_bytes = 512ll << 20, write_index = 1;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of the host-buffer paths
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_done = nullptr;
   LzParams lz{4, 16, 32768, 32768, 32768, 0};   // greedy, every match >= 4 bytes accepted: tuned on synthetic AP/LFP
   // device scratch
-  Buf d_pstreams, d_surv, d_cand, d_pcount, d_cells, d_ptab, d_plist, d_pbad;   // block-parallel inflate scratch
+  Buf d_pstreams, d_surv, d_cand, d_pcount, d_tokens, d_ptab, d_plist, d_pbad;   // block-parallel inflate scratch
   Buf d_raw, d_raw2, d_out2, d_comp2, d_T, d_tok, d_hist, d_codes, d_hdrs, d_tab, d_so, d_seg_adler, d_chunk_adler, d_chunk_off, d_out,
       d_partial, d_comp, d_status, d_tadler, d_gather;
   Buf h_tab, h_small;
@@ -143,6 +144,9 @@ int set_attrs(mtsb_ctx* c) {
   CK(cudaFuncSetAttribute(inv_apply_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
   CK(cudaFuncSetAttribute(lz77_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LzSmem<1>::total));
   CK(cudaFuncSetAttribute(lz77_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LzSmem<2>::total));
+  // thread-per-block decoder: 36 KB of tables per 32-thread CTA, six CTAs per SM need the largest carve-out
+  CK(cudaFuncSetAttribute(par_decode_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(par_decode_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   c->attr_set = true;
   return 0;
 }
@@ -310,7 +314,7 @@ void mtsb_destroy(mtsb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  Buf* bufs[] = {&c->d_pstreams, &c->d_surv, &c->d_cand, &c->d_pcount, &c->d_cells, &c->d_ptab, &c->d_plist, &c->d_pbad,
+  Buf* bufs[] = {&c->d_pstreams, &c->d_surv, &c->d_cand, &c->d_pcount, &c->d_tokens, &c->d_ptab, &c->d_plist, &c->d_pbad,
                  &c->d_raw, &c->d_raw2, &c->d_out2, &c->d_comp2, &c->d_T, &c->d_tok, &c->d_hist, &c->d_codes, &c->d_hdrs, &c->d_tab, &c->d_so,
                  &c->d_seg_adler, &c->d_chunk_adler, &c->d_chunk_off, &c->d_out, &c->d_partial, &c->d_comp,
                  &c->d_status, &c->d_tadler, &c->d_gather, &c->h_tab, &c->h_small};
@@ -340,6 +344,7 @@ int mtsb_set_param(mtsb_ctx* c, const char* name, long long v) {
   else if (s == "host_batch_bytes") { if (v < (1 << 20)) return fail(c, MTSB_E_ARG, "host_batch_bytes too small"); c->host_batch_bytes = v; }
   else if (s == "write_index") c->write_index = v ? 1 : 0;
   else if (s == "par_inflate") c->par_inflate = v ? 1 : 0;
+  else if (s == "par_batch_bytes") { if (v < (1 << 20)) return fail(c, MTSB_E_ARG, "par_batch_bytes too small"); c->par_batch_bytes = v; }
   else if (s == "max_chain") c->lz.max_chain = (int)std::max<long long>(1, v);
   else if (s == "nice_len") c->lz.nice_len = (int)std::min<long long>(258, std::max<long long>(4, v));
   else if (s == "far4") c->lz.far4 = (int)v;
@@ -358,6 +363,7 @@ long long mtsb_get_param(mtsb_ctx* c, const char* name) {
   if (s == "host_batch_bytes") return c->host_batch_bytes;
   if (s == "write_index") return c->write_index;
   if (s == "par_inflate") return c->par_inflate;
+  if (s == "par_batch_bytes") return c->par_batch_bytes;
   if (s == "par_survivors") return c->par_stats[0];
   if (s == "par_candidates") return c->par_stats[1];
   if (s == "par_chained") return c->par_stats[2];
@@ -736,17 +742,14 @@ static int par_phase(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Inflat
                      unsigned char* dT) {
   const int ns = (int)whole.size();
   std::vector<ParStream> ps(ns);
-  long long in_total = 0, out_min = (1ll << 62), out_max = 0;
+  long long in_total = 0;
   int max_in = 0;
   for (int i = 0; i < ns; i++) {
     const InflateSeg& s = segs[whole[i]];
     ps[i].in_off = s.in_off; ps[i].out_off = s.out_off; ps[i].in_len = s.in_len; ps[i].out_len = s.out_len;
     in_total += s.in_len;
-    out_min = std::min(out_min, s.out_off);
-    out_max = std::max(out_max, s.out_off + s.out_len);
     max_in = std::max(max_in, s.in_len);
   }
-  const long long cells_n = out_max - out_min;
   const size_t surv_cap = (size_t)std::max<long long>(1 << 20, in_total * 8 / 300);
   const size_t cand_cap = (size_t)std::max<long long>(1 << 16, in_total / 4096 + 64ll * ns);
   NEED(c->d_pstreams, (size_t)ns * sizeof(ParStream));
@@ -781,11 +784,11 @@ static int par_phase(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Inflat
   c->par_stats[1] += n_cand;
   if (n_cand == 0 || n_cand > cand_cap) return 0;
   NEED(c->d_ptab, (size_t)n_cand * sizeof(ParTables));
-  NEED(c->d_cells, (size_t)cells_n * 2 + 64);
   {
     auto k = par_decode_kernel<0>;
-    MTS_LAUNCH(k, dim3((n_cand + 127) / 128), dim3(128), 0, c->stream, dcomp, d_ps, (ParCand*)c->d_cand.p,
-               (const unsigned*)nullptr, n_cand, (ParTables*)c->d_ptab.p, (unsigned short*)nullptr, out_min);
+    MTS_LAUNCH(k, dim3((n_cand + PAR_DEC_THREADS - 1) / PAR_DEC_THREADS), dim3(PAR_DEC_THREADS), 0, c->stream, dcomp, d_ps,
+               (ParCand*)c->d_cand.p, (const unsigned*)nullptr, n_cand, (ParTables*)c->d_ptab.p, (unsigned*)nullptr,
+               (const ParLz*)nullptr);
     CKL();
     c->launches++;
   }
@@ -799,45 +802,53 @@ static int par_phase(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Inflat
   std::vector<unsigned> chain, first(ns + 1, 0);
   std::vector<unsigned> tail_bit(ns, 16), tail_out(ns, 0);
   std::vector<char> fin(ns, 0);
+  std::vector<ParLz> lz(ns);
+  long long total_tok = 0;
   for (int sidx = 0; sidx < ns; sidx++) {
     auto& v = by_stream[sidx];
     std::sort(v.begin(), v.end());
     first[sidx] = (unsigned)chain.size();
     unsigned cur = 16, run = 0;
+    unsigned long long run_tok = 0;
     for (;;) {
       auto it = std::lower_bound(v.begin(), v.end(), std::make_pair(cur, 0u));
       if (it == v.end() || it->first != cur) break;
       ParCand& cd = hc[it->second];
-      if ((long long)run + cd.out_len > ps[sidx].out_len || cd.end_bit <= cur) break;
-      cd.out_off = run;
+      if ((long long)run + cd.out_len > ps[sidx].out_len || cd.end_bit <= cur || run_tok + cd.n_tok > 0xfffffff0ull) break;
+      cd.tok_off = (unsigned)run_tok;
       chain.push_back(it->second);
       run += cd.out_len;
+      run_tok += cd.n_tok;
       cur = cd.end_bit;
       if (cd.final_) { fin[sidx] = 1; break; }
     }
     tail_bit[sidx] = cur; tail_out[sidx] = run;
+    lz[sidx].tok_base = total_tok; lz[sidx].n_tok = (unsigned)run_tok; lz[sidx].out_len = run;
+    total_tok += (long long)run_tok;
   }
   first[ns] = (unsigned)chain.size();
   const unsigned n_chain = (unsigned)chain.size();
   c->par_stats[2] += n_chain;
   if (n_chain == 0) return 0;
-  // upload the candidates (now with output offsets), the chain and its per-stream ranges
+  // upload the candidates (now with token offsets), the chain and the per-stream token ranges
   { int r = small_copy(c, c->d_cand.p, c->h_tab.p, (size_t)n_cand * sizeof(ParCand)); if (r) return r; }
   CK(cudaStreamSynchronize(c->stream));                       // h_tab is reused below
-  const size_t o_first = ((size_t)n_chain * 4 + 255) & ~(size_t)255;
-  NEED(c->d_plist, o_first + (size_t)(ns + 1) * 4);
-  NEED(c->h_tab, o_first + (size_t)(ns + 1) * 4 + 64);
+  const size_t o_lz = ((size_t)n_chain * 4 + 255) & ~(size_t)255;
+  NEED(c->d_plist, o_lz + (size_t)ns * sizeof(ParLz));
+  NEED(c->h_tab, o_lz + (size_t)ns * sizeof(ParLz) + 64);
+  NEED(c->d_tokens, (size_t)total_tok * 4 + 64);
   memcpy(c->h_tab.p, chain.data(), (size_t)n_chain * 4);
-  memcpy((char*)c->h_tab.p + o_first, first.data(), (size_t)(ns + 1) * 4);
-  { int r = small_copy(c, c->d_plist.p, c->h_tab.p, o_first + (size_t)(ns + 1) * 4); if (r) return r; }
+  memcpy((char*)c->h_tab.p + o_lz, lz.data(), (size_t)ns * sizeof(ParLz));
+  { int r = small_copy(c, c->d_plist.p, c->h_tab.p, o_lz + (size_t)ns * sizeof(ParLz)); if (r) return r; }
   {
+    const ParLz* d_lz = (const ParLz*)((const char*)c->d_plist.p + o_lz);
     auto k = par_decode_kernel<1>;
-    MTS_LAUNCH(k, dim3((n_chain + 127) / 128), dim3(128), 0, c->stream, dcomp, d_ps, (ParCand*)c->d_cand.p,
-               (const unsigned*)c->d_plist.p, n_chain, (ParTables*)c->d_ptab.p, (unsigned short*)c->d_cells.p, out_min);
+    MTS_LAUNCH(k, dim3((n_chain + PAR_DEC_THREADS - 1) / PAR_DEC_THREADS), dim3(PAR_DEC_THREADS), 0, c->stream, dcomp, d_ps,
+               (ParCand*)c->d_cand.p, (const unsigned*)c->d_plist.p, n_chain, (ParTables*)c->d_ptab.p,
+               (unsigned*)c->d_tokens.p, d_lz);
     CKL();
-    MTS_LAUNCH(par_resolve_kernel, dim3(ns), dim3(1024), 0, c->stream, d_ps, (const ParCand*)c->d_cand.p,
-               (const unsigned*)c->d_plist.p, (const unsigned*)((const char*)c->d_plist.p + o_first),
-               (const unsigned short*)c->d_cells.p, out_min, dT, (int*)c->d_pbad.p);
+    MTS_LAUNCH(par_lz_kernel, dim3(ns), dim3(PAR_LZ_THREADS), 0, c->stream, d_ps, d_lz, (const unsigned*)c->d_tokens.p, dT,
+               (int*)c->d_pbad.p);
     CKL();
     c->launches += 2;
   }
@@ -935,6 +946,15 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
   // a sub-batch must also hold enough independent streams to fill the GPU: chunks without a segment index (e.g.
   // reference-written ones) are ONE serial stream each, so they are batched by count (up to 16 GiB of output)
   const long long min_streams = 8ll * c->sm_count, hard_limit = std::max<long long>(c->batch_bytes, 16ll << 30);
+  // index-less chunks with host buffers: equal sub-batches of about par_batch_bytes
+  long long par_limit = std::max(sb_limit, c->par_batch_bytes);
+  {
+    long long total_par = 0, max_cb = 0;
+    for (int i = 0; i < n_chunks; i++)
+      if (!nseg[i]) { long long cb = (chunk_rows[i + 1] - chunk_rows[i]) * row_bytes; total_par += cb; max_cb = std::max(max_cb, cb); }
+    const long long n_par = std::max<long long>(1, (total_par + par_limit / 2) / par_limit);
+    par_limit = (total_par + n_par - 1) / n_par + max_cb;
+  }
   std::vector<int> sb_first;
   long long max_sb_bytes = 0, max_sb_comp = 0;
   for (int a = 0; a < n_chunks;) {
@@ -944,7 +964,11 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
     while (b < n_chunks && b - a < 60000) {
       long long cb = (chunk_rows[b + 1] - chunk_rows[b]) * row_bytes;
       if (b > a && bb + cb > hard_limit) break;
-      if (b > a && bb + cb > sb_limit && streams >= min_streams) break;
+      // index-less chunks decoded block-parallel have thousands of independent blocks: with host buffers they are
+      // batched by bytes so that copies overlap the decode of the neighbouring sub-batches
+      const bool par_b = host_io && c->par_inflate && !nseg[b];
+      if (b > a && par_b && bb + cb > par_limit) break;
+      if (b > a && !par_b && bb + cb > sb_limit && streams >= min_streams) break;
       bb += cb; streams += nseg[b] ? nseg[b] : 1; b++;
     }
     max_sb_bytes = std::max(max_sb_bytes, bb);

@@ -82,6 +82,7 @@ __device__ __forceinline__ unsigned d_extra_bits(unsigned sym) { return sym < 4 
 static const int LZ_THREADS = 1024;
 static const int LZ_UNITS = 960;              // units searched per step = 30 searcher warps x 32 lanes
 static const int LZ_RING = 65536;
+static const int LZ_MIRROR = 288;             // ring[65536 + i] mirrors ring[i]: reads of up to 258 + 16 + 4 bytes never wrap
 static const int LZ_HASHS_BITS = 14;
 static const unsigned LZ_BIAS = 32768;
 
@@ -92,7 +93,7 @@ template <int STRIDE> struct LzSmem {
   // the inserters run one step ahead, so chain entries older than PREV_N - 2 steps may already be recycled
   static const int MAXD_UNITS = PREV_N - 2 * LZ_UNITS - 8;
   static const size_t ring_off = 0;
-  static const size_t headl_off = LZ_RING;
+  static const size_t headl_off = LZ_RING + LZ_MIRROR;
   static const size_t heads_off = headl_off + (size_t)(1 << HL_BITS) * 2;
   static const size_t prevl_off = heads_off + (size_t)(1 << LZ_HASHS_BITS) * 2;
   static const size_t prevs_off = prevl_off + (size_t)PREV_N * 2;
@@ -105,11 +106,15 @@ template <int STRIDE> struct LzSmem {
   static const size_t total = misc_off + 512;
 };
 
-__device__ __forceinline__ unsigned ring_load4(const unsigned char* ring, unsigned r) {
-  unsigned a = r & 0xfffcu;
-  unsigned lo = *(const unsigned*)(ring + a);
-  unsigned hi = *(const unsigned*)(ring + ((a + 4) & 0xffffu));
-  return __funnelshift_r(lo, hi, (r & 3) * 8);
+__device__ __forceinline__ unsigned ring_load4(const unsigned char* ring, unsigned r) {   // r: any ring coordinate
+  const unsigned m = r & 0xffffu;
+  const unsigned* w = (const unsigned*)(ring + (m & 0xfffcu));
+  return __funnelshift_r(w[0], w[1], m << 3);              // w[1] may lie in the mirror
+}
+// store 16 bytes at ring offset o (multiple of 16, < LZ_RING), keeping the mirror in step
+__device__ __forceinline__ void ring_store16(unsigned char* ring, unsigned o, uint4 v) {
+  *(uint4*)(ring + o) = v;
+  if (o < (unsigned)LZ_MIRROR) *(uint4*)(ring + LZ_RING + o) = v;
 }
 __device__ __forceinline__ unsigned lz_hash4(unsigned w) { return (w * 0x9E3779B1u) >> (32 - LZ_HASHS_BITS); }
 template <int BITS> __device__ __forceinline__ unsigned lz_hash6(unsigned w0, unsigned w1) {
@@ -177,17 +182,21 @@ __device__ __forceinline__ void lz_insert_step(const unsigned short* hbuf, unsig
   __syncwarp();
 }
 
-// Length of the match between ring positions pr (whose first 16 bytes are w0..w3) and qr, up to lim.
-__device__ __forceinline__ unsigned lz_match_len(const unsigned char* ring, unsigned pr, unsigned qr, unsigned lim,
+// Length of the match between the position whose first 16 bytes are w0..w3 (ring offset pm < LZ_RING) and the candidate
+// at ring offset qm < LZ_RING, up to lim.  All reads run forward without wrapping (mirror).
+__device__ __forceinline__ unsigned lz_match_len(const unsigned char* ring, unsigned pm, unsigned qm, unsigned lim,
                                                  unsigned w0, unsigned w1, unsigned w2, unsigned w3) {
+  const unsigned* qw = (const unsigned*)(ring + (qm & 0xfffcu));
+  const unsigned sh = qm << 3;
   unsigned len = 0;
-  unsigned x = ring_load4(ring, qr) ^ w0;
-  if (!x) { len = 4; x = ring_load4(ring, qr + 4) ^ w1;
-    if (!x) { len = 8; x = ring_load4(ring, qr + 8) ^ w2;
-      if (!x) { len = 12; x = ring_load4(ring, qr + 12) ^ w3;
+  unsigned t0 = qw[0], t1 = qw[1];
+  unsigned x = __funnelshift_r(t0, t1, sh) ^ w0;
+  if (!x) { len = 4; t0 = qw[2]; x = __funnelshift_r(t1, t0, sh) ^ w1;
+    if (!x) { len = 8; t1 = qw[3]; x = __funnelshift_r(t0, t1, sh) ^ w2;
+      if (!x) { len = 12; t0 = qw[4]; x = __funnelshift_r(t1, t0, sh) ^ w3;
         if (!x) { len = 16;
           while (len < lim) {
-            x = ring_load4(ring, pr + len) ^ ring_load4(ring, qr + len);
+            x = ring_load4(ring, pm + len) ^ ring_load4(ring, qm + len);
             if (x) break;
             len += 4;
           } } } } }
@@ -247,7 +256,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
     for (unsigned i = tid; i < HIST_STRIDE; i += LZ_THREADS) shist[i] = 0;
     if (tid == 0) { misc[33] = 0; misc[34] = 0; }
     for (unsigned v = tid; v * 16 < 3 * SEG + 32; v += LZ_THREADS)
-      if (v * 16 < n_ring) *(uint4*)(ring + v * 16) = in16[v];
+      if (v * 16 < n_ring) ring_store16(ring, v * 16, in16[v]);
     __syncthreads();
     // hashes of the units of steps 0 and 1 (later steps: computed two steps ahead by the searchers)
     for (unsigned k = tid; k < 2 * LZ_UNITS; k += LZ_THREADS) {
@@ -295,13 +304,12 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
         if (li < slen && p + 4 <= n && prm.lazy != 2) {
           const unsigned u = p / STRIDE;
           const unsigned lim = min(258u, n - p);
-          const unsigned pr = p + off0;
+          const unsigned pr = (p + off0) & 0xffffu;       // ring offset of this unit
           unsigned w0, w1, w2, w3;                        // the first 16 bytes at p stay in registers
           {
-            const unsigned a = pr & 0xfffcu, sh = (pr & 3) * 8;
-            unsigned t0 = *(const unsigned*)(ring + a), t1 = *(const unsigned*)(ring + ((a + 4) & 0xffffu)),
-                     t2 = *(const unsigned*)(ring + ((a + 8) & 0xffffu)), t3 = *(const unsigned*)(ring + ((a + 12) & 0xffffu)),
-                     t4 = *(const unsigned*)(ring + ((a + 16) & 0xffffu));
+            const unsigned* pw = (const unsigned*)(ring + (pr & 0xfffcu));
+            const unsigned sh = pr << 3;
+            const unsigned t0 = pw[0], t1 = pw[1], t2 = pw[2], t3 = pw[3], t4 = pw[4];
             w0 = __funnelshift_r(t0, t1, sh); w1 = __funnelshift_r(t1, t2, sh);
             w2 = __funnelshift_r(t2, t3, sh); w3 = __funnelshift_r(t3, t4, sh);
           }
@@ -317,9 +325,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
               if (du - 1 >= (unsigned)L::MAXD_UNITS || du <= lastd || du > u) break;
               lastd = du;
               const unsigned dist = du * STRIDE;
-              const unsigned qr = pr - dist;
+              const unsigned qr = (pr - dist) & 0xffffu;
               cand = prevL[(cand - LZ_BIAS) & PM];
-              if (ring_load4(ring, qr + best - 3) != wq) continue;
+              if (bdist && ring_load4(ring, qr + best - 3) != wq) continue;   // cannot beat the match in hand
               const unsigned len = lz_match_len(ring, pr, qr, lim, w0, w1, w2, w3);
               if (len > best) {
                 best = len; bdist = dist;
@@ -334,7 +342,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
             const unsigned du = (ub - prevS[u % (2 * LZ_UNITS)]) & 0xffffu;
             if (du - 1 < (unsigned)L::MAXD_UNITS && du <= u) {
               const unsigned dist = du * STRIDE;
-              const unsigned len = lz_match_len(ring, pr, pr - dist, lim, w0, w1, w2, w3);
+              const unsigned len = lz_match_len(ring, pr, (pr - dist) & 0xffffu, lim, w0, w1, w2, w3);
               if (len >= 4) { best = len; bdist = dist; }
             }
           }
@@ -347,7 +355,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
           hb[tid] = hs;
           hb[LZ_UNITS + tid] = hl;
         }
-        if (pf) *(uint4*)(ring + (pf_rc & 0xffffu)) = pf_v;
+        if (pf) ring_store16(ring, pf_rc & 0xffffu, pf_v);
         if (tid == 0) { LZ_PROF_T(t_s); LZ_PROF_ADD(2, t_s - t_step); }
         unsigned bext = 0;
         if (STRIDE == 2 && bdist) {

@@ -33,35 +33,52 @@ struct ParCand {         // a candidate dynamic block
   unsigned stream, bit;  // owning stream, bit offset of the block header inside it
   unsigned end_bit;      // bit offset just after the end-of-block code (dry decode)
   unsigned out_len;      // bytes the block produces
-  unsigned out_off;      // offset of those bytes inside the stream's output (set on the host for chained blocks)
+  unsigned tok_off;      // first token of the block inside its stream's token array (set on the host for chained blocks)
   int state;             // 1 = decoded cleanly, <= 0 = rejected
   unsigned final_;       // BFINAL
-  unsigned pad_;
+  unsigned n_tok;        // tokens (literals + matches) the block decodes to
 };
 
-// Per-thread decoding tables (global memory scratch, one per candidate).
-static const int PAR_LBITS = 9, PAR_DBITS = 6;
+struct ParLz {           // per stream, for par_lz_kernel
+  long long tok_base;    // first token of the stream in the token buffer
+  unsigned n_tok;        // tokens of its chained blocks
+  unsigned out_len;      // bytes they must produce
+};
+
+// Decoding tables.  The fast tables live in SHARED memory, one column of 32-bit words per thread (word w of lane l at
+// tabw[w * 32 + l]: every lane owns a bank, so 32 unrelated lookups never conflict); entries are 16 bits, two per word:
+//   literal/length (9 index bits): code length | kind << 4 | (literal byte or length symbol - 257) << 6
+//   distance       (7 index bits): code length | symbol << 4
+// A zero entry means "longer code": see the limit words below; only the symbol order (sorted[]) is in global scratch.
+// Longer codes: per code length l one word  limit | oend << 17  where limit = one past the last l-bit code, left-justified
+// to 16 bits, and oend = number of symbols with codes of length <= l; the symbol is sorted[oend - ((limit - code16) >> (16-l))].
+static const int PAR_LBITS = 9, PAR_DBITS = 7;
+static const int PAR_LWORDS = (1 << PAR_LBITS) / 2, PAR_DWORDS = (1 << PAR_DBITS) / 2;
+static const int PAR_LLONG = 16 - PAR_LBITS, PAR_DLONG = 16 - PAR_DBITS;      // limit words of lengths tb..15
+static const int PAR_TWORDS = PAR_LWORDS + PAR_DWORDS + PAR_LLONG + PAR_DLONG;
+static const int PAR_DEC_THREADS = 32;       // one warp per CTA: 42 KB of tables, 5 CTAs per SM
 struct ParTables {
-  unsigned ltab[1 << PAR_LBITS];
-  unsigned dtab[1 << PAR_DBITS];
   unsigned short lsorted[288], dsorted[32];
   unsigned short lcount[16], dcount[16];
   unsigned char lens[320];
 };
+
+// A token is 32 bits: a literal byte, or 0x80000000 | length << 16 | (distance - 1).
 
 // ---------------------------------------------------------------------------------------------- per-thread bit reader
 struct TBits {
   const unsigned* w;     // 4-byte aligned base of the stream
   unsigned sh;           // 8 * (stream address & 3)
   unsigned kmax;         // last readable word
-  unsigned k;            // next raw word
-  unsigned raw, lo, hi;  // raw = w[k-1]; (lo, hi) = 64 stream bits
+  unsigned k;            // index of the raw word held in `ahead`
+  unsigned raw, ahead;   // raw = w[k-1]; ahead = w[k], loaded one refill early so that its latency is hidden
+  unsigned lo, hi;       // 64 stream bits
   unsigned pos;          // cursor inside (lo, hi), < 32 after refill
   unsigned base_bit;     // stream bit offset of bit 0 of lo
   __device__ __forceinline__ unsigned next_word() {
-    unsigned nw = w[min(k, kmax)];
-    unsigned v = __funnelshift_r(raw, nw, sh);
-    raw = nw; k++;
+    const unsigned v = __funnelshift_r(raw, ahead, sh);
+    raw = ahead; k++;
+    ahead = w[min(k, kmax)];
     return v;
   }
   __device__ __forceinline__ void init(const unsigned char* in, unsigned in_len, unsigned bit) {
@@ -72,6 +89,7 @@ struct TBits {
     const unsigned word = bit >> 5;           // stream word that holds `bit`
     k = word;
     raw = w[min(k, kmax)]; k++;
+    ahead = w[min(k, kmax)];
     lo = next_word();
     hi = next_word();
     pos = bit & 31;
@@ -163,10 +181,11 @@ __device__ bool par_parse_header(TBits& br, unsigned char* lens, int& nl, int& n
   return true;
 }
 
-// Fast table + canonical arrays for one code (per thread, serial).  KIND 1 literal/length, 2 distance.
+// Fast table (this thread's shared-memory column starting at word w0) + canonical arrays for one code (serial, per
+// thread).  KIND 1 literal/length, 2 distance.
 template <int KIND>
-__device__ bool par_build(const unsigned char* lens, int n, unsigned* tab, int tb, unsigned short* sorted,
-                          unsigned short* count) {
+__device__ bool par_build(const unsigned char* lens, int n, unsigned* tabw, unsigned lane, int w0, int tb, int wlong,
+                          unsigned short* sorted, unsigned short* count) {
   for (int i = 0; i < 16; i++) count[i] = 0;
   for (int i = 0; i < n; i++) count[lens[i]]++;
   count[0] = 0;
@@ -180,36 +199,63 @@ __device__ bool par_build(const unsigned char* lens, int n, unsigned* tab, int t
     o += count[l];
     left = (left << 1) - count[l];
     if (left < 0) return false;
+    if (l >= tb) tabw[(wlong + l - tb) * 32 + lane] = ((code + count[l]) << (16 - l)) | (o << 17);
   }
-  for (int i = 0; i < (1 << tb); i++) tab[i] = 0;
+  for (int w = 0; w < (1 << tb) / 2; w++) tabw[(w0 + w) * 32 + lane] = 0;
+  unsigned short* col = (unsigned short*)(tabw + w0 * 32 + lane);   // entry k at col[(k >> 1) * 64 + (k & 1)]
   for (int s = 0; s < n; s++) {
     const unsigned l = lens[s];
     if (!l) continue;
     sorted[offs[l]++] = (unsigned short)s;
     if ((int)l <= tb) {
       const unsigned r = __brev(first[l]++) >> (32 - l);
-      const unsigned e = KIND == 1 ? ll_entry((unsigned)s, l) : d_entry((unsigned)s, l);
-      for (unsigned k = r; k < (1u << tb); k += 1u << l) tab[k] = e;
+      unsigned e;
+      if (KIND == 1) e = l | ((s < 256 ? (unsigned)K_LIT : s == 256 ? (unsigned)K_EOB : s < 286 ? (unsigned)K_LEN : (unsigned)K_BAD) << 4) |
+                         ((unsigned)(s < 256 ? s : s > 256 ? s - 257 : 0) << 6);
+      else e = l | ((unsigned)s << 4);
+      for (unsigned k = r; k < (1u << tb); k += 1u << l) col[(k >> 1) * 64 + (k & 1)] = (unsigned short)e;
     } else first[l]++;
   }
   return true;
 }
 
-template <int KIND>
-__device__ __forceinline__ unsigned par_slow(unsigned win, const unsigned short* count, const unsigned short* sorted) {
-  unsigned code = 0, first = 0, index = 0;
-  for (int l = 1; l <= 15; l++) {
-    code |= (win >> (l - 1)) & 1;
-    const unsigned c = count[l];
-    if (code - first < c) {
-      const unsigned s = sorted[index + (code - first)];
-      return KIND == 1 ? ll_entry(s, (unsigned)l) : d_entry(s, (unsigned)l);
-    }
-    index += c;
-    first = (first + c) << 1;
-    code <<= 1;
+// Decode of a code longer than the fast table (tb bits): the limit words of lengths tb+1..15 are scanned (the first
+// length whose limit exceeds the left-justified code), then one global load fetches the symbol.
+template <int TB>
+__device__ __forceinline__ bool par_long(unsigned win, const unsigned* tabw, unsigned lane, int wlong,
+                                         const unsigned short* sorted, unsigned& sym, unsigned& nbits) {
+  const unsigned c16 = __brev(win) >> 16;
+  unsigned word = 0, prev = 0, l = 0;
+  unsigned below = tabw[wlong * 32 + lane];                 // length TB: only its symbol count matters
+#pragma unroll
+  for (int j = 1; j <= 15 - TB; j++) {                      // the limits grow with the length: the first that fits
+    const unsigned wj = tabw[(wlong + j) * 32 + lane];
+    if (!l && c16 < (wj & 0x1ffffu)) { word = wj; prev = below; l = (unsigned)(TB + j); }
+    below = wj;
   }
-  return 0;
+  if (!l) return false;
+  const unsigned back = ((word & 0x1ffffu) - c16 - 1) >> (16 - l);      // codes between this one and the last of length l
+  const unsigned idx = (word >> 17) - 1 - back;
+  // idx must lie among the symbols of length l (an incomplete code leaves holes that are not codes)
+  if ((int)idx < (int)(prev >> 17)) return false;
+  sym = sorted[idx];
+  nbits = l;
+  return true;
+}
+
+// base | extra bits << 12 of length symbol 257 + i; base | extra bits << 16 of distance symbol i (0 = invalid)
+__device__ __forceinline__ unsigned par_len_info(unsigned i) {
+  if (i < 8) return 3 + i;
+  if (i == 28) return 258;
+  if (i > 28) return 0;
+  const unsigned nb = (i - 4) >> 2;
+  return (3 + ((4 + (i & 3)) << nb)) | (nb << 12);
+}
+__device__ __forceinline__ unsigned par_dist_info(unsigned i) {
+  if (i < 4) return i + 1;
+  if (i >= 30) return 0;
+  const unsigned nb = (i >> 1) - 1;
+  return (1 + ((2 + (i & 1)) << nb)) | (nb << 16);
 }
 
 // ---------------------------------------------------------------------------------------------- kernels
@@ -287,20 +333,30 @@ __global__ void __launch_bounds__(128) par_validate_kernel(const unsigned char* 
   const unsigned at = atomicAdd(&counters[1], 1u);
   if (at < cap) {
     ParCand c;
-    c.stream = sidx; c.bit = bit; c.end_bit = 0; c.out_len = 0; c.out_off = 0; c.state = 0; c.final_ = fin; c.pad_ = 0;
+    c.stream = sidx; c.bit = bit; c.end_bit = 0; c.out_len = 0; c.tok_off = 0; c.state = 0; c.final_ = fin; c.n_tok = 0;
     cand[at] = c;
   }
 }
 
-// 3/4. Thread per block.  REAL = 0: dry decode of every candidate (end bit, output length).  REAL = 1: decode the
-// chained blocks (list[] holds their candidate indices) into 16-bit cells.
+// 3/4. Thread per block, one warp per CTA, fast tables in shared memory.  REAL = 0: dry decode of every candidate (end
+// bit, output length, token count).  REAL = 1: decode the chained blocks (list[] holds their candidate indices) into
+// tokens; the back-references are resolved afterwards by par_lz_kernel, in stream order.
 template <int REAL>
-__global__ void __launch_bounds__(128) par_decode_kernel(const unsigned char* __restrict__ comp,
-                                                         const ParStream* __restrict__ streams,
-                                                         ParCand* __restrict__ cand, const unsigned* __restrict__ list,
-                                                         unsigned n, ParTables* __restrict__ tables,
-                                                         unsigned short* __restrict__ cells, long long cells_base) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(PAR_DEC_THREADS) par_decode_kernel(const unsigned char* __restrict__ comp,
+                                                                     const ParStream* __restrict__ streams,
+                                                                     ParCand* __restrict__ cand,
+                                                                     const unsigned* __restrict__ list, unsigned n,
+                                                                     ParTables* __restrict__ tables,
+                                                                     unsigned* __restrict__ tokens,
+                                                                     const ParLz* __restrict__ lz) {
+  __shared__ unsigned tabw[PAR_TWORDS * 32];
+  __shared__ unsigned short lenx[32];
+  __shared__ unsigned distx[32];
+  const unsigned lane = threadIdx.x;
+  lenx[lane] = (unsigned short)par_len_info(lane);
+  distx[lane] = par_dist_info(lane);
+  __syncwarp();
+  const unsigned i = blockIdx.x * PAR_DEC_THREADS + lane;
   if (i >= n) return;
   const unsigned ci = REAL ? list[i] : i;
   ParCand c = cand[ci];
@@ -311,101 +367,167 @@ __global__ void __launch_bounds__(128) par_decode_kernel(const unsigned char* __
   int nl, nd;
   unsigned fin;
   bool ok = par_parse_header(br, T.lens, nl, nd, fin, false);
-  ok = ok && par_build<1>(T.lens, nl, T.ltab, PAR_LBITS, T.lsorted, T.lcount);
-  ok = ok && par_build<2>(T.lens + nl, nd, T.dtab, PAR_DBITS, T.dsorted, T.dcount);
+  const int wll = PAR_LWORDS + PAR_DWORDS, wdl = wll + PAR_LLONG;       // limit words of the two codes
+  ok = ok && par_build<1>(T.lens, nl, tabw, lane, 0, PAR_LBITS, wll, T.lsorted, T.lcount);
+  ok = ok && par_build<2>(T.lens + nl, nd, tabw, lane, PAR_LWORDS, PAR_DBITS, wdl, T.dsorted, T.dcount);
+  const unsigned short* lcol = (const unsigned short*)(tabw + lane);
+  const unsigned short* dcol = (const unsigned short*)(tabw + PAR_LWORDS * 32 + lane);
   const unsigned in_bits = (unsigned)st.in_len * 8;
   // output budget: a block cannot produce more than what is left of the stream
   const unsigned cap = REAL ? c.out_len : (unsigned)st.out_len;
-  unsigned short* out = REAL ? cells + (st.out_off - cells_base) + c.out_off : nullptr;
-  unsigned opos = 0;
+  unsigned* tok = REAL ? tokens + lz[c.stream].tok_base + c.tok_off : nullptr;
+  unsigned opos = 0, ntok = 0;
   bool done = false;
   while (ok && !done) {
     br.refill();
     if (br.bit_pos() > in_bits) { ok = false; break; }
     unsigned win = br.window();
-    unsigned e = T.ltab[win & ((1u << PAR_LBITS) - 1)];
-    if ((e & 15) == 0) { e = par_slow<1>(win, T.lcount, T.lsorted); if (!e) { ok = false; break; } }
-    const unsigned kind = e >> 24;
-    unsigned val = (e >> 8) & 0xffff;
+    unsigned k = win & ((1u << PAR_LBITS) - 1);
+    unsigned e = lcol[(k >> 1) * 64 + (k & 1)];
+    unsigned cl = e & 15, kind = (e >> 4) & 3, val = e >> 6;
+    if (cl == 0) {
+      unsigned sym;
+      if (!par_long<PAR_LBITS>(win, tabw, lane, wll, T.lsorted, sym, cl)) { ok = false; break; }
+      kind = sym < 256 ? (unsigned)K_LIT : sym == 256 ? (unsigned)K_EOB : sym < 286 ? (unsigned)K_LEN : (unsigned)K_BAD;
+      val = sym < 256 ? sym : sym > 256 ? sym - 257 : 0;
+    }
     if (kind == K_LIT) {
-      br.drop(e & 15);
+      br.drop(cl);
       if (opos >= cap) { ok = false; break; }
-      if (REAL) out[opos] = (unsigned short)val;
-      opos++;
+      if (REAL) tok[ntok] = val;
+      ntok++; opos++;
       continue;
     }
     if (kind != K_LEN) {
-      br.drop(e & 15);
+      br.drop(cl);
       if (kind == K_EOB) done = true; else ok = false;
       break;
     }
-    const unsigned cl = e & 15, xb = (e >> 4) & 15;
-    val += (win >> cl) & ((1u << xb) - 1);
+    const unsigned lx = lenx[val];
+    const unsigned xb = lx >> 12;
+    const unsigned len = (lx & 0xfffu) + ((win >> cl) & ((1u << xb) - 1));
     br.drop(cl + xb);
     br.refill();
     win = br.window();
-    unsigned e2 = T.dtab[win & ((1u << PAR_DBITS) - 1)];
-    if ((e2 & 15) == 0) { e2 = par_slow<2>(win, T.dcount, T.dsorted); if (!e2) { ok = false; break; } }
-    if ((e2 >> 24) != 0) { ok = false; break; }
-    const unsigned cl2 = e2 & 15, xb2 = (e2 >> 4) & 15;
-    const unsigned dist = ((e2 >> 8) & 0xffff) + ((win >> cl2) & ((1u << xb2) - 1));
+    k = win & ((1u << PAR_DBITS) - 1);
+    const unsigned e2 = dcol[(k >> 1) * 64 + (k & 1)];
+    unsigned cl2 = e2 & 15, dsym = e2 >> 4;
+    if (cl2 == 0 && !par_long<PAR_DBITS>(win, tabw, lane, wdl, T.dsorted, dsym, cl2)) { ok = false; break; }
+    const unsigned dx = distx[dsym & 31];
+    if (dx == 0) { ok = false; break; }
+    const unsigned xb2 = dx >> 16;
+    const unsigned dist = (dx & 0xffffu) + ((win >> cl2) & ((1u << xb2) - 1));
     br.drop(cl2 + xb2);
-    if (opos + val > cap || br.bit_pos() > in_bits) { ok = false; break; }
-    if (REAL) {
-      if (dist >= val && dist <= opos) {
-        // non-overlapping copy inside the block: loads first, then stores, 8 cells at a time (one memory latency)
-        const unsigned short* sp = out + (opos - dist);
-        unsigned short* dp = out + opos;
-        for (unsigned j0 = 0; j0 < val; j0 += 8) {
-          unsigned short t[8];
-#pragma unroll
-          for (unsigned j = 0; j < 8; j++) t[j] = (j0 + j < val) ? sp[j0 + j] : (unsigned short)0;
-#pragma unroll
-          for (unsigned j = 0; j < 8; j++) if (j0 + j < val) dp[j0 + j] = t[j];
-        }
-      } else {
-        for (unsigned j = 0; j < val; j++) {
-          const int src = (int)(opos + j) - (int)dist;
-          out[opos + j] = src >= 0 ? out[src] : (unsigned short)(0x8000u | (unsigned)(32768 + src));
-        }
-      }
-    }
-    opos += val;
+    if (opos + len > cap || br.bit_pos() > in_bits) { ok = false; break; }
+    if (REAL) tok[ntok] = 0x80000000u | (len << 16) | (dist - 1);
+    ntok++; opos += len;
   }
   if (!REAL) {
     c.end_bit = br.bit_pos();
     c.out_len = opos;
+    c.n_tok = ntok;
     c.state = (ok && done && c.end_bit <= in_bits) ? 1 : -1;
     cand[ci] = c;
-  } else if (!(ok && done && opos == c.out_len)) {
+  } else if (!(ok && done && opos == c.out_len && ntok == c.n_tok)) {
     cand[ci].state = -2;      // cannot happen if the dry pass succeeded; the host falls back if it does
   }
 }
 
-// 5. Cells -> bytes, one CTA per stream, chained blocks in order.  chain[first[s] .. first[s+1]) = candidate indices.
-__global__ void __launch_bounds__(1024) par_resolve_kernel(const ParStream* __restrict__ streams,
-                                                           const ParCand* __restrict__ cand,
-                                                           const unsigned* __restrict__ chain,
-                                                           const unsigned* __restrict__ first,
-                                                           const unsigned short* __restrict__ cells, long long cells_base,
-                                                           unsigned char* __restrict__ out_base, int* __restrict__ bad) {
+// 5. Tokens -> bytes: one CTA per stream walks the stream's tokens in order, one tile of up to PAR_LZ_THREADS tokens /
+//    PAR_LZ_CAP output bytes at a time (thread = token).  A block-wide scan of the token lengths gives every token its
+//    position; the tile's output is assembled in shared memory and then stored coalesced.  Literals and the bytes that
+//    matches copy from before the tile (global memory, written by earlier tiles) are placed at once; bytes copied from
+//    inside the tile wait, without block barriers, until the PENDING bitmap (one bit per staged byte, set by the
+//    matches that still have to produce it) is clear over their source range.
+static const int PAR_LZ_THREADS = 256;
+static const int PAR_LZ_CAP = 4096;
+__device__ __forceinline__ unsigned par_bits(unsigned a, unsigned b, unsigned w) {   // bits of [a, b) that fall in word w
+  const unsigned lo = max(a, w * 32), hi = min(b, w * 32 + 32);
+  if (hi <= lo) return 0;
+  return (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1) << (lo & 31));
+}
+__global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream* __restrict__ streams,
+                                                                const ParLz* __restrict__ lz,
+                                                                const unsigned* __restrict__ tokens,
+                                                                unsigned char* out_base, int* __restrict__ bad) {
+  const int NT = PAR_LZ_THREADS;
+  __shared__ unsigned ob_w[PAR_LZ_CAP / 4];
+  __shared__ unsigned pend_w[PAR_LZ_CAP / 32];
+  __shared__ unsigned wsum[NT / 32];
+  __shared__ unsigned s_total;
+  unsigned char* ob = (unsigned char*)ob_w;
+  volatile unsigned* pend = pend_w;
   const ParStream st = streams[blockIdx.x];
+  const ParLz z = lz[blockIdx.x];
   unsigned char* out = out_base + st.out_off;
-  const unsigned short* cl = cells + (st.out_off - cells_base);
-  for (unsigned j = first[blockIdx.x]; j < first[blockIdx.x + 1]; j++) {
-    const ParCand c = cand[chain[j]];
-    const unsigned o = c.out_off, n = c.out_len;
-    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
-      const unsigned v = cl[o + i];
-      unsigned char b;
-      if (v & 0x8000u) {
-        const int src = (int)o - 32768 + (int)(v & 0x7fffu);
-        if (src < 0) { bad[blockIdx.x] = 1; b = 0; } else b = out[src];
-      } else b = (unsigned char)v;
-      out[o + i] = b;
+  const unsigned* tk = tokens + z.tok_base;
+  const unsigned T = z.n_tok;
+  const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (unsigned i = tid; i < PAR_LZ_CAP / 32; i += NT) pend_w[i] = 0;
+  unsigned obase = 0, t0 = 0;
+  bool fail = false;
+  unsigned nxt = tid < T ? tk[tid] : 0;
+  while (t0 < T) {
+    const unsigned t = nxt;
+    const bool has = t0 + tid < T;
+    if (t0 + NT + tid < T) nxt = tk[t0 + NT + tid];                 // assumes that the whole tile fits (the usual case)
+    const bool isM = has && (t >> 31);
+    const unsigned L = has ? (isM ? (t >> 16) & 0x1ffu : 1u) : 0u;
+    unsigned incl = L;
+    for (int d = 1; d < 32; d <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += v; }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();                                                // also orders the previous tile's stores before the loads below
+    unsigned woff = 0;
+    for (int w = 0; w < NT / 32; w++) { const unsigned v = wsum[w]; if (w < (int)wid) woff += v; }
+    const unsigned rel = woff + incl - L;                           // position inside the tile
+    const bool fits = has && rel + L <= (unsigned)PAR_LZ_CAP;       // monotone: the tile is the longest fitting prefix
+    const unsigned ncut = (unsigned)__syncthreads_count(fits);
+    if (fits && tid + 1 == ncut) s_total = rel + L;
+    const unsigned dist = (t & 0x7fffu) + 1;
+    bool m = fits && isM;
+    if (m && dist > obase + rel) { fail = true; m = false; }
+    if (fits && obase + rel + L > z.out_len) { fail = true; m = false; }
+    else if (fits && !isM) ob[rel] = (unsigned char)t;
+    const int srel = (int)rel - (int)dist;                          // source position inside the tile (negative: before it)
+    unsigned n_old = 0;
+    if (m) {
+      n_old = srel < 0 ? min(L, (unsigned)(-srel)) : 0u;
+      if (n_old < L) {                                              // has an in-tile part: its bytes are pending
+        for (unsigned w = rel >> 5; w <= (rel + L - 1) >> 5; w++) atomicOr(&pend_w[w], par_bits(rel, rel + L, w));
+      }
+      const unsigned char* sp = out + obase + srel;                 // bytes from before the tile
+      for (unsigned j0 = 0; j0 < n_old; j0 += 8) {
+        unsigned char v[8];
+#pragma unroll
+        for (unsigned j = 0; j < 8; j++) v[j] = (j0 + j < n_old) ? sp[j0 + j] : (unsigned char)0;
+#pragma unroll
+        for (unsigned j = 0; j < 8; j++) if (j0 + j < n_old) ob[rel + j0 + j] = v[j];
+      }
+      if (n_old == L) m = false;
     }
-    __syncthreads();   // the next block's markers read these bytes
+    __syncthreads();                                                // literals, old bytes, pending bits and s_total are visible
+    const unsigned a = (unsigned)max(srel, 0), b = min((unsigned)(srel + (int)L), rel);   // in-tile source bytes outside my own output
+    while (__any_sync(0xffffffffu, m)) {
+      if (m) {
+        bool clear = true;
+        if (b > a) for (unsigned w = a >> 5; w <= (b - 1) >> 5; w++) if (pend[w] & par_bits(a, b, w)) { clear = false; break; }
+        if (clear) {
+          __threadfence_block();
+          for (unsigned j = n_old; j < L; j++) ob[rel + j] = ob[(unsigned)(srel + (int)j)];   // in order: may read my own bytes
+          __threadfence_block();
+          for (unsigned w = rel >> 5; w <= (rel + L - 1) >> 5; w++) atomicAnd(&pend_w[w], ~par_bits(rel, rel + L, w));
+          m = false;
+        }
+      }
+    }
+    __syncthreads();
+    const unsigned total = s_total;
+    for (unsigned i = tid; i < total; i += NT) out[obase + i] = ob[i];
+    obase += total;
+    t0 += ncut;
+    if (ncut != (unsigned)NT && t0 < T) nxt = t0 + tid < T ? tk[t0 + tid] : 0;   // the tile was cut short: reload
   }
+  if (__syncthreads_or(fail) || obase != z.out_len) { if (tid == 0) bad[blockIdx.x] = 1; }
 }
 
 }  // namespace mts
