@@ -259,9 +259,11 @@ __device__ __forceinline__ unsigned par_dist_info(unsigned i) {
 }
 
 // ---------------------------------------------------------------------------------------------- kernels
-// 1. Survivors of the cheap header test: one thread per stream byte (8 bit offsets).  Phase 1 tests the fixed fields of
-//    all 8 offsets (BTYPE = dynamic, HLIT <= 29, HDIST <= 29); phase 2 visits only the passing offsets and checks that the
-//    code-length code is complete: its 3-bit lengths are summed 3 at a time through a 512-entry table of 2^(7-len).
+// 1. Survivors of the cheap header test: one thread per aligned stream word (32 bit offsets).  Phase 1 tests the fixed
+//    fields of all 32 offsets at once with word-parallel logic (BTYPE = dynamic: bit 1 clear, bit 2 set; HLIT <= 29 and
+//    HDIST <= 29: their upper four bits not all ones); phase 2 visits the ~22 % passing offsets and checks that the
+//    code-length code is complete: its 3-bit lengths are summed 3 at a time through a 512-entry table of 2^(7-len),
+//    leaving as soon as the sum exceeds 1.
 __global__ void __launch_bounds__(256) par_find_kernel(const unsigned char* __restrict__ comp,
                                                        const ParStream* __restrict__ streams,
                                                        unsigned long long* __restrict__ surv, unsigned cap,
@@ -273,26 +275,26 @@ __global__ void __launch_bounds__(256) par_find_kernel(const unsigned char* __re
   }
   __syncthreads();
   const ParStream st = streams[blockIdx.y];
-  const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
-  // a dynamic header is at least 17 + 12 bits + two codes: ignore the last bytes (zlib trailer + shortest block)
-  if (st.in_len < 16 || b < 2 || b + 12 > (unsigned)st.in_len) return;
-  const unsigned char* p = comp + st.in_off + b;
-  const unsigned mis = (unsigned)((uintptr_t)p & 3);
-  const unsigned* w = (const unsigned*)(p - mis);
-  const unsigned kmax = (mis + (unsigned)st.in_len - b - 1) >> 2;
-  unsigned x[4];
-  {
-    unsigned r0 = w[0], r1 = w[min(1u, kmax)], r2 = w[min(2u, kmax)], r3 = w[min(3u, kmax)], r4 = w[min(4u, kmax)];
-    x[0] = __funnelshift_r(r0, r1, mis * 8); x[1] = __funnelshift_r(r1, r2, mis * 8);
-    x[2] = __funnelshift_r(r2, r3, mis * 8); x[3] = __funnelshift_r(r3, r4, mis * 8);
-  }
-  unsigned mask = 0;
+  const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;          // aligned word index
+  const unsigned char* in = comp + st.in_off;
+  const unsigned mis = (unsigned)((uintptr_t)in & 3);
+  const unsigned* w = (const unsigned*)(in - mis);
+  if (st.in_len < 16) return;
+  const unsigned kmax = (mis + (unsigned)st.in_len - 1) >> 2;
+  if (j > kmax) return;
+  // stream bit of this word's bit 0 (may be negative for the first word); valid header bits: [16, 8 * (in_len - 12)]
+  // (a dynamic header is at least 17 + 12 bits + two codes: the zlib trailer and the shortest block are ignored)
+  const long long bit0 = 32ll * j - 8ll * mis;
+  const long long first_ok = 16, last_ok = 8ll * ((long long)st.in_len - 12) + 7;
+  if (bit0 + 31 < first_ok || bit0 > last_ok) return;
+  unsigned x[5];
 #pragma unroll
-  for (unsigned s = 0; s < 8; s++) {
-    const unsigned t0 = __funnelshift_r(x[0], x[1], s);
-    const bool pass = ((t0 >> 1) & 3) == 2 && ((t0 >> 3) & 31) <= 29 && ((t0 >> 8) & 31) <= 29;
-    mask |= (unsigned)pass << s;
-  }
+  for (unsigned i = 0; i < 5; i++) x[i] = w[min(j + i, kmax)];
+  const unsigned long long X = ((unsigned long long)x[1] << 32) | x[0];
+  unsigned mask = (unsigned)(~(X >> 1) & (X >> 2) & ~((X >> 4) & (X >> 5) & (X >> 6) & (X >> 7)) &
+                             ~((X >> 9) & (X >> 10) & (X >> 11) & (X >> 12)));
+  if (bit0 < first_ok) mask &= 0xffffffffu << (unsigned)(first_ok - bit0);
+  if (bit0 + 31 > last_ok) mask &= 0xffffffffu >> (unsigned)(bit0 + 31 - last_ok);
   while (mask) {
     const unsigned s = (unsigned)__ffs((int)mask) - 1;
     mask &= mask - 1;
@@ -303,12 +305,12 @@ __global__ void __launch_bounds__(256) par_find_kernel(const unsigned char* __re
     unsigned long long f = ((((unsigned long long)t1 << 32) | t0) >> 17) | ((unsigned long long)t2 << 47);
     f &= (1ull << (3 * ncl)) - 1;
     const unsigned lo = (unsigned)f, hi = (unsigned)(f >> 32);
-    const unsigned kraft = k9[lo & 511] + k9[(lo >> 9) & 511] + k9[(lo >> 18) & 511] +
-                           k9[((lo >> 27) | (hi << 5)) & 511] + k9[(hi >> 4) & 511] + k9[(hi >> 13) & 511] +
-                           k9[(hi >> 22) & 511];
+    unsigned kraft = k9[lo & 511] + k9[(lo >> 9) & 511] + k9[(lo >> 18) & 511] + k9[((lo >> 27) | (hi << 5)) & 511];
+    if (kraft > 128) continue;
+    kraft += k9[(hi >> 4) & 511] + k9[(hi >> 13) & 511] + k9[(hi >> 22) & 511];
     if (kraft != 128) continue;
     const unsigned at = atomicAdd(&counters[0], 1u);
-    if (at < cap) surv[at] = ((unsigned long long)blockIdx.y << 32) | (b * 8 + s);
+    if (at < cap) surv[at] = ((unsigned long long)blockIdx.y << 32) | (unsigned)(bit0 + s);
   }
 }
 
