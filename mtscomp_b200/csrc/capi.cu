@@ -144,9 +144,7 @@ int set_attrs(mtsb_ctx* c) {
   CK(cudaFuncSetAttribute(inv_apply_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
   CK(cudaFuncSetAttribute(lz77_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LzSmem<1>::total));
   CK(cudaFuncSetAttribute(lz77_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LzSmem<2>::total));
-  // thread-per-block decoder: 36 KB of tables per 32-thread CTA, six CTAs per SM need the largest carve-out
-  CK(cudaFuncSetAttribute(par_decode_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-  CK(cudaFuncSetAttribute(par_decode_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(par_block_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   c->attr_set = true;
   return 0;
 }
@@ -754,15 +752,14 @@ static int par_phase(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Inflat
   const size_t cand_cap = (size_t)std::max<long long>(1 << 16, in_total / 4096 + 64ll * ns);
   NEED(c->d_pstreams, (size_t)ns * sizeof(ParStream));
   NEED(c->d_surv, surv_cap * 8);
-  NEED(c->d_cand, cand_cap * sizeof(ParCand));
+  NEED(c->d_cand, cand_cap * 8);
   NEED(c->d_pcount, 256);
-  NEED(c->d_pbad, (size_t)ns * 4 + 64);
-  NEED(c->h_tab, std::max((size_t)ns * sizeof(ParStream), cand_cap * sizeof(ParCand)) + 4096);
-  NEED(c->h_small, 4096 + (size_t)ns * 4);
+  NEED(c->d_pbad, (size_t)ns * sizeof(ParRes) + 64);
+  NEED(c->h_tab, std::max((size_t)ns * sizeof(ParStream), cand_cap * 8) + 4096);
+  NEED(c->h_small, 4096 + (size_t)ns * sizeof(ParRes));
   memcpy(c->h_tab.p, ps.data(), (size_t)ns * sizeof(ParStream));
   { int r = small_copy(c, c->d_pstreams.p, c->h_tab.p, (size_t)ns * sizeof(ParStream)); if (r) return r; }
   CK(cudaMemsetAsync(c->d_pcount.p, 0, 256, c->stream));
-  CK(cudaMemsetAsync(c->d_pbad.p, 0, (size_t)ns * 4, c->stream));
   const ParStream* d_ps = (const ParStream*)c->d_pstreams.p;
   unsigned* d_cnt = (unsigned*)c->d_pcount.p;
   MTS_LAUNCH(par_find_kernel, dim3((max_in / 4 + 2 + 255) / 256, ns), dim3(256), 0, c->stream, dcomp, d_ps,
@@ -775,7 +772,7 @@ static int par_phase(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Inflat
   c->par_stats[0] += n_surv;
   if (n_surv == 0 || n_surv > surv_cap) return 0;
   MTS_LAUNCH(par_validate_kernel, dim3((n_surv + 127) / 128), dim3(128), 0, c->stream, dcomp, d_ps,
-             (const unsigned long long*)c->d_surv.p, n_surv, (ParCand*)c->d_cand.p, (unsigned)cand_cap, d_cnt);
+             (const unsigned long long*)c->d_surv.p, n_surv, (unsigned long long*)c->d_cand.p, (unsigned)cand_cap, d_cnt);
   CKL();
   c->launches++;
   { int r = small_copy(c, c->h_small.p, c->d_pcount.p, 64); if (r) return r; }
@@ -783,88 +780,59 @@ static int par_phase(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Inflat
   const unsigned n_cand = ((const unsigned*)c->h_small.p)[1];
   c->par_stats[1] += n_cand;
   if (n_cand == 0 || n_cand > cand_cap) return 0;
-  NEED(c->d_ptab, (size_t)n_cand * sizeof(ParTables));
-  {
-    auto k = par_decode_kernel<0>;
-    MTS_LAUNCH(k, dim3((n_cand + PAR_DEC_THREADS - 1) / PAR_DEC_THREADS), dim3(PAR_DEC_THREADS), 0, c->stream, dcomp, d_ps,
-               (ParCand*)c->d_cand.p, (const unsigned*)nullptr, n_cand, (ParTables*)c->d_ptab.p, (unsigned*)nullptr,
-               (const ParLz*)nullptr);
-    CKL();
-    c->launches++;
-  }
-  { int r = small_copy(c, c->h_tab.p, c->d_cand.p, (size_t)n_cand * sizeof(ParCand)); if (r) return r; }
+  { int r = small_copy(c, c->h_tab.p, c->d_cand.p, (size_t)n_cand * 8); if (r) return r; }
   CK(cudaStreamSynchronize(c->stream));
-  // ---- host: chain the blocks of every stream
-  ParCand* hc = (ParCand*)c->h_tab.p;
-  std::vector<std::vector<std::pair<unsigned, unsigned>>> by_stream(ns);
-  for (unsigned i = 0; i < n_cand; i++)
-    if (hc[i].state == 1 && hc[i].stream < (unsigned)ns) by_stream[hc[i].stream].push_back({hc[i].bit, i});
-  std::vector<unsigned> chain, first(ns + 1, 0);
-  std::vector<unsigned> tail_bit(ns, 16), tail_out(ns, 0);
-  std::vector<char> fin(ns, 0);
-  std::vector<ParLz> lz(ns);
-  long long total_tok = 0;
-  for (int sidx = 0; sidx < ns; sidx++) {
-    auto& v = by_stream[sidx];
-    std::sort(v.begin(), v.end());
-    first[sidx] = (unsigned)chain.size();
-    unsigned cur = 16, run = 0;
-    unsigned long long run_tok = 0;
-    for (;;) {
-      auto it = std::lower_bound(v.begin(), v.end(), std::make_pair(cur, 0u));
-      if (it == v.end() || it->first != cur) break;
-      ParCand& cd = hc[it->second];
-      if ((long long)run + cd.out_len > ps[sidx].out_len || cd.end_bit <= cur || run_tok + cd.n_tok > 0xfffffff0ull) break;
-      cd.tok_off = (unsigned)run_tok;
-      chain.push_back(it->second);
-      run += cd.out_len;
-      run_tok += cd.n_tok;
-      cur = cd.end_bit;
-      if (cd.final_) { fin[sidx] = 1; break; }
+  // ---- host: candidates in stream order; a block's bit range ends where the next candidate of its stream begins
+  std::vector<unsigned long long> keys((const unsigned long long*)c->h_tab.p, (const unsigned long long*)c->h_tab.p + n_cand);
+  std::sort(keys.begin(), keys.end());
+  std::vector<ParBlk> blks(n_cand);
+  std::vector<unsigned> bfirst(ns + 1, 0);
+  // token slots: one per 6 bits of input (typical streams spend 9..15 bits per token); if that is not enough the blocks
+  // that do not fit end the chain of their stream (serial decode of the rest)
+  const long long tok_total = in_total * 8 / 6 + 4096;
+  {
+    unsigned i = 0;
+    for (int sidx = 0; sidx < ns; sidx++) {
+      bfirst[sidx] = i;
+      while (i < n_cand && (int)(keys[i] >> 32) == sidx) {
+        ParBlk& b = blks[i];
+        b.stream = (unsigned)sidx; b.bit = (unsigned)keys[i];
+        const bool more = i + 1 < n_cand && (int)(keys[i + 1] >> 32) == sidx;
+        b.limit = more ? (unsigned)keys[i + 1] : (unsigned)ps[sidx].in_len * 8u;
+        b.end_bit = 0; b.n_tok = 0; b.out_len = 0; b.flags = 0;
+        b.pad_ = 0; b.tok_off = 0;
+        i++;
+      }
     }
-    tail_bit[sidx] = cur; tail_out[sidx] = run;
-    lz[sidx].tok_base = total_tok; lz[sidx].n_tok = (unsigned)run_tok; lz[sidx].out_len = run;
-    total_tok += (long long)run_tok;
+    bfirst[ns] = i;
+    if (i != n_cand) return 0;                                  // a key with an unknown stream: do not trust the list
   }
-  first[ns] = (unsigned)chain.size();
-  const unsigned n_chain = (unsigned)chain.size();
-  c->par_stats[2] += n_chain;
-  if (n_chain == 0) return 0;
-  // upload the candidates (now with token offsets), the chain and the per-stream token ranges
-  { int r = small_copy(c, c->d_cand.p, c->h_tab.p, (size_t)n_cand * sizeof(ParCand)); if (r) return r; }
-  CK(cudaStreamSynchronize(c->stream));                       // h_tab is reused below
-  const size_t o_lz = ((size_t)n_chain * 4 + 255) & ~(size_t)255;
-  NEED(c->d_plist, o_lz + (size_t)ns * sizeof(ParLz));
-  NEED(c->h_tab, o_lz + (size_t)ns * sizeof(ParLz) + 64);
-  NEED(c->d_tokens, (size_t)total_tok * 4 + 64);
-  memcpy(c->h_tab.p, chain.data(), (size_t)n_chain * 4);
-  memcpy((char*)c->h_tab.p + o_lz, lz.data(), (size_t)ns * sizeof(ParLz));
-  { int r = small_copy(c, c->d_plist.p, c->h_tab.p, o_lz + (size_t)ns * sizeof(ParLz)); if (r) return r; }
-  {
-    const ParLz* d_lz = (const ParLz*)((const char*)c->d_plist.p + o_lz);
-    auto k = par_decode_kernel<1>;
-    MTS_LAUNCH(k, dim3((n_chain + PAR_DEC_THREADS - 1) / PAR_DEC_THREADS), dim3(PAR_DEC_THREADS), 0, c->stream, dcomp, d_ps,
-               (ParCand*)c->d_cand.p, (const unsigned*)c->d_plist.p, n_chain, (ParTables*)c->d_ptab.p,
-               (unsigned*)c->d_tokens.p, d_lz);
-    CKL();
-    MTS_LAUNCH(par_lz_kernel, dim3(ns), dim3(PAR_LZ_THREADS), 0, c->stream, d_ps, d_lz, (const unsigned*)c->d_tokens.p, dT,
-               (int*)c->d_pbad.p);
-    CKL();
-    c->launches += 2;
-  }
-  CK(cudaStreamSynchronize(c->stream));                       // h_tab free again
-  { int r = small_copy(c, c->h_tab.p, c->d_cand.p, (size_t)n_cand * sizeof(ParCand)); if (r) return r; }
-  { int r = small_copy(c, c->h_small.p, c->d_pbad.p, (size_t)ns * 4); if (r) return r; }
+  const size_t o_first = ((size_t)n_cand * sizeof(ParBlk) + 255) & ~(size_t)255;
+  NEED(c->d_plist, o_first + (size_t)(ns + 1) * 4);
+  NEED(c->h_tab, o_first + (size_t)(ns + 1) * 4 + 64);
+  NEED(c->d_tokens, (size_t)tok_total * 4 + 64);
+  memcpy(c->h_tab.p, blks.data(), (size_t)n_cand * sizeof(ParBlk));
+  memcpy((char*)c->h_tab.p + o_first, bfirst.data(), (size_t)(ns + 1) * 4);
+  { int r = small_copy(c, c->d_plist.p, c->h_tab.p, o_first + (size_t)(ns + 1) * 4); if (r) return r; }
+  MTS_LAUNCH(par_block_kernel, dim3((n_cand + PAR_BLK_WARPS - 1) / PAR_BLK_WARPS), dim3(PAR_BLK_WARPS * 32), 0, c->stream, dcomp,
+             d_ps, (ParBlk*)c->d_plist.p, n_cand, (unsigned*)c->d_tokens.p, (unsigned long long*)((char*)c->d_pcount.p + 16),
+             (unsigned long long)tok_total);
+  CKL();
+  MTS_LAUNCH(par_lz_kernel, dim3(ns), dim3(PAR_LZ_THREADS), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p,
+             (const unsigned*)((const char*)c->d_plist.p + o_first), (const unsigned*)c->d_tokens.p, dT, (ParRes*)c->d_pbad.p);
+  CKL();
+  c->launches += 2;
+  { int r = small_copy(c, c->h_small.p, c->d_pbad.p, (size_t)ns * sizeof(ParRes)); if (r) return r; }
   CK(cudaStreamSynchronize(c->stream));
-  const int* bad = (const int*)c->h_small.p;
+  const ParRes* res = (const ParRes*)c->h_small.p;
   for (int sidx = 0; sidx < ns; sidx++) {
-    bool ok = !bad[sidx] && first[sidx + 1] > first[sidx];
-    for (unsigned j = first[sidx]; ok && j < first[sidx + 1]; j++) ok = hc[chain[j]].state == 1;
-    if (!ok) continue;                                         // full serial decode of this stream
+    const ParRes& r = res[sidx];
+    c->par_stats[2] += r.n_done;
+    if (r.n_done == 0 || (r.flags & 2)) continue;              // full serial decode of this stream
     InflateSeg& s = segs[whole[sidx]];
-    s.flags = INF_ZLIB | INF_RESUME | (fin[sidx] ? INF_NO_BLOCKS : 0);
-    s.start_bit = tail_bit[sidx];
-    s.opos0 = tail_out[sidx];
+    s.flags = INF_ZLIB | INF_RESUME | ((r.flags & 1) ? INF_NO_BLOCKS : 0);
+    s.start_bit = r.tail_bit;
+    s.opos0 = r.tail_out;
     c->par_stats[3]++;
   }
   return 0;

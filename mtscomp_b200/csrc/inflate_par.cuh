@@ -2,19 +2,17 @@
 //
 // A zlib stream has no index: its DEFLATE blocks (~300 dynamic-Huffman blocks per 23 MB chunk at zlib level 6) can only
 // be located by decoding.  One warp per stream (inflate.cuh) therefore leaves the GPU idle.  This path finds the blocks
-// speculatively and decodes them with ONE THREAD PER BLOCK (thousands of blocks in flight):
+// speculatively and decodes them all at once:
 //   1 par_find_kernel      every bit offset is tested for a plausible dynamic-block header (BTYPE, HLIT/HDIST ranges,
 //                          complete code-length code); survivors (~8e-4 of the offsets) are appended to a list
 //   2 par_validate_kernel  thread per survivor: full header parse; both Huffman codes must be complete and have an
 //                          end-of-block code (what zlib's deflate always emits) -> candidate blocks
-//   3 par_decode_kernel<0> thread per candidate: dry decode -> end bit offset and output length
-//   (host)                 per stream: follow end -> next start from the first block; blocks on that chain get their
-//                          output offsets; whatever follows the last chained block is the "tail"
-//   4 par_decode_kernel<1> thread per chained block: decode into 16-bit cells; a back-reference that reaches before the
-//                          block's own output becomes a MARKER (0x8000 | index into the previous 32 KB), and markers are
-//                          copied like data, so every cell ends up as a byte or as a direct reference to the window
-//   5 par_resolve_kernel   CTA per stream, blocks in order: cells -> bytes (markers read the already resolved window)
-//   6 (inflate.cuh)        one warp per stream decodes the tail serially (usually nothing or the final small block)
+//   (host)                 sort the candidates (stream, bit); a block's bit range ends at the next candidate
+//   3 par_block_kernel     WARP per candidate: tables in shared memory, the 32 lanes decode 32 sub-chunks of the block
+//                          in parallel (self-synchronising Huffman decoding) into 32-bit tokens (literal / length+distance)
+//   4 par_lz_kernel        CTA per stream: follows the chain of blocks (each must start where the previous one ended) and
+//                          turns their tokens into bytes, a tile of 256 tokens at a time, staged in shared memory
+//   5 (inflate.cuh)        one warp per stream decodes the tail serially (usually nothing or the final small block)
 // Anything unexpected (no chain, overflow of a list, bad data) falls back to the serial decoder, which also produces
 // the error status; this path never decides that a stream is corrupt by itself.
 #pragma once
@@ -29,37 +27,38 @@ struct ParStream {       // one whole zlib stream
   int in_len, out_len;
 };
 
-struct ParCand {         // a candidate dynamic block
-  unsigned stream, bit;  // owning stream, bit offset of the block header inside it
-  unsigned end_bit;      // bit offset just after the end-of-block code (dry decode)
-  unsigned out_len;      // bytes the block produces
-  unsigned tok_off;      // first token of the block inside its stream's token array (set on the host for chained blocks)
-  int state;             // 1 = decoded cleanly, <= 0 = rejected
-  unsigned final_;       // BFINAL
-  unsigned n_tok;        // tokens (literals + matches) the block decodes to
+struct ParBlk {          // a candidate block in stream order (host-sorted), filled in by par_block_kernel
+  unsigned stream, bit;  // owning stream, bit offset of the block header
+  unsigned limit;        // bit offset of the next candidate of the stream (or the end of the stream)
+  unsigned end_bit;      // OUT: bit offset just after the end-of-block code
+  unsigned n_tok;        // OUT: tokens decoded
+  unsigned out_len;      // OUT: bytes they produce
+  unsigned flags;        // OUT: 1 = decoded cleanly, 2 = BFINAL
+  unsigned pad_;
+  long long tok_off;     // OUT: first slot in the token buffer
 };
 
-struct ParLz {           // per stream, for par_lz_kernel
-  long long tok_base;    // first token of the stream in the token buffer
-  unsigned n_tok;        // tokens of its chained blocks
-  unsigned out_len;      // bytes they must produce
+struct ParRes {          // per stream, written by par_lz_kernel
+  unsigned tail_bit;     // bit offset where the serial decoder has to resume
+  unsigned tail_out;     // output bytes produced so far
+  unsigned n_done;       // blocks resolved
+  unsigned flags;        // 1 = the last resolved block was final, 2 = inconsistent tokens (decode the stream serially)
 };
 
-// Decoding tables.  The fast tables live in SHARED memory, one column of 32-bit words per thread (word w of lane l at
-// tabw[w * 32 + l]: every lane owns a bank, so 32 unrelated lookups never conflict); entries are 16 bits, two per word:
-//   literal/length (9 index bits): code length | kind << 4 | (literal byte or length symbol - 257) << 6
-//   distance       (7 index bits): code length | symbol << 4
-// A zero entry means "longer code": see the limit words below; only the symbol order (sorted[]) is in global scratch.
-// Longer codes: per code length l one word  limit | oend << 17  where limit = one past the last l-bit code, left-justified
-// to 16 bits, and oend = number of symbols with codes of length <= l; the symbol is sorted[oend - ((limit - code16) >> (16-l))].
-static const int PAR_LBITS = 9, PAR_DBITS = 7;
-static const int PAR_LWORDS = (1 << PAR_LBITS) / 2, PAR_DWORDS = (1 << PAR_DBITS) / 2;
-static const int PAR_LLONG = 16 - PAR_LBITS, PAR_DLONG = 16 - PAR_DBITS;      // limit words of lengths tb..15
-static const int PAR_TWORDS = PAR_LWORDS + PAR_DWORDS + PAR_LLONG + PAR_DLONG;
-static const int PAR_DEC_THREADS = 32;       // one warp per CTA: 42 KB of tables, 5 CTAs per SM
-struct ParTables {
+// Decoding tables of one block, in SHARED memory, owned by the warp that decodes the block.  Entries are 16 bits:
+//   literal/length (PAR_LBITS index bits): code length | kind << 4 | (literal byte or length symbol - 257) << 6
+//   distance       (PAR_DBITS index bits): code length | symbol << 4
+// A zero entry means "longer code".  Those are resolved with one word per code length l >= table bits:
+//   limit | oend << 17,  limit = one past the last l-bit code, left-justified to 16 bits,
+//                        oend  = number of symbols with codes of length <= l;
+// the symbol is sorted[oend - 1 - ((limit - 1 - code16) >> (16 - l))] for the first l whose limit exceeds code16.
+static const int PAR_LBITS = 10, PAR_DBITS = 8;
+struct BlkTabs {
+  unsigned short ltab[1 << PAR_LBITS];
+  unsigned short dtab[1 << PAR_DBITS];
+  unsigned llong[16 - PAR_LBITS], dlong[16 - PAR_DBITS];
   unsigned short lsorted[288], dsorted[32];
-  unsigned short lcount[16], dcount[16];
+  unsigned short code[288];        // scratch of the table build: first table index of every short symbol
   unsigned char lens[320];
 };
 
@@ -181,63 +180,71 @@ __device__ bool par_parse_header(TBits& br, unsigned char* lens, int& nl, int& n
   return true;
 }
 
-// Fast table (this thread's shared-memory column starting at word w0) + canonical arrays for one code (serial, per
-// thread).  KIND 1 literal/length, 2 distance.
+// Tables of one code, built by the whole warp from lens[0..n) (shared memory).  Lane 0 assigns the canonical codes
+// (serial, n <= 288); the replication of the short codes over the fast table is spread over the lanes.
+// KIND 1 literal/length, 2 distance.  Returns false for an over-subscribed code (warp-uniform).
 template <int KIND>
-__device__ bool par_build(const unsigned char* lens, int n, unsigned* tabw, unsigned lane, int w0, int tb, int wlong,
-                          unsigned short* sorted, unsigned short* count) {
-  for (int i = 0; i < 16; i++) count[i] = 0;
-  for (int i = 0; i < n; i++) count[lens[i]]++;
-  count[0] = 0;
-  unsigned first[16], offs[16];
-  unsigned code = 0, o = 0;
-  int left = 1;
-  for (int l = 1; l <= 15; l++) {
-    code = (code + (l > 1 ? count[l - 1] : 0)) << 1;
-    first[l] = code;
-    offs[l] = o;
-    o += count[l];
-    left = (left << 1) - count[l];
-    if (left < 0) return false;
-    if (l >= tb) tabw[(wlong + l - tb) * 32 + lane] = ((code + count[l]) << (16 - l)) | (o << 17);
+__device__ bool blk_build(const unsigned char* lens, int n, unsigned short* tab, int tb, unsigned* longw,
+                          unsigned short* sorted, unsigned short* code_s, unsigned lane) {
+  int ok = 1;
+  for (int k = (int)lane; k < (1 << tb); k += 32) tab[k] = 0;
+  if (lane == 0) {
+    unsigned count[16], first[16], offs[16];
+    for (int i = 0; i < 16; i++) count[i] = 0;
+    for (int i = 0; i < n; i++) count[lens[i]]++;
+    count[0] = 0;
+    unsigned code = 0, o = 0;
+    int left = 1;
+    for (int l = 1; l <= 15; l++) {
+      code = (code + (l > 1 ? count[l - 1] : 0)) << 1;
+      first[l] = code;
+      offs[l] = o;
+      o += count[l];
+      left = (left << 1) - (int)count[l];
+      if (left < 0) ok = 0;
+      if (l >= tb) longw[l - tb] = ((code + count[l]) << (16 - l)) | (o << 17);
+    }
+    if (ok)
+      for (int s = 0; s < n; s++) {
+        const unsigned l = lens[s];
+        if (!l) continue;
+        sorted[offs[l]++] = (unsigned short)s;
+        code_s[s] = (unsigned short)(__brev(first[l]++) >> (32 - l));      // bit-reversed: the table is indexed LSB first
+      }
   }
-  for (int w = 0; w < (1 << tb) / 2; w++) tabw[(w0 + w) * 32 + lane] = 0;
-  unsigned short* col = (unsigned short*)(tabw + w0 * 32 + lane);   // entry k at col[(k >> 1) * 64 + (k & 1)]
-  for (int s = 0; s < n; s++) {
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  __syncwarp();
+  if (!ok) return false;
+  for (int s = (int)lane; s < n; s += 32) {
     const unsigned l = lens[s];
-    if (!l) continue;
-    sorted[offs[l]++] = (unsigned short)s;
-    if ((int)l <= tb) {
-      const unsigned r = __brev(first[l]++) >> (32 - l);
-      unsigned e;
-      if (KIND == 1) e = l | ((s < 256 ? (unsigned)K_LIT : s == 256 ? (unsigned)K_EOB : s < 286 ? (unsigned)K_LEN : (unsigned)K_BAD) << 4) |
-                         ((unsigned)(s < 256 ? s : s > 256 ? s - 257 : 0) << 6);
-      else e = l | ((unsigned)s << 4);
-      for (unsigned k = r; k < (1u << tb); k += 1u << l) col[(k >> 1) * 64 + (k & 1)] = (unsigned short)e;
-    } else first[l]++;
+    if (!l || (int)l > tb) continue;
+    unsigned e;
+    if (KIND == 1) e = l | ((s < 256 ? (unsigned)K_LIT : s == 256 ? (unsigned)K_EOB : s < 286 ? (unsigned)K_LEN : (unsigned)K_BAD) << 4) |
+                       ((unsigned)(s < 256 ? s : s > 256 ? s - 257 : 0) << 6);
+    else e = l | ((unsigned)s << 4);
+    for (unsigned k = code_s[s]; k < (1u << tb); k += 1u << l) tab[k] = (unsigned short)e;
   }
+  __syncwarp();
   return true;
 }
 
-// Decode of a code longer than the fast table (tb bits): the limit words of lengths tb+1..15 are scanned (the first
-// length whose limit exceeds the left-justified code), then one global load fetches the symbol.
+// Decode of a code longer than the fast table (TB bits): first length whose limit exceeds the left-justified code.
 template <int TB>
-__device__ __forceinline__ bool par_long(unsigned win, const unsigned* tabw, unsigned lane, int wlong,
-                                         const unsigned short* sorted, unsigned& sym, unsigned& nbits) {
+__device__ __forceinline__ bool blk_long(unsigned win, const unsigned* longw, const unsigned short* sorted,
+                                         unsigned& sym, unsigned& nbits) {
   const unsigned c16 = __brev(win) >> 16;
   unsigned word = 0, prev = 0, l = 0;
-  unsigned below = tabw[wlong * 32 + lane];                 // length TB: only its symbol count matters
+  unsigned below = longw[0];                                // length TB: only its symbol count matters
 #pragma unroll
-  for (int j = 1; j <= 15 - TB; j++) {                      // the limits grow with the length: the first that fits
-    const unsigned wj = tabw[(wlong + j) * 32 + lane];
+  for (int j = 1; j <= 15 - TB; j++) {
+    const unsigned wj = longw[j];
     if (!l && c16 < (wj & 0x1ffffu)) { word = wj; prev = below; l = (unsigned)(TB + j); }
     below = wj;
   }
   if (!l) return false;
   const unsigned back = ((word & 0x1ffffu) - c16 - 1) >> (16 - l);      // codes between this one and the last of length l
   const unsigned idx = (word >> 17) - 1 - back;
-  // idx must lie among the symbols of length l (an incomplete code leaves holes that are not codes)
-  if ((int)idx < (int)(prev >> 17)) return false;
+  if ((int)idx < (int)(prev >> 17)) return false;           // a hole of an incomplete code
   sym = sorted[idx];
   nbits = l;
   return true;
@@ -314,11 +321,12 @@ __global__ void __launch_bounds__(256) par_find_kernel(const unsigned char* __re
   }
 }
 
-// 2. Full header validation: thread per survivor, valid ones are appended to the candidate list.
+// 2. Full header validation: thread per survivor; the valid ones are appended to the candidate list as
+//    stream << 32 | bit (the host sorts the list: that is stream order).
 __global__ void __launch_bounds__(128) par_validate_kernel(const unsigned char* __restrict__ comp,
                                                            const ParStream* __restrict__ streams,
                                                            const unsigned long long* __restrict__ surv, unsigned n_surv,
-                                                           ParCand* __restrict__ cand, unsigned cap,
+                                                           unsigned long long* __restrict__ cand, unsigned cap,
                                                            unsigned* __restrict__ counters) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_surv) return;
@@ -333,105 +341,236 @@ __global__ void __launch_bounds__(128) par_validate_kernel(const unsigned char* 
   if (!par_parse_header(br, lens, nl, nd, fin, true)) return;
   if (br.bit_pos() > (unsigned)st.in_len * 8) return;
   const unsigned at = atomicAdd(&counters[1], 1u);
-  if (at < cap) {
-    ParCand c;
-    c.stream = sidx; c.bit = bit; c.end_bit = 0; c.out_len = 0; c.tok_off = 0; c.state = 0; c.final_ = fin; c.n_tok = 0;
-    cand[at] = c;
-  }
+  if (at < cap) cand[at] = sv;
 }
 
-// 3/4. Thread per block, one warp per CTA, fast tables in shared memory.  REAL = 0: dry decode of every candidate (end
-// bit, output length, token count).  REAL = 1: decode the chained blocks (list[] holds their candidate indices) into
-// tokens; the back-references are resolved afterwards by par_lz_kernel, in stream order.
-template <int REAL>
-__global__ void __launch_bounds__(PAR_DEC_THREADS) par_decode_kernel(const unsigned char* __restrict__ comp,
-                                                                     const ParStream* __restrict__ streams,
-                                                                     ParCand* __restrict__ cand,
-                                                                     const unsigned* __restrict__ list, unsigned n,
-                                                                     ParTables* __restrict__ tables,
-                                                                     unsigned* __restrict__ tokens,
-                                                                     const ParLz* __restrict__ lz) {
-  __shared__ unsigned tabw[PAR_TWORDS * 32];
-  __shared__ unsigned short lenx[32];
-  __shared__ unsigned distx[32];
-  const unsigned lane = threadIdx.x;
-  lenx[lane] = (unsigned short)par_len_info(lane);
-  distx[lane] = par_dist_info(lane);
-  __syncwarp();
-  const unsigned i = blockIdx.x * PAR_DEC_THREADS + lane;
-  if (i >= n) return;
-  const unsigned ci = REAL ? list[i] : i;
-  ParCand c = cand[ci];
-  const ParStream st = streams[c.stream];
-  ParTables& T = tables[i];
+// 3. One WARP per candidate block.  The warp parses the header and builds the tables in shared memory, then its 32
+//    lanes decode 32 consecutive sub-chunks of the block's bit range in parallel.  Only lane 0 knows where its first
+//    symbol starts; the others start at a guess (the sub-chunk boundary, usually in the middle of a symbol).  Huffman
+//    streams re-synchronise within a few symbols, so after the first pass most lanes END on a true symbol boundary;
+//    every lane then restarts from where its predecessor ended, until nothing changes (typically two passes; lane k is
+//    certainly right after k passes).  A last pass writes the tokens at the lane's offset (prefix sum of the counts).
+struct SpanRes { unsigned end, ntok, nout, flags; };   // flags: 1 end-of-block seen, 2 error, 4 nothing to do (after the EOB)
+
+// The symbol loop is written WITHOUT data-dependent branches on the common paths (a literal goes through the distance
+// lookup too and discards it): the 32 lanes decode 32 different bit streams, and any branch on the symbol kind would
+// let them drift apart until every lane runs alone (measured: 2.5 active lanes per instruction with a branchy loop).
+// Called by ALL lanes of the warp (run = false: nothing to decode, r is left alone).  Every iteration starts with a
+// warp vote, which makes the lanes reconverge once per symbol; finished lanes idle until the last one is done.
+template <bool EMIT>
+__device__ __forceinline__ void blk_span(bool run, const unsigned char* in, unsigned in_len, unsigned start,
+                                         unsigned bound, const BlkTabs& T, const unsigned short* lenx,
+                                         const unsigned* distx, unsigned* tok, SpanRes& r) {
+  const unsigned in_bits = in_len * 8;
   TBits br;
-  br.init(comp + st.in_off, (unsigned)st.in_len, c.bit);
-  int nl, nd;
-  unsigned fin;
-  bool ok = par_parse_header(br, T.lens, nl, nd, fin, false);
-  const int wll = PAR_LWORDS + PAR_DWORDS, wdl = wll + PAR_LLONG;       // limit words of the two codes
-  ok = ok && par_build<1>(T.lens, nl, tabw, lane, 0, PAR_LBITS, wll, T.lsorted, T.lcount);
-  ok = ok && par_build<2>(T.lens + nl, nd, tabw, lane, PAR_LWORDS, PAR_DBITS, wdl, T.dsorted, T.dcount);
-  const unsigned short* lcol = (const unsigned short*)(tabw + lane);
-  const unsigned short* dcol = (const unsigned short*)(tabw + PAR_LWORDS * 32 + lane);
-  const unsigned in_bits = (unsigned)st.in_len * 8;
-  // output budget: a block cannot produce more than what is left of the stream
-  const unsigned cap = REAL ? c.out_len : (unsigned)st.out_len;
-  unsigned* tok = REAL ? tokens + lz[c.stream].tok_base + c.tok_off : nullptr;
-  unsigned opos = 0, ntok = 0;
-  bool done = false;
-  while (ok && !done) {
+  br.init(in, in_len, run ? start : 0u);
+  unsigned ntok = 0, nout = 0, flags = 0;
+  bool active = run;
+  while (__any_sync(0xffffffffu, active)) {
+    if (!active) continue;
     br.refill();
-    if (br.bit_pos() > in_bits) { ok = false; break; }
-    unsigned win = br.window();
-    unsigned k = win & ((1u << PAR_LBITS) - 1);
-    unsigned e = lcol[(k >> 1) * 64 + (k & 1)];
+    if (br.bit_pos() >= bound) { active = false; continue; }
+    const unsigned win = br.window();
+    const unsigned e = T.ltab[win & ((1u << PAR_LBITS) - 1)];
     unsigned cl = e & 15, kind = (e >> 4) & 3, val = e >> 6;
-    if (cl == 0) {
+    if (cl == 0) {                                                  // rare: a code longer than the table
       unsigned sym;
-      if (!par_long<PAR_LBITS>(win, tabw, lane, wll, T.lsorted, sym, cl)) { ok = false; break; }
+      if (!blk_long<PAR_LBITS>(win, T.llong, T.lsorted, sym, cl)) { flags = 2; active = false; continue; }
       kind = sym < 256 ? (unsigned)K_LIT : sym == 256 ? (unsigned)K_EOB : sym < 286 ? (unsigned)K_LEN : (unsigned)K_BAD;
       val = sym < 256 ? sym : sym > 256 ? sym - 257 : 0;
     }
-    if (kind == K_LIT) {
+    if (kind >= (unsigned)K_EOB) {                                  // once per block, or an error
       br.drop(cl);
-      if (opos >= cap) { ok = false; break; }
-      if (REAL) tok[ntok] = val;
-      ntok++; opos++;
+      flags = kind == K_EOB ? 1u : 2u;
+      active = false;
       continue;
     }
-    if (kind != K_LEN) {
-      br.drop(cl);
-      if (kind == K_EOB) done = true; else ok = false;
-      break;
-    }
-    const unsigned lx = lenx[val];
-    const unsigned xb = lx >> 12;
+    const bool isl = kind == K_LEN;
+    const unsigned lx = lenx[isl ? val : 0u];
+    const unsigned xb = isl ? lx >> 12 : 0u;
     const unsigned len = (lx & 0xfffu) + ((win >> cl) & ((1u << xb) - 1));
     br.drop(cl + xb);
     br.refill();
-    win = br.window();
-    k = win & ((1u << PAR_DBITS) - 1);
-    const unsigned e2 = dcol[(k >> 1) * 64 + (k & 1)];
+    const unsigned win2 = br.window();
+    const unsigned e2 = T.dtab[win2 & ((1u << PAR_DBITS) - 1)];
     unsigned cl2 = e2 & 15, dsym = e2 >> 4;
-    if (cl2 == 0 && !par_long<PAR_DBITS>(win, tabw, lane, wdl, T.dsorted, dsym, cl2)) { ok = false; break; }
+    if (isl && cl2 == 0 && !blk_long<PAR_DBITS>(win2, T.dlong, T.dsorted, dsym, cl2)) { flags = 2; active = false; continue; }
     const unsigned dx = distx[dsym & 31];
-    if (dx == 0) { ok = false; break; }
+    if (isl && dx == 0) { flags = 2; active = false; continue; }
     const unsigned xb2 = dx >> 16;
-    const unsigned dist = (dx & 0xffffu) + ((win >> cl2) & ((1u << xb2) - 1));
-    br.drop(cl2 + xb2);
-    if (opos + len > cap || br.bit_pos() > in_bits) { ok = false; break; }
-    if (REAL) tok[ntok] = 0x80000000u | (len << 16) | (dist - 1);
-    ntok++; opos += len;
+    const unsigned dist = (dx & 0xffffu) + ((win2 >> cl2) & ((1u << xb2) - 1));
+    br.drop(isl ? cl2 + xb2 : 0u);
+    if (EMIT) tok[ntok] = isl ? (0x80000000u | (len << 16) | (dist - 1)) : val;
+    ntok++;
+    nout += isl ? len : 1u;
   }
-  if (!REAL) {
-    c.end_bit = br.bit_pos();
-    c.out_len = opos;
-    c.n_tok = ntok;
-    c.state = (ok && done && c.end_bit <= in_bits) ? 1 : -1;
-    cand[ci] = c;
-  } else if (!(ok && done && opos == c.out_len && ntok == c.n_tok)) {
-    cand[ci].state = -2;      // cannot happen if the dry pass succeeded; the host falls back if it does
+  if (!run) return;
+  if (br.bit_pos() > in_bits) flags |= 2;
+  r.end = br.bit_pos(); r.ntok = ntok; r.nout = nout; r.flags = flags;
+}
+
+// Dynamic block header at bit `bit`, parsed by ONE lane with a 7-bit table for the code-length code (tab7: 128 bytes of
+// scratch).  On success lens[0..nl) and lens[nl..nl+nd) hold the code lengths and hdr_end the bit of the first symbol.
+__device__ bool blk_parse_header(const unsigned char* in, unsigned in_len, unsigned bit, unsigned char* lens,
+                                 unsigned char* tab7, int& nl, int& nd, unsigned& final_, unsigned& hdr_end) {
+  TBits br;
+  br.init(in, in_len, bit);
+  final_ = br.get(1);
+  if (br.get(2) != 2) return false;
+  nl = (int)br.get(5) + 257;
+  nd = (int)br.get(5) + 1;
+  const int ncl = (int)br.get(4) + 4;
+  if (nl > 286 || nd > 30) return false;
+  // code-length code: 19 lengths of 3 bits in the order 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15, packed 4 bits each
+  const unsigned long long order = 0xf1e2d3c4b5a69780ull;           // nibbles 3..18 of the order (low nibble first)
+  unsigned long long cl = 0;                                         // cl nibble s = length of symbol s (s < 16)
+  unsigned cl16 = 0, cl17 = 0, cl18 = 0;
+  unsigned count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < ncl; i++) {
+    const unsigned v = br.get(3);
+    if (i == 0) cl16 = v; else if (i == 1) cl17 = v; else if (i == 2) cl18 = v;
+    else cl |= (unsigned long long)v << (4 * (unsigned)((order >> (4 * (i - 3))) & 15));
+    count[v]++;
+  }
+  count[0] = 0;
+  unsigned first[8];
+  {
+    unsigned code = 0;
+    int left = 1;
+    for (int l = 1; l <= 7; l++) {
+      code = (code + (l > 1 ? count[l - 1] : 0)) << 1;
+      first[l] = code;
+      left = (left << 1) - (int)count[l];
+      if (left < 0) return false;
+    }
+  }
+  for (int k = 0; k < 128; k += 4) *(unsigned*)(tab7 + k) = 0;
+  for (unsigned sy = 0; sy < 19; sy++) {
+    const unsigned l = sy < 16 ? (unsigned)((cl >> (4 * sy)) & 15) : sy == 16 ? cl16 : sy == 17 ? cl17 : cl18;
+    if (!l) continue;
+    const unsigned rv = __brev(first[l]++) >> (32 - l);
+    for (unsigned k = rv; k < 128; k += 1u << l) tab7[k] = (unsigned char)(l | (sy << 3));
+  }
+  int idx = 0;
+  unsigned prev = 0;
+  while (idx < nl + nd) {
+    br.refill();
+    const unsigned win = br.window();
+    const unsigned e = tab7[win & 127];
+    if (!e) return false;
+    const unsigned sy = e >> 3;
+    br.drop(e & 7);
+    unsigned rep = 1, val = sy;
+    if (sy == 16) { if (idx == 0) return false; val = prev; rep = 3 + br.get(2); }
+    else if (sy == 17) { val = 0; rep = 3 + br.get(3); }
+    else if (sy == 18) { val = 0; rep = 11 + br.get(7); }
+    if (idx + (int)rep > nl + nd) return false;
+    for (unsigned k = 0; k < rep; k++) lens[idx + k] = (unsigned char)val;
+    idx += (int)rep;
+    prev = val;
+  }
+  if (lens[256] == 0) return false;
+  hdr_end = br.bit_pos();
+  return true;
+}
+
+static const int PAR_BLK_WARPS = 8;
+static const unsigned PAR_RUN_ON_BITS = 1u << 20;   // how far past the next candidate the last lane may look for the end-of-block code
+__global__ void __launch_bounds__(PAR_BLK_WARPS * 32) par_block_kernel(const unsigned char* __restrict__ comp,
+                                                                       const ParStream* __restrict__ streams,
+                                                                       ParBlk* __restrict__ blks, unsigned n,
+                                                                       unsigned* __restrict__ tokens,
+                                                                       unsigned long long* __restrict__ tok_cursor,
+                                                                       unsigned long long tok_capacity) {
+  __shared__ BlkTabs tabs[PAR_BLK_WARPS];
+  __shared__ unsigned short lenx[32];
+  __shared__ unsigned distx[32];
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x < 32) { lenx[lane] = (unsigned short)par_len_info(lane); distx[lane] = par_dist_info(lane); }
+  __syncthreads();
+  const unsigned bi = blockIdx.x * PAR_BLK_WARPS + wid;
+  if (bi >= n) return;
+  BlkTabs& T = tabs[wid];
+  ParBlk blk = blks[bi];
+  const ParStream st = streams[blk.stream];
+  const unsigned char* in = comp + st.in_off;
+  const unsigned in_len = (unsigned)st.in_len, in_bits = in_len * 8;
+  // ---- header (lane 0) and tables (warp)
+  int nl = 0, nd = 0, hok = 0;
+  unsigned fin = 0, hdr_end = 0;
+  if (lane == 0) hok = blk_parse_header(in, in_len, blk.bit, T.lens, (unsigned char*)T.dtab, nl, nd, fin, hdr_end) ? 1 : 0;
+  hok = __shfl_sync(0xffffffffu, hok, 0);
+  nl = __shfl_sync(0xffffffffu, nl, 0);
+  nd = __shfl_sync(0xffffffffu, nd, 0);
+  fin = __shfl_sync(0xffffffffu, fin, 0);
+  hdr_end = __shfl_sync(0xffffffffu, hdr_end, 0);
+  __syncwarp();
+  bool ok = hok && hdr_end < in_bits;
+  ok = ok && blk_build<1>(T.lens, nl, T.ltab, PAR_LBITS, T.llong, T.lsorted, T.code, lane);
+  ok = ok && blk_build<2>(T.lens + nl, nd, T.dtab, PAR_DBITS, T.dlong, T.dsorted, T.code, lane);
+  SpanRes r;
+  r.end = 0; r.ntok = 0; r.nout = 0; r.flags = 2;
+  unsigned start = 0, total_tok = 0, total_out = 0;
+  if (ok) {
+    // ---- sub-chunks of the bit range [hdr_end, limit); the last lane may run on to the end-of-block code
+    const unsigned limit = min(max(blk.limit, hdr_end), in_bits);
+    const unsigned sc = max(64u, (limit - hdr_end + 31) / 32);
+    start = hdr_end + lane * sc;
+    // (the "next candidate" can be a false positive inside this block: the last lane then decodes the rest alone, and
+    // the chain walk skips the false candidate because it starts before this block's end)
+    const unsigned bound = lane == 31 ? (unsigned)min((unsigned long long)in_bits, (unsigned long long)limit + PAR_RUN_ON_BITS)
+                                      : hdr_end + (lane + 1) * sc;
+    blk_span<false>(true, in, in_len, start, bound, T, lenx, distx, nullptr, r);
+    for (int it = 0; it < 34; it++) {
+      const unsigned pe = __shfl_up_sync(0xffffffffu, r.end, 1), pf = __shfl_up_sync(0xffffffffu, r.flags, 1);
+      bool ch = false, rerun = false;
+      if (lane > 0) {
+        if (pf & 1) {                                   // the block ended before my sub-chunk
+          if (!(r.flags & 4) || r.end != pe) { r.end = pe; r.ntok = 0; r.nout = 0; r.flags = 1 | 4; start = pe; ch = true; }
+        } else if (pe != start || (r.flags & 4)) {
+          start = pe;
+          rerun = true;
+          ch = true;
+        }
+      }
+      if (__any_sync(0xffffffffu, rerun)) blk_span<false>(rerun, in, in_len, start, bound, T, lenx, distx, nullptr, r);
+      if (!__any_sync(0xffffffffu, ch)) break;
+    }
+    // ---- totals and token offsets
+    const unsigned bad = __ballot_sync(0xffffffffu, (r.flags & 2) != 0);
+    const unsigned eob = __shfl_sync(0xffffffffu, r.flags, 31) & 1;
+    unsigned pre = r.ntok, sum_out = r.nout;
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, pre, d);
+      if ((int)lane >= d) pre += v;
+    }
+    for (int d = 16; d >= 1; d >>= 1) sum_out += __shfl_xor_sync(0xffffffffu, sum_out, d);
+    total_tok = __shfl_sync(0xffffffffu, pre, 31);
+    total_out = sum_out;
+    ok = !bad && eob;
+    // token slots are handed out from one cursor once the count is known (false candidates take some too)
+    unsigned long long toff = 0;
+    if (ok && lane == 0) toff = atomicAdd(tok_cursor, (unsigned long long)total_tok);
+    toff = __shfl_sync(0xffffffffu, toff, 0);
+    if (toff + total_tok > tok_capacity) ok = false;
+    blk.tok_off = (long long)toff;
+    {
+      const bool emit = ok && !(r.flags & 4) && r.ntok;
+      if (__any_sync(0xffffffffu, emit)) {
+        SpanRes r2 = r;
+        blk_span<true>(emit, in, in_len, start, bound, T, lenx, distx, tokens + blk.tok_off + (pre - r.ntok), r2);
+        if (emit && (r2.ntok != r.ntok || r2.end != r.end)) ok = false;           // cannot happen
+      }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+  }
+  if (lane == 31) {
+    ParBlk* o = blks + bi;
+    o->end_bit = r.end;
+    o->n_tok = total_tok;
+    o->out_len = total_out;
+    o->flags = (ok ? 1u : 0u) | (fin ? 2u : 0u);
+    o->tok_off = blk.tok_off;
   }
 }
 
@@ -449,9 +588,10 @@ __device__ __forceinline__ unsigned par_bits(unsigned a, unsigned b, unsigned w)
   return (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1) << (lo & 31));
 }
 __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream* __restrict__ streams,
-                                                                const ParLz* __restrict__ lz,
+                                                                const ParBlk* __restrict__ blks,
+                                                                const unsigned* __restrict__ bfirst,
                                                                 const unsigned* __restrict__ tokens,
-                                                                unsigned char* out_base, int* __restrict__ bad) {
+                                                                unsigned char* out_base, ParRes* __restrict__ res) {
   const int NT = PAR_LZ_THREADS;
   __shared__ unsigned ob_w[PAR_LZ_CAP / 4];
   __shared__ unsigned pend_w[PAR_LZ_CAP / 32];
@@ -460,14 +600,26 @@ __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream*
   unsigned char* ob = (unsigned char*)ob_w;
   volatile unsigned* pend = pend_w;
   const ParStream st = streams[blockIdx.x];
-  const ParLz z = lz[blockIdx.x];
   unsigned char* out = out_base + st.out_off;
-  const unsigned* tk = tokens + z.tok_base;
-  const unsigned T = z.n_tok;
+  const unsigned out_cap = (unsigned)st.out_len;
   const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (unsigned i = tid; i < PAR_LZ_CAP / 32; i += NT) pend_w[i] = 0;
-  unsigned obase = 0, t0 = 0;
+  unsigned obase = 0;
   bool fail = false;
+  // ---- walk the chain of blocks: the first block starts right after the zlib header, every next one where its
+  //      predecessor ended; the walk stops at the first block that is missing or was not decoded cleanly
+  unsigned cur_bit = 16, n_done = 0, fin = 0;
+  unsigned bj = bfirst[blockIdx.x];
+  const unsigned bend = bfirst[blockIdx.x + 1];
+  for (;;) {
+    while (bj < bend && blks[bj].bit < cur_bit) bj++;
+    if (bj >= bend) break;
+    const ParBlk blk = blks[bj];
+    if (blk.bit != cur_bit || !(blk.flags & 1) || blk.end_bit <= cur_bit || (unsigned long long)obase + blk.out_len > out_cap) break;
+    const unsigned* tk = tokens + blk.tok_off;
+    const unsigned T = blk.n_tok;
+    const unsigned block_end = obase + blk.out_len;
+  unsigned t0 = 0;
   unsigned nxt = tid < T ? tk[tid] : 0;
   while (t0 < T) {
     const unsigned t = nxt;
@@ -488,7 +640,7 @@ __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream*
     const unsigned dist = (t & 0x7fffu) + 1;
     bool m = fits && isM;
     if (m && dist > obase + rel) { fail = true; m = false; }
-    if (fits && obase + rel + L > z.out_len) { fail = true; m = false; }
+    if (fits && obase + rel + L > block_end) { fail = true; m = false; }
     else if (fits && !isM) ob[rel] = (unsigned char)t;
     const int srel = (int)rel - (int)dist;                          // source position inside the tile (negative: before it)
     unsigned n_old = 0;
@@ -529,7 +681,18 @@ __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream*
     t0 += ncut;
     if (ncut != (unsigned)NT && t0 < T) nxt = t0 + tid < T ? tk[t0 + tid] : 0;   // the tile was cut short: reload
   }
-  if (__syncthreads_or(fail) || obase != z.out_len) { if (tid == 0) bad[blockIdx.x] = 1; }
+    if (__syncthreads_or(fail || obase != block_end)) { fail = true; break; }
+    cur_bit = blk.end_bit;
+    n_done++;
+    fin = (blk.flags >> 1) & 1;
+    bj++;
+    if (fin) break;
+  }
+  if (tid == 0) {
+    ParRes r;
+    r.tail_bit = cur_bit; r.tail_out = obase; r.n_done = n_done; r.flags = fin | (fail ? 2u : 0u);
+    res[blockIdx.x] = r;
+  }
 }
 
 }  // namespace mts
