@@ -53,7 +53,8 @@ struct mtsb_ctx {
   std::string err;
   // params
   long long par_inflate = 1;   // decode index-less zlib streams block-parallel (inflate_par.cuh)
-  long long par_batch_bytes = 6ll << 30;   // host-buffer sub-batch of index-less chunks (output bytes): large enough to amortise the block search
+  long long par_lz_wide = -1;   // LZ resolve kernel shape: -1 by stream count, 1 = 1024-thread CTAs, 0 = 256-thread CTAs
+  long long par_batch_bytes = 4ll << 30;   // host-buffer sub-batch of index-less chunks (output bytes): large enough to amortise the block search
   long long par_stats[4] = {0, 0, 0, 0};   // last call: survivors, candidates, chained blocks, streams resumed
   long long seg_bytes = 262144, batch_bytes = 2ll << 30, host_batch_bytes = 512ll << 20, write_index = 1;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of the host-buffer paths
@@ -342,6 +343,7 @@ int mtsb_set_param(mtsb_ctx* c, const char* name, long long v) {
   else if (s == "host_batch_bytes") { if (v < (1 << 20)) return fail(c, MTSB_E_ARG, "host_batch_bytes too small"); c->host_batch_bytes = v; }
   else if (s == "write_index") c->write_index = v ? 1 : 0;
   else if (s == "par_inflate") c->par_inflate = v ? 1 : 0;
+  else if (s == "par_lz_wide") c->par_lz_wide = v < 0 ? -1 : (v ? 1 : 0);
   else if (s == "par_batch_bytes") { if (v < (1 << 20)) return fail(c, MTSB_E_ARG, "par_batch_bytes too small"); c->par_batch_bytes = v; }
   else if (s == "max_chain") c->lz.max_chain = (int)std::max<long long>(1, v);
   else if (s == "nice_len") c->lz.nice_len = (int)std::min<long long>(258, std::max<long long>(4, v));
@@ -361,6 +363,7 @@ long long mtsb_get_param(mtsb_ctx* c, const char* name) {
   if (s == "host_batch_bytes") return c->host_batch_bytes;
   if (s == "write_index") return c->write_index;
   if (s == "par_inflate") return c->par_inflate;
+  if (s == "par_lz_wide") return c->par_lz_wide;
   if (s == "par_batch_bytes") return c->par_batch_bytes;
   if (s == "par_survivors") return c->par_stats[0];
   if (s == "par_candidates") return c->par_stats[1];
@@ -818,8 +821,15 @@ static int par_phase(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Inflat
              d_ps, (ParBlk*)c->d_plist.p, n_cand, (unsigned*)c->d_tokens.p, (unsigned long long*)((char*)c->d_pcount.p + 16),
              (unsigned long long)tok_total);
   CKL();
-  MTS_LAUNCH(par_lz_kernel, dim3(ns), dim3(PAR_LZ_THREADS), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p,
-             (const unsigned*)((const char*)c->d_plist.p + o_first), (const unsigned*)c->d_tokens.p, dT, (ParRes*)c->d_pbad.p);
+  if (c->par_lz_wide < 0 ? ns <= 2 * c->sm_count : c->par_lz_wide == 1) {
+    auto k = par_lz_kernel<1024, 16384>;
+    MTS_LAUNCH(k, dim3(ns), dim3(1024), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p,
+               (const unsigned*)((const char*)c->d_plist.p + o_first), (const unsigned*)c->d_tokens.p, dT, (ParRes*)c->d_pbad.p);
+  } else {
+    auto k = par_lz_kernel<256, 4096>;
+    MTS_LAUNCH(k, dim3(ns), dim3(256), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p,
+               (const unsigned*)((const char*)c->d_plist.p + o_first), (const unsigned*)c->d_tokens.p, dT, (ParRes*)c->d_pbad.p);
+  }
   CKL();
   c->launches += 2;
   { int r = small_copy(c, c->h_small.p, c->d_pbad.p, (size_t)ns * sizeof(ParRes)); if (r) return r; }

@@ -580,13 +580,14 @@ __global__ void __launch_bounds__(PAR_BLK_WARPS * 32) par_block_kernel(const uns
 //    matches copy from before the tile (global memory, written by earlier tiles) are placed at once; bytes copied from
 //    inside the tile wait, without block barriers, until the PENDING bitmap (one bit per staged byte, set by the
 //    matches that still have to produce it) is clear over their source range.
-static const int PAR_LZ_THREADS = 256;
-static const int PAR_LZ_CAP = 4096;
+// Two shapes: 256 threads / 4 KB (up to 8 CTAs per SM: many streams) and 1024 threads / 16 KB (few streams: a stream
+// is a serial chain of tiles, so its latency is what counts).
 __device__ __forceinline__ unsigned par_bits(unsigned a, unsigned b, unsigned w) {   // bits of [a, b) that fall in word w
   const unsigned lo = max(a, w * 32), hi = min(b, w * 32 + 32);
   if (hi <= lo) return 0;
   return (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1) << (lo & 31));
 }
+template <int PAR_LZ_THREADS, int PAR_LZ_CAP>
 __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream* __restrict__ streams,
                                                                 const ParBlk* __restrict__ blks,
                                                                 const unsigned* __restrict__ bfirst,
@@ -631,8 +632,9 @@ __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream*
     for (int d = 1; d < 32; d <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += v; }
     if (lane == 31) wsum[wid] = incl;
     __syncthreads();                                                // also orders the previous tile's stores before the loads below
-    unsigned woff = 0;
-    for (int w = 0; w < NT / 32; w++) { const unsigned v = wsum[w]; if (w < (int)wid) woff += v; }
+    unsigned ws = lane < (unsigned)(NT / 32) ? wsum[lane] : 0u;     // every warp scans the warp totals itself
+    for (int d = 1; d < NT / 32; d <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, ws, d); if ((int)lane >= d) ws += v; }
+    const unsigned woff = __shfl_sync(0xffffffffu, ws, (wid + 31) & 31) * (wid > 0);
     const unsigned rel = woff + incl - L;                           // position inside the tile
     const bool fits = has && rel + L <= (unsigned)PAR_LZ_CAP;       // monotone: the tile is the longest fitting prefix
     const unsigned ncut = (unsigned)__syncthreads_count(fits);
@@ -649,13 +651,19 @@ __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream*
       if (n_old < L) {                                              // has an in-tile part: its bytes are pending
         for (unsigned w = rel >> 5; w <= (rel + L - 1) >> 5; w++) atomicOr(&pend_w[w], par_bits(rel, rel + L, w));
       }
-      const unsigned char* sp = out + obase + srel;                 // bytes from before the tile
+      // bytes from before the tile: aligned 32-bit loads (the output buffer is 4-byte aligned and padded), 8 bytes a turn
+      const unsigned char* sp = out + obase + srel;
+      const unsigned mis = (unsigned)((uintptr_t)sp & 3);
+      const unsigned* sw = (const unsigned*)(sp - mis);
       for (unsigned j0 = 0; j0 < n_old; j0 += 8) {
-        unsigned char v[8];
+        const unsigned w0 = sw[0], w1 = (mis + n_old - j0 > 4) ? sw[1] : 0u, w2 = (mis + n_old - j0 > 8) ? sw[2] : 0u;
+        unsigned v0 = __funnelshift_r(w0, w1, mis * 8), v1 = __funnelshift_r(w1, w2, mis * 8);
+        unsigned char* dp = ob + rel + j0;
 #pragma unroll
-        for (unsigned j = 0; j < 8; j++) v[j] = (j0 + j < n_old) ? sp[j0 + j] : (unsigned char)0;
+        for (unsigned j = 0; j < 4; j++) { if (j0 + j < n_old) dp[j] = (unsigned char)v0; v0 >>= 8; }
 #pragma unroll
-        for (unsigned j = 0; j < 8; j++) if (j0 + j < n_old) ob[rel + j0 + j] = v[j];
+        for (unsigned j = 4; j < 8; j++) { if (j0 + j < n_old) dp[j] = (unsigned char)v1; v1 >>= 8; }
+        sw += 2;
       }
       if (n_old == L) m = false;
     }
