@@ -53,6 +53,7 @@ struct mtsb_ctx {
   std::string err;
   // params
   long long par_inflate = 1;   // decode index-less zlib streams block-parallel (inflate_par.cuh)
+  long long par_indexed = 1;    // indexed segments of GPU-written chunks also go through the block kernels
   long long par_lz_wide = -1;   // LZ resolve kernel shape: -1 by stream count, 1 = 1024-thread CTAs, 0 = 256-thread CTAs
   long long par_batch_bytes = 4ll << 30;   // host-buffer sub-batch of index-less chunks (output bytes): large enough to amortise the block search
   long long par_stats[4] = {0, 0, 0, 0};   // last call: survivors, candidates, chained blocks, streams resumed
@@ -343,6 +344,7 @@ int mtsb_set_param(mtsb_ctx* c, const char* name, long long v) {
   else if (s == "host_batch_bytes") { if (v < (1 << 20)) return fail(c, MTSB_E_ARG, "host_batch_bytes too small"); c->host_batch_bytes = v; }
   else if (s == "write_index") c->write_index = v ? 1 : 0;
   else if (s == "par_inflate") c->par_inflate = v ? 1 : 0;
+  else if (s == "par_indexed") c->par_indexed = v ? 1 : 0;
   else if (s == "par_lz_wide") c->par_lz_wide = v < 0 ? -1 : (v ? 1 : 0);
   else if (s == "par_batch_bytes") { if (v < (1 << 20)) return fail(c, MTSB_E_ARG, "par_batch_bytes too small"); c->par_batch_bytes = v; }
   else if (s == "max_chain") c->lz.max_chain = (int)std::max<long long>(1, v);
@@ -364,6 +366,7 @@ long long mtsb_get_param(mtsb_ctx* c, const char* name) {
   if (s == "write_index") return c->write_index;
   if (s == "par_inflate") return c->par_inflate;
   if (s == "par_lz_wide") return c->par_lz_wide;
+  if (s == "par_indexed") return c->par_indexed;
   if (s == "par_batch_bytes") return c->par_batch_bytes;
   if (s == "par_survivors") return c->par_stats[0];
   if (s == "par_candidates") return c->par_stats[1];
@@ -737,6 +740,90 @@ static int fetch_ranges(mtsb_ctx* c, const unsigned char* comp, int comp_is_devi
 
 static uint32_t rd32(const unsigned char* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
 
+// Steps 3..5 of the block-parallel decoder for the streams `ps` (segs[ids[i]] each) and their candidate blocks `blks`
+// (stream order, bfirst[i] = first block of stream i).  The streams whose chain of blocks was resolved are rewritten as
+// INF_RESUME tails; the others are left untouched (full serial decode).  zflag: INF_ZLIB for whole zlib streams.
+static int par_decode_blocks(mtsb_ctx* c, const unsigned char* dcomp, std::vector<InflateSeg>& segs, const std::vector<int>& whole,
+                             const std::vector<ParStream>& ps, std::vector<ParBlk>& blks, const std::vector<unsigned>& bfirst,
+                             long long in_total, unsigned char* dT, int zflag) {
+  const int ns = (int)ps.size();
+  const unsigned n_cand = (unsigned)blks.size();
+  if (n_cand == 0) return 0;
+  // token slots: one per 6 bits of input (typical streams spend 9..15 bits per token); if that is not enough the blocks
+  // that do not fit end the chain of their stream (serial decode of the rest)
+  const long long tok_total = in_total * 8 / 6 + 4096;
+  NEED(c->d_pstreams, (size_t)ns * sizeof(ParStream));
+  NEED(c->d_pcount, 256);
+  NEED(c->d_pbad, (size_t)ns * sizeof(ParRes) + 64);
+  NEED(c->h_small, 4096 + (size_t)ns * sizeof(ParRes));
+  const ParStream* d_ps = (const ParStream*)c->d_pstreams.p;
+  const size_t o_first = ((size_t)n_cand * sizeof(ParBlk) + 255) & ~(size_t)255;
+  const size_t list_bytes = o_first + (size_t)(ns + 1) * 4;
+  const size_t o_ps = (list_bytes + 255) & ~(size_t)255;          // host staging: [blocks | bfirst | streams]
+  NEED(c->d_plist, list_bytes);
+  NEED(c->h_tab, o_ps + (size_t)ns * sizeof(ParStream) + 64);
+  NEED(c->d_tokens, (size_t)tok_total * 4 + 64);
+  memcpy(c->h_tab.p, blks.data(), (size_t)n_cand * sizeof(ParBlk));
+  memcpy((char*)c->h_tab.p + o_first, bfirst.data(), (size_t)(ns + 1) * 4);
+  memcpy((char*)c->h_tab.p + o_ps, ps.data(), (size_t)ns * sizeof(ParStream));
+  { int r = small_copy(c, c->d_plist.p, c->h_tab.p, list_bytes); if (r) return r; }
+  { int r = small_copy(c, c->d_pstreams.p, (char*)c->h_tab.p + o_ps, (size_t)ns * sizeof(ParStream)); if (r) return r; }
+  CK(cudaMemsetAsync((char*)c->d_pcount.p + 16, 0, 8, c->stream));     // the token cursor
+  MTS_LAUNCH(par_block_kernel, dim3((n_cand + PAR_BLK_WARPS - 1) / PAR_BLK_WARPS), dim3(PAR_BLK_WARPS * 32), 0, c->stream, dcomp,
+             d_ps, (ParBlk*)c->d_plist.p, n_cand, (unsigned*)c->d_tokens.p, (unsigned long long*)((char*)c->d_pcount.p + 16),
+             (unsigned long long)tok_total);
+  CKL();
+  if (c->par_lz_wide < 0 ? ns <= 2 * c->sm_count : c->par_lz_wide == 1) {
+    auto k = par_lz_kernel<1024, 16384>;
+    MTS_LAUNCH(k, dim3(ns), dim3(1024), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p,
+               (const unsigned*)((const char*)c->d_plist.p + o_first), (const unsigned*)c->d_tokens.p, dT, (ParRes*)c->d_pbad.p);
+  } else {
+    auto k = par_lz_kernel<256, 4096>;
+    MTS_LAUNCH(k, dim3(ns), dim3(256), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p,
+               (const unsigned*)((const char*)c->d_plist.p + o_first), (const unsigned*)c->d_tokens.p, dT, (ParRes*)c->d_pbad.p);
+  }
+  CKL();
+  c->launches += 2;
+  { int r = small_copy(c, c->h_small.p, c->d_pbad.p, (size_t)ns * sizeof(ParRes)); if (r) return r; }
+  CK(cudaStreamSynchronize(c->stream));
+  const ParRes* res = (const ParRes*)c->h_small.p;
+  for (int sidx = 0; sidx < ns; sidx++) {
+    const ParRes& r = res[sidx];
+    c->par_stats[2] += r.n_done;
+    if (r.n_done == 0 || (r.flags & 2)) continue;              // full serial decode of this stream
+    InflateSeg& s = segs[whole[sidx]];
+    s.flags = zflag | INF_RESUME | ((r.flags & 1) ? INF_NO_BLOCKS : 0);
+    s.start_bit = r.tail_bit;
+    s.opos0 = r.tail_out;
+    c->par_stats[3]++;
+  }
+  return 0;
+}
+
+// The indexed segments of GPU-written chunks (`ids`: indices into segs) through the same kernels: every segment is one
+// dynamic block at bit 0 followed by the empty stored block that byte-aligns the next segment (deflate.cuh), so the
+// blocks are known without any search; a segment stored uncompressed simply fails the header parse and stays serial.
+static int par_phase_indexed(mtsb_ctx* c, const unsigned char* dcomp, std::vector<InflateSeg>& segs, const std::vector<int>& ids,
+                             unsigned char* dT) {
+  const int ns = (int)ids.size();
+  std::vector<ParStream> ps(ns);
+  std::vector<ParBlk> blks(ns);
+  std::vector<unsigned> bfirst(ns + 1);
+  long long in_total = 0;
+  for (int i = 0; i < ns; i++) {
+    const InflateSeg& s = segs[ids[i]];
+    ps[i].in_off = s.in_off; ps[i].out_off = s.out_off; ps[i].in_len = s.in_len; ps[i].out_len = s.out_len;
+    ps[i].first_bit = 0; ps[i].pad_ = 0;
+    ParBlk& b = blks[i];
+    b.stream = (unsigned)i; b.bit = 0; b.limit = (unsigned)s.in_len * 8u;
+    b.end_bit = 0; b.n_tok = 0; b.out_len = 0; b.flags = 0; b.pad_ = 0; b.tok_off = 0;
+    bfirst[i] = (unsigned)i;
+    in_total += s.in_len;
+  }
+  bfirst[ns] = (unsigned)ns;
+  return par_decode_blocks(c, dcomp, segs, ids, ps, blks, bfirst, in_total, dT, 0);
+}
+
 // Block-parallel decode of the whole-stream segments `whole` (indices into segs).  On success the listed segments are
 // rewritten as INF_RESUME tails; on any doubt they are left untouched (full serial decode).
 static int par_phase(mtsb_ctx* c, const unsigned char* dcomp, std::vector<InflateSeg>& segs, const std::vector<int>& whole,
@@ -748,6 +835,7 @@ static int par_phase(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Inflat
   for (int i = 0; i < ns; i++) {
     const InflateSeg& s = segs[whole[i]];
     ps[i].in_off = s.in_off; ps[i].out_off = s.out_off; ps[i].in_len = s.in_len; ps[i].out_len = s.out_len;
+    ps[i].first_bit = 16; ps[i].pad_ = 0;
     in_total += s.in_len;
     max_in = std::max(max_in, s.in_len);
   }
@@ -790,9 +878,6 @@ static int par_phase(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Inflat
   std::sort(keys.begin(), keys.end());
   std::vector<ParBlk> blks(n_cand);
   std::vector<unsigned> bfirst(ns + 1, 0);
-  // token slots: one per 6 bits of input (typical streams spend 9..15 bits per token); if that is not enough the blocks
-  // that do not fit end the chain of their stream (serial decode of the rest)
-  const long long tok_total = in_total * 8 / 6 + 4096;
   {
     unsigned i = 0;
     for (int sidx = 0; sidx < ns; sidx++) {
@@ -810,41 +895,7 @@ static int par_phase(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Inflat
     bfirst[ns] = i;
     if (i != n_cand) return 0;                                  // a key with an unknown stream: do not trust the list
   }
-  const size_t o_first = ((size_t)n_cand * sizeof(ParBlk) + 255) & ~(size_t)255;
-  NEED(c->d_plist, o_first + (size_t)(ns + 1) * 4);
-  NEED(c->h_tab, o_first + (size_t)(ns + 1) * 4 + 64);
-  NEED(c->d_tokens, (size_t)tok_total * 4 + 64);
-  memcpy(c->h_tab.p, blks.data(), (size_t)n_cand * sizeof(ParBlk));
-  memcpy((char*)c->h_tab.p + o_first, bfirst.data(), (size_t)(ns + 1) * 4);
-  { int r = small_copy(c, c->d_plist.p, c->h_tab.p, o_first + (size_t)(ns + 1) * 4); if (r) return r; }
-  MTS_LAUNCH(par_block_kernel, dim3((n_cand + PAR_BLK_WARPS - 1) / PAR_BLK_WARPS), dim3(PAR_BLK_WARPS * 32), 0, c->stream, dcomp,
-             d_ps, (ParBlk*)c->d_plist.p, n_cand, (unsigned*)c->d_tokens.p, (unsigned long long*)((char*)c->d_pcount.p + 16),
-             (unsigned long long)tok_total);
-  CKL();
-  if (c->par_lz_wide < 0 ? ns <= 2 * c->sm_count : c->par_lz_wide == 1) {
-    auto k = par_lz_kernel<1024, 16384>;
-    MTS_LAUNCH(k, dim3(ns), dim3(1024), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p,
-               (const unsigned*)((const char*)c->d_plist.p + o_first), (const unsigned*)c->d_tokens.p, dT, (ParRes*)c->d_pbad.p);
-  } else {
-    auto k = par_lz_kernel<256, 4096>;
-    MTS_LAUNCH(k, dim3(ns), dim3(256), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p,
-               (const unsigned*)((const char*)c->d_plist.p + o_first), (const unsigned*)c->d_tokens.p, dT, (ParRes*)c->d_pbad.p);
-  }
-  CKL();
-  c->launches += 2;
-  { int r = small_copy(c, c->h_small.p, c->d_pbad.p, (size_t)ns * sizeof(ParRes)); if (r) return r; }
-  CK(cudaStreamSynchronize(c->stream));
-  const ParRes* res = (const ParRes*)c->h_small.p;
-  for (int sidx = 0; sidx < ns; sidx++) {
-    const ParRes& r = res[sidx];
-    c->par_stats[2] += r.n_done;
-    if (r.n_done == 0 || (r.flags & 2)) continue;              // full serial decode of this stream
-    InflateSeg& s = segs[whole[sidx]];
-    s.flags = INF_ZLIB | INF_RESUME | ((r.flags & 1) ? INF_NO_BLOCKS : 0);
-    s.start_bit = r.tail_bit;
-    s.opos0 = r.tail_out;
-    c->par_stats[3]++;
-  }
+  return par_decode_blocks(c, dcomp, segs, whole, ps, blks, bfirst, in_total, dT, INF_ZLIB);
   return 0;
 }
 
@@ -1037,6 +1088,13 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
       long long whole_in = 0;
       for (int w : whole) whole_in += segs[w].in_len;
       if (whole_in >= 65536) { int r = par_phase(c, dcomp, segs, whole, (unsigned char*)c->d_T.p); if (r) return r; }
+    }
+    if (c->par_inflate && c->par_indexed && (int)whole.size() < n_segs) {
+      std::vector<int> ids;
+      size_t wi = 0;
+      for (int j = 0; j < n_segs; j++) { if (wi < whole.size() && whole[wi] == j) { wi++; continue; } ids.push_back(j); }
+      int r = par_phase_indexed(c, dcomp, segs, ids, (unsigned char*)c->d_T.p);
+      if (r) return r;
     }
     NEED(c->h_tab, tab_bytes);
     NEED(c->d_tab, tab_bytes);

@@ -21,10 +21,12 @@
 
 namespace mts {
 
-struct ParStream {       // one whole zlib stream
+struct ParStream {       // one DEFLATE stream: a whole zlib stream, or one indexed segment of a GPU-written chunk
   long long in_off;      // byte offset in the compressed buffer
   long long out_off;     // byte offset of its output in the transformed buffer
   int in_len, out_len;
+  unsigned first_bit;    // bit offset of its first block header (16 after a zlib header, 0 for a segment)
+  unsigned pad_;
 };
 
 struct ParBlk {          // a candidate block in stream order (host-sorted), filled in by par_block_kernel
@@ -609,7 +611,7 @@ __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream*
   bool fail = false;
   // ---- walk the chain of blocks: the first block starts right after the zlib header, every next one where its
   //      predecessor ended; the walk stops at the first block that is missing or was not decoded cleanly
-  unsigned cur_bit = 16, n_done = 0, fin = 0;
+  unsigned cur_bit = st.first_bit, n_done = 0, fin = 0;
   unsigned bj = bfirst[blockIdx.x];
   const unsigned bend = bfirst[blockIdx.x + 1];
   for (;;) {
