@@ -121,13 +121,15 @@ __device__ __forceinline__ int par_cl_decode(unsigned win, const unsigned char* 
   return -1;
 }
 
-// Parse a dynamic block header at the reader's position.  On success the reader is at the first symbol, lens[0..nl) and
-// lens[nl..nl+nd) hold the code lengths.  strict: require complete literal/length and distance codes (zlib's output).
-__device__ bool par_parse_header(TBits& br, unsigned char* lens, int& nl, int& nd, unsigned& final_, bool strict) {
-  final_ = br.get(1);
+// Does a dynamic block header that zlib's deflate could have written start at the reader's position?  The code
+// lengths are not stored: a complete literal/length code and a complete (or single-symbol) distance code are checked
+// through running Kraft sums (units of 2^-15) — a random bit string over-subscribes one of the codes within a few
+// dozen lengths, so false survivors are dropped long before the end of the header — and an end-of-block code must exist.
+__device__ bool par_check_header(TBits& br) {
+  br.get(1);
   if (br.get(2) != 2) return false;
-  nl = (int)br.get(5) + 257;
-  nd = (int)br.get(5) + 1;
+  const int nl = (int)br.get(5) + 257;
+  const int nd = (int)br.get(5) + 1;
   const int ncl = (int)br.get(4) + 4;
   if (nl > 286 || nd > 30) return false;
   const unsigned char order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
@@ -145,10 +147,11 @@ __device__ bool par_parse_header(TBits& br, unsigned char* lens, int& nl, int& n
     if (left < 0) return false;
     if (l < 7) offs[l + 1] = (unsigned char)(offs[l] + count[l]);
   }
-  if (strict && left != 0) return false;
+  if (left != 0) return false;
   for (int i = 0; i < 19; i++) if (cl[i]) sorted[offs[cl[i]]++] = (unsigned char)i;
   int idx = 0;
-  unsigned prev = 0, kl_run = 0, kd_run = 0;
+  unsigned prev = 0, kl = 0, kd = 0, ndist = 0;
+  bool eob = false;
   while (idx < nl + nd) {
     br.refill();
     unsigned nb;
@@ -160,25 +163,19 @@ __device__ bool par_parse_header(TBits& br, unsigned char* lens, int& nl, int& n
     else if (sym == 17) { val = 0; rep = 3 + br.get(3); }
     else if (sym == 18) { val = 0; rep = 11 + br.get(7); }
     if (idx + (int)rep > nl + nd) return false;
-    for (unsigned k = 0; k < rep; k++) lens[idx + k] = (unsigned char)val;
-    if (strict && val) {
-      // running Kraft sums (units of 2^-15): a random bit string over-subscribes one of the codes within a few dozen
-      // lengths, so false survivors are dropped long before the end of the header
-      for (unsigned k = 0; k < rep; k++) { if (idx + (int)k < nl) kl_run += 32768u >> val; else kd_run += 32768u >> val; }
-      if (kl_run > 32768u || kd_run > 32768u) return false;
+    if (val) {
+      const unsigned n_ll = (unsigned)min(max(nl - idx, 0), (int)rep);      // how many of the run are literal/length codes
+      kl += n_ll * (32768u >> val);
+      kd += (rep - n_ll) * (32768u >> val);
+      ndist += rep - n_ll;
+      if (kl > 32768u || kd > 32768u) return false;
+      if (idx <= 256 && 256 < idx + (int)rep) eob = true;
     }
     idx += (int)rep;
     prev = val;
   }
-  if (lens[256] == 0) return false;
-  if (strict) {
-    // Kraft sums in units of 2^-15
-    unsigned kl = 0, kd = 0, ndist = 0;
-    for (int i = 0; i < nl; i++) if (lens[i]) kl += 32768u >> lens[i];
-    for (int i = 0; i < nd; i++) if (lens[nl + i]) { kd += 32768u >> lens[nl + i]; ndist++; }
-    if (kl != 32768u) return false;
-    if (kd != 32768u && !(ndist <= 1 && kd <= 16384u)) return false;   // zlib emits >= 2 distance codes; tolerate 0/1
-  }
+  if (!eob || kl != 32768u) return false;
+  if (kd != 32768u && !(ndist <= 1 && kd <= 16384u)) return false;   // zlib emits >= 2 distance codes; tolerate 0/1
   return true;
 }
 
@@ -337,10 +334,7 @@ __global__ void __launch_bounds__(128) par_validate_kernel(const unsigned char* 
   const ParStream st = streams[sidx];
   TBits br;
   br.init(comp + st.in_off, (unsigned)st.in_len, bit);
-  unsigned char lens[320];
-  int nl, nd;
-  unsigned fin;
-  if (!par_parse_header(br, lens, nl, nd, fin, true)) return;
+  if (!par_check_header(br)) return;
   if (br.bit_pos() > (unsigned)st.in_len * 8) return;
   const unsigned at = atomicAdd(&counters[1], 1u);
   if (at < cap) cand[at] = sv;
