@@ -54,7 +54,12 @@ int mtsb_sync(mtsb_ctx* ctx);
 
 /* Tunables (by name): "seg_bytes" target encoder segment size (default 262144), "max_chain", "nice_len", "far4",
  * "far5", "far6", "lazy" (match finder), "write_index" (append the segment index after each chunk's zlib stream, 1),
- * "batch_bytes" (raw bytes processed per internal sub-batch).  Returns MTSB_E_ARG for unknown names. */
+ * "batch_bytes" (raw bytes processed per internal sub-batch), "host_batch_bytes" (the same when a host buffer is
+ * involved: copies of one sub-batch overlap the kernels of the next), "par_batch_bytes" (host-buffer sub-batch of
+ * index-less chunks on the decode side), "par_inflate" (1: block-parallel decoder; 0: serial warp per stream),
+ * "par_indexed" (1: indexed segments go through the block kernels as well), "par_lz_wide" (-1 auto / 0 / 1: shape of
+ * the token-resolve kernel).  Read-only: "par_survivors", "par_candidates", "par_chained", "par_resumed" (what the
+ * block-parallel decoder did in the last call).  Returns MTSB_E_ARG for unknown names. */
 int mtsb_set_param(mtsb_ctx* ctx, const char* name, long long value);
 long long mtsb_get_param(mtsb_ctx* ctx, const char* name);
 

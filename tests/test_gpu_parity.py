@@ -248,3 +248,55 @@ def test_block_parallel_inflate_reports_corruption(codec):
         assert st[0] != 0, pos
     out, st = codec.decompress(good + b'\x00' * 7, [0, len(good) + 7], [0, 30000], 32, np.int16, F())
     assert st[0] == 0 and np.array_equal(out, x)        # trailing bytes are ignored, as zlib does
+
+
+def test_block_parallel_skips_a_false_candidate(codec):
+    """Chunk seed 101 of the bench workload has one bit pattern inside a block that passes the full header validation
+    (314 candidates for 313 blocks).  The block before it must run on to its real end and the chain must skip it."""
+    from mtscomp_b200 import synth
+    x = np.ascontiguousarray(synth.ap_chunk(30000, 385, seed=101))
+    good = ora.encode_chunk(x)
+    out, st = codec.decompress(good, [0, len(good)], [0, 30000], 385, np.int16, F())
+    assert st[0] == 0 and np.array_equal(out, x)
+    cands, chained = codec.get_param('par_candidates'), codec.get_param('par_chained')
+    assert codec.get_param('par_resumed') == 1 and chained >= 300
+    assert cands >= chained                     # (cands > chained on this chunk; >= keeps the test data-independent)
+
+
+def test_indexed_segments_block_kernels_match_serial(codec):
+    """GPU-written chunks: the indexed segments decode through the block kernels (default) or through the serial warp
+    decoder (par_indexed = 0); both must give the input back, including chunks with segments stored uncompressed."""
+    from mtscomp_b200 import synth
+    rng = np.random.default_rng(12)
+    x = np.concatenate([synth.ap_chunk(ns=20000, nc=64, seed=70),
+                        rng.integers(-32768, 32767, (20000, 64)).astype(np.int16),      # incompressible: stored segments
+                        synth.ap_chunk(ns=20000, nc=64, seed=71)])
+    rows = [0, 20000, 40000, 60000]
+    comp, offs = codec.compress(x, rows, F())
+    try:
+        codec.set_param('par_indexed', 1)
+        out1, st1 = codec.decompress(comp, offs, rows, 64, np.int16, F())
+        resumed = codec.get_param('par_resumed')
+        codec.set_param('par_indexed', 0)
+        out0, st0 = codec.decompress(comp, offs, rows, 64, np.int16, F())
+        assert codec.get_param('par_resumed') == 0
+    finally:
+        codec.set_param('par_indexed', 1)
+    assert not st1.any() and not st0.any()
+    assert np.array_equal(out1, x) and np.array_equal(out0, x)
+    assert resumed >= 10                        # the segments of the two compressible chunks went through the block kernels
+    bad = bytearray(comp)
+    bad[offs[0] + (offs[1] - offs[0]) // 2] ^= 0x11
+    _, st = codec.decompress(bytes(bad), offs, rows, 64, np.int16, F())
+    assert st[0] != 0 and st[1] == 0 and st[2] == 0
+
+
+def test_block_parallel_long_codes(codec):
+    """Heavy-tailed data gives Huffman codes longer than the fast tables (10 / 8 bits): the limit-word path."""
+    rng = np.random.default_rng(5)
+    for x in ((rng.laplace(0, 40, (60000, 6))).astype(np.int16),
+              np.where(rng.random((60000, 6)) < 0.02, rng.integers(-30000, 30000, (60000, 6)),
+                       rng.normal(0, 3, (60000, 6))).astype(np.int16)):
+        good = ora.encode_chunk(x)
+        out, st = codec.decompress(good, [0, len(good)], [0, 60000], 6, np.int16, F())
+        assert st[0] == 0 and np.array_equal(out, x) and codec.get_param('par_resumed') == 1
