@@ -146,8 +146,8 @@ __device__ __forceinline__ void lz_insert_step(const unsigned short* hbuf, unsig
                                                unsigned u0, unsigned units, unsigned lane) {
   const unsigned PM = LzSmem<STRIDE>::PREV_N - 1;
   const unsigned pbase = LONG ? 0 : (u0 % (2 * LZ_UNITS));     // S links live in a two-step array
-  // software pipeline: the next batch's hashes and head lookups are issued right after this batch's stores (shared
-  // memory is in order per warp), so the warp does not wait for the read-back that settles collisions
+  // software pipeline: the next batch's hashes are fetched before, and its head lookups right after, this batch's stores
+  // have settled
   unsigned hA = (2 * lane < units) ? hbuf[2 * lane] : 0xffffu;
   unsigned hB = (2 * lane + 1 < units) ? hbuf[2 * lane + 1] : 0xffffu;
   unsigned short oldA = hA != 0xffffu ? head[hA] : (unsigned short)0;
@@ -163,8 +163,6 @@ __device__ __forceinline__ void lz_insert_step(const unsigned short* hbuf, unsig
     if (vA && !same) head[hA] = ubA;
     if (vB) head[hB] = ubB;
     __syncwarp();
-    const unsigned short noA = nA != 0xffffu ? head[nA] : (unsigned short)0;
-    const unsigned short noB = nB != 0xffffu ? head[nB] : (unsigned short)0;
     // a later unit of this batch must end up as the head: re-store while an earlier one is visible
     bool wA = vA && !same && (unsigned short)(ubA - head[hA] - 1) < 63;
     bool wB = vB && (unsigned short)(ubB - head[hB] - 1) < 63;
@@ -175,6 +173,10 @@ __device__ __forceinline__ void lz_insert_step(const unsigned short* hbuf, unsig
       wA = vA && !same && (unsigned short)(ubA - head[hA] - 1) < 63;
       wB = vB && (unsigned short)(ubB - head[hB] - 1) < 63;
     }
+    // only now (the heads are settled, whichever store the hardware let win first) look up the next batch's links;
+    // they are not needed before the end of the next iteration, so this load is off the critical path
+    const unsigned short noA = nA != 0xffffu ? head[nA] : (unsigned short)0;
+    const unsigned short noB = nB != 0xffffu ? head[nB] : (unsigned short)0;
     if (iA < units) prev[LONG ? ((u0 + iA) & PM) : (pbase + iA)] = vA ? oldA : ubA;   // invalid: distance 0 = none
     if (iB < units) prev[LONG ? ((u0 + iB) & PM) : (pbase + iB)] = vB ? (same ? ubA : oldB) : ubB;
     hA = nA; hB = nB; oldA = noA; oldB = noB;
@@ -408,15 +410,29 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
         xe[tid] = (sb + (v & 0xffffu)) | (v & 0xffff0000u);
         named_barrier(1, NSW * 32);
         if (tid == 0) { LZ_PROF_T(t_b); LZ_PROF_ADD(6, t_b - t_p0); }
-        if (tid == 0) {
-          unsigned p = start, acc = 0;
-          for (unsigned w = 0; w < NSW; w++) {
-            ent[w] = p;
-            misc[w] = acc;
-            if (p < min((w + 1) * 32, nu)) { const unsigned t = xe[p]; acc += t >> 16; p = t & 0xffffu; }
+        if (wid == 0) {
+          // Stage 2, by relaxation in one warp (lane = stretch): every lane guesses that its stretch is entered at
+          // its first unit, looks up where that chain leaves, and hands the exit to the next lane as ITS entry; repeat
+          // until no entry changes.  Lane w is certainly right after w rounds, but greedy parses that start a few
+          // units apart merge almost at once, so the exits barely depend on the entries: 2-4 rounds instead of a
+          // 30-step serial walk.
+          const unsigned my_se = min((lane + 1) * 32, nu);
+          unsigned e = lane == 0 ? start : lane * 32, t = 0;
+          for (;;) {
+            t = (lane < NSW && e < my_se) ? xe[e] : e;              // exit | elements << 16 (entry beyond the stretch: pass)
+            unsigned ne = __shfl_up_sync(0xffffffffu, t & 0xffffu, 1);
+            if (lane == 0) ne = start;
+            const bool ch = lane < NSW && ne != e;
+            e = ne;
+            if (!__any_sync(0xffffffffu, ch)) break;
           }
-          misc[35] = acc;                                   // elements emitted by this step
-          misc[33 + ((step + 1) & 1)] = p - nu;            // p >= nu: where the last token of this step ends
+          unsigned acc = lane < NSW ? t >> 16 : 0u;                  // elements emitted by my stretch; inclusive scan
+          for (int d = 1; d < 32; d <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, acc, d); if ((int)lane >= d) acc += v; }
+          if (lane < NSW) { ent[lane] = e; misc[lane] = acc - (t >> 16); }
+          if (lane == NSW - 1) {
+            misc[35] = acc;                                         // elements emitted by this step
+            misc[33 + ((step + 1) & 1)] = (t & 0xffffu) - nu;       // >= 0: where the last token of this step ends
+          }
         }
         named_barrier(1, NSW * 32);
         if (tid == 0) { LZ_PROF_T(t_b); LZ_PROF_ADD(7, t_b - t_p0); }

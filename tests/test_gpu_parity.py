@@ -300,3 +300,21 @@ def test_block_parallel_long_codes(codec):
         good = ora.encode_chunk(x)
         out, st = codec.decompress(good, [0, len(good)], [0, 60000], 6, np.int16, F())
         assert st[0] == 0 and np.array_equal(out, x) and codec.get_param('par_resumed') == 1
+
+
+def test_gpu_stream_bytes_equal_the_host_emulation(codec):
+    """The encoder's output must not depend on how the hardware orders same-address shared-memory stores or schedules
+    warps: the same kernel sources compiled for the host (csrc/emu, cooperative fibers, a completely different
+    schedule) must produce byte-identical streams.  Runs/zeros make every unit of a batch collide in the hash tables."""
+    from mtscomp_b200 import _native, build, synth
+    try:
+        emu = _native.Codec(0, lib=_native.load_library(build.build_emulation()))
+    except Exception as e:                                   # no host compiler on the box: nothing to compare with
+        pytest.skip('emulation build unavailable: %s' % e)
+    z = np.zeros((2000, 16), dtype=np.int16); z[:, 3] = 17; z[1000:, 5] = -3
+    rng = np.random.default_rng(3)
+    flat = np.repeat(rng.integers(-200, 200, (40, 12)), 100, axis=0).astype(np.int16)       # plateaus
+    for x, rows in ((z, [0, 1000, 2000]), (flat, [0, 4000]), (synth.ap_chunk(ns=3000, nc=24, seed=5), [0, 3000])):
+        g, go = codec.compress(x, rows, F())
+        e, eo = emu.compress(x, rows, F())
+        assert list(go) == list(eo) and bytes(g) == bytes(e)
