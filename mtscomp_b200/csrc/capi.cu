@@ -853,7 +853,7 @@ static int par_phase(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Inflat
   CK(cudaMemsetAsync(c->d_pcount.p, 0, 256, c->stream));
   const ParStream* d_ps = (const ParStream*)c->d_pstreams.p;
   unsigned* d_cnt = (unsigned*)c->d_pcount.p;
-  MTS_LAUNCH(par_find_kernel, dim3((max_in / 4 + 2 + 255) / 256, ns), dim3(256), 0, c->stream, dcomp, d_ps,
+  MTS_LAUNCH(par_find_kernel, dim3((max_in / 4 + 2 + 256 * PAR_FIND_WORDS - 1) / (256 * PAR_FIND_WORDS), ns), dim3(256), 0, c->stream, dcomp, d_ps,
              (unsigned long long*)c->d_surv.p, (unsigned)surv_cap, d_cnt);
   CKL();
   c->launches++;

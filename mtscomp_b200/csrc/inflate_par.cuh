@@ -270,6 +270,7 @@ __device__ __forceinline__ unsigned par_dist_info(unsigned i) {
 //    HDIST <= 29: their upper four bits not all ones); phase 2 visits the ~22 % passing offsets and checks that the
 //    code-length code is complete: its 3-bit lengths are summed 3 at a time through a 512-entry table of 2^(7-len),
 //    leaving as soon as the sum exceeds 1.
+static const unsigned PAR_FIND_WORDS = 8;     // stream words per thread (amortises the table set-up of the CTA)
 __global__ void __launch_bounds__(256) par_find_kernel(const unsigned char* __restrict__ comp,
                                                        const ParStream* __restrict__ streams,
                                                        unsigned long long* __restrict__ surv, unsigned cap,
@@ -281,42 +282,44 @@ __global__ void __launch_bounds__(256) par_find_kernel(const unsigned char* __re
   }
   __syncthreads();
   const ParStream st = streams[blockIdx.y];
-  const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;          // aligned word index
   const unsigned char* in = comp + st.in_off;
   const unsigned mis = (unsigned)((uintptr_t)in & 3);
   const unsigned* w = (const unsigned*)(in - mis);
   if (st.in_len < 16) return;
   const unsigned kmax = (mis + (unsigned)st.in_len - 1) >> 2;
-  if (j > kmax) return;
-  // stream bit of this word's bit 0 (may be negative for the first word); valid header bits: [16, 8 * (in_len - 12)]
-  // (a dynamic header is at least 17 + 12 bits + two codes: the zlib trailer and the shortest block are ignored)
-  const long long bit0 = 32ll * j - 8ll * mis;
+  // valid header bits: [16, 8 * (in_len - 12)] (a dynamic header is at least 17 + 12 bits + two codes: the zlib trailer
+  // and the shortest block are ignored)
   const long long first_ok = 16, last_ok = 8ll * ((long long)st.in_len - 12) + 7;
-  if (bit0 + 31 < first_ok || bit0 > last_ok) return;
-  unsigned x[5];
+  for (unsigned rep = 0; rep < PAR_FIND_WORDS; rep++) {
+    const unsigned j = (blockIdx.x * PAR_FIND_WORDS + rep) * blockDim.x + threadIdx.x;      // aligned word index
+    if (j > kmax) break;
+    const long long bit0 = 32ll * j - 8ll * mis;                      // stream bit of this word's bit 0 (may be negative)
+    if (bit0 + 31 < first_ok || bit0 > last_ok) continue;
+    unsigned x[5];
 #pragma unroll
-  for (unsigned i = 0; i < 5; i++) x[i] = w[min(j + i, kmax)];
-  const unsigned long long X = ((unsigned long long)x[1] << 32) | x[0];
-  unsigned mask = (unsigned)(~(X >> 1) & (X >> 2) & ~((X >> 4) & (X >> 5) & (X >> 6) & (X >> 7)) &
-                             ~((X >> 9) & (X >> 10) & (X >> 11) & (X >> 12)));
-  if (bit0 < first_ok) mask &= 0xffffffffu << (unsigned)(first_ok - bit0);
-  if (bit0 + 31 > last_ok) mask &= 0xffffffffu >> (unsigned)(bit0 + 31 - last_ok);
-  while (mask) {
-    const unsigned s = (unsigned)__ffs((int)mask) - 1;
-    mask &= mask - 1;
-    const unsigned t0 = __funnelshift_r(x[0], x[1], s), t1 = __funnelshift_r(x[1], x[2], s),
-                   t2 = __funnelshift_r(x[2], x[3], s);
-    const unsigned ncl = ((t0 >> 13) & 15) + 4;
-    // stream bits [17, 17 + 3 * ncl) = the code-length code lengths (<= 57 bits)
-    unsigned long long f = ((((unsigned long long)t1 << 32) | t0) >> 17) | ((unsigned long long)t2 << 47);
-    f &= (1ull << (3 * ncl)) - 1;
-    const unsigned lo = (unsigned)f, hi = (unsigned)(f >> 32);
-    unsigned kraft = k9[lo & 511] + k9[(lo >> 9) & 511] + k9[(lo >> 18) & 511] + k9[((lo >> 27) | (hi << 5)) & 511];
-    if (kraft > 128) continue;
-    kraft += k9[(hi >> 4) & 511] + k9[(hi >> 13) & 511] + k9[(hi >> 22) & 511];
-    if (kraft != 128) continue;
-    const unsigned at = atomicAdd(&counters[0], 1u);
-    if (at < cap) surv[at] = ((unsigned long long)blockIdx.y << 32) | (unsigned)(bit0 + s);
+    for (unsigned i = 0; i < 5; i++) x[i] = w[min(j + i, kmax)];
+    const unsigned long long X = ((unsigned long long)x[1] << 32) | x[0];
+    unsigned mask = (unsigned)(~(X >> 1) & (X >> 2) & ~((X >> 4) & (X >> 5) & (X >> 6) & (X >> 7)) &
+                               ~((X >> 9) & (X >> 10) & (X >> 11) & (X >> 12)));
+    if (bit0 < first_ok) mask &= 0xffffffffu << (unsigned)(first_ok - bit0);
+    if (bit0 + 31 > last_ok) mask &= 0xffffffffu >> (unsigned)(bit0 + 31 - last_ok);
+    while (mask) {
+      const unsigned s = (unsigned)__ffs((int)mask) - 1;
+      mask &= mask - 1;
+      const unsigned t0 = __funnelshift_r(x[0], x[1], s), t1 = __funnelshift_r(x[1], x[2], s),
+                     t2 = __funnelshift_r(x[2], x[3], s);
+      const unsigned ncl = ((t0 >> 13) & 15) + 4;
+      // stream bits [17, 17 + 3 * ncl) = the code-length code lengths (<= 57 bits)
+      unsigned long long f = ((((unsigned long long)t1 << 32) | t0) >> 17) | ((unsigned long long)t2 << 47);
+      f &= (1ull << (3 * ncl)) - 1;
+      const unsigned lo = (unsigned)f, hi = (unsigned)(f >> 32);
+      unsigned kraft = k9[lo & 511] + k9[(lo >> 9) & 511] + k9[(lo >> 18) & 511] + k9[((lo >> 27) | (hi << 5)) & 511];
+      if (kraft > 128) continue;
+      kraft += k9[(hi >> 4) & 511] + k9[(hi >> 13) & 511] + k9[(hi >> 22) & 511];
+      if (kraft != 128) continue;
+      const unsigned at = atomicAdd(&counters[0], 1u);
+      if (at < cap) surv[at] = ((unsigned long long)blockIdx.y << 32) | (unsigned)(bit0 + s);
+    }
   }
 }
 
@@ -583,6 +586,27 @@ __device__ __forceinline__ unsigned par_bits(unsigned a, unsigned b, unsigned w)
   if (hi <= lo) return 0;
   return (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1) << (lo & 31));
 }
+// Apply OP (0 = or, 1 = and-not, 2 = test) to the bits [a, b) of the bitmap; ranges of up to 33 bits (the usual case)
+// touch at most two words and get their masks from one 64-bit shift.
+template <int OP>
+__device__ __forceinline__ bool par_range(unsigned* bm, unsigned a, unsigned b) {
+  bool hit = false;
+  if (b - a <= 33) {
+    const unsigned long long m = ((1ull << (b - a)) - 1) << (a & 31);
+    const unsigned m0 = (unsigned)m, m1 = (unsigned)(m >> 32), w = a >> 5;
+    if (OP == 0) { atomicOr(&bm[w], m0); if (m1) atomicOr(&bm[w + 1], m1); }
+    else if (OP == 1) { atomicAnd(&bm[w], ~m0); if (m1) atomicAnd(&bm[w + 1], ~m1); }
+    else { hit = (((volatile unsigned*)bm)[w] & m0) != 0; if (m1 && !hit) hit = (((volatile unsigned*)bm)[w + 1] & m1) != 0; }
+  } else {
+    for (unsigned w = a >> 5; w <= (b - 1) >> 5; w++) {
+      const unsigned mk = par_bits(a, b, w);
+      if (OP == 0) atomicOr(&bm[w], mk);
+      else if (OP == 1) atomicAnd(&bm[w], ~mk);
+      else if (((volatile unsigned*)bm)[w] & mk) { hit = true; break; }
+    }
+  }
+  return hit;
+}
 template <int PAR_LZ_THREADS, int PAR_LZ_CAP>
 __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream* __restrict__ streams,
                                                                 const ParBlk* __restrict__ blks,
@@ -590,17 +614,16 @@ __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream*
                                                                 const unsigned* __restrict__ tokens,
                                                                 unsigned char* out_base, ParRes* __restrict__ res) {
   const int NT = PAR_LZ_THREADS;
-  __shared__ unsigned ob_w[PAR_LZ_CAP / 4];
-  __shared__ unsigned pend_w[PAR_LZ_CAP / 32];
+  __shared__ unsigned ob_w[PAR_LZ_CAP / 4 + 1];
+  __shared__ unsigned pend_w[PAR_LZ_CAP / 32 + 1];
   __shared__ unsigned wsum[NT / 32];
   __shared__ unsigned s_total;
   unsigned char* ob = (unsigned char*)ob_w;
-  volatile unsigned* pend = pend_w;
   const ParStream st = streams[blockIdx.x];
   unsigned char* out = out_base + st.out_off;
   const unsigned out_cap = (unsigned)st.out_len;
   const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  for (unsigned i = tid; i < PAR_LZ_CAP / 32; i += NT) pend_w[i] = 0;
+  for (unsigned i = tid; i < PAR_LZ_CAP / 32 + 1; i += NT) pend_w[i] = 0;
   unsigned obase = 0;
   bool fail = false;
   // ---- walk the chain of blocks: the first block starts right after the zlib header, every next one where its
@@ -645,7 +668,7 @@ __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream*
     if (m) {
       n_old = srel < 0 ? min(L, (unsigned)(-srel)) : 0u;
       if (n_old < L) {                                              // has an in-tile part: its bytes are pending
-        for (unsigned w = rel >> 5; w <= (rel + L - 1) >> 5; w++) atomicOr(&pend_w[w], par_bits(rel, rel + L, w));
+        par_range<0>(pend_w, rel, rel + L);
       }
       // bytes from before the tile: aligned 32-bit loads (the output buffer is 4-byte aligned and padded), 8 bytes a turn
       const unsigned char* sp = out + obase + srel;
@@ -667,20 +690,38 @@ __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream*
     const unsigned a = (unsigned)max(srel, 0), b = min((unsigned)(srel + (int)L), rel);   // in-tile source bytes outside my own output
     while (__any_sync(0xffffffffu, m)) {
       if (m) {
-        bool clear = true;
-        if (b > a) for (unsigned w = a >> 5; w <= (b - 1) >> 5; w++) if (pend[w] & par_bits(a, b, w)) { clear = false; break; }
+        const bool clear = !(b > a && par_range<2>(pend_w, a, b));
         if (clear) {
           __threadfence_block();
           for (unsigned j = n_old; j < L; j++) ob[rel + j] = ob[(unsigned)(srel + (int)j)];   // in order: may read my own bytes
           __threadfence_block();
-          for (unsigned w = rel >> 5; w <= (rel + L - 1) >> 5; w++) atomicAnd(&pend_w[w], ~par_bits(rel, rel + L, w));
+          par_range<1>(pend_w, rel, rel + L);
           m = false;
         }
       }
     }
     __syncthreads();
     const unsigned total = s_total;
-    for (unsigned i = tid; i < total; i += NT) out[obase + i] = ob[i];
+    {
+      // coalesced store of the tile: bytes up to the first 16-byte boundary, 16-byte vectors (assembled from the
+      // staging words, whose alignment differs), bytes of the rest
+      unsigned char* gp = out + obase;
+      const unsigned head = min(total, (unsigned)((16 - ((uintptr_t)gp & 15)) & 15));
+      if (tid < head) gp[tid] = ob[tid];
+      const unsigned nvec = (total - head) >> 4;
+      for (unsigned v = tid; v < nvec; v += NT) {
+        const unsigned o = head + v * 16;
+        const unsigned* ww = ob_w + (o >> 2);
+        const unsigned sh = (o & 3) * 8;
+        const unsigned a0 = ww[0], a1 = ww[1], a2 = ww[2], a3 = ww[3], a4 = sh ? ww[4] : 0u;
+        uint4 val;
+        val.x = __funnelshift_r(a0, a1, sh); val.y = __funnelshift_r(a1, a2, sh);
+        val.z = __funnelshift_r(a2, a3, sh); val.w = __funnelshift_r(a3, a4, sh);
+        *(uint4*)(gp + o) = val;
+      }
+      const unsigned rest = head + nvec * 16;
+      if (rest + tid < total) gp[rest + tid] = ob[rest + tid];
+    }
     obase += total;
     t0 += ncut;
     if (ncut != (unsigned)NT && t0 < T) nxt = t0 + tid < T ? tk[t0 + tid] : 0;   // the tile was cut short: reload
