@@ -474,6 +474,7 @@ __device__ bool blk_parse_header(const unsigned char* in, unsigned in_len, unsig
 }
 
 static const int PAR_BLK_WARPS = 8;
+static const unsigned PAR_PREROLL_BITS = 768;       // see par_block_kernel
 static const unsigned PAR_RUN_ON_BITS = 1u << 20;   // how far past the next candidate the last lane may look for the end-of-block code
 __global__ void __launch_bounds__(PAR_BLK_WARPS * 32) par_block_kernel(const unsigned char* __restrict__ comp,
                                                                        const ParStream* __restrict__ streams,
@@ -519,6 +520,17 @@ __global__ void __launch_bounds__(PAR_BLK_WARPS * 32) par_block_kernel(const uns
     // the chain walk skips the false candidate because it starts before this block's end)
     const unsigned bound = lane == 31 ? (unsigned)min((unsigned long long)in_bits, (unsigned long long)limit + PAR_RUN_ON_BITS)
                                       : hdr_end + (lane + 1) * sc;
+    // pre-roll: lanes 1..31 start decoding PAR_PREROLL_BITS before their sub-chunk and adopt the first symbol boundary
+    // inside it as their start; by then the decoder has usually re-synchronised, so the start already equals the
+    // point where the predecessor will end and the whole second pass below is skipped (it stays as the safety net)
+    {
+      const unsigned guess = start;
+      const unsigned back = min(guess - hdr_end, PAR_PREROLL_BITS);
+      SpanRes pr;
+      pr.end = guess; pr.ntok = 0; pr.nout = 0; pr.flags = 0;
+      blk_span<false>(lane > 0 && back > 0, in, in_len, guess - back, guess, T, lenx, distx, nullptr, pr);
+      if (lane > 0 && pr.flags == 0 && pr.end >= guess && pr.end < bound) start = pr.end;
+    }
     blk_span<false>(true, in, in_len, start, bound, T, lenx, distx, nullptr, r);
     for (int it = 0; it < 34; it++) {
       const unsigned pe = __shfl_up_sync(0xffffffffu, r.end, 1), pf = __shfl_up_sync(0xffffffffu, r.flags, 1);
