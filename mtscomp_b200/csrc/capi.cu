@@ -55,7 +55,7 @@ struct mtsb_ctx {
   long long par_inflate = 1;   // decode index-less zlib streams block-parallel (inflate_par.cuh)
   long long par_indexed = 1;    // indexed segments of GPU-written chunks also go through the block kernels
   long long par_lz_wide = -1;   // LZ resolve kernel shape: -1 by stream count, 1 = 1024-thread CTAs, 0 = 256-thread CTAs
-  long long par_batch_bytes = 4ll << 30;   // host-buffer sub-batch of index-less chunks (output bytes): large enough to amortise the block search
+  long long par_batch_bytes = 2ll << 30;   // host-buffer sub-batch of index-less chunks (output bytes): large enough to amortise the block search
   long long par_stats[4] = {0, 0, 0, 0};   // last call: survivors, candidates, chained blocks, streams resumed
   long long seg_bytes = 262144, batch_bytes = 2ll << 30, host_batch_bytes = 512ll << 20, write_index = 1;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of the host-buffer paths
