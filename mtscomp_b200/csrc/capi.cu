@@ -740,58 +740,90 @@ static int fetch_ranges(mtsb_ctx* c, const unsigned char* comp, int comp_is_devi
 
 static uint32_t rd32(const unsigned char* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
 
-// Steps 3..5 of the block-parallel decoder for the streams `ps` (segs[ids[i]] each) and their candidate blocks `blks`
-// (stream order, bfirst[i] = first block of stream i).  The streams whose chain of blocks was resolved are rewritten as
-// INF_RESUME tails; the others are left untouched (full serial decode).  zflag: INF_ZLIB for whole zlib streams.
-static int par_decode_blocks(mtsb_ctx* c, const unsigned char* dcomp, std::vector<InflateSeg>& segs, const std::vector<int>& whole,
-                             const std::vector<ParStream>& ps, std::vector<ParBlk>& blks, const std::vector<unsigned>& bfirst,
-                             long long in_total, unsigned char* dT, int zflag) {
+// The block-parallel decoder for the streams `ps` (segs[ids[i]] each).  blks == nullptr: plain zlib streams, the
+// blocks are searched for on the device (find -> validate into per-stream buckets -> sort).  Otherwise blks holds one
+// known block per stream (the indexed segments of GPU-written chunks).  No host round trip between the kernels: one
+// synchronisation at the end fetches the per-stream results.  The streams whose chain of blocks was resolved are
+// rewritten as INF_RESUME tails; the others are left untouched (full serial decode).
+static int par_decode(mtsb_ctx* c, const unsigned char* dcomp, std::vector<InflateSeg>& segs, const std::vector<int>& ids,
+                      const std::vector<ParStream>& ps, const std::vector<ParBlk>* blks, long long in_total, int max_in,
+                      unsigned char* dT, int zflag) {
   const int ns = (int)ps.size();
-  const unsigned n_cand = (unsigned)blks.size();
-  if (n_cand == 0) return 0;
+  if (ns == 0) return 0;
+  // bucket of candidate blocks per stream: zlib level 6 closes a block about every 29 KB of output here; streams with
+  // denser candidates overflow their bucket and are decoded serially
+  const unsigned bcap = blks ? 1u : (unsigned)(max_in / 8192 + 64);
+  const size_t n_slots = (size_t)ns * bcap;
+  if (n_slots > 0x7fffffffull) return 0;
+  const size_t surv_cap = (size_t)std::max<long long>(1 << 20, in_total * 8 / 300);
   // token slots: one per 6 bits of input (typical streams spend 9..15 bits per token); if that is not enough the blocks
   // that do not fit end the chain of their stream (serial decode of the rest)
   const long long tok_total = in_total * 8 / 6 + 4096;
+  const size_t o_keys = ((size_t)ns * 4 + 255) & ~(size_t)255;      // d_cand: [bucket fill counts | bucket keys]
   NEED(c->d_pstreams, (size_t)ns * sizeof(ParStream));
   NEED(c->d_pcount, 256);
   NEED(c->d_pbad, (size_t)ns * sizeof(ParRes) + 64);
-  NEED(c->h_small, 4096 + (size_t)ns * sizeof(ParRes));
-  const ParStream* d_ps = (const ParStream*)c->d_pstreams.p;
-  const size_t o_first = ((size_t)n_cand * sizeof(ParBlk) + 255) & ~(size_t)255;
-  const size_t list_bytes = o_first + (size_t)(ns + 1) * 4;
-  const size_t o_ps = (list_bytes + 255) & ~(size_t)255;          // host staging: [blocks | bfirst | streams]
-  NEED(c->d_plist, list_bytes);
-  NEED(c->h_tab, o_ps + (size_t)ns * sizeof(ParStream) + 64);
+  NEED(c->d_plist, n_slots * sizeof(ParBlk));
   NEED(c->d_tokens, (size_t)tok_total * 4 + 64);
-  memcpy(c->h_tab.p, blks.data(), (size_t)n_cand * sizeof(ParBlk));
-  memcpy((char*)c->h_tab.p + o_first, bfirst.data(), (size_t)(ns + 1) * 4);
-  memcpy((char*)c->h_tab.p + o_ps, ps.data(), (size_t)ns * sizeof(ParStream));
-  { int r = small_copy(c, c->d_plist.p, c->h_tab.p, list_bytes); if (r) return r; }
-  { int r = small_copy(c, c->d_pstreams.p, (char*)c->h_tab.p + o_ps, (size_t)ns * sizeof(ParStream)); if (r) return r; }
-  CK(cudaMemsetAsync((char*)c->d_pcount.p + 16, 0, 8, c->stream));     // the token cursor
-  MTS_LAUNCH(par_block_kernel, dim3((n_cand + PAR_BLK_WARPS - 1) / PAR_BLK_WARPS), dim3(PAR_BLK_WARPS * 32), 0, c->stream, dcomp,
-             d_ps, (ParBlk*)c->d_plist.p, n_cand, (unsigned*)c->d_tokens.p, (unsigned long long*)((char*)c->d_pcount.p + 16),
-             (unsigned long long)tok_total);
+  const size_t o_blk = ((size_t)ns * sizeof(ParStream) + 255) & ~(size_t)255;   // host staging: [streams | blocks]
+  NEED(c->h_tab, o_blk + (blks ? n_slots * sizeof(ParBlk) : 0) + 64);
+  NEED(c->h_small, 4096 + (size_t)ns * (sizeof(ParRes) + 4) + 64);
+  memcpy(c->h_tab.p, ps.data(), (size_t)ns * sizeof(ParStream));
+  { int r = small_copy(c, c->d_pstreams.p, c->h_tab.p, (size_t)ns * sizeof(ParStream)); if (r) return r; }
+  CK(cudaMemsetAsync(c->d_pcount.p, 0, 256, c->stream));           // [0] survivors, [4..5] token cursor
+  const ParStream* d_ps = (const ParStream*)c->d_pstreams.p;
+  unsigned* d_cnt = (unsigned*)c->d_pcount.p;
+  if (blks) {
+    memcpy((char*)c->h_tab.p + o_blk, blks->data(), n_slots * sizeof(ParBlk));
+    { int r = small_copy(c, c->d_plist.p, (char*)c->h_tab.p + o_blk, n_slots * sizeof(ParBlk)); if (r) return r; }
+  } else {
+    NEED(c->d_surv, surv_cap * 8);
+    NEED(c->d_cand, o_keys + n_slots * 4);
+    unsigned* d_bcount = (unsigned*)c->d_cand.p;
+    unsigned* d_keys = (unsigned*)((char*)c->d_cand.p + o_keys);
+    CK(cudaMemsetAsync(d_bcount, 0, (size_t)ns * 4, c->stream));
+    MTS_LAUNCH(par_find_kernel, dim3((max_in / 4 + 2 + 256 * PAR_FIND_WORDS - 1) / (256 * PAR_FIND_WORDS), ns), dim3(256), 0,
+               c->stream, dcomp, d_ps, (unsigned long long*)c->d_surv.p, (unsigned)surv_cap, d_cnt);
+    CKL();
+    MTS_LAUNCH(par_validate_kernel, dim3(c->sm_count * 16), dim3(128), 0, c->stream, dcomp, d_ps,
+               (const unsigned long long*)c->d_surv.p, (unsigned)surv_cap, d_keys, bcap, d_bcount, (const unsigned*)d_cnt);
+    CKL();
+    MTS_LAUNCH(par_sort_kernel, dim3(ns), dim3(32), 0, c->stream, d_ps, (const unsigned*)d_keys, bcap, (const unsigned*)d_bcount,
+               (const unsigned*)d_cnt, (unsigned)surv_cap, (ParBlk*)c->d_plist.p);
+    CKL();
+    c->launches += 3;
+  }
+  MTS_LAUNCH(par_block_kernel, dim3((unsigned)((n_slots + PAR_BLK_WARPS - 1) / PAR_BLK_WARPS)), dim3(PAR_BLK_WARPS * 32), 0, c->stream,
+             dcomp, d_ps, (ParBlk*)c->d_plist.p, (unsigned)n_slots, (unsigned*)c->d_tokens.p,
+             (unsigned long long*)((char*)c->d_pcount.p + 16), (unsigned long long)tok_total);
   CKL();
   if (c->par_lz_wide < 0 ? ns <= 2 * c->sm_count : c->par_lz_wide == 1) {
     auto k = par_lz_kernel<1024, 16384>;
-    MTS_LAUNCH(k, dim3(ns), dim3(1024), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p,
-               (const unsigned*)((const char*)c->d_plist.p + o_first), (const unsigned*)c->d_tokens.p, dT, (ParRes*)c->d_pbad.p);
+    MTS_LAUNCH(k, dim3(ns), dim3(1024), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p, bcap, (const unsigned*)c->d_tokens.p, dT,
+               (ParRes*)c->d_pbad.p);
   } else {
     auto k = par_lz_kernel<256, 4096>;
-    MTS_LAUNCH(k, dim3(ns), dim3(256), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p,
-               (const unsigned*)((const char*)c->d_plist.p + o_first), (const unsigned*)c->d_tokens.p, dT, (ParRes*)c->d_pbad.p);
+    MTS_LAUNCH(k, dim3(ns), dim3(256), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p, bcap, (const unsigned*)c->d_tokens.p, dT,
+               (ParRes*)c->d_pbad.p);
   }
   CKL();
   c->launches += 2;
-  { int r = small_copy(c, c->h_small.p, c->d_pbad.p, (size_t)ns * sizeof(ParRes)); if (r) return r; }
+  char* hs = (char*)c->h_small.p;
+  { int r = small_copy(c, hs, c->d_pcount.p, 64); if (r) return r; }
+  { int r = small_copy(c, hs + 4096, c->d_pbad.p, (size_t)ns * sizeof(ParRes)); if (r) return r; }
+  const size_t o_bc = 4096 + (((size_t)ns * sizeof(ParRes) + 15) & ~(size_t)15);
+  if (!blks) { int r = small_copy(c, hs + o_bc, c->d_cand.p, (size_t)ns * 4); if (r) return r; }
   CK(cudaStreamSynchronize(c->stream));
-  const ParRes* res = (const ParRes*)c->h_small.p;
+  if (!blks) {
+    c->par_stats[0] += ((const unsigned*)hs)[0];
+    for (int i = 0; i < ns; i++) c->par_stats[1] += ((const unsigned*)(hs + o_bc))[i];
+  }
+  const ParRes* res = (const ParRes*)(hs + 4096);
   for (int sidx = 0; sidx < ns; sidx++) {
     const ParRes& r = res[sidx];
     c->par_stats[2] += r.n_done;
     if (r.n_done == 0 || (r.flags & 2)) continue;              // full serial decode of this stream
-    InflateSeg& s = segs[whole[sidx]];
+    InflateSeg& s = segs[ids[sidx]];
     s.flags = zflag | INF_RESUME | ((r.flags & 1) ? INF_NO_BLOCKS : 0);
     s.start_bit = r.tail_bit;
     s.opos0 = r.tail_out;
@@ -800,16 +832,16 @@ static int par_decode_blocks(mtsb_ctx* c, const unsigned char* dcomp, std::vecto
   return 0;
 }
 
-// The indexed segments of GPU-written chunks (`ids`: indices into segs) through the same kernels: every segment is one
-// dynamic block at bit 0 followed by the empty stored block that byte-aligns the next segment (deflate.cuh), so the
-// blocks are known without any search; a segment stored uncompressed simply fails the header parse and stays serial.
+// The indexed segments of GPU-written chunks (`ids`: indices into segs): every segment is one dynamic block at bit 0
+// followed by the empty stored block that byte-aligns the next segment (deflate.cuh), so the blocks are known without
+// any search; a segment stored uncompressed simply fails the header parse and stays serial.
 static int par_phase_indexed(mtsb_ctx* c, const unsigned char* dcomp, std::vector<InflateSeg>& segs, const std::vector<int>& ids,
                              unsigned char* dT) {
   const int ns = (int)ids.size();
   std::vector<ParStream> ps(ns);
   std::vector<ParBlk> blks(ns);
-  std::vector<unsigned> bfirst(ns + 1);
   long long in_total = 0;
+  int max_in = 0;
   for (int i = 0; i < ns; i++) {
     const InflateSeg& s = segs[ids[i]];
     ps[i].in_off = s.in_off; ps[i].out_off = s.out_off; ps[i].in_len = s.in_len; ps[i].out_len = s.out_len;
@@ -817,15 +849,13 @@ static int par_phase_indexed(mtsb_ctx* c, const unsigned char* dcomp, std::vecto
     ParBlk& b = blks[i];
     b.stream = (unsigned)i; b.bit = 0; b.limit = (unsigned)s.in_len * 8u;
     b.end_bit = 0; b.n_tok = 0; b.out_len = 0; b.flags = 0; b.pad_ = 0; b.tok_off = 0;
-    bfirst[i] = (unsigned)i;
     in_total += s.in_len;
+    max_in = std::max(max_in, s.in_len);
   }
-  bfirst[ns] = (unsigned)ns;
-  return par_decode_blocks(c, dcomp, segs, ids, ps, blks, bfirst, in_total, dT, 0);
+  return par_decode(c, dcomp, segs, ids, ps, &blks, in_total, max_in, dT, 0);
 }
 
-// Block-parallel decode of the whole-stream segments `whole` (indices into segs).  On success the listed segments are
-// rewritten as INF_RESUME tails; on any doubt they are left untouched (full serial decode).
+// Block-parallel decode of the whole-stream segments `whole` (indices into segs): plain zlib streams.
 static int par_phase(mtsb_ctx* c, const unsigned char* dcomp, std::vector<InflateSeg>& segs, const std::vector<int>& whole,
                      unsigned char* dT) {
   const int ns = (int)whole.size();
@@ -839,64 +869,7 @@ static int par_phase(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Inflat
     in_total += s.in_len;
     max_in = std::max(max_in, s.in_len);
   }
-  const size_t surv_cap = (size_t)std::max<long long>(1 << 20, in_total * 8 / 300);
-  const size_t cand_cap = (size_t)std::max<long long>(1 << 16, in_total / 4096 + 64ll * ns);
-  NEED(c->d_pstreams, (size_t)ns * sizeof(ParStream));
-  NEED(c->d_surv, surv_cap * 8);
-  NEED(c->d_cand, cand_cap * 8);
-  NEED(c->d_pcount, 256);
-  NEED(c->d_pbad, (size_t)ns * sizeof(ParRes) + 64);
-  NEED(c->h_tab, std::max((size_t)ns * sizeof(ParStream), cand_cap * 8) + 4096);
-  NEED(c->h_small, 4096 + (size_t)ns * sizeof(ParRes));
-  memcpy(c->h_tab.p, ps.data(), (size_t)ns * sizeof(ParStream));
-  { int r = small_copy(c, c->d_pstreams.p, c->h_tab.p, (size_t)ns * sizeof(ParStream)); if (r) return r; }
-  CK(cudaMemsetAsync(c->d_pcount.p, 0, 256, c->stream));
-  const ParStream* d_ps = (const ParStream*)c->d_pstreams.p;
-  unsigned* d_cnt = (unsigned*)c->d_pcount.p;
-  MTS_LAUNCH(par_find_kernel, dim3((max_in / 4 + 2 + 256 * PAR_FIND_WORDS - 1) / (256 * PAR_FIND_WORDS), ns), dim3(256), 0, c->stream, dcomp, d_ps,
-             (unsigned long long*)c->d_surv.p, (unsigned)surv_cap, d_cnt);
-  CKL();
-  c->launches++;
-  { int r = small_copy(c, c->h_small.p, c->d_pcount.p, 64); if (r) return r; }
-  CK(cudaStreamSynchronize(c->stream));
-  const unsigned n_surv = ((const unsigned*)c->h_small.p)[0];
-  c->par_stats[0] += n_surv;
-  if (n_surv == 0 || n_surv > surv_cap) return 0;
-  MTS_LAUNCH(par_validate_kernel, dim3((n_surv + 127) / 128), dim3(128), 0, c->stream, dcomp, d_ps,
-             (const unsigned long long*)c->d_surv.p, n_surv, (unsigned long long*)c->d_cand.p, (unsigned)cand_cap, d_cnt);
-  CKL();
-  c->launches++;
-  { int r = small_copy(c, c->h_small.p, c->d_pcount.p, 64); if (r) return r; }
-  CK(cudaStreamSynchronize(c->stream));
-  const unsigned n_cand = ((const unsigned*)c->h_small.p)[1];
-  c->par_stats[1] += n_cand;
-  if (n_cand == 0 || n_cand > cand_cap) return 0;
-  { int r = small_copy(c, c->h_tab.p, c->d_cand.p, (size_t)n_cand * 8); if (r) return r; }
-  CK(cudaStreamSynchronize(c->stream));
-  // ---- host: candidates in stream order; a block's bit range ends where the next candidate of its stream begins
-  std::vector<unsigned long long> keys((const unsigned long long*)c->h_tab.p, (const unsigned long long*)c->h_tab.p + n_cand);
-  std::sort(keys.begin(), keys.end());
-  std::vector<ParBlk> blks(n_cand);
-  std::vector<unsigned> bfirst(ns + 1, 0);
-  {
-    unsigned i = 0;
-    for (int sidx = 0; sidx < ns; sidx++) {
-      bfirst[sidx] = i;
-      while (i < n_cand && (int)(keys[i] >> 32) == sidx) {
-        ParBlk& b = blks[i];
-        b.stream = (unsigned)sidx; b.bit = (unsigned)keys[i];
-        const bool more = i + 1 < n_cand && (int)(keys[i + 1] >> 32) == sidx;
-        b.limit = more ? (unsigned)keys[i + 1] : (unsigned)ps[sidx].in_len * 8u;
-        b.end_bit = 0; b.n_tok = 0; b.out_len = 0; b.flags = 0;
-        b.pad_ = 0; b.tok_off = 0;
-        i++;
-      }
-    }
-    bfirst[ns] = i;
-    if (i != n_cand) return 0;                                  // a key with an unknown stream: do not trust the list
-  }
-  return par_decode_blocks(c, dcomp, segs, whole, ps, blks, bfirst, in_total, dT, INF_ZLIB);
-  return 0;
+  return par_decode(c, dcomp, segs, whole, ps, nullptr, in_total, max_in, dT, INF_ZLIB);
 }
 
 int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, const long long* comp_offsets,

@@ -323,24 +323,58 @@ __global__ void __launch_bounds__(256) par_find_kernel(const unsigned char* __re
   }
 }
 
-// 2. Full header validation: thread per survivor; the valid ones are appended to the candidate list as
-//    stream << 32 | bit (the host sorts the list: that is stream order).
+// 2. Full header validation: the survivors (their number is read from the device counter, so the host does not have
+//    to wait for the search) are spread over a fixed grid; the bit offset of a valid one is appended to the bucket of
+//    its stream (bcap slots per stream; a stream with more candidates is left to the serial decoder).
 __global__ void __launch_bounds__(128) par_validate_kernel(const unsigned char* __restrict__ comp,
                                                            const ParStream* __restrict__ streams,
-                                                           const unsigned long long* __restrict__ surv, unsigned n_surv,
-                                                           unsigned long long* __restrict__ cand, unsigned cap,
-                                                           unsigned* __restrict__ counters) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_surv) return;
-  const unsigned long long sv = surv[i];
-  const unsigned sidx = (unsigned)(sv >> 32), bit = (unsigned)sv;
+                                                           const unsigned long long* __restrict__ surv, unsigned surv_cap,
+                                                           unsigned* __restrict__ keys, unsigned bcap,
+                                                           unsigned* __restrict__ bcount,
+                                                           const unsigned* __restrict__ counters) {
+  const unsigned n_surv = min(counters[0], surv_cap);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_surv; i += gridDim.x * blockDim.x) {
+    const unsigned long long sv = surv[i];
+    const unsigned sidx = (unsigned)(sv >> 32), bit = (unsigned)sv;
+    const ParStream st = streams[sidx];
+    TBits br;
+    br.init(comp + st.in_off, (unsigned)st.in_len, bit);
+    if (!par_check_header(br)) continue;
+    if (br.bit_pos() > (unsigned)st.in_len * 8) continue;
+    const unsigned at = atomicAdd(&bcount[sidx], 1u);
+    if (at < bcap) keys[(size_t)sidx * bcap + at] = bit;
+  }
+}
+
+// 2b. One warp per stream: rank-sort the bucket (a few hundred bit offsets) and write the block descriptors in stream
+//     order, each block's bit range ending where the next candidate begins; unused slots get the sentinel bit ~0.
+__global__ void __launch_bounds__(32) par_sort_kernel(const ParStream* __restrict__ streams,
+                                                      const unsigned* __restrict__ keys, unsigned bcap,
+                                                      const unsigned* __restrict__ bcount, const unsigned* __restrict__ counters,
+                                                      unsigned surv_cap, ParBlk* __restrict__ blks) {
+  const unsigned sidx = blockIdx.x, lane = threadIdx.x;
   const ParStream st = streams[sidx];
-  TBits br;
-  br.init(comp + st.in_off, (unsigned)st.in_len, bit);
-  if (!par_check_header(br)) return;
-  if (br.bit_pos() > (unsigned)st.in_len * 8) return;
-  const unsigned at = atomicAdd(&counters[1], 1u);
-  if (at < cap) cand[at] = sv;
+  const unsigned* k = keys + (size_t)sidx * bcap;
+  ParBlk* out = blks + (size_t)sidx * bcap;
+  unsigned n = bcount[sidx];
+  if (n > bcap || counters[0] > surv_cap) n = 0;              // a list overflowed: candidates may be missing, do not chain
+  for (unsigned i = lane; i < bcap; i += 32) {
+    ParBlk b;
+    b.stream = sidx; b.bit = 0xffffffffu; b.limit = 0; b.end_bit = 0; b.n_tok = 0; b.out_len = 0; b.flags = 0; b.pad_ = 0; b.tok_off = 0;
+    if (i >= n) out[i] = b;
+  }
+  for (unsigned i = lane; i < n; i += 32) {
+    const unsigned key = k[i];
+    unsigned rank = 0, next = (unsigned)st.in_len * 8u;        // next larger key = where this block's bit range ends
+    for (unsigned j = 0; j < n; j++) {
+      const unsigned kj = k[j];
+      rank += kj < key;
+      if (kj > key) next = min(next, kj);
+    }
+    ParBlk b;
+    b.stream = sidx; b.bit = key; b.limit = next; b.end_bit = 0; b.n_tok = 0; b.out_len = 0; b.flags = 0; b.pad_ = 0; b.tok_off = 0;
+    out[rank] = b;
+  }
 }
 
 // 3. One WARP per candidate block.  The warp parses the header and builds the tables in shared memory, then its 32
@@ -492,6 +526,7 @@ __global__ void __launch_bounds__(PAR_BLK_WARPS * 32) par_block_kernel(const uns
   if (bi >= n) return;
   BlkTabs& T = tabs[wid];
   ParBlk blk = blks[bi];
+  if (blk.bit == 0xffffffffu) return;                         // unused slot of a stream's bucket
   const ParStream st = streams[blk.stream];
   const unsigned char* in = comp + st.in_off;
   const unsigned in_len = (unsigned)st.in_len, in_bits = in_len * 8;
@@ -622,7 +657,7 @@ __device__ __forceinline__ bool par_range(unsigned* bm, unsigned a, unsigned b) 
 template <int PAR_LZ_THREADS, int PAR_LZ_CAP>
 __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream* __restrict__ streams,
                                                                 const ParBlk* __restrict__ blks,
-                                                                const unsigned* __restrict__ bfirst,
+                                                                unsigned bstride,
                                                                 const unsigned* __restrict__ tokens,
                                                                 unsigned char* out_base, ParRes* __restrict__ res) {
   const int NT = PAR_LZ_THREADS;
@@ -641,8 +676,8 @@ __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream*
   // ---- walk the chain of blocks: the first block starts right after the zlib header, every next one where its
   //      predecessor ended; the walk stops at the first block that is missing or was not decoded cleanly
   unsigned cur_bit = st.first_bit, n_done = 0, fin = 0;
-  unsigned bj = bfirst[blockIdx.x];
-  const unsigned bend = bfirst[blockIdx.x + 1];
+  unsigned bj = blockIdx.x * bstride;                        // this stream's blocks: [bj, bend), unused slots have bit ~0
+  const unsigned bend = bj + bstride;
   for (;;) {
     while (bj < bend && blks[bj].bit < cur_bit) bj++;
     if (bj >= bend) break;
