@@ -58,7 +58,8 @@ int mtsb_sync(mtsb_ctx* ctx);
  * involved: copies of one sub-batch overlap the kernels of the next), "par_batch_bytes" (host-buffer sub-batch of
  * index-less chunks on the decode side), "par_inflate" (1: block-parallel decoder; 0: serial warp per stream),
  * "par_indexed" (1: indexed segments go through the block kernels as well), "par_lz_wide" (-1 auto / 0 / 1: shape of
- * the token-resolve kernel).  Read-only: "par_survivors", "par_candidates", "par_chained", "par_resumed" (what the
+ * the token-resolve kernel), "par_cells" (-1 auto / 0 / 1: resolve the blocks of an index-less stream in parallel —
+ * the low-latency path for few streams).  Read-only: "par_survivors", "par_candidates", "par_chained", "par_resumed" (what the
  * block-parallel decoder did in the last call).  Returns MTSB_E_ARG for unknown names. */
 int mtsb_set_param(mtsb_ctx* ctx, const char* name, long long value);
 long long mtsb_get_param(mtsb_ctx* ctx, const char* name);

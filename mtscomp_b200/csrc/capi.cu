@@ -54,6 +54,7 @@ struct mtsb_ctx {
   // params
   long long par_inflate = 1;   // decode index-less zlib streams block-parallel (inflate_par.cuh)
   long long par_indexed = 1;    // indexed segments of GPU-written chunks also go through the block kernels
+  long long par_cells = 0;      // (default off until validated on the GPU) index-less streams: -1 by stream count, 1 = blocks resolved in parallel into cells, 0 = chain of tiles
   long long par_lz_wide = -1;   // LZ resolve kernel shape: -1 by stream count, 1 = 1024-thread CTAs, 0 = 256-thread CTAs
   long long par_batch_bytes = 2ll << 30;   // host-buffer sub-batch of index-less chunks (output bytes): large enough to amortise the block search
   long long par_stats[4] = {0, 0, 0, 0};   // last call: survivors, candidates, chained blocks, streams resumed
@@ -62,7 +63,7 @@ struct mtsb_ctx {
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_done = nullptr;
   LzParams lz{4, 16, 32768, 32768, 32768, 0};   // greedy, every match >= 4 bytes accepted: tuned on synthetic AP/LFP
   // device scratch
-  Buf d_pstreams, d_surv, d_cand, d_pcount, d_tokens, d_ptab, d_plist, d_pbad;   // block-parallel inflate scratch
+  Buf d_pstreams, d_surv, d_cand, d_pcount, d_tokens, d_cells, d_ptab, d_plist, d_pbad;   // block-parallel inflate scratch
   Buf d_raw, d_raw2, d_out2, d_comp2, d_T, d_tok, d_hist, d_codes, d_hdrs, d_tab, d_so, d_seg_adler, d_chunk_adler, d_chunk_off, d_out,
       d_partial, d_comp, d_status, d_tadler, d_gather;
   Buf h_tab, h_small;
@@ -314,7 +315,7 @@ void mtsb_destroy(mtsb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  Buf* bufs[] = {&c->d_pstreams, &c->d_surv, &c->d_cand, &c->d_pcount, &c->d_tokens, &c->d_ptab, &c->d_plist, &c->d_pbad,
+  Buf* bufs[] = {&c->d_pstreams, &c->d_surv, &c->d_cand, &c->d_pcount, &c->d_tokens, &c->d_cells, &c->d_ptab, &c->d_plist, &c->d_pbad,
                  &c->d_raw, &c->d_raw2, &c->d_out2, &c->d_comp2, &c->d_T, &c->d_tok, &c->d_hist, &c->d_codes, &c->d_hdrs, &c->d_tab, &c->d_so,
                  &c->d_seg_adler, &c->d_chunk_adler, &c->d_chunk_off, &c->d_out, &c->d_partial, &c->d_comp,
                  &c->d_status, &c->d_tadler, &c->d_gather, &c->h_tab, &c->h_small};
@@ -345,6 +346,7 @@ int mtsb_set_param(mtsb_ctx* c, const char* name, long long v) {
   else if (s == "write_index") c->write_index = v ? 1 : 0;
   else if (s == "par_inflate") c->par_inflate = v ? 1 : 0;
   else if (s == "par_indexed") c->par_indexed = v ? 1 : 0;
+  else if (s == "par_cells") c->par_cells = v < 0 ? -1 : (v ? 1 : 0);
   else if (s == "par_lz_wide") c->par_lz_wide = v < 0 ? -1 : (v ? 1 : 0);
   else if (s == "par_batch_bytes") { if (v < (1 << 20)) return fail(c, MTSB_E_ARG, "par_batch_bytes too small"); c->par_batch_bytes = v; }
   else if (s == "max_chain") c->lz.max_chain = (int)std::max<long long>(1, v);
@@ -366,6 +368,7 @@ long long mtsb_get_param(mtsb_ctx* c, const char* name) {
   if (s == "write_index") return c->write_index;
   if (s == "par_inflate") return c->par_inflate;
   if (s == "par_lz_wide") return c->par_lz_wide;
+  if (s == "par_cells") return c->par_cells;
   if (s == "par_indexed") return c->par_indexed;
   if (s == "par_batch_bytes") return c->par_batch_bytes;
   if (s == "par_survivors") return c->par_stats[0];
@@ -797,17 +800,37 @@ static int par_decode(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Infla
              dcomp, d_ps, (ParBlk*)c->d_plist.p, (unsigned)n_slots, (unsigned*)c->d_tokens.p,
              (unsigned long long*)((char*)c->d_pcount.p + 16), (unsigned long long)tok_total);
   CKL();
-  if (c->par_lz_wide < 0 ? ns <= 2 * c->sm_count : c->par_lz_wide == 1) {
+  const bool use_cells = !blks && (c->par_cells < 0 ? ns <= 2 * c->sm_count : c->par_cells == 1);
+  if (use_cells) {
+    // few streams: resolve the blocks of a stream in parallel (cells + markers), then cells -> bytes per stream
+    long long lo = ps[0].out_off, hi = ps[0].out_off + ps[0].out_len;
+    for (int i = 1; i < ns; i++) { lo = std::min(lo, ps[i].out_off); hi = std::max(hi, ps[i].out_off + ps[i].out_len); }
+    NEED(c->d_cells, (size_t)(hi - lo) * 2 + 64);
+    MTS_LAUNCH(par_chain_kernel, dim3((ns + 63) / 64), dim3(64), 0, c->stream, d_ps, (ParBlk*)c->d_plist.p, bcap, (unsigned)ns,
+               (ParRes*)c->d_pbad.p);
+    CKL();
+    auto k = par_lzc_kernel<256, 4096>;
+    MTS_LAUNCH(k, dim3((unsigned)n_slots), dim3(256), 0, c->stream, d_ps, (ParBlk*)c->d_plist.p, (const unsigned*)c->d_tokens.p,
+               (unsigned short*)c->d_cells.p, lo);
+    CKL();
+    MTS_LAUNCH(par_cells_kernel, dim3(ns), dim3(1024), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p, bcap,
+               (const unsigned short*)c->d_cells.p, lo, dT, (ParRes*)c->d_pbad.p);
+    CKL();
+    c->launches += 3;
+  } else if (c->par_lz_wide < 0 ? ns <= 2 * c->sm_count : c->par_lz_wide == 1) {
     auto k = par_lz_kernel<1024, 16384>;
     MTS_LAUNCH(k, dim3(ns), dim3(1024), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p, bcap, (const unsigned*)c->d_tokens.p, dT,
                (ParRes*)c->d_pbad.p);
+    CKL();
+    c->launches++;
   } else {
     auto k = par_lz_kernel<256, 4096>;
     MTS_LAUNCH(k, dim3(ns), dim3(256), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p, bcap, (const unsigned*)c->d_tokens.p, dT,
                (ParRes*)c->d_pbad.p);
+    CKL();
+    c->launches++;
   }
-  CKL();
-  c->launches += 2;
+  c->launches++;
   char* hs = (char*)c->h_small.p;
   { int r = small_copy(c, hs, c->d_pcount.p, 64); if (r) return r; }
   { int r = small_copy(c, hs + 4096, c->d_pbad.p, (size_t)ns * sizeof(ParRes)); if (r) return r; }

@@ -787,4 +787,157 @@ __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream*
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------- few streams: low latency
+// par_lz_kernel makes every stream a serial chain of tiles (~20 ms for a 23 MB chunk, whatever the batch size).  With
+// few streams the blocks of a stream are resolved IN PARALLEL instead, one CTA per block, into 16-bit cells: a byte, or a
+// MARKER 0x8000 | index into the 32 KB before the block for what is copied from there (markers are copied like data, so
+// every cell ends up as a byte or as a direct reference to the window).  A last pass per stream turns the cells into
+// bytes in block order (the markers then read bytes that are already final).
+//   par_chain_kernel  thread per stream: follow the chain (as par_lz_kernel does), give every chained block its output
+//                     offset (kept in ParBlk::limit, which nobody needs any more) and flag 4, write the stream's result
+//   par_lzc_kernel    CTA per block slot: tokens -> cells, same tile scheme as par_lz_kernel
+//   par_cells_kernel  CTA per stream: cells -> bytes, chained blocks in order
+__global__ void __launch_bounds__(64) par_chain_kernel(const ParStream* __restrict__ streams, ParBlk* __restrict__ blks,
+                                                       unsigned bstride, unsigned ns, ParRes* __restrict__ res) {
+  const unsigned sidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sidx >= ns) return;
+  const ParStream st = streams[sidx];
+  unsigned cur_bit = st.first_bit, n_done = 0, fin = 0, obase = 0;
+  unsigned bj = sidx * bstride;
+  const unsigned bend = bj + bstride;
+  for (;;) {
+    while (bj < bend && blks[bj].bit < cur_bit) bj++;
+    if (bj >= bend) break;
+    const ParBlk blk = blks[bj];
+    if (blk.bit != cur_bit || !(blk.flags & 1) || blk.end_bit <= cur_bit ||
+        (unsigned long long)obase + blk.out_len > (unsigned)st.out_len) break;
+    blks[bj].limit = obase;
+    blks[bj].flags = blk.flags | 4;
+    obase += blk.out_len;
+    cur_bit = blk.end_bit;
+    n_done++;
+    fin = (blk.flags >> 1) & 1;
+    bj++;
+    if (fin) break;
+  }
+  ParRes r;
+  r.tail_bit = cur_bit; r.tail_out = obase; r.n_done = n_done; r.flags = fin;
+  res[sidx] = r;
+}
+
+template <int NT, int CAP>
+__global__ void __launch_bounds__(NT) par_lzc_kernel(const ParStream* __restrict__ streams, ParBlk* __restrict__ blks,
+                                                     const unsigned* __restrict__ tokens,
+                                                     unsigned short* cells_base, long long cells_origin) {
+  __shared__ unsigned short ob[CAP];
+  __shared__ unsigned pend_w[CAP / 32 + 1];
+  __shared__ unsigned wsum[NT / 32];
+  __shared__ unsigned s_total;
+  const ParBlk blk = blks[blockIdx.x];
+  if (blk.bit == 0xffffffffu || !(blk.flags & 4)) return;
+  const ParStream st = streams[blk.stream];
+  const unsigned boff = blk.limit;                               // output offset of the block inside its stream
+  unsigned short* cells = cells_base + (st.out_off - cells_origin) + boff;
+  const unsigned* tk = tokens + blk.tok_off;
+  const unsigned T = blk.n_tok, block_end = blk.out_len;
+  const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (unsigned i = tid; i < CAP / 32 + 1; i += NT) pend_w[i] = 0;
+  unsigned obase = 0, t0 = 0;
+  bool fail = false;
+  unsigned nxt = tid < T ? tk[tid] : 0;
+  while (t0 < T) {
+    const unsigned t = nxt;
+    const bool has = t0 + tid < T;
+    if (t0 + NT + tid < T) nxt = tk[t0 + NT + tid];
+    const bool isM = has && (t >> 31);
+    const unsigned L = has ? (isM ? (t >> 16) & 0x1ffu : 1u) : 0u;
+    unsigned incl = L;
+    for (int d = 1; d < 32; d <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += v; }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    unsigned ws = lane < (unsigned)(NT / 32) ? wsum[lane] : 0u;
+    for (int d = 1; d < NT / 32; d <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, ws, d); if ((int)lane >= d) ws += v; }
+    const unsigned woff = __shfl_sync(0xffffffffu, ws, (wid + 31) & 31) * (wid > 0);
+    const unsigned rel = woff + incl - L;
+    const bool fits = has && rel + L <= (unsigned)CAP;
+    const unsigned ncut = (unsigned)__syncthreads_count(fits);
+    if (fits && tid + 1 == ncut) s_total = rel + L;
+    const unsigned dist = (t & 0x7fffu) + 1;
+    bool m = fits && isM;
+    if (m && dist > boff + obase + rel) { fail = true; m = false; }              // reaches before the stream
+    if (fits && obase + rel + L > block_end) { fail = true; m = false; }
+    else if (fits && !isM) ob[rel] = (unsigned short)(t & 0xffu);
+    const int srel = (int)rel - (int)dist;
+    unsigned n_old = 0;
+    if (m) {
+      n_old = srel < 0 ? min(L, (unsigned)(-srel)) : 0u;
+      if (n_old < L) par_range<0>(pend_w, rel, rel + L);
+      // cells from before the tile: earlier tiles of this block (global), or markers for what precedes the block
+      const int g0 = (int)obase + srel;                          // block-local position of the first source cell
+      for (unsigned j0 = 0; j0 < n_old; j0 += 8) {
+        unsigned short v[8];
+#pragma unroll
+        for (unsigned j = 0; j < 8; j++) {
+          const int g = g0 + (int)(j0 + j);
+          v[j] = (j0 + j < n_old) ? (g >= 0 ? cells[g] : (unsigned short)(0x8000u | (unsigned)(32768 + g))) : (unsigned short)0;
+        }
+#pragma unroll
+        for (unsigned j = 0; j < 8; j++) if (j0 + j < n_old) ob[rel + j0 + j] = v[j];
+      }
+      if (n_old == L) m = false;
+    }
+    __syncthreads();
+    const unsigned a = (unsigned)max(srel, 0), b = min((unsigned)(srel + (int)L), rel);
+    while (__any_sync(0xffffffffu, m)) {
+      if (m) {
+        const bool clear = !(b > a && par_range<2>(pend_w, a, b));
+        if (clear) {
+          __threadfence_block();
+          for (unsigned j = n_old; j < L; j++) ob[rel + j] = ob[(unsigned)(srel + (int)j)];
+          __threadfence_block();
+          par_range<1>(pend_w, rel, rel + L);
+          m = false;
+        }
+      }
+    }
+    __syncthreads();
+    const unsigned total = s_total;
+    for (unsigned i = tid; i < total; i += NT) cells[obase + i] = ob[i];
+    obase += total;
+    t0 += ncut;
+    if (ncut != (unsigned)NT && t0 < T) nxt = t0 + tid < T ? tk[t0 + tid] : 0;
+  }
+  if (__syncthreads_or(fail || obase != block_end)) { if (tid == 0) blks[blockIdx.x].flags = blk.flags | 8; }
+}
+
+__global__ void __launch_bounds__(1024) par_cells_kernel(const ParStream* __restrict__ streams, const ParBlk* __restrict__ blks,
+                                                         unsigned bstride, const unsigned short* __restrict__ cells_base,
+                                                         long long cells_origin, unsigned char* out_base,
+                                                         ParRes* __restrict__ res) {
+  const ParStream st = streams[blockIdx.x];
+  unsigned char* out = out_base + st.out_off;
+  const unsigned short* cl = cells_base + (st.out_off - cells_origin);
+  bool bad = false;
+  const unsigned bj0 = blockIdx.x * bstride;
+  for (unsigned bj = bj0; bj < bj0 + bstride; bj++) {          // slots are in bit order = chain order
+    const ParBlk blk = blks[bj];
+    if (blk.bit == 0xffffffffu) break;
+    if (!(blk.flags & 4)) continue;
+    if (blk.flags & 8) bad = true;
+    const unsigned o = blk.limit, n = blk.out_len;
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned v = cl[o + i];
+      unsigned char b;
+      if (v & 0x8000u) {
+        const int src = (int)o - 32768 + (int)(v & 0x7fffu);
+        if (src < 0) { bad = true; b = 0; } else b = out[src];
+      } else b = (unsigned char)v;
+      out[o + i] = b;
+    }
+    __syncthreads();                                            // the next block's markers read these bytes
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) res[blockIdx.x].flags |= 2;
+}
+
 }  // namespace mts

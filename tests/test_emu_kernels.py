@@ -80,8 +80,9 @@ def test_emulated_block_parallel_inflate(emu):
     from mtscomp_b200 import synth, _native
     x = synth.ap_chunk(ns=20000, nc=16, seed=33)
     good = ora.encode_chunk(x)
-    for wide in (1, 0, -1):                     # both shapes of the LZ resolve kernel, then the automatic choice
+    for wide, cells in ((1, 0), (0, 0), (-1, 1), (-1, -1)):   # both chain-of-tiles shapes, the cells path, automatic
         emu.set_param('par_lz_wide', wide)
+        emu.set_param('par_cells', cells)
         out, st = emu.decompress(good, [0, len(good)], [0, 20000], 16, np.int16, _native.TIME_DIFF)
         assert not st.any() and np.array_equal(out, x)
         assert emu.get_param('par_chained') >= 5 and emu.get_param('par_resumed') == 1

@@ -217,11 +217,16 @@ def test_block_parallel_inflate_matches_serial(codec):
     blob = b''.join(parts)
     try:
         codec.set_param('par_inflate', 1)
-        for wide in (0, 1):                      # both shapes of the LZ resolve kernel
+        codec.set_param('par_cells', 0)
+        for wide in (0, 1):                      # both shapes of the chain-of-tiles resolve kernel
             codec.set_param('par_lz_wide', wide)
             outw, stw = codec.decompress(blob, offs, rows, 48, np.int16, F())
             assert not stw.any() and np.array_equal(outw, x) and codec.get_param('par_resumed') == 3
         codec.set_param('par_lz_wide', -1)
+        codec.set_param('par_cells', 1)          # blocks resolved in parallel into cells (the few-streams path)
+        outc, stc = codec.decompress(blob, offs, rows, 48, np.int16, F())
+        assert not stc.any() and np.array_equal(outc, x) and codec.get_param('par_resumed') == 3
+        codec.set_param('par_cells', -1)
         out1, st1 = codec.decompress(blob, offs, rows, 48, np.int16, F())
         chained, resumed = codec.get_param('par_chained'), codec.get_param('par_resumed')
         codec.set_param('par_inflate', 0)
@@ -230,6 +235,7 @@ def test_block_parallel_inflate_matches_serial(codec):
     finally:
         codec.set_param('par_inflate', 1)
         codec.set_param('par_lz_wide', -1)
+        codec.set_param('par_cells', -1)
     assert not st1.any() and not st0.any()
     assert np.array_equal(out1, x) and np.array_equal(out0, x)
     assert resumed == 3 and chained >= 3 * 30          # ~39 zlib blocks per 2.9 MB stream
