@@ -1,3 +1,5 @@
+"""Development probe: decode n reference-written chunks (device path through host arrays), print what the
+block-parallel decoder did and its stage times.  usage: dbg_par.py [n_chunks] [param=value ...]"""
 import sys, time, zlib
 sys.path.insert(0, '/root/repo')
 import numpy as np
@@ -5,6 +7,9 @@ from mtscomp_b200 import _native, synth
 from oracle import codec as ora
 cd = _native.default_codec(0)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+for kv in sys.argv[2:]:
+    k, v = kv.split('=')
+    cd.set_param(k, int(v))
 base = [np.ascontiguousarray(synth.ap_chunk(30000, 385, seed=100 + i)) for i in range(min(n, 8))]
 zs = [ora.encode_chunk(b) for b in base]
 comp = b''.join(zs[i % len(zs)] for i in range(n))
