@@ -54,7 +54,7 @@ struct mtsb_ctx {
   // params
   long long par_inflate = 1;   // decode index-less zlib streams block-parallel (inflate_par.cuh)
   long long par_indexed = 1;    // indexed segments of GPU-written chunks also go through the block kernels
-  long long par_cells = 0;      // (default off until validated on the GPU) index-less streams: -1 by stream count, 1 = blocks resolved in parallel into cells, 0 = chain of tiles
+  long long par_cells = -1;     // index-less streams: -1 by stream count, 1 = blocks resolved in parallel into cells, 0 = chain of tiles
   long long par_lz_wide = -1;   // LZ resolve kernel shape: -1 by stream count, 1 = 1024-thread CTAs, 0 = 256-thread CTAs
   long long par_batch_bytes = 2ll << 30;   // host-buffer sub-batch of index-less chunks (output bytes): large enough to amortise the block search
   long long par_stats[4] = {0, 0, 0, 0};   // last call: survivors, candidates, chained blocks, streams resumed
@@ -800,7 +800,9 @@ static int par_decode(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Infla
              dcomp, d_ps, (ParBlk*)c->d_plist.p, (unsigned)n_slots, (unsigned*)c->d_tokens.p,
              (unsigned long long*)((char*)c->d_pcount.p + 16), (unsigned long long)tok_total);
   CKL();
-  const bool use_cells = !blks && (c->par_cells < 0 ? ns <= 2 * c->sm_count : c->par_cells == 1);
+  // measured (ms of inflate, chain of tiles / cells): 1 stream 23.4 / 4.3, 8 streams 25.4 / 10.4, 64 streams 35 / 53,
+  // 600 streams 180 / 464 -> the cells path is the low-latency path for a handful of streams only
+  const bool use_cells = !blks && (c->par_cells < 0 ? ns <= 16 : c->par_cells == 1);
   if (use_cells) {
     // few streams: resolve the blocks of a stream in parallel (cells + markers), then cells -> bytes per stream
     long long lo = ps[0].out_off, hi = ps[0].out_off + ps[0].out_len;
@@ -813,7 +815,7 @@ static int par_decode(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Infla
     MTS_LAUNCH(k, dim3((unsigned)n_slots), dim3(256), 0, c->stream, d_ps, (ParBlk*)c->d_plist.p, (const unsigned*)c->d_tokens.p,
                (unsigned short*)c->d_cells.p, lo);
     CKL();
-    MTS_LAUNCH(par_cells_kernel, dim3(ns), dim3(1024), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p, bcap,
+    MTS_LAUNCH(par_cells_kernel, dim3((unsigned)n_slots), dim3(256), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p, bcap,
                (const unsigned short*)c->d_cells.p, lo, dT, (ParRes*)c->d_pbad.p);
     CKL();
     c->launches += 3;

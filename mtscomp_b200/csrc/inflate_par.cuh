@@ -792,12 +792,12 @@ __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream*
 // par_lz_kernel makes every stream a serial chain of tiles (~20 ms for a 23 MB chunk, whatever the batch size).  With
 // few streams the blocks of a stream are resolved IN PARALLEL instead, one CTA per block, into 16-bit cells: a byte, or a
 // MARKER 0x8000 | index into the 32 KB before the block for what is copied from there (markers are copied like data, so
-// every cell ends up as a byte or as a direct reference to the window).  A last pass per stream turns the cells into
-// bytes in block order (the markers then read bytes that are already final).
+// every cell ends up as a byte or as a direct reference to the window).  A last, fully parallel pass turns the cells
+// into bytes.
 //   par_chain_kernel  thread per stream: follow the chain (as par_lz_kernel does), give every chained block its output
 //                     offset (kept in ParBlk::limit, which nobody needs any more) and flag 4, write the stream's result
 //   par_lzc_kernel    CTA per block slot: tokens -> cells, same tile scheme as par_lz_kernel
-//   par_cells_kernel  CTA per stream: cells -> bytes, chained blocks in order
+//   par_cells_kernel  CTA per block: cells -> bytes, markers chased back through the cells of the earlier blocks
 __global__ void __launch_bounds__(64) par_chain_kernel(const ParStream* __restrict__ streams, ParBlk* __restrict__ blks,
                                                        unsigned bstride, unsigned ns, ParRes* __restrict__ res) {
   const unsigned sidx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -911,33 +911,38 @@ __global__ void __launch_bounds__(NT) par_lzc_kernel(const ParStream* __restrict
   if (__syncthreads_or(fail || obase != block_end)) { if (tid == 0) blks[blockIdx.x].flags = blk.flags | 8; }
 }
 
-__global__ void __launch_bounds__(1024) par_cells_kernel(const ParStream* __restrict__ streams, const ParBlk* __restrict__ blks,
-                                                         unsigned bstride, const unsigned short* __restrict__ cells_base,
-                                                         long long cells_origin, unsigned char* out_base,
-                                                         ParRes* __restrict__ res) {
-  const ParStream st = streams[blockIdx.x];
+// cells -> bytes, fully parallel: one CTA per block slot.  A marker is chased through the cells of the earlier blocks
+// (the block that holds the referenced position is found by walking back over the stream's slots; every hop goes at
+// least one block back, and in practice one or two hops reach a byte).
+__global__ void __launch_bounds__(256) par_cells_kernel(const ParStream* __restrict__ streams, const ParBlk* __restrict__ blks,
+                                                        unsigned bstride, const unsigned short* __restrict__ cells_base,
+                                                        long long cells_origin, unsigned char* __restrict__ out_base,
+                                                        ParRes* __restrict__ res) {
+  const ParBlk blk = blks[blockIdx.x];
+  if (blk.bit == 0xffffffffu || !(blk.flags & 4)) return;
+  const ParStream st = streams[blk.stream];
   unsigned char* out = out_base + st.out_off;
   const unsigned short* cl = cells_base + (st.out_off - cells_origin);
-  bool bad = false;
-  const unsigned bj0 = blockIdx.x * bstride;
-  for (unsigned bj = bj0; bj < bj0 + bstride; bj++) {          // slots are in bit order = chain order
-    const ParBlk blk = blks[bj];
-    if (blk.bit == 0xffffffffu) break;
-    if (!(blk.flags & 4)) continue;
-    if (blk.flags & 8) bad = true;
-    const unsigned o = blk.limit, n = blk.out_len;
-    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
-      const unsigned v = cl[o + i];
-      unsigned char b;
-      if (v & 0x8000u) {
-        const int src = (int)o - 32768 + (int)(v & 0x7fffu);
-        if (src < 0) { bad = true; b = 0; } else b = out[src];
-      } else b = (unsigned char)v;
-      out[o + i] = b;
+  const int slot0 = (int)(blk.stream * bstride);
+  const unsigned o = blk.limit, n = blk.out_len;
+  bool bad = (blk.flags & 8) != 0;
+  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+    unsigned v = cl[o + i];
+    unsigned cur_o = o;
+    int cur_slot = (int)blockIdx.x;
+    while (v & 0x8000u) {
+      const int p = (int)cur_o - 32768 + (int)(v & 0x7fffu);     // position in the stream, before block cur_slot
+      if (p < 0) { bad = true; v = 0; break; }
+      int k = cur_slot;
+      do { k--; } while (k >= slot0 && (!(blks[k].flags & 4) || blks[k].limit > (unsigned)p));
+      if (k < slot0) { bad = true; v = 0; break; }
+      cur_slot = k;
+      cur_o = blks[k].limit;
+      v = cl[p];
     }
-    __syncthreads();                                            // the next block's markers read these bytes
+    out[o + i] = (unsigned char)v;
   }
-  if (__syncthreads_or(bad) && threadIdx.x == 0) res[blockIdx.x].flags |= 2;
+  if (bad) atomicOr(&res[blk.stream].flags, 2u);
 }
 
 }  // namespace mts

@@ -324,3 +324,20 @@ def test_gpu_stream_bytes_equal_the_host_emulation(codec):
         g, go = codec.compress(x, rows, F())
         e, eo = emu.compress(x, rows, F())
         assert list(go) == list(eo) and bytes(g) == bytes(e)
+
+
+def test_block_parallel_marker_chains(codec):
+    """Period-20 KB data: every deflate block consists of references into the block before it, so in the cells path
+    (blocks resolved in parallel) a marker has to be chased through several blocks."""
+    rng = np.random.default_rng(9)
+    pat = rng.integers(-3000, 3000, 10000).astype(np.int16)
+    x = np.tile(pat, 900).reshape(-1, 1)
+    good = ora.encode_chunk(x)
+    try:
+        for cells in (1, 0):
+            codec.set_param('par_cells', cells)
+            out, st = codec.decompress(good, [0, len(good)], [0, x.shape[0]], 1, np.int16, F())
+            assert st[0] == 0 and np.array_equal(out, x)
+            assert codec.get_param('par_resumed') == 1 and codec.get_param('par_chained') >= 3
+    finally:
+        codec.set_param('par_cells', -1)
