@@ -90,3 +90,21 @@ def test_emulated_block_parallel_inflate(emu):
     bad[len(bad) // 2] ^= 0x33
     _, st = emu.decompress(bytes(bad), [0, len(bad)], [0, 20000], 16, np.int16, _native.TIME_DIFF)
     assert st[0] != 0
+
+
+def test_emulated_marker_chains(emu):
+    """Cells path of the block-parallel decoder on period-20 KB data: every block is made of references into the block
+    before it, so markers have to be chased through several blocks."""
+    from mtscomp_b200 import _native
+    rng = np.random.default_rng(9)
+    pat = rng.integers(-3000, 3000, 10000).astype(np.int16)
+    x = np.tile(pat, 500).reshape(-1, 1)
+    good = ora.encode_chunk(x)
+    assert len(good) >= 65536
+    try:
+        emu.set_param('par_cells', 1)
+        out, st = emu.decompress(good, [0, len(good)], [0, x.shape[0]], 1, np.int16, _native.TIME_DIFF)
+        assert st[0] == 0 and np.array_equal(out, x)
+        assert emu.get_param('par_resumed') == 1 and emu.get_param('par_chained') >= 3
+    finally:
+        emu.set_param('par_cells', -1)
