@@ -800,8 +800,8 @@ static int par_decode(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Infla
              dcomp, d_ps, (ParBlk*)c->d_plist.p, (unsigned)n_slots, (unsigned*)c->d_tokens.p,
              (unsigned long long*)((char*)c->d_pcount.p + 16), (unsigned long long)tok_total);
   CKL();
-  // measured (ms of inflate, chain of tiles / cells): 1 stream 23.4 / 4.3, 8 streams 25.4 / 10.4, 64 streams 35 / 53,
-  // 600 streams 180 / 464 -> the cells path is the low-latency path for a handful of streams only
+  // measured (ms of inflate, chain of tiles / cells): 1 stream 23.4 / 4.1, 8 streams 25.4 / 9.6, 64 streams 35 / 48,
+  // 600 streams 180 / 415 -> the cells path is the low-latency path for a handful of streams only
   const bool use_cells = !blks && (c->par_cells < 0 ? ns <= 16 : c->par_cells == 1);
   if (use_cells) {
     // few streams: resolve the blocks of a stream in parallel (cells + markers), then cells -> bytes per stream

@@ -911,13 +911,17 @@ __global__ void __launch_bounds__(NT) par_lzc_kernel(const ParStream* __restrict
   if (__syncthreads_or(fail || obase != block_end)) { if (tid == 0) blks[blockIdx.x].flags = blk.flags | 8; }
 }
 
-// cells -> bytes, fully parallel: one CTA per block slot.  A marker is chased through the cells of the earlier blocks
-// (the block that holds the referenced position is found by walking back over the stream's slots; every hop goes at
-// least one block back, and in practice one or two hops reach a byte).
+// cells -> bytes, fully parallel: one CTA per block slot, four cells per thread and turn.  A marker is chased through
+// the cells of the earlier blocks; the output offsets of the PAR_CELLS_BACK chained blocks before this one are kept in
+// shared memory, so a hop costs one global load (every hop goes at least one block back; one or two reach a byte).
+static const int PAR_CELLS_BACK = 32;
 __global__ void __launch_bounds__(256) par_cells_kernel(const ParStream* __restrict__ streams, const ParBlk* __restrict__ blks,
                                                         unsigned bstride, const unsigned short* __restrict__ cells_base,
                                                         long long cells_origin, unsigned char* __restrict__ out_base,
                                                         ParRes* __restrict__ res) {
+  __shared__ unsigned pb[PAR_CELLS_BACK];                       // output offsets of the previous chained blocks, nearest first
+  __shared__ int pbs[PAR_CELLS_BACK];                           // ... and their slots
+  __shared__ int npb;
   const ParBlk blk = blks[blockIdx.x];
   if (blk.bit == 0xffffffffu || !(blk.flags & 4)) return;
   const ParStream st = streams[blk.stream];
@@ -925,22 +929,41 @@ __global__ void __launch_bounds__(256) par_cells_kernel(const ParStream* __restr
   const unsigned short* cl = cells_base + (st.out_off - cells_origin);
   const int slot0 = (int)(blk.stream * bstride);
   const unsigned o = blk.limit, n = blk.out_len;
+  if (threadIdx.x == 0) {
+    int cnt = 0;
+    for (int k = (int)blockIdx.x - 1; k >= slot0 && cnt < PAR_CELLS_BACK; k--)
+      if (blks[k].flags & 4) { pb[cnt] = blks[k].limit; pbs[cnt] = k; cnt++; }
+    npb = cnt;
+  }
+  __syncthreads();
+  const int np = npb;
   bool bad = (blk.flags & 8) != 0;
-  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
-    unsigned v = cl[o + i];
-    unsigned cur_o = o;
-    int cur_slot = (int)blockIdx.x;
-    while (v & 0x8000u) {
-      const int p = (int)cur_o - 32768 + (int)(v & 0x7fffu);     // position in the stream, before block cur_slot
-      if (p < 0) { bad = true; v = 0; break; }
-      int k = cur_slot;
-      do { k--; } while (k >= slot0 && (!(blks[k].flags & 4) || blks[k].limit > (unsigned)p));
-      if (k < slot0) { bad = true; v = 0; break; }
-      cur_slot = k;
-      cur_o = blks[k].limit;
-      v = cl[p];
+  for (unsigned i0 = threadIdx.x * 4; i0 < n; i0 += blockDim.x * 4) {
+    unsigned v[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) v[q] = i0 + q < n ? cl[o + i0 + q] : 0u;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      unsigned cur_o = o;
+      int j = -1, cur_slot = 0;                                 // index in pb of the block being looked at (-1: this block)
+      while (v[q] & 0x8000u) {
+        const int p = (int)cur_o - 32768 + (int)(v[q] & 0x7fffu);   // position in the stream, before the block looked at
+        if (p < 0) { bad = true; v[q] = 0; break; }
+        if (j < np) { do { j++; } while (j < np && pb[j] > (unsigned)p); }
+        if (j < np) cur_o = pb[j];
+        else {
+          // further back than the table (long chains through many blocks, e.g. periodic data): walk the slots
+          if (j == np) cur_slot = np ? pbs[np - 1] : (int)blockIdx.x;
+          int k = cur_slot;
+          do { k--; } while (k >= slot0 && (!(blks[k].flags & 4) || blks[k].limit > (unsigned)p));
+          if (k < slot0) { bad = true; v[q] = 0; break; }
+          cur_slot = k; cur_o = blks[k].limit; j = np + 1;
+        }
+        v[q] = cl[p];
+      }
     }
-    out[o + i] = (unsigned char)v;
+#pragma unroll
+    for (int q = 0; q < 4; q++) if (i0 + q < n) out[o + i0 + q] = (unsigned char)v[q];
   }
   if (bad) atomicOr(&res[blk.stream].flags, 2u);
 }
