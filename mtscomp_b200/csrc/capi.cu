@@ -1084,15 +1084,21 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
     }
     c->end();
     c->begin(2);
+    // (the block kernels address bits with 32-bit offsets: streams of 256 MB and more stay with the serial decoder)
+    const int PAR_MAX_IN = 1 << 28;
     if (c->par_inflate && !whole.empty()) {
       long long whole_in = 0;
-      for (int w : whole) whole_in += segs[w].in_len;
-      if (whole_in >= 65536) { int r = par_phase(c, dcomp, segs, whole, (unsigned char*)c->d_T.p); if (r) return r; }
+      std::vector<int> fit;
+      for (int w : whole) if (segs[w].in_len < PAR_MAX_IN) { whole_in += segs[w].in_len; fit.push_back(w); }
+      if (whole_in >= 65536) { int r = par_phase(c, dcomp, segs, fit, (unsigned char*)c->d_T.p); if (r) return r; }
     }
     if (c->par_inflate && c->par_indexed && (int)whole.size() < n_segs) {
       std::vector<int> ids;
       size_t wi = 0;
-      for (int j = 0; j < n_segs; j++) { if (wi < whole.size() && whole[wi] == j) { wi++; continue; } ids.push_back(j); }
+      for (int j = 0; j < n_segs; j++) {
+        if (wi < whole.size() && whole[wi] == j) { wi++; continue; }
+        if (segs[j].in_len < PAR_MAX_IN) ids.push_back(j);
+      }
       int r = par_phase_indexed(c, dcomp, segs, ids, (unsigned char*)c->d_T.p);
       if (r) return r;
     }
