@@ -195,7 +195,7 @@ def run_b200(args):
     # ---- data: distinct seeded chunks, tiled; reference-written streams of the same chunks (CPU zlib)
     base = [synth.ap_chunk(NS, NC, seed=1234 + i + 1000 * rank, t0=i * NS) for i in range(n_distinct)]
     t0 = time.perf_counter()
-    n_cpu = args.cpu_sample or max(n_distinct, min(threads, 32))
+    n_cpu = max(n_distinct, args.cpu_sample or min(threads, 32))   # every distinct chunk is needed as a reference stream
     cpu_c, cpu_d, ref_streams = cpu_codec_sample(base, n_cpu, threads) if rank == 0 else (None, None, None)
     cpu_secs = time.perf_counter() - t0
     if rank != 0:
