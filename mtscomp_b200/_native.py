@@ -111,6 +111,10 @@ class Codec:
             raise NativeUnavailable('mtsb_create failed: %s' % self.lib.mtsb_last_error(None).decode())
         self.device = int(device)
         self.lock = threading.Lock()
+        # tunables for experiments without touching code: MTSCOMP_B200_PARAMS="par_batch_bytes=4294967296,max_chain=8"
+        for kv in filter(None, os.environ.get('MTSCOMP_B200_PARAMS', '').split(',')):
+            k, v = kv.split('=')
+            self.set_param(k.strip(), int(v))
 
     def close(self):
         if getattr(self, 'ctx', None):
@@ -225,12 +229,7 @@ def default_codec(device=None):
         device = int(os.environ.get('MTSCOMP_B200_DEVICE', os.environ.get('LOCAL_RANK', 0)))
     with _default_lock:
         if device not in _default:
-            cd = Codec(device)
-            # tunables for experiments without touching code: MTSCOMP_B200_PARAMS="par_batch_bytes=4294967296,max_chain=8"
-            for kv in filter(None, os.environ.get('MTSCOMP_B200_PARAMS', '').split(',')):
-                k, v = kv.split('=')
-                cd.set_param(k.strip(), int(v))
-            _default[device] = cd
+            _default[device] = Codec(device)
         return _default[device]
 
 
