@@ -108,3 +108,26 @@ def test_emulated_marker_chains(emu):
         assert emu.get_param('par_resumed') == 1 and emu.get_param('par_chained') >= 3
     finally:
         emu.set_param('par_cells', -1)
+
+
+def test_emulated_indexed_segments_both_decoders(emu):
+    """GPU-written chunk (kernel logic under emulation): the indexed segments through the block kernels and through
+    the serial warp decoder give the same bytes; a segment stored uncompressed stays with the serial decoder."""
+    from mtscomp_b200 import _native, synth
+    rng = np.random.default_rng(2)
+    x = np.concatenate([synth.ap_chunk(ns=4000, nc=48, seed=11),
+                        rng.integers(-32768, 32767, (4000, 48)).astype(np.int16)])
+    rows = [0, 4000, 8000]
+    try:
+        emu.set_param('seg_bytes', 65536)
+        comp, offs = emu.compress(x, rows, _native.TIME_DIFF)
+        outs = []
+        for indexed in (1, 0):
+            emu.set_param('par_indexed', indexed)
+            out, st = emu.decompress(comp, offs, rows, 48, np.int16, _native.TIME_DIFF)
+            assert not st.any() and np.array_equal(out, x)
+            outs.append(emu.get_param('par_resumed'))
+        assert outs[0] >= 4 and outs[1] == 0
+    finally:
+        emu.set_param('seg_bytes', 262144)
+        emu.set_param('par_indexed', 1)
