@@ -134,6 +134,19 @@ __device__ __forceinline__ void lz_unit_hashes(const unsigned char* ring, unsign
   }
 }
 
+// Work a searcher thread does for LATER steps: hashes of its unit two steps ahead (position p2) into hbuf, and the
+// store of its prefetched 16 input bytes into the ring.
+template <int STRIDE>
+__device__ __forceinline__ void lz_ahead(unsigned char* ring, unsigned short* hbuf, unsigned step, unsigned tid, unsigned p2,
+                                         unsigned n, unsigned off0, bool pf, unsigned pf_rc, uint4 pf_v) {
+  unsigned short hs, hl;
+  lz_unit_hashes<STRIDE>(ring, p2, n, off0, hs, hl);
+  unsigned short* hb = hbuf + (step & 1) * 2 * LZ_UNITS;
+  hb[tid] = hs;
+  hb[LZ_UNITS + tid] = hl;
+  if (pf) ring_store16(ring, pf_rc & 0xffffu, pf_v);
+}
+
 // Thread `units` consecutive units starting at unit u0 into one hash table (one warp), batches of 64 units (two
 // consecutive units per lane) in position order.  Every unit links to the table head as it was BEFORE its batch — or to
 // its lane's first unit when both have the same hash; units of different lanes of one batch never link to each other
@@ -282,6 +295,11 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
       const unsigned slen = min(SEG, n - s0);
 
       LZ_PROF_T(t_step);
+      // prefetch of ring coordinates [(step+3)*SEG + 32, (step+4)*SEG + 32) by the first SEG/16 searcher threads: loaded
+      // before the search, stored (with the hashes of the units two steps ahead) where the thread has nothing else to do
+      const unsigned pf_rc = (step + 3) * SEG + 32 + tid * 16;
+      const bool pf = wid < NSW && tid * 16 < SEG && pf_rc < n_ring;
+      uint4 pf_v = make_uint4(0, 0, 0, 0);
       if (wid >= NSW) {
         // ---- (A) inserters (the two highest warp ids: the issue arbiter favours them over the searchers): prefetch
         //          ring coordinates [(step+3)*SEG, (step+4)*SEG) and thread step+1's units into the tables
@@ -299,9 +317,6 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
         const unsigned li = tid * STRIDE;                 // local position in the step
         const unsigned p = s0 + li;
         unsigned best = 0, bdist = 0;
-        const unsigned pf_rc = (step + 3) * SEG + 32 + tid * 16;
-        const bool pf = tid * 16 < SEG && pf_rc < n_ring;
-        uint4 pf_v = make_uint4(0, 0, 0, 0);
         if (pf) pf_v = in16[pf_rc >> 4];
         if (li < slen && p + 4 <= n && prm.lazy != 2) {
           const unsigned u = p / STRIDE;
@@ -349,15 +364,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
             }
           }
         }
-        {
-          // hashes of this thread's unit two steps ahead (consumed by the inserters during the next step)
-          unsigned short hs, hl;
-          lz_unit_hashes<STRIDE>(ring, p + 2 * SEG, n, off0, hs, hl);
-          unsigned short* hb = hbuf + (step & 1) * 2 * LZ_UNITS;
-          hb[tid] = hs;
-          hb[LZ_UNITS + tid] = hl;
-        }
-        if (pf) ring_store16(ring, pf_rc & 0xffffu, pf_v);
+        // hashes of this thread's unit two steps ahead (consumed by the inserters during the next step) and the prefetch
+        // store: warp 0 does them here, the other warps while warp 0 chains the stretches (they would only wait there)
+        if (wid == 0) lz_ahead<STRIDE>(ring, hbuf, step, tid, s0 + li + 2 * SEG, n, off0, pf, pf_rc, pf_v);
         if (tid == 0) { LZ_PROF_T(t_s); LZ_PROF_ADD(2, t_s - t_step); }
         unsigned bext = 0;
         if (STRIDE == 2 && bdist) {
@@ -410,6 +419,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
         xe[tid] = (sb + (v & 0xffffu)) | (v & 0xffff0000u);
         named_barrier(1, NSW * 32);
         if (tid == 0) { LZ_PROF_T(t_b); LZ_PROF_ADD(6, t_b - t_p0); }
+        if (wid != 0) lz_ahead<STRIDE>(ring, hbuf, step, tid, s0 + tid * STRIDE + 2 * SEG, n, off0, pf, pf_rc, pf_v);
         if (wid == 0) {
           // Stage 2, by relaxation in one warp (lane = stretch): every lane guesses that its stretch is entered at
           // its first unit, looks up where that chain leaves, and hands the exit to the next lane as ITS entry; repeat
@@ -474,6 +484,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
         run_tok += misc[35];
       } else {
         if (tid == 0) misc[33 + ((step + 1) & 1)] = start - nu;
+        if (wid != 0) lz_ahead<STRIDE>(ring, hbuf, step, tid, s0 + tid * STRIDE + 2 * SEG, n, off0, pf, pf_rc, pf_v);
       }
       }   // wid < NSW
       __syncthreads();
