@@ -30,7 +30,9 @@ enum {
 };
 
 /* transform flags (Writer options do_time_diff / do_spatial_diff / chunk_order, mtscomp.py:250-255) */
-enum { MTSB_TIME_DIFF = 1, MTSB_SPATIAL_DIFF = 2, MTSB_ORDER_C = 4 };
+enum { MTSB_TIME_DIFF = 1, MTSB_SPATIAL_DIFF = 2, MTSB_ORDER_C = 4,
+       MTSB_FLOAT = 8 /* elements are IEEE float32 / float64 (itemsize 4 / 8) instead of integers: the differences are
+                         float subtractions and the inverse adds sequentially, as np.diff / np.cumsum do */ };
 
 /* per-chunk decode status (chunk_status[]); non-zero maps to the reference's
  * IOError("Compressed chunk #%d is corrupted.") raised at mtscomp.py:618-621 */

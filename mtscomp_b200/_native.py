@@ -15,7 +15,12 @@ import numpy as np
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / '_build' / 'libmtscomp_b200.so'
 
-TIME_DIFF, SPATIAL_DIFF, ORDER_C = 1, 2, 4
+TIME_DIFF, SPATIAL_DIFF, ORDER_C, FLOAT = 1, 2, 4, 8
+
+
+def _fl(flags, dtype):
+    """flags with the FLOAT bit set for floating point dtypes (the array-level helpers below add it themselves)."""
+    return flags | FLOAT if np.dtype(dtype).kind == 'f' else flags
 E_CORRUPT = -5
 
 SYMBOLS = (
@@ -182,7 +187,8 @@ class Codec:
         out = np.empty(chunk.nbytes, dtype=np.uint8)
         with self.lock:
             self._check(self.lib.mtsb_delta_transform(
-                self.ctx, _ptr(chunk), 0, chunk.shape[0], chunk.shape[1], chunk.dtype.itemsize, flags, _ptr(out), 0))
+                self.ctx, _ptr(chunk), 0, chunk.shape[0], chunk.shape[1], chunk.dtype.itemsize, _fl(flags, chunk.dtype),
+                _ptr(out), 0))
         return out
 
     def inverse_transform(self, buf, ns, nc, dtype, flags, want_adler=False):
@@ -194,7 +200,7 @@ class Codec:
         ad = C.c_uint32(0)
         with self.lock:
             self._check(self.lib.mtsb_inverse_transform(
-                self.ctx, _ptr(src), 0, ns, nc, dtype.itemsize, flags, _ptr(out), 0,
+                self.ctx, _ptr(src), 0, ns, nc, dtype.itemsize, _fl(flags, dtype), _ptr(out), 0,
                 C.byref(ad) if want_adler else None))
         return (out, int(ad.value)) if want_adler else out
 
@@ -203,6 +209,7 @@ class Codec:
         data = np.ascontiguousarray(data)
         rows = _i64(chunk_rows)
         nc, isz = data.shape[1], data.dtype.itemsize
+        flags = _fl(flags, data.dtype)
         cap = sum(self.compress_bound(int(rows[i + 1] - rows[i]), nc, isz, flags) for i in range(len(rows) - 1))
         dst = np.empty(cap, dtype=np.uint8)
         offs = self.compress_ptr(data.ctypes.data, 0, rows, nc, isz, flags, dst.ctypes.data, 0, cap)
@@ -214,7 +221,7 @@ class Codec:
         comp = np.frombuffer(comp, dtype=np.uint8)
         rows = _i64(chunk_rows)
         out = np.empty((int(rows[-1]), nc), dtype=dtype)
-        status = self.decompress_ptr(comp.ctypes.data, 0, comp_offsets, rows, nc, dtype.itemsize, flags,
+        status = self.decompress_ptr(comp.ctypes.data, 0, comp_offsets, rows, nc, dtype.itemsize, _fl(flags, dtype),
                                      out.ctypes.data, 0)
         return out, status
 

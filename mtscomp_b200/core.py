@@ -34,10 +34,15 @@ GPU_BATCH_CHUNKS = 64  # chunks handed to the GPU per call by Writer.write / Rea
 
 
 def _require_integer_dtype(dtype):
+    """dtypes the CUDA codec handles: int8..int64 / uint8..uint64 (modular arithmetic, as NumPy's) and float32 /
+    float64 (IEEE differences, sequential sums in np.cumsum's order: the decoded values equal the reference Reader's
+    bit for bit, which — as in the reference — are close to, not identical with, what was written)."""
     dtype = np.dtype(dtype)
-    if not np.issubdtype(dtype, np.integer) or dtype.itemsize not in (1, 2, 4, 8):
+    ok_int = np.issubdtype(dtype, np.integer) and dtype.itemsize in (1, 2, 4, 8)
+    ok_float = dtype.kind == 'f' and dtype.itemsize in (4, 8)
+    if not (ok_int or ok_float):
         raise NotImplementedError(
-            "mtscomp_b200 implements the integer codec path (int8..int64, modular arithmetic); dtype %s is not "
+            "mtscomp_b200 implements the codec for int8..int64 and float32/float64; dtype %s is not "
             "supported and there is no CPU fallback." % dtype)
     return dtype
 

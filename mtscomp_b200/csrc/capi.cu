@@ -193,6 +193,11 @@ int launch_fwd_t(mtsb_ctx* c, const void* raw, void* tbuf, const ChunkDesc* d_cd
 }
 int launch_fwd(mtsb_ctx* c, int isz, const void* raw, void* tbuf, const ChunkDesc* d_cd, int n_chunks, int max_ns,
                int nc, int flags) {
+  if (flags & FLAG_FLOAT) {
+    if (isz == 4) return launch_fwd_t<float>(c, raw, tbuf, d_cd, n_chunks, max_ns, nc, flags);
+    if (isz == 8) return launch_fwd_t<double>(c, raw, tbuf, d_cd, n_chunks, max_ns, nc, flags);
+    return fail(c, MTSB_E_ARG, "floating point itemsize %d not supported (4, 8)", isz);
+  }
   switch (isz) {
     case 1: return launch_fwd_t<uint8_t>(c, raw, tbuf, d_cd, n_chunks, max_ns, nc, flags);
     case 2: return launch_fwd_t<uint16_t>(c, raw, tbuf, d_cd, n_chunks, max_ns, nc, flags);
@@ -233,8 +238,33 @@ int launch_inv_t(mtsb_ctx* c, const void* tbuf, void* out, const ChunkDesc* d_cd
   CKL();
   return 0;
 }
+// float32 / float64: sequential sums in the reference's order (transform.cuh); the spatial pass works on a scratch copy
+template <class T>
+int launch_inv_float(mtsb_ctx* c, const void* tbuf, void* out, const ChunkDesc* d_cd, int n_chunks, int max_ns, int nc,
+                     int flags, size_t span_elems) {
+  const T* in = (const T*)tbuf;
+  if (flags & FLAG_SPATIAL_DIFF) {
+    NEED(c->d_partial, span_elems * sizeof(T) + 256);
+    auto k1 = inv_float_space_kernel<T>;
+    MTS_LAUNCH(k1, dim3((max_ns + 127) / 128, n_chunks), dim3(128), 0, c->stream, in, (T*)c->d_partial.p, d_cd, nc, flags);
+    CKL();
+    c->launches++;
+    in = (const T*)c->d_partial.p;
+  }
+  auto k2 = inv_float_time_kernel<T>;
+  MTS_LAUNCH(k2, dim3((nc + 127) / 128, n_chunks), dim3(128), 0, c->stream, in, (T*)out, d_cd, nc, flags);
+  CKL();
+  c->launches++;
+  return 0;
+}
+
 int launch_inv(mtsb_ctx* c, int isz, const void* tbuf, void* out, const ChunkDesc* d_cd, int n_chunks, int max_ns,
-               int nc, int flags) {
+               int nc, int flags, size_t span_elems) {
+  if (flags & FLAG_FLOAT) {
+    if (isz == 4) return launch_inv_float<float>(c, tbuf, out, d_cd, n_chunks, max_ns, nc, flags, span_elems);
+    if (isz == 8) return launch_inv_float<double>(c, tbuf, out, d_cd, n_chunks, max_ns, nc, flags, span_elems);
+    return fail(c, MTSB_E_ARG, "floating point itemsize %d not supported (4, 8)", isz);
+  }
   switch (isz) {
     case 1: return launch_inv_t<uint8_t>(c, tbuf, out, d_cd, n_chunks, max_ns, nc, flags);
     case 2: return launch_inv_t<uint16_t>(c, tbuf, out, d_cd, n_chunks, max_ns, nc, flags);
@@ -497,7 +527,7 @@ int mtsb_inverse_transform(mtsb_ctx* c, const void* src, int src_is_device, long
     c->launches += 2;
     CK(cudaMemcpyAsync(adler32_out, c->d_chunk_adler.p, 4, cudaMemcpyDeviceToHost, c->stream));
   }
-  int r = launch_inv(c, itemsize, t, o, (const ChunkDesc*)d, 1, (int)ns, nc, flags);
+  int r = launch_inv(c, itemsize, t, o, (const ChunkDesc*)d, 1, (int)ns, nc, flags, (size_t)ns * nc);
   if (r) return r;
   if (!dst_is_device) CK(cudaMemcpyAsync(dst, o, bytes, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -1143,7 +1173,7 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
       outp = out_buf[k & 1]->p;
     }
     c->begin(4);
-    int r = launch_inv(c, itemsize, c->d_T.p, outp, d_cd, nb, max_ns, nc, flags);
+    int r = launch_inv(c, itemsize, c->d_T.p, outp, d_cd, nb, max_ns, nc, flags, (size_t)(bbytes / itemsize));
     if (r) return r;
     c->end();
     char* hs = (char*)c->h_small.p;

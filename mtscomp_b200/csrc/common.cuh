@@ -22,7 +22,7 @@ struct ChunkDesc {
   int pad_;
 };
 
-enum { FLAG_TIME_DIFF = 1, FLAG_SPATIAL_DIFF = 2, FLAG_ORDER_C = 4 };
+enum { FLAG_TIME_DIFF = 1, FLAG_SPATIAL_DIFF = 2, FLAG_ORDER_C = 4, FLAG_FLOAT = 8 };   // FLAG_FLOAT: IEEE float32 / float64 elements
 
 static const uint32_t ADLER_BASE = 65521u;
 

@@ -275,6 +275,49 @@ __global__ void __launch_bounds__(128) inv_cols_kernel(const T* __restrict__ in,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ floating point inverse
+// float32 / float64 (FLAG_FLOAT): the forward differences are single IEEE subtractions, so the integer kernels above
+// are simply instantiated for float / double.  The inverse is different: np.cumsum accumulates sequentially in the
+// array's own precision (mtscomp.py:162-169), and reproducing the reference Reader bit for bit means adding in the
+// same order — one thread per row (spatial pass, into a scratch copy) and one thread per channel (time pass).
+template <class T>
+__global__ void __launch_bounds__(128) inv_float_space_kernel(const T* __restrict__ in, T* __restrict__ tmp,
+                                                              const ChunkDesc* __restrict__ chunks, int nc, int flags) {
+  const ChunkDesc cd = chunks[blockIdx.y];
+  const int ns = cd.ns;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ns) return;
+  const T* x = in + cd.elem_off;
+  T* y = tmp + cd.elem_off;
+  const bool oc = (flags & FLAG_ORDER_C) != 0;
+  T acc = 0;
+  for (int c = 0; c < nc; c++) {
+    const long long i = oc ? (long long)t * nc + c : (long long)c * ns + t;
+    const T v = x[i];
+    acc = c == 0 ? v : acc + v;
+    y[i] = acc;
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(128) inv_float_time_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                             const ChunkDesc* __restrict__ chunks, int nc, int flags) {
+  const ChunkDesc cd = chunks[blockIdx.y];
+  const int ns = cd.ns;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const T* x = in + cd.elem_off;
+  T* y = out + cd.elem_off;
+  const bool oc = (flags & FLAG_ORDER_C) != 0, td = (flags & FLAG_TIME_DIFF) != 0;
+  T acc = 0;
+  for (int t = 0; t < ns; t++) {
+    const T v = x[oc ? (long long)t * nc + c : (long long)c * ns + t];
+    acc = (t == 0 || !td) ? v : acc + v;
+    y[(long long)t * nc + c] = acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ adler32
 // One CTA per segment: standalone adler32 of bytes [off, off+len) (i.e. starting from adler = 1).  Segments are
 // folded per chunk with zlib's adler32_combine rule by adler_combine_kernel / the deflate scan.

@@ -85,9 +85,29 @@ def case_dtypes(tmp_path):   # reference tests.py:240-243 (integer dtypes)
         unc.close()
 
 
-def case_float_is_refused_loudly(tmp_path):
+def case_float_dtypes(tmp_path):   # reference tests.py:240-243 (floating point dtypes)
+    """float32 / float64: as in the reference the round trip is close, not exact (cumsum of differences), and what the
+    Reader returns is exactly what the reference Reader returns: np.cumsum's sequential sums of the stored differences."""
+    from oracle import codec as ora
+    _use_tmp_config(tmp_path)
+    for dt, kw in ((np.float32, {}), (np.float64, dict(do_spatial_diff=True)), (np.float32, dict(chunk_order='C'))):
+        # (offset: the reference's post-compression check is np.allclose with rtol 1e-5, which float32 sums near zero fail)
+        arr = (_arr16(4).astype(np.float64) / 7.3 + 20000.).astype(dt)
+        path = tmp_path / 'f.bin'
+        arr.tofile(path)
+        out, outmeta = tmp_path / 'f.cbin', tmp_path / 'f.ch'
+        compress(path, out, outmeta, sample_rate=sample_rate, n_channels=arr.shape[1], dtype=arr.dtype, quiet=True, **kw)
+        unc = decompress(out, outmeta)
+        got = unc[:]
+        assert got.dtype == np.dtype(dt) and np.allclose(got, arr, atol=0.5 if dt == np.float32 else 1e-8)
+        b = unc.chunk_bounds
+        flags = dict(do_time_diff=True, do_spatial_diff=kw.get('do_spatial_diff', False), chunk_order=kw.get('chunk_order', 'F'))
+        want = np.concatenate([ora.decode_chunk(ora.encode_chunk(arr[b[i]:b[i + 1]], **flags), b[i + 1] - b[i],
+                                                arr.shape[1], dt, **flags) for i in range(len(b) - 1)])
+        assert got.tobytes() == want.tobytes()
+        unc.close()
     with raises(NotImplementedError):
-        _round_trip(tmp_path, np.zeros((100, 4), np.float32), quiet=True)
+        _round_trip(tmp_path, np.zeros((100, 4), np.float16), quiet=True)
 
 
 def case_comp_decomp_hashes(tmp_path):   # reference tests.py:381-410

@@ -131,3 +131,23 @@ def test_emulated_indexed_segments_both_decoders(emu):
     finally:
         emu.set_param('seg_bytes', 262144)
         emu.set_param('par_indexed', 1)
+
+
+@pytest.mark.parametrize('name', sorted(json.loads((GOLDEN / 'manifest.json').read_text()).get('float_cases', {})))
+def test_emulated_float_golden(emu, name):
+    """float32 / float64 (kernel logic under emulation): decode of the reference-written file == the reference
+    Reader's output bit for bit; the encoder's streams inflate to the reference's transform bytes."""
+    from mtscomp_b200 import _native
+    m = json.loads((GOLDEN / 'manifest.json').read_text())['float_cases'][name]
+    ch = json.loads((GOLDEN / (name + '.ch')).read_text())
+    raw = np.fromfile(GOLDEN / (name + '.bin'), dtype=m['dtype']).reshape(m['shape'])
+    dec = np.fromfile(GOLDEN / (name + '.dec'), dtype=m['dtype']).reshape(m['shape'])
+    cbin = (GOLDEN / (name + '.cbin')).read_bytes()
+    fl = _flags(ch)
+    out, st = emu.decompress(cbin, ch['chunk_offsets'], ch['chunk_bounds'], ch['n_channels'], raw.dtype, fl)
+    assert not st.any() and out.tobytes() == dec.tobytes()
+    comp, offs = emu.compress(raw, ch['chunk_bounds'], fl)
+    b = ch['chunk_bounds']
+    assert zlib.decompress(bytes(comp[offs[0]:offs[1]])) == (GOLDEN / (name + '.tr')).read_bytes()
+    out2, st2 = emu.decompress(comp, offs, b, ch['n_channels'], raw.dtype, fl)
+    assert not st2.any() and out2.tobytes() == dec.tobytes()

@@ -341,3 +341,30 @@ def test_block_parallel_marker_chains(codec):
             assert codec.get_param('par_resumed') == 1 and codec.get_param('par_chained') >= 3
     finally:
         codec.set_param('par_cells', -1)
+
+
+FLOAT_CASES = sorted(json.loads((GOLDEN / 'manifest.json').read_text()).get('float_cases', {}))
+
+
+@pytest.mark.parametrize('name', FLOAT_CASES)
+def test_float_golden_reference_files(codec, name):
+    """float32 / float64: the CUDA path returns what the reference Reader returns, bit for bit (also where that
+    differs from the input: float32_wild), for the reference-written file and for its own streams; the reference's
+    decoder (zlib) gets the reference's transform bytes out of the GPU-written streams."""
+    from mtscomp_b200 import _native
+    m = json.loads((GOLDEN / 'manifest.json').read_text())['float_cases'][name]
+    ch = json.loads((GOLDEN / (name + '.ch')).read_text())
+    raw = np.fromfile(GOLDEN / (name + '.bin'), dtype=m['dtype']).reshape(m['shape'])
+    dec = np.fromfile(GOLDEN / (name + '.dec'), dtype=m['dtype']).reshape(m['shape'])
+    cbin = (GOLDEN / (name + '.cbin')).read_bytes()
+    fl = _native.flags_of(ch['do_time_diff'], ch['do_spatial_diff'], ch['chunk_order'])
+    b = ch['chunk_bounds']
+    out, st = codec.decompress(cbin, ch['chunk_offsets'], b, ch['n_channels'], raw.dtype, fl)
+    assert not st.any() and out.tobytes() == dec.tobytes()
+    comp, offs = codec.compress(raw, b, fl)
+    for i in range(len(b) - 1):
+        assert zlib.decompress(bytes(comp[offs[i]:offs[i + 1]])) == ora.transform_chunk(
+            raw[b[i]:b[i + 1]], ch['do_time_diff'], ch['do_spatial_diff'], ch['chunk_order'])
+    out2, st2 = codec.decompress(comp, offs, b, ch['n_channels'], raw.dtype, fl)
+    assert not st2.any() and out2.tobytes() == dec.tobytes()
+    assert codec.delta_transform(raw[b[0]:b[1]], fl).tobytes() == (GOLDEN / (name + '.tr')).read_bytes()

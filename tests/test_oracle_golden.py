@@ -111,3 +111,30 @@ def test_c_oracle_rejects_bad_adler_and_accepts_trailing_bytes():
     for level, strategy in [(0, 0), (1, 0), (9, 0), (6, zlib.Z_FIXED)]:
         c = zlib.compressobj(level, zlib.DEFLATED, 15, 8, strategy)
         assert cport.inflate(c.compress(data) + c.flush(), len(data)) == data
+
+
+# ---- floating point: the parity target is what the reference READER returns (<name>.dec), which differs from the
+#      input in the last bits when the differences are not exact (float32_wild)
+FLOAT_CASES = sorted(MANIFEST.get('float_cases', {}))
+
+
+def load_float_case(name):
+    m = MANIFEST['float_cases'][name]
+    ch = json.loads((GOLDEN / (name + '.ch')).read_text())
+    raw = np.fromfile(GOLDEN / (name + '.bin'), dtype=m['dtype']).reshape(m['shape'])
+    dec = np.fromfile(GOLDEN / (name + '.dec'), dtype=m['dtype']).reshape(m['shape'])
+    return m, ch, raw, dec, (GOLDEN / (name + '.cbin')).read_bytes()
+
+
+@pytest.mark.parametrize('name', FLOAT_CASES)
+def test_oracle_float_matches_reference_reader(name):
+    m, ch, raw, dec, cbin = load_float_case(name)
+    assert hashlib.sha1(cbin).hexdigest() == m['sha1_cbin'] == ch['sha1_compressed']
+    out = ora.decode_array(cbin, ch['chunk_bounds'], ch['chunk_offsets'], ch['n_channels'], ch['dtype'], **flags_of(ch))
+    assert out.dtype == dec.dtype and out.tobytes() == dec.tobytes()
+    assert np.array_equal(out, raw) == m['exact_round_trip']
+    b = ch['chunk_bounds']
+    assert ora.transform_chunk(raw[b[0]:b[1]], **flags_of(ch)) == (GOLDEN / (name + '.tr')).read_bytes()
+    if zlib.ZLIB_RUNTIME_VERSION == MANIFEST['zlib_version']:
+        got, bounds, offsets = ora.encode_array(raw, ch['sample_rate'], 1.0, n_threads=1, **flags_of(ch))
+        assert got == cbin and offsets == ch['chunk_offsets']

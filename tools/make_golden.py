@@ -79,5 +79,57 @@ def main():
     (OUT / 'manifest.json').write_text(json.dumps(manifest, indent=1, sort_keys=True))
 
 
+def float_cases():
+    rng = np.random.default_rng(21)
+    t = np.arange(1500) / 1000.
+    base = 300. * np.sin(2 * np.pi * 7 * t)[:, None] + rng.normal(0, 20., (1500, 9)).cumsum(axis=0) + 5000.
+    yield 'float32_time', base.astype(np.float32), 500., {}
+    yield 'float64_spatial_c', base.astype(np.float64), 500., dict(do_spatial_diff=True, chunk_order='C')
+    # wide dynamic range: the differences are NOT exact, the reference Reader returns values that differ from the
+    # input in the last bits (and its own post-compression check would refuse the file: it is switched off)
+    wild = rng.normal(0, 1, (1200, 7)) * 10. ** rng.integers(-3, 5, (1200, 7))
+    wild[10, 2] = -0.0
+    yield 'float32_wild', wild.astype(np.float32), 400., dict(do_spatial_diff=True, check_after_compress=False)
+
+
+def main_float():
+    """Floating point fixtures (added later; the integer fixtures above are left untouched).  The reference's round trip
+    is not exact for floats (cumsum of differences), so the parity target is what the reference READER returns: it is
+    stored as <name>.dec next to the reference-written .cbin / .ch."""
+    mpath = OUT / 'manifest.json'
+    manifest = json.loads(mpath.read_text())
+    manifest['float_cases'] = {}
+    for name, arr, sr, kw in float_cases():
+        arr = np.ascontiguousarray(arr)
+        raw = OUT / (name + '.bin')
+        arr.tofile(raw)
+        cbin, ch = OUT / (name + '.cbin'), OUT / (name + '.ch')
+        ref.compress(raw, cbin, ch, sample_rate=sr, n_channels=arr.shape[1], dtype=arr.dtype,
+                     n_threads=1, quiet=True, **dict(dict(check_after_compress=True), **kw))
+        r = ref.decompress(cbin, ch)
+        dec = np.ascontiguousarray(r[:])
+        assert dec.dtype == arr.dtype and np.allclose(dec, arr, rtol=1e-3, atol=1.)
+        (OUT / (name + '.dec')).write_bytes(dec.tobytes())
+        b = r.chunk_bounds
+        c0 = arr[b[0]:b[1]]
+        d = ref.diff_along_axis(c0, axis=0 if r.cmeta.do_time_diff else None)
+        d = ref.diff_along_axis(d, axis=1 if r.cmeta.do_spatial_diff else None)
+        tr = d.tobytes(order=r.cmeta.chunk_order)
+        (OUT / (name + '.tr')).write_bytes(tr)
+        manifest['float_cases'][name] = dict(
+            shape=list(arr.shape), dtype=str(arr.dtype), sample_rate=sr,
+            kwargs={k: v for k, v in kw.items() if k != 'check_after_compress'}, n_chunks=r.n_chunks,
+            cbin_bytes=cbin.stat().st_size, exact_round_trip=bool(np.array_equal(dec, arr)),
+            sha1_decoded=hashlib.sha1(dec.tobytes()).hexdigest(),
+            sha1_cbin=hashlib.sha1(cbin.read_bytes()).hexdigest(), sha1_tr0=hashlib.sha1(tr).hexdigest())
+        r.close()
+        print(name, arr.shape, kw, 'chunks', r.n_chunks, 'cbin', cbin.stat().st_size, 'exact', manifest['float_cases'][name]['exact_round_trip'])
+    mpath.write_text(json.dumps(manifest, indent=1, sort_keys=True))
+
+
 if __name__ == '__main__':
-    main()
+    import sys
+    if 'float' in sys.argv[1:]:
+        main_float()
+    else:
+        main()
