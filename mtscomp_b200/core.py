@@ -16,6 +16,7 @@ import bisect
 from functools import lru_cache
 import hashlib
 import json
+from concurrent.futures import ThreadPoolExecutor
 import os
 import os.path as op
 from pathlib import Path
@@ -210,18 +211,33 @@ class Writer:
         self.chunk_offsets = [0]
         logger.info("Starting compression on the GPU.")
         step = max(int(self.batch_size), GPU_BATCH_CHUNKS)
-        with open(out, 'wb') as fb:
+        # The two SHA-1 digests of the .ch format run at ~1 GB/s per core, far below the GPU: each digest gets its own
+        # worker (one thread each keeps the update order; hashlib releases the GIL) and works on batch k while the
+        # GPU compresses batch k+1.  The file is written by the worker that hashes the compressed bytes.
+        def _hash_raw(batch):
+            for idx in sorted(batch.keys()):
+                self.sha1_uncompressed.update(batch[idx][0])
+
+        def _write_and_hash(fb, batch):
+            for idx in sorted(batch.keys()):
+                cbytes = batch[idx][1]
+                fb.write(cbytes)
+                self.sha1_compressed.update(cbytes)
+
+        with open(out, 'wb') as fb, ThreadPoolExecutor(1) as raw_worker, ThreadPoolExecutor(1) as out_worker:
+            pending = []
             for first in tqdm(range(0, self.n_chunks, step), desc='Compressing', disable=self.quiet):
                 last = min(first + step, self.n_chunks)
                 batch = self.compress_batch(first, last)
                 assert set(batch.keys()) <= set(range(first, last))
                 for idx in sorted(batch.keys()):
-                    raw, cbytes = batch[idx]
-                    fb.write(cbytes)
-                    offset += len(cbytes)
+                    offset += len(batch[idx][1])
                     self.chunk_offsets.append(offset)
-                    self.sha1_uncompressed.update(raw)
-                    self.sha1_compressed.update(cbytes)
+                for f in pending:                      # at most one batch in flight per worker: bounded memory
+                    f.result()
+                pending = [raw_worker.submit(_hash_raw, batch), out_worker.submit(_write_and_hash, fb, batch)]
+            for f in pending:
+                f.result()
             csize = fb.tell()
         assert self.chunk_offsets[-1] == csize
         ratio = csize / self.file_size
@@ -330,18 +346,27 @@ class Reader:
         assert len(buf) == length
         return buf
 
-    def _decode(self, chunk_ids, spans):
-        """Decode several chunks in one GPU call.  spans: [(start, length)] in the .cbin."""
+    def _decode_block(self, chunk_ids, spans):
+        """Decode several chunks in one GPU call -> (array of all their rows, row offsets).
+        spans: [(start, length)] in the .cbin; consecutive chunks are fetched with a single read."""
         _require_integer_dtype(self.dtype)
-        bufs = [self._pread(length, start) for start, length in spans]
-        offs = np.concatenate(([0], np.cumsum([len(b) for b in bufs]))).astype(np.int64)
+        lengths = [length for _, length in spans]
+        offs = np.concatenate(([0], np.cumsum(lengths))).astype(np.int64)
+        if all(spans[k][0] + spans[k][1] == spans[k + 1][0] for k in range(len(spans) - 1)):
+            blob = self._pread(int(offs[-1]), spans[0][0])
+        else:
+            blob = b''.join(self._pread(length, start) for start, length in spans)
         sizes = [self.chunk_bounds[i + 1] - self.chunk_bounds[i] for i in chunk_ids]
         rows = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
-        out, status = _codec_for(self.config).decompress(
-            b''.join(bufs), offs, rows, self.n_channels, self.dtype, self._flags())
+        out, status = _codec_for(self.config).decompress(blob, offs, rows, self.n_channels, self.dtype, self._flags())
         bad = np.flatnonzero(status)
         if len(bad):
             raise IOError("Compressed chunk #%d is corrupted." % chunk_ids[int(bad[0])])
+        return out, rows
+
+    def _decode(self, chunk_ids, spans):
+        """Decode several chunks in one GPU call -> list of per-chunk arrays (views of one block)."""
+        out, rows = self._decode_block(chunk_ids, spans)
         return [out[rows[k]:rows[k + 1]] for k in range(len(chunk_ids))]
 
     def read_chunk(self, chunk_idx, chunk_start, chunk_length):
@@ -403,7 +428,17 @@ class Reader:
             if i1 <= i0:
                 return empty
             first, last = self._chunks_for_interval(i0, i1)
-            chunks = [self.read_chunk(idx, start, length) for idx, start, length in self.iter_chunks(first, last)]
+            if first == last:
+                chunks = [self.read_chunk(idx, start, length) for idx, start, length in self.iter_chunks(first, last)]
+            else:
+                # several chunks: batched GPU calls (the reference decodes them one by one, mtscomp.py:826-829); a
+                # single batch is returned as is, without the concatenation copy
+                todo = list(self.iter_chunks(first, last))
+                chunks = []
+                for g in range(0, len(todo), GPU_BATCH_CHUNKS):
+                    part = todo[g:g + GPU_BATCH_CHUNKS]
+                    chunks.append(self._decode_block([idx for idx, _, _ in part],
+                                                     [(start, length) for _, start, length in part])[0])
             if not chunks:  # pragma: no cover
                 return empty
             arr = chunks[0] if len(chunks) == 1 else np.concatenate(chunks)
