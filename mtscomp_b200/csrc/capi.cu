@@ -61,7 +61,8 @@ struct mtsb_ctx {
   long long seg_bytes = 262144, batch_bytes = 2ll << 30, host_batch_bytes = 512ll << 20, write_index = 1;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of the host-buffer paths
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_done = nullptr;
-  LzParams lz{4, 16, 32768, 32768, 32768, 0};   // greedy, every match >= 4 bytes accepted: tuned on synthetic AP/LFP
+  LzParams lz{2, 1, 32, 0};   // two 6-byte-hash candidates + the nearest 4-byte-hash one, greedy: tuned on synthetic AP/LFP
+  int lz_ctas_per_sm = 2;
   // device scratch
   Buf d_pstreams, d_surv, d_cand, d_pcount, d_tokens, d_cells, d_ptab, d_plist, d_pbad;   // block-parallel inflate scratch
   Buf d_raw, d_raw2, d_out2, d_comp2, d_T, d_tok, d_hist, d_codes, d_hdrs, d_tab, d_so, d_seg_adler, d_chunk_adler, d_chunk_off, d_out,
@@ -133,7 +134,14 @@ size_t tile_smem(int nc, int isz, int rows) {
   return (size_t)(P * isz * rows);
 }
 
-static_assert(LzSmem<1>::total <= 232448 && LzSmem<2>::total <= 232448, "lz77_kernel exceeds the 227 KB opt-in shared memory of sm_100");
+#ifndef MTS_LZ_NT
+#define MTS_LZ_NT 512
+#endif
+static const int LZ_NT = MTS_LZ_NT;   // threads (= units per step) of an lz77 CTA
+#ifndef MTS_NO_SMEM_ASSERT
+static_assert(2 * (LzSmem<1, LZ_NT>::total + 1024) <= 233472 && 2 * (LzSmem<2, LZ_NT>::total + 1024) <= 233472,
+              "two lz77 CTAs must fit the 228 KB shared memory of an sm_100 SM");
+#endif
 
 int set_attrs(mtsb_ctx* c) {
   if (c->attr_set) return 0;
@@ -145,8 +153,10 @@ int set_attrs(mtsb_ctx* c) {
   CK(cudaFuncSetAttribute(inv_apply_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
   CK(cudaFuncSetAttribute(inv_apply_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
   CK(cudaFuncSetAttribute(inv_apply_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
-  CK(cudaFuncSetAttribute(lz77_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LzSmem<1>::total));
-  CK(cudaFuncSetAttribute(lz77_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LzSmem<2>::total));
+  CK(cudaFuncSetAttribute(lz77_kernel<1, LZ_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LzSmem<1, LZ_NT>::total));
+  CK(cudaFuncSetAttribute(lz77_kernel<2, LZ_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LzSmem<2, LZ_NT>::total));
+  CK(cudaFuncSetAttribute(lz77_kernel<1, LZ_NT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(lz77_kernel<2, LZ_NT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(par_block_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   c->attr_set = true;
   return 0;
@@ -379,12 +389,11 @@ int mtsb_set_param(mtsb_ctx* c, const char* name, long long v) {
   else if (s == "par_cells") c->par_cells = v < 0 ? -1 : (v ? 1 : 0);
   else if (s == "par_lz_wide") c->par_lz_wide = v < 0 ? -1 : (v ? 1 : 0);
   else if (s == "par_batch_bytes") { if (v < (1 << 20)) return fail(c, MTSB_E_ARG, "par_batch_bytes too small"); c->par_batch_bytes = v; }
-  else if (s == "max_chain") c->lz.max_chain = (int)std::max<long long>(1, v);
+  else if (s == "max_chain") c->lz.max_chain = (int)std::min<long long>(2, std::max<long long>(1, v));
+  else if (s == "s_ways") c->lz.s_ways = (int)std::min<long long>(2, std::max<long long>(1, v));
   else if (s == "nice_len") c->lz.nice_len = (int)std::min<long long>(258, std::max<long long>(4, v));
-  else if (s == "far4") c->lz.far4 = (int)v;
-  else if (s == "far5") c->lz.far5 = (int)v;
-  else if (s == "far6") c->lz.far6 = (int)v;
   else if (s == "lazy") c->lz.lazy = (int)v;
+  else if (s == "lz_ctas_per_sm") c->lz_ctas_per_sm = (int)std::min<long long>(8, std::max<long long>(1, v));
   else return fail(c, MTSB_E_ARG, "unknown parameter %s", name);
   return 0;
 }
@@ -407,10 +416,9 @@ long long mtsb_get_param(mtsb_ctx* c, const char* name) {
   if (s == "par_resumed") return c->par_stats[3];
   if (s == "max_chain") return c->lz.max_chain;
   if (s == "nice_len") return c->lz.nice_len;
-  if (s == "far4") return c->lz.far4;
-  if (s == "far5") return c->lz.far5;
-  if (s == "far6") return c->lz.far6;
+  if (s == "s_ways") return c->lz.s_ways;
   if (s == "lazy") return c->lz.lazy;
+  if (s == "lz_ctas_per_sm") return c->lz_ctas_per_sm;
   if (s == "sm_count") return c->sm_count;
   return MTSB_E_ARG;
 }
@@ -688,13 +696,13 @@ int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_
     c->end();
     c->begin(3);
     {
-      int grid = std::min(n_segs, c->sm_count);
+      int grid = std::min(n_segs, c->sm_count * c->lz_ctas_per_sm);
       if (itemsize == 2) {
-        auto k = lz77_kernel<2>;
-        MTS_LAUNCH(k, dim3(grid), dim3(LZ_THREADS), LzSmem<2>::total, c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p, c->lz);
+        auto k = lz77_kernel<2, LZ_NT>;
+        MTS_LAUNCH(k, dim3(grid), dim3(LZ_NT), (LzSmem<2, LZ_NT>::total), c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p, c->lz);
       } else {
-        auto k = lz77_kernel<1>;
-        MTS_LAUNCH(k, dim3(grid), dim3(LZ_THREADS), LzSmem<1>::total, c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p, c->lz);
+        auto k = lz77_kernel<1, LZ_NT>;
+        MTS_LAUNCH(k, dim3(grid), dim3(LZ_NT), (LzSmem<1, LZ_NT>::total), c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p, c->lz);
       }
       CKL();
       c->launches++;

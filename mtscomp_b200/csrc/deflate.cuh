@@ -43,12 +43,10 @@ static const int HDR_WORDS = 192;            // dynamic header capacity (u32) pe
 static const int CODE_STRIDE = 320;          // u32 per segment: code | len<<16, same layout as the histogram
 
 struct LzParams {
-  int max_chain;    // candidates examined per position
-  int nice_len;     // stop searching at this length
-  int far4;         // a 4-byte match is accepted only if dist <= far4
-  int far5;         // a 5-byte match is accepted only if dist <= far5
-  int far6;         // a 6-byte match is accepted only if dist <= far6
-  int lazy;         // 1: defer to a longer match at the next position
+  int max_chain;    // entries of a 6-byte-hash bucket examined per position (1 or 2)
+  int s_ways;       // entries of a 4-byte-hash bucket examined per position (1 or 2)
+  int nice_len;     // a match this long ends the search of the remaining candidates
+  int lazy;         // 2: no match search at all (Huffman only; development aid)
 };
 
 __device__ __forceinline__ void len_symbol(unsigned len, unsigned& sym, unsigned& nb, unsigned& ev) {
@@ -69,139 +67,100 @@ __device__ __forceinline__ unsigned ll_extra_bits(unsigned sym) {   // sym in [0
 __device__ __forceinline__ unsigned d_extra_bits(unsigned sym) { return sym < 4 ? 0 : (sym >> 1) - 1; }
 
 // ------------------------------------------------------------------------------------------------ lz77_kernel
-// One persistent CTA (1024 threads, 1 per SM) per segment.  STRIDE = bytes between indexed positions: 2 for int16
-// streams (matches are searched at sample boundaries, the byte in between inherits the next sample's match extended
-// backwards), 1 generic.  Two match finders share the 64 KB data ring:
-//   L ("long")   hash of the 6 bytes at a unit -> headL (2^15 x u16) + prevL chain over the whole window; the searcher
-//                walks up to max_chain candidates and keeps the longest match (>= 6 bytes)
-//   S ("short")  hash of the 4 bytes at a unit -> headS (2^14 x u16); only the NEAREST previous unit with the same 4
-//                bytes is kept (prevS, two steps deep) and is used when L finds nothing
-// The segment is processed in steps of 960 units.  Warps 0 and 1 are the INSERTERS (S resp. L table; warp 0 also
-// prefetches input): they thread the units of step s+1 into the tables, in position order, while warps 2..31 SEARCH
-// step s, one unit per thread.  Then all warps parse the step (greedy, pointer doubling) and emit tokens + histogram.
-static const int LZ_THREADS = 1024;
-static const int LZ_UNITS = 960;              // units searched per step = 30 searcher warps x 32 lanes
-static const int LZ_RING = 65536;
-static const int LZ_MIRROR = 288;             // ring[65536 + i] mirrors ring[i]: reads of up to 258 + 16 + 4 bytes never wrap
-static const int LZ_HASHS_BITS = 14;
+// One CTA of NT threads per segment (persistent over segments), several CTAs per SM.  STRIDE = bytes between indexed
+// positions ("units"): 2 for int16 streams (matches start at sample boundaries and cover whole samples; the byte in
+// between inherits the next sample's match extended backwards), 1 generic.  The segment is processed in steps of NT
+// units, one unit per thread, every phase of a step data-parallel over the whole CTA (no serial inserter):
+//   (A) lookup   each unit hashes its first 6 bytes (table L) and 4 bytes (table S) and reads its two buckets.  A bucket
+//                is one u32 = the two newest units with that hash (newest << 16 | second newest) as of the END OF THE
+//                PREVIOUS STEP: units of one step do not see each other (matches nearer than the step are found
+//                through the next older entry or not at all; measured cost in DESIGN.md)
+//   (C) compare  up to 3 candidates (L newest, L second, S newest) against the unit's 16 bytes held in registers; the
+//                longest wins, ties go to the nearer one
+//   (B) insert   after a barrier every unit stores (itself << 16 | old newest) into its buckets; where several units of
+//                the step share a bucket the highest one must win whatever order the hardware applied the stores in,
+//                so after a second barrier each unit that finds a LOWER unit of its step in its bucket atomicMax'es its
+//                word in (rare, a few lanes per step).  The result depends on the data only (test_chop determinism).
+//   (D) parse    greedy over units, hierarchical: pointer doubling in registers inside each warp, one warp chains the
+//                warps' stretches by relaxation, then every warp emits its tokens (ballot prefix) and histogram counts
+// Input reaches the 32 KB ring (+ mirror of its first bytes, so that compares never wrap) by TMA bulk copies
+// (cp.async.bulk, one elected thread, completion on an mbarrier) issued two steps ahead.
+static const int LZ_RING = 32768;
+static const int LZ_MIRROR = 288;             // ring[RING + i] mirrors ring[i]: reads of up to 258 + 16 + 4 bytes never wrap
 static const unsigned LZ_BIAS = 32768;
 
-template <int STRIDE> struct LzSmem {
-  static const int SEG = LZ_UNITS * STRIDE;   // bytes per step
-  static const int PREV_N = 32768 / STRIDE;
-  static const int HL_BITS = STRIDE == 1 ? 14 : 15;   // headL size: what still fits next to the 64 KB prev ring of STRIDE 1
-  // the inserters run one step ahead, so chain entries older than PREV_N - 2 steps may already be recycled
-  static const int MAXD_UNITS = PREV_N - 2 * LZ_UNITS - 8;
+template <int STRIDE, int NT> struct LzSmem {
+  static const int SEG = NT * STRIDE;         // bytes per step
+#ifndef MTS_HL_BITS
+#define MTS_HL_BITS 13
+#define MTS_HS_BITS 12
+#endif
+  static const int HL_BITS = MTS_HL_BITS;     // buckets of table L (u32 each)
+  static const int HS_BITS = MTS_HS_BITS;     // buckets of table S
+  // the piece loaded during step s overwrites ring coordinates up to (s + 3) * SEG - RING; step s + 1 reads back to
+  // (s + 1) * SEG - MAXD
+  static const int MAXD = LZ_RING - 2 * SEG - 8;           // bytes
+  static const int MAXD_UNITS = MAXD / STRIDE;
+  static const int NSW = NT / 32;
   static const size_t ring_off = 0;
-  static const size_t headl_off = LZ_RING + LZ_MIRROR;
-  static const size_t heads_off = headl_off + (size_t)(1 << HL_BITS) * 2;
-  static const size_t prevl_off = heads_off + (size_t)(1 << LZ_HASHS_BITS) * 2;
-  static const size_t prevs_off = prevl_off + (size_t)PREV_N * 2;
-  static const size_t hbuf_off = prevs_off + (size_t)(2 * LZ_UNITS) * 2;   // [2 steps][S,L][LZ_UNITS] u16 hashes
-  static const size_t mlen_off = hbuf_off + (size_t)(4 * LZ_UNITS) * 2;
-  static const size_t mdist_off = mlen_off + (size_t)(LZ_UNITS + 8) * 2;       // per unit: match length | back-extension flag
-  static const size_t jump_off = (mdist_off + (size_t)(LZ_UNITS + 8) * 2 + 3) & ~(size_t)3;
-  static const size_t hist_off = (jump_off + (size_t)(LZ_UNITS + 8) * 4 + 15) & ~(size_t)15;
-  static const size_t misc_off = hist_off + (size_t)HIST_STRIDE * 4;
-  static const size_t total = misc_off + 512;
+  static const size_t headl_off = LZ_RING + LZ_MIRROR;     // multiple of 16
+  static const size_t heads_off = headl_off + ((size_t)4 << HL_BITS);
+  static const size_t mlen_off = heads_off + ((size_t)4 << HS_BITS);
+  static const size_t mdist_off = mlen_off + (size_t)(NT + 8) * 2;       // per unit: match length | back-extension flag
+  static const size_t xe_off = (mdist_off + (size_t)(NT + 8) * 2 + 3) & ~(size_t)3;
+  static const size_t hist_off = (xe_off + (size_t)(NT + 8) * 4 + 15) & ~(size_t)15;
+  static const size_t misc_off = hist_off + (size_t)HIST_STRIDE * 4;     // [0..31] element base of each stretch, [32..63] entries, [64],[65] carry, [66] step total
+  static const size_t mbar_off = misc_off + 72 * 4;                      // 8-byte aligned
+  static const size_t total = mbar_off + 16;
 };
 
-__device__ __forceinline__ unsigned ring_load4(const unsigned char* ring, unsigned r) {   // r: any ring coordinate
-  const unsigned m = r & 0xffffu;
-  const unsigned* w = (const unsigned*)(ring + (m & 0xfffcu));
+#ifdef MTSCOMP_EMU
+// host emulation: the "asynchronous" copy completes at once
+__device__ __forceinline__ void mbar_init(unsigned long long* bar) { *bar = 0; }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long*, unsigned) {}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long*) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void mbar_wait(unsigned long long*, unsigned) {}
+#else
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (16-byte aligned addresses, size a multiple of 16); completes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+#endif
+
+__device__ __forceinline__ unsigned ring_load4(const unsigned char* ring, unsigned m) {   // m < LZ_RING
+  const unsigned* w = (const unsigned*)(ring + (m & ~3u));
   return __funnelshift_r(w[0], w[1], m << 3);              // w[1] may lie in the mirror
 }
-// store 16 bytes at ring offset o (multiple of 16, < LZ_RING), keeping the mirror in step
-__device__ __forceinline__ void ring_store16(unsigned char* ring, unsigned o, uint4 v) {
-  *(uint4*)(ring + o) = v;
-  if (o < (unsigned)LZ_MIRROR) *(uint4*)(ring + LZ_RING + o) = v;
-}
-__device__ __forceinline__ unsigned lz_hash4(unsigned w) { return (w * 0x9E3779B1u) >> (32 - LZ_HASHS_BITS); }
-template <int BITS> __device__ __forceinline__ unsigned lz_hash6(unsigned w0, unsigned w1) {
-  return ((w0 * 0x9E3779B1u) ^ ((w1 & 0xffffu) * 0x85EBCA6Bu)) >> (32 - BITS);
+__device__ __forceinline__ unsigned lz_hash4(unsigned w, int bits) { return (w * 0x9E3779B1u) >> (32 - bits); }
+__device__ __forceinline__ unsigned lz_hash6(unsigned w0, unsigned w1, int bits) {
+  return ((w0 * 0x9E3779B1u) ^ ((w1 & 0xffffu) * 0x85EBCA6Bu)) >> (32 - bits);
 }
 
-// Hashes of the unit at position p for both tables, 0xffff where the key would run past the end of the segment.
-// (Computed by the searcher threads two steps ahead of their use, so the serial inserters only touch the tables.)
-template <int STRIDE>
-__device__ __forceinline__ void lz_unit_hashes(const unsigned char* ring, unsigned p, unsigned n, unsigned off0,
-                                               unsigned short& hs, unsigned short& hl) {
-  hs = 0xffff; hl = 0xffff;
-  if (p + 4 <= n) {
-    const unsigned w0 = ring_load4(ring, p + off0);
-    hs = (unsigned short)lz_hash4(w0);
-    if (p + 6 <= n) hl = (unsigned short)lz_hash6<LzSmem<STRIDE>::HL_BITS>(w0, ring_load4(ring, p + off0 + 4));
-  }
-}
-
-// Work a searcher thread does for LATER steps: hashes of its unit two steps ahead (position p2) into hbuf, and the
-// store of its prefetched 16 input bytes into the ring.
-template <int STRIDE>
-__device__ __forceinline__ void lz_ahead(unsigned char* ring, unsigned short* hbuf, unsigned step, unsigned tid, unsigned p2,
-                                         unsigned n, unsigned off0, bool pf, unsigned pf_rc, uint4 pf_v) {
-  unsigned short hs, hl;
-  lz_unit_hashes<STRIDE>(ring, p2, n, off0, hs, hl);
-  unsigned short* hb = hbuf + (step & 1) * 2 * LZ_UNITS;
-  hb[tid] = hs;
-  hb[LZ_UNITS + tid] = hl;
-  if (pf) ring_store16(ring, pf_rc & 0xffffu, pf_v);
-}
-
-// Thread `units` consecutive units starting at unit u0 into one hash table (one warp), batches of 64 units (two
-// consecutive units per lane) in position order.  Every unit links to the table head as it was BEFORE its batch — or to
-// its lane's first unit when both have the same hash; units of different lanes of one batch never link to each other
-// (such matches are < 64 units away and later batches find them anyway).  Then the batch's LAST unit of each hash
-// becomes the new head: colliding lanes re-store until the highest one has won, so the result does not depend on how
-// the hardware orders same-address stores.  No __match_any_sync: it costs > 1000 cycles per call when many warps use it.
-// LONG: links go to the prev ring (index u & pmask); otherwise to a two-step array.
-template <int STRIDE, bool LONG>
-__device__ __forceinline__ void lz_insert_step(const unsigned short* hbuf, unsigned short* head, unsigned short* prev,
-                                               unsigned u0, unsigned units, unsigned lane) {
-  const unsigned PM = LzSmem<STRIDE>::PREV_N - 1;
-  const unsigned pbase = LONG ? 0 : (u0 % (2 * LZ_UNITS));     // S links live in a two-step array
-  // software pipeline: the next batch's hashes are fetched before, and its head lookups right after, this batch's stores
-  // have settled
-  unsigned hA = (2 * lane < units) ? hbuf[2 * lane] : 0xffffu;
-  unsigned hB = (2 * lane + 1 < units) ? hbuf[2 * lane + 1] : 0xffffu;
-  unsigned short oldA = hA != 0xffffu ? head[hA] : (unsigned short)0;
-  unsigned short oldB = hB != 0xffffu ? head[hB] : (unsigned short)0;
-  for (unsigned b = 0; b < units; b += 64) {
-    const unsigned iA = b + 2 * lane, iB = iA + 1;
-    const unsigned short ubA = (unsigned short)(u0 + iA + LZ_BIAS), ubB = (unsigned short)(ubA + 1);
-    const bool vA = hA != 0xffffu, vB = hB != 0xffffu;
-    const bool same = vA && hA == hB;                          // the lane's second unit follows its first
-    const unsigned nA = (iA + 64 < units) ? hbuf[iA + 64] : 0xffffu;
-    const unsigned nB = (iB + 64 < units) ? hbuf[iB + 64] : 0xffffu;
-    __syncwarp();
-    if (vA && !same) head[hA] = ubA;
-    if (vB) head[hB] = ubB;
-    __syncwarp();
-    // a later unit of this batch must end up as the head: re-store while an earlier one is visible
-    bool wA = vA && !same && (unsigned short)(ubA - head[hA] - 1) < 63;
-    bool wB = vB && (unsigned short)(ubB - head[hB] - 1) < 63;
-    while (__any_sync(0xffffffffu, wA || wB)) {
-      if (wA) head[hA] = ubA;
-      if (wB) head[hB] = ubB;
-      __syncwarp();
-      wA = vA && !same && (unsigned short)(ubA - head[hA] - 1) < 63;
-      wB = vB && (unsigned short)(ubB - head[hB] - 1) < 63;
-    }
-    // only now (the heads are settled, whichever store the hardware let win first) look up the next batch's links;
-    // they are not needed before the end of the next iteration, so this load is off the critical path
-    const unsigned short noA = nA != 0xffffu ? head[nA] : (unsigned short)0;
-    const unsigned short noB = nB != 0xffffu ? head[nB] : (unsigned short)0;
-    if (iA < units) prev[LONG ? ((u0 + iA) & PM) : (pbase + iA)] = vA ? oldA : ubA;   // invalid: distance 0 = none
-    if (iB < units) prev[LONG ? ((u0 + iB) & PM) : (pbase + iB)] = vB ? (same ? ubA : oldB) : ubB;
-    hA = nA; hB = nB; oldA = noA; oldB = noB;
-  }
-  __syncwarp();
-}
-
-// Length of the match between the position whose first 16 bytes are w0..w3 (ring offset pm < LZ_RING) and the candidate
-// at ring offset qm < LZ_RING, up to lim.  All reads run forward without wrapping (mirror).
+// Length of the match between the position whose first 16 bytes are w0..w3 (ring offset pm) and the candidate at ring
+// offset qm (both < LZ_RING), up to lim.  All reads run forward without wrapping (mirror).
 __device__ __forceinline__ unsigned lz_match_len(const unsigned char* ring, unsigned pm, unsigned qm, unsigned lim,
                                                  unsigned w0, unsigned w1, unsigned w2, unsigned w3) {
-  const unsigned* qw = (const unsigned*)(ring + (qm & 0xfffcu));
+  const unsigned* qw = (const unsigned*)(ring + (qm & ~3u));
   const unsigned sh = qm << 3;
   unsigned len = 0;
   unsigned t0 = qw[0], t1 = qw[1];
@@ -211,7 +170,7 @@ __device__ __forceinline__ unsigned lz_match_len(const unsigned char* ring, unsi
       if (!x) { len = 12; t0 = qw[4]; x = __funnelshift_r(t1, t0, sh) ^ w3;
         if (!x) { len = 16;
           while (len < lim) {
-            x = ring_load4(ring, pm + len) ^ ring_load4(ring, qm + len);
+            x = ring_load4(ring, (pm + len) & (LZ_RING - 1)) ^ ring_load4(ring, (qm + len) & (LZ_RING - 1));
             if (x) break;
             len += 4;
           } } } } }
@@ -220,154 +179,110 @@ __device__ __forceinline__ unsigned lz_match_len(const unsigned char* ring, unsi
 }
 
 #if defined(MTS_LZ_PROFILE) && !defined(MTSCOMP_EMU)
-// development instrumentation: cycles per phase, summed over steps and CTAs
-// [0] steps [1] A/B phase (thread 0) [2] thread 0's own search [3] S inserter [4] L inserter [5] parse+emit phase
+// development instrumentation: cycles per phase (thread 0 of CTA 0), summed over steps
+// [0] steps [1] lookup+compare [2] insert+parse stage 1 [3] settle+chain [4] emit [5] whole step
 __device__ unsigned long long g_lz_prof[16];
 #define LZ_PROF_T(var) long long var = clock64()
-#define LZ_PROF_ADD(i, v) do { if (blockIdx.x == 0) atomicAdd(&g_lz_prof[i], (unsigned long long)(v)); } while (0)
+#define LZ_PROF_ADD(i, v) do { if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_lz_prof[i], (unsigned long long)(v)); } while (0)
 #else
 #define LZ_PROF_T(var)
 #define LZ_PROF_ADD(i, v)
 #endif
 
-template <int STRIDE>
-__global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char* __restrict__ tbuf,
-                                                             const DeflateSeg* __restrict__ segs, int n_segs,
-                                                             unsigned short* __restrict__ tokens,
-                                                             unsigned* __restrict__ hist, DeflateSegOut* __restrict__ so,
-                                                             LzParams prm) {
-  typedef LzSmem<STRIDE> L;
-  const unsigned SEG = L::SEG;
-  const unsigned NSW = 30;                          // searcher / parser warps; warps 30 and 31 are the inserters
+template <int STRIDE, int NT>
+__global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1) lz77_kernel(const unsigned char* __restrict__ tbuf,
+                                                                     const DeflateSeg* __restrict__ segs, int n_segs,
+                                                                     unsigned short* __restrict__ tokens,
+                                                                     unsigned* __restrict__ hist,
+                                                                     DeflateSegOut* __restrict__ so, LzParams prm) {
+  typedef LzSmem<STRIDE, NT> L;
+  const unsigned SEG = L::SEG, NSW = L::NSW, RM = LZ_RING - 1;
   MTS_DYN_SMEM(sm);
   unsigned char* ring = sm + L::ring_off;
-  unsigned short* headL = (unsigned short*)(sm + L::headl_off);
-  unsigned short* headS = (unsigned short*)(sm + L::heads_off);
-  unsigned short* prevL = (unsigned short*)(sm + L::prevl_off);
-  unsigned short* prevS = (unsigned short*)(sm + L::prevs_off);
-  unsigned short* hbuf = (unsigned short*)(sm + L::hbuf_off);   // hbuf[(step & 1) * 2 * LZ_UNITS + (LONG ? LZ_UNITS : 0) + k]
+  unsigned* headL = (unsigned*)(sm + L::headl_off);
+  unsigned* headS = (unsigned*)(sm + L::heads_off);
   unsigned short* mlen = (unsigned short*)(sm + L::mlen_off);
   unsigned short* mdist = (unsigned short*)(sm + L::mdist_off);
-  unsigned* xe = (unsigned*)(sm + L::jump_off);                   // per unit: exit of its stretch | token elements << 16
+  unsigned* xe = (unsigned*)(sm + L::xe_off);                    // per unit: exit of its stretch | token elements << 16
   unsigned* shist = (unsigned*)(sm + L::hist_off);
-  unsigned* misc = (unsigned*)(sm + L::misc_off);   // [0..29] element base of each stretch, [33],[34] carry, [35] step total
-  unsigned* ent = misc + 36;                         // [0..29] parse entry position of each stretch
+  unsigned* misc = (unsigned*)(sm + L::misc_off);
+  unsigned* ent = misc + 32;                                      // parse entry position of each stretch
+  unsigned long long* mbar = (unsigned long long*)(sm + L::mbar_off);
   const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const unsigned PM = L::PREV_N - 1;
+  unsigned phase = 0;                                             // mbarrier phases completed so far (uniform)
+
+  if (tid == 0) mbar_init(mbar);
+  __syncthreads();
 
   for (int sidx = blockIdx.x; sidx < n_segs; sidx += gridDim.x) {
     const DeflateSeg sg = segs[sidx];
     const unsigned n = (unsigned)sg.in_len;
     const unsigned char* in = tbuf + sg.in_off;
     const unsigned off0 = (unsigned)((uintptr_t)in & 15);
-    const uint4* in16 = (const uint4*)(in - off0);
+    const unsigned char* in16 = in - off0;                   // 16-byte aligned; ring coordinate c holds in16[c]
     unsigned short* tok = tokens + sg.tok_off;
-    const unsigned n_ring = n + off0;                    // ring coordinates [off0, n_ring) are real input
-    unsigned run_tok = 0;                                // token elements emitted so far (uniform across threads)
+    const unsigned n_ring = n + off0;                        // ring coordinates [off0, n_ring) are real input
+    unsigned run_tok = 0;                                    // token elements emitted so far (uniform across threads)
 
-    // reset tables (headL and headS are contiguous); initial load: ring coordinates [0, 3*SEG + 32) (the hashes of
-    // step 2 read up to 3*SEG + 8 + 15)
-    for (unsigned i = tid; i < ((1u << L::HL_BITS) + (1u << LZ_HASHS_BITS)) / 2; i += LZ_THREADS) ((unsigned*)headL)[i] = 0;
-    for (unsigned i = tid; i < HIST_STRIDE; i += LZ_THREADS) shist[i] = 0;
-    if (tid == 0) { misc[33] = 0; misc[34] = 0; }
-    for (unsigned v = tid; v * 16 < 3 * SEG + 32; v += LZ_THREADS)
-      if (v * 16 < n_ring) ring_store16(ring, v * 16, in16[v]);
-    __syncthreads();
-    // hashes of the units of steps 0 and 1 (later steps: computed two steps ahead by the searchers)
-    for (unsigned k = tid; k < 2 * LZ_UNITS; k += LZ_THREADS) {
-      unsigned short hs, hl;
-      lz_unit_hashes<STRIDE>(ring, k * STRIDE, n, off0, hs, hl);
-      const unsigned st = k / LZ_UNITS, kk = k % LZ_UNITS;
-      hbuf[st * 2 * LZ_UNITS + kk] = hs;
-      hbuf[st * 2 * LZ_UNITS + LZ_UNITS + kk] = hl;
+    // reset tables (headL and headS are contiguous); pieces 0 and 1 of the input
+    for (unsigned i = tid; i < (1u << L::HL_BITS) + (1u << L::HS_BITS); i += NT) headL[i] = 0;
+    for (unsigned i = tid; i < HIST_STRIDE; i += NT) shist[i] = 0;
+    if (tid == 0) {
+      misc[64] = 0; misc[65] = 0;
+      const unsigned len = min(2 * SEG, (n_ring + 15) & ~15u), mir = min((unsigned)LZ_MIRROR, len);
+      mbar_expect_tx(mbar, len + mir);
+      bulk_g2s(ring, in16, len, mbar);
+      bulk_g2s(ring + LZ_RING, in16, mir, mbar);
     }
     __syncthreads();
-    {
-      const unsigned units0 = min((unsigned)LZ_UNITS, (n + STRIDE - 1) / STRIDE);
-      if (wid == 30) lz_insert_step<STRIDE, false>(hbuf, headS, prevS, 0, units0, lane);
-      if (wid == 31) lz_insert_step<STRIDE, true>(hbuf + LZ_UNITS, headL, prevL, 0, units0, lane);
-    }
-    __syncthreads();
+    mbar_wait(mbar, phase & 1); phase++;
 
     const unsigned n_steps = (n + SEG - 1) / SEG;
     for (unsigned step = 0; step < n_steps; step++) {
       const unsigned s0 = step * SEG;                    // first position of this step
       const unsigned slen = min(SEG, n - s0);
-
       LZ_PROF_T(t_step);
-      // prefetch of ring coordinates [(step+3)*SEG + 32, (step+4)*SEG + 32) by the first SEG/16 searcher threads: loaded
-      // before the search, stored (with the hashes of the units two steps ahead) where the thread has nothing else to do
-      const unsigned pf_rc = (step + 3) * SEG + 32 + tid * 16;
-      const bool pf = wid < NSW && tid * 16 < SEG && pf_rc < n_ring;
-      uint4 pf_v = make_uint4(0, 0, 0, 0);
-      if (wid >= NSW) {
-        // ---- (A) inserters (the two highest warp ids: the issue arbiter favours them over the searchers): prefetch
-        //          ring coordinates [(step+3)*SEG, (step+4)*SEG) and thread step+1's units into the tables
-        const unsigned s1 = s0 + SEG;
-        if (s1 < n) {
-          const unsigned units1 = (min(SEG, n - s1) + STRIDE - 1) / STRIDE;
-          const unsigned short* hb = hbuf + ((step + 1) & 1) * 2 * LZ_UNITS;
-          if (wid == 30) lz_insert_step<STRIDE, false>(hb, headS, prevS, s1 / STRIDE, units1, lane);
-          else lz_insert_step<STRIDE, true>(hb + LZ_UNITS, headL, prevL, s1 / STRIDE, units1, lane);
+      // piece step + 1 (issued during the previous step) must have landed: this step reads up to s0 + SEG + 294
+      if (step > 0 && (step + 1) * SEG < n_ring) { mbar_wait(mbar, phase & 1); phase++; }
+
+      // ---- (A) lookup + (C) compare
+      const unsigned li = tid * STRIDE;                   // local position in the step
+      const unsigned p = s0 + li;
+      const unsigned u = p / STRIDE;
+      const unsigned ub = (u + LZ_BIAS) & 0xffffu;
+      unsigned best = 0, bdist = 0, hs = 0, hl = 0, cwl = 0, cws = 0;
+      bool vS = false, vL = false;
+      if (li < slen && p + 4 <= n) {
+        const unsigned lim = min(258u, n - p);
+        const unsigned pr = (p + off0) & RM;              // ring offset of this unit
+        unsigned w0, w1, w2, w3;                          // the first 16 bytes at p stay in registers
+        {
+          const unsigned* pw = (const unsigned*)(ring + (pr & ~3u));
+          const unsigned sh = pr << 3;
+          const unsigned t0 = pw[0], t1 = pw[1], t2 = pw[2], t3 = pw[3], t4 = pw[4];
+          w0 = __funnelshift_r(t0, t1, sh); w1 = __funnelshift_r(t1, t2, sh);
+          w2 = __funnelshift_r(t2, t3, sh); w3 = __funnelshift_r(t3, t4, sh);
         }
-        if (lane == 0) { LZ_PROF_T(t_i); LZ_PROF_ADD(wid == 30 ? 3 : 4, t_i - t_step); }
-      } else {
-        // ---- (B) searchers: one unit per thread.  The first SEG/16 of them also prefetch ring coordinates
-        //      [(step+3)*SEG + 32, (step+4)*SEG + 32): load now, store after the search has hidden the latency.
-        const unsigned li = tid * STRIDE;                 // local position in the step
-        const unsigned p = s0 + li;
-        unsigned best = 0, bdist = 0;
-        if (pf) pf_v = in16[pf_rc >> 4];
-        if (li < slen && p + 4 <= n && prm.lazy != 2) {
-          const unsigned u = p / STRIDE;
-          const unsigned lim = min(258u, n - p);
-          const unsigned pr = (p + off0) & 0xffffu;       // ring offset of this unit
-          unsigned w0, w1, w2, w3;                        // the first 16 bytes at p stay in registers
-          {
-            const unsigned* pw = (const unsigned*)(ring + (pr & 0xfffcu));
-            const unsigned sh = pr << 3;
-            const unsigned t0 = pw[0], t1 = pw[1], t2 = pw[2], t3 = pw[3], t4 = pw[4];
-            w0 = __funnelshift_r(t0, t1, sh); w1 = __funnelshift_r(t1, t2, sh);
-            w2 = __funnelshift_r(t2, t3, sh); w3 = __funnelshift_r(t3, t4, sh);
-          }
-          const unsigned ub = (u + LZ_BIAS) & 0xffffu;
-          if (lim >= 6) {
-            // L chain: candidates share (the hash of) 6 bytes; keep the longest
-            best = 5;
-            unsigned wq = __funnelshift_r(w0, w1, 16);     // bytes [best-3, best] of p
-            unsigned short cand = prevL[u & PM];
-            unsigned lastd = 0;
-            for (int depth = prm.max_chain; depth > 0; depth--) {
-              const unsigned du = (ub - cand) & 0xffffu;
-              if (du - 1 >= (unsigned)L::MAXD_UNITS || du <= lastd || du > u) break;
-              lastd = du;
+        hs = lz_hash4(w0, L::HS_BITS); vS = true; cws = headS[hs];
+        if (p + 6 <= n) { hl = lz_hash6(w0, w1, L::HL_BITS); vL = true; cwl = headL[hl]; }
+        if (prm.lazy != 2) {
+          // candidates in order of preference: L newest, L second newest, S newest (S second newest if s_ways == 2)
+          unsigned cand[4] = {cwl >> 16, cwl & 0xffffu, cws >> 16, cws & 0xffffu};
+          const bool use[4] = {vL, vL && prm.max_chain >= 2, true, prm.s_ways >= 2};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const unsigned du = (ub - cand[k]) & 0xffffu;
+            if (use[k] && du - 1 < (unsigned)L::MAXD_UNITS && du <= u && best < (unsigned)prm.nice_len) {
               const unsigned dist = du * STRIDE;
-              const unsigned qr = (pr - dist) & 0xffffu;
-              cand = prevL[(cand - LZ_BIAS) & PM];
-              if (bdist && ring_load4(ring, qr + best - 3) != wq) continue;   // cannot beat the match in hand
-              const unsigned len = lz_match_len(ring, pr, qr, lim, w0, w1, w2, w3);
-              if (len > best) {
-                best = len; bdist = dist;
-                if (len >= (unsigned)prm.nice_len || len >= lim) break;
-                wq = ring_load4(ring, pr + best - 3);
+              if (dist != bdist) {
+                const unsigned len = lz_match_len(ring, pr, (pr - dist) & RM, lim, w0, w1, w2, w3);
+                if (len >= 4 && (len > best || (len == best && dist < bdist))) { best = len; bdist = dist; }
               }
             }
           }
-          if (!bdist) {
-            // S: the nearest previous unit with the same 4 bytes
-            best = 0;
-            const unsigned du = (ub - prevS[u % (2 * LZ_UNITS)]) & 0xffffu;
-            if (du - 1 < (unsigned)L::MAXD_UNITS && du <= u) {
-              const unsigned dist = du * STRIDE;
-              const unsigned len = lz_match_len(ring, pr, (pr - dist) & 0xffffu, lim, w0, w1, w2, w3);
-              if (len >= 4) { best = len; bdist = dist; }
-            }
-          }
         }
-        // hashes of this thread's unit two steps ahead (consumed by the inserters during the next step) and the prefetch
-        // store: warp 0 does them here, the other warps while warp 0 chains the stretches (they would only wait there)
-        if (wid == 0) lz_ahead<STRIDE>(ring, hbuf, step, tid, s0 + li + 2 * SEG, n, off0, pf, pf_rc, pf_v);
-        if (tid == 0) { LZ_PROF_T(t_s); LZ_PROF_ADD(2, t_s - t_step); }
+      }
+      {
         unsigned bext = 0;
         if (STRIDE == 2 && bdist) {
           // The parse works on units, so matches cover whole units (length truncated to even: a sample whose low byte
@@ -376,40 +291,48 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
           best &= ~1u;
           const unsigned q = p - 1;
           bext = (lane > 0 && best < 258 && q >= bdist &&
-                  ring[(q + off0) & 0xffffu] == ring[(q + off0 - bdist) & 0xffffu]) ? 0x8000u : 0u;
+                  ring[(q + off0) & RM] == ring[(q + off0 - bdist) & RM]) ? 0x8000u : 0u;
         }
         mlen[tid] = (unsigned short)(bdist ? (best | bext) : 0);
         mdist[tid] = (unsigned short)bdist;
       }
-      // The 30 searcher warps now parse and emit the step among themselves (hardware barrier 1, 960 threads); the two
-      // inserter warps keep threading step+1 into the tables and only rejoin at the end of the step.
-      if (wid < NSW) {
-      named_barrier(1, NSW * 32);
-      LZ_PROF_T(t_p0);
-      if (tid == 0) { LZ_PROF_ADD(0, 1); LZ_PROF_ADD(1, t_p0 - t_step); }
-      // ---- (C) greedy parse over units, hierarchical; thread = unit, warp = stretch of 32 units.
+      LZ_PROF_T(t_a);
+      __syncthreads();                                    // #1: every lookup and compare of the step is done
+
+      // ---- (B) insert, first round: any unit of the step becomes the bucket's newest; the next piece of input
+      const unsigned myL = (ub << 16) | (cwl >> 16), myS = (ub << 16) | (cws >> 16);
+      if (vL) headL[hl] = myL;
+      if (vS) headS[hs] = myS;
+      if (tid == 0 && (step + 2) * SEG < n_ring) {
+        const unsigned c0 = (step + 2) * SEG, o = c0 & RM;
+        const unsigned len = min(SEG, (n_ring - c0 + 15) & ~15u), mir = o == 0 ? min((unsigned)LZ_MIRROR, len) : 0u;
+        mbar_expect_tx(mbar, len + mir);
+        bulk_g2s(ring + o, in16 + c0, len, mbar);
+        if (mir) bulk_g2s(ring + LZ_RING, in16 + c0, mir, mbar);
+      }
+      // ---- (D) greedy parse over units, hierarchical; thread = unit, warp = stretch of 32 units.
       //      Stage 1 (registers, shuffles): pointer doubling gives every unit the exit of the token chain that starts
       //      there (where it leaves the stretch), the token elements it emits on the way and the mask of units it visits.
-      //      Stage 2: one thread chains the 30 stretches from the carried start (entry + element base per stretch).
+      //      Stage 2: one warp chains the stretches from the carried start (entry + element base per stretch).
       //      Stage 3: the warp picks the mask of its entry unit and emits those tokens (ballot prefix -> offsets).
       const unsigned nu = (slen + STRIDE - 1) / STRIDE;   // units in this step
-      const unsigned start = misc[33 + (step & 1)];       // local start unit carried from the previous step
-      if (start < nu) {
-        const unsigned sb = wid * 32, se = min(sb + 32, nu);
-        const unsigned sel = se > sb ? se - sb : 0;        // valid lanes of this stretch
-        const unsigned m = tid < nu ? mlen[tid] : 0;
-        const unsigned mnext = tid + 1 < nu ? mlen[tid + 1] : 0;
-        const unsigned l = m & 0x7fffu;
-        unsigned el = 0;                                   // token elements of the token starting at this unit
-        if (tid < nu) {
-          if (l) el = 2;
-          else {
-            el = (STRIDE == 2 && s0 + tid * STRIDE + 1 < n) ? 2 : 1;       // a literal per byte ...
-            if (mnext & 0x8000u) el--;                                     // ... unless the next match takes the last one
-          }
+      const unsigned start = misc[64 + (step & 1)];       // local start unit carried from the previous step
+      const unsigned sb = wid * 32, se = min(sb + 32, nu);
+      const unsigned sel = se > sb ? se - sb : 0;          // valid lanes of this stretch
+      const unsigned m = tid < nu ? mlen[tid] : 0;
+      const unsigned mnext = tid + 1 < nu ? mlen[tid + 1] : 0;
+      const unsigned l = m & 0x7fffu;
+      unsigned el = 0;                                     // token elements of the token starting at this unit
+      if (tid < nu) {
+        if (l) el = 2;
+        else {
+          el = (STRIDE == 2 && s0 + tid * STRIDE + 1 < n) ? 2 : 1;       // a literal per byte ...
+          if (mnext & 0x8000u) el--;                                     // ... unless the next match takes the last one
         }
+      }
+      unsigned M = 1u << lane;
+      {
         unsigned v = (lane + (l ? l / STRIDE : 1u)) | (el << 16);   // next unit (stretch-local) | elements
-        unsigned M = 1u << lane;
         for (unsigned r = 0; r < 5; r++) {
           const unsigned j = v & 0xffffu;
           const unsigned tv = __shfl_sync(0xffffffffu, v, j & 31);
@@ -417,15 +340,19 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
           if (j < sel) { v = (tv & 0xffffu) | ((v & 0xffff0000u) + (tv & 0xffff0000u)); M |= tM; }
         }
         xe[tid] = (sb + (v & 0xffffu)) | (v & 0xffff0000u);
-        named_barrier(1, NSW * 32);
-        if (tid == 0) { LZ_PROF_T(t_b); LZ_PROF_ADD(6, t_b - t_p0); }
-        if (wid != 0) lz_ahead<STRIDE>(ring, hbuf, step, tid, s0 + tid * STRIDE + 2 * SEG, n, off0, pf, pf_rc, pf_v);
-        if (wid == 0) {
-          // Stage 2, by relaxation in one warp (lane = stretch): every lane guesses that its stretch is entered at
-          // its first unit, looks up where that chain leaves, and hands the exit to the next lane as ITS entry; repeat
-          // until no entry changes.  Lane w is certainly right after w rounds, but greedy parses that start a few
-          // units apart merge almost at once, so the exits barely depend on the entries: 2-4 rounds instead of a
-          // 30-step serial walk.
+      }
+      LZ_PROF_T(t_b);
+      __syncthreads();                                    // #2: first-round stores and xe[] are visible
+
+      // ---- (B) insert, second round: a lower unit of this step in my bucket gives way
+      if (vL) { const unsigned d = (ub - (headL[hl] >> 16)) & 0xffffu; if (d - 1 < NT - 1) atomicMax(&headL[hl], myL); }
+      if (vS) { const unsigned d = (ub - (headS[hs] >> 16)) & 0xffffu; if (d - 1 < NT - 1) atomicMax(&headS[hs], myS); }
+      if (wid == 0) {
+        // Stage 2, by relaxation (lane = stretch): every lane guesses that its stretch is entered at its first unit,
+        // looks up where that chain leaves, and hands the exit to the next lane as ITS entry; repeat until no entry
+        // changes.  Lane w is certainly right after w rounds, but greedy parses that start a few units apart merge
+        // almost at once, so the exits barely depend on the entries: 2-4 rounds instead of a serial walk.
+        if (start < nu) {
           const unsigned my_se = min((lane + 1) * 32, nu);
           unsigned e = lane == 0 ? start : lane * 32, t = 0;
           for (;;) {
@@ -440,59 +367,62 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_kernel(const unsigned char
           for (int d = 1; d < 32; d <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, acc, d); if ((int)lane >= d) acc += v; }
           if (lane < NSW) { ent[lane] = e; misc[lane] = acc - (t >> 16); }
           if (lane == NSW - 1) {
-            misc[35] = acc;                                         // elements emitted by this step
-            misc[33 + ((step + 1) & 1)] = (t & 0xffffu) - nu;       // >= 0: where the last token of this step ends
+            misc[66] = acc;                                         // elements emitted by this step
+            misc[64 + ((step + 1) & 1)] = (t & 0xffffu) - nu;       // >= 0: where the last token of this step ends
           }
+        } else if (lane == 0) {
+          misc[66] = 0;
+          misc[64 + ((step + 1) & 1)] = start - nu;
         }
-        named_barrier(1, NSW * 32);
-        if (tid == 0) { LZ_PROF_T(t_b); LZ_PROF_ADD(7, t_b - t_p0); }
-        const unsigned entry = ent[wid];
-        if (entry < se) {                                   // warp-uniform
-          const unsigned reach = __shfl_sync(0xffffffffu, M, entry - sb);
-          const bool isr = (reach >> lane) & 1u;
-          const unsigned mine = isr ? el : 0u;
-          const unsigned lt = (1u << lane) - 1;
-          const unsigned excl = __popc(__ballot_sync(0xffffffffu, mine & 1) & lt) +
-                                2 * __popc(__ballot_sync(0xffffffffu, mine & 2) & lt);
-          const unsigned pos = run_tok + misc[wid] + excl;
-          if (isr) {
-            if (l) {
-              const unsigned d = mdist[tid];
-              // back-extended over the last byte of the previous unit when that one is a (literal) token start
-              const unsigned le = l + ((m >> 15) & (reach >> ((lane + 31) & 31)) & 1u);
-              tok[pos] = (unsigned short)(0x8000u | le);
-              tok[pos + 1] = (unsigned short)(d - 1);
-              unsigned sym, nb, ev;
-              len_symbol(le, sym, nb, ev);
-              atomicAdd(&shist[sym], 1u);
-              dist_symbol(d, sym, nb, ev);
-              atomicAdd(&shist[288 + sym], 1u);
-            } else {
-              const unsigned r0 = s0 + tid * STRIDE + off0;
-              const unsigned b0 = ring[r0 & 0xffffu];
-              tok[pos] = (unsigned short)b0;
-              atomicAdd(&shist[b0], 1u);
-              if (mine == 2) {
-                const unsigned b1 = ring[(r0 + 1) & 0xffffu];
-                tok[pos + 1] = (unsigned short)b1;
-                atomicAdd(&shist[b1], 1u);
-              }
+      }
+      LZ_PROF_T(t_c);
+      __syncthreads();                                    // #3: buckets settled; entries and bases of the stretches known
+
+      // ---- stage 3: emit
+      const unsigned entry = ent[wid];
+      if (start < nu && entry < se) {                     // warp-uniform
+        const unsigned reach = __shfl_sync(0xffffffffu, M, entry - sb);
+        const bool isr = (reach >> lane) & 1u;
+        const unsigned mine = isr ? el : 0u;
+        const unsigned lt = (1u << lane) - 1;
+        const unsigned excl = __popc(__ballot_sync(0xffffffffu, mine & 1) & lt) +
+                              2 * __popc(__ballot_sync(0xffffffffu, mine & 2) & lt);
+        const unsigned pos = run_tok + misc[wid] + excl;
+        if (isr) {
+          if (l) {
+            const unsigned d = mdist[tid];
+            // back-extended over the last byte of the previous unit when that one is a (literal) token start
+            const unsigned le = l + ((m >> 15) & (reach >> ((lane + 31) & 31)) & 1u);
+            tok[pos] = (unsigned short)(0x8000u | le);
+            tok[pos + 1] = (unsigned short)(d - 1);
+            unsigned sym, nb, ev;
+            len_symbol(le, sym, nb, ev);
+            atomicAdd(&shist[sym], 1u);
+            dist_symbol(d, sym, nb, ev);
+            atomicAdd(&shist[288 + sym], 1u);
+          } else {
+            const unsigned r0 = s0 + tid * STRIDE + off0;
+            const unsigned b0 = ring[r0 & RM];
+            tok[pos] = (unsigned short)b0;
+            atomicAdd(&shist[b0], 1u);
+            if (mine == 2) {
+              const unsigned b1 = ring[(r0 + 1) & RM];
+              tok[pos + 1] = (unsigned short)b1;
+              atomicAdd(&shist[b1], 1u);
             }
           }
         }
-        if (tid == 0) { LZ_PROF_T(t_b); LZ_PROF_ADD(8, t_b - t_p0); }
-        run_tok += misc[35];
-      } else {
-        if (tid == 0) misc[33 + ((step + 1) & 1)] = start - nu;
-        if (wid != 0) lz_ahead<STRIDE>(ring, hbuf, step, tid, s0 + tid * STRIDE + 2 * SEG, n, off0, pf, pf_rc, pf_v);
       }
-      }   // wid < NSW
-      __syncthreads();
-      if (tid == 0) { LZ_PROF_T(t_end); LZ_PROF_ADD(5, t_end - t_step); }
+      run_tok += misc[66];
+      LZ_PROF_T(t_d);
+      LZ_PROF_ADD(0, 1); LZ_PROF_ADD(1, t_a - t_step); LZ_PROF_ADD(2, t_b - t_a); LZ_PROF_ADD(3, t_c - t_b);
+      LZ_PROF_ADD(4, t_d - t_c); LZ_PROF_ADD(5, t_d - t_step);
     }
 
-    // ---- segment done: publish histogram + token count
-    for (unsigned i = tid; i < HIST_STRIDE; i += LZ_THREADS) hist[(size_t)sidx * HIST_STRIDE + i] = shist[i];
+    // ---- segment done: publish histogram + token count (the barrier also keeps the next segment's table reset and
+    //      input pieces away from threads still emitting)
+    __syncthreads();
+    for (unsigned i = tid; i < HIST_STRIDE; i += NT) hist[(size_t)sidx * HIST_STRIDE + i] = shist[i];
     if (tid == 0) so[sidx].n_tok = run_tok;
     __syncthreads();
   }
