@@ -340,7 +340,7 @@ def run_b200(args):
                    l2='inputs larger than L2 (%.0f MB distinct raw per GPU, %.1f GB per step)' % (
                        n_distinct * CHUNK_BYTES / 1e6, raw_bytes / 1e9),
                    sharding='contiguous chunk ranges per GPU, no collective on the data path',
-                   seg_bytes=cd.get_param('seg_bytes'), max_chain=cd.get_param('max_chain'),
+                   seg_bytes=cd.get_param('seg_bytes'), 
                    e2e_chunks_per_gpu=n_e2e),
         'e2e': {'value': gbps['ce'], 'unit': UNIT, 'h2d_bytes_per_step': e2e_bytes, 'd2h_bytes_per_step': rec[-1]['csize_e']},
         'decompress': {

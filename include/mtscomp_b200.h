@@ -54,8 +54,8 @@ const char* mtsb_last_error(mtsb_ctx* ctx);
 /* Block until everything queued by this context has finished. */
 int mtsb_sync(mtsb_ctx* ctx);
 
-/* Tunables (by name): "seg_bytes" target encoder segment size (default 262144), "max_chain", "nice_len", "far4",
- * "far5", "far6", "lazy" (match finder), "write_index" (append the segment index after each chunk's zlib stream, 1),
+/* Tunables (by name): "seg_bytes" target encoder segment size (default 262144), "lz_ctas_per_sm" (resident
+ * match-finder CTAs per SM, 2), "write_index" (append the segment index after each chunk's zlib stream, 1),
  * "batch_bytes" (raw bytes processed per internal sub-batch), "host_batch_bytes" (the same when a host buffer is
  * involved: copies of one sub-batch overlap the kernels of the next), "par_batch_bytes" (host-buffer sub-batch of
  * index-less chunks on the decode side), "par_inflate" (1: block-parallel decoder; 0: serial warp per stream),

@@ -61,7 +61,6 @@ struct mtsb_ctx {
   long long seg_bytes = 262144, batch_bytes = 2ll << 30, host_batch_bytes = 512ll << 20, write_index = 1;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of the host-buffer paths
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_done = nullptr;
-  LzParams lz{2, 1, 32, 0};   // two 6-byte-hash candidates + the nearest 4-byte-hash one, greedy: tuned on synthetic AP/LFP
   int lz_ctas_per_sm = 2;
   // device scratch
   Buf d_pstreams, d_surv, d_cand, d_pcount, d_tokens, d_cells, d_ptab, d_plist, d_pbad;   // block-parallel inflate scratch
@@ -290,7 +289,8 @@ long long seg_size_for(const mtsb_ctx* c, long long ns, int itemsize, int flags)
   long long run = ns * itemsize;
   long long s = target;
   if (!(flags & FLAG_ORDER_C) && run > 0 && run <= target) s = std::max<long long>(1, target / run) * run;
-  return std::min<long long>(s, 1ll << 30);
+  s = std::min<long long>(s, 1ll << 30);
+  return std::max<long long>(itemsize, s / itemsize * itemsize);   // whole elements: int16 units stay 2-byte aligned
 }
 long long stored_bound(long long m) { return m + 5 * ((m + 65534) / 65535); }
 long long chunk_bound(const mtsb_ctx* c, long long raw, long long seg) {
@@ -389,10 +389,6 @@ int mtsb_set_param(mtsb_ctx* c, const char* name, long long v) {
   else if (s == "par_cells") c->par_cells = v < 0 ? -1 : (v ? 1 : 0);
   else if (s == "par_lz_wide") c->par_lz_wide = v < 0 ? -1 : (v ? 1 : 0);
   else if (s == "par_batch_bytes") { if (v < (1 << 20)) return fail(c, MTSB_E_ARG, "par_batch_bytes too small"); c->par_batch_bytes = v; }
-  else if (s == "max_chain") c->lz.max_chain = (int)std::min<long long>(2, std::max<long long>(1, v));
-  else if (s == "s_ways") c->lz.s_ways = (int)std::min<long long>(2, std::max<long long>(1, v));
-  else if (s == "nice_len") c->lz.nice_len = (int)std::min<long long>(258, std::max<long long>(4, v));
-  else if (s == "lazy") c->lz.lazy = (int)v;
   else if (s == "lz_ctas_per_sm") c->lz_ctas_per_sm = (int)std::min<long long>(8, std::max<long long>(1, v));
   else return fail(c, MTSB_E_ARG, "unknown parameter %s", name);
   return 0;
@@ -414,10 +410,6 @@ long long mtsb_get_param(mtsb_ctx* c, const char* name) {
   if (s == "par_candidates") return c->par_stats[1];
   if (s == "par_chained") return c->par_stats[2];
   if (s == "par_resumed") return c->par_stats[3];
-  if (s == "max_chain") return c->lz.max_chain;
-  if (s == "nice_len") return c->lz.nice_len;
-  if (s == "s_ways") return c->lz.s_ways;
-  if (s == "lazy") return c->lz.lazy;
   if (s == "lz_ctas_per_sm") return c->lz_ctas_per_sm;
   if (s == "sm_count") return c->sm_count;
   return MTSB_E_ARG;
@@ -699,10 +691,10 @@ int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_
       int grid = std::min(n_segs, c->sm_count * c->lz_ctas_per_sm);
       if (itemsize == 2) {
         auto k = lz77_kernel<2, LZ_NT>;
-        MTS_LAUNCH(k, dim3(grid), dim3(LZ_NT), (LzSmem<2, LZ_NT>::total), c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p, c->lz);
+        MTS_LAUNCH(k, dim3(grid), dim3(LZ_NT), (LzSmem<2, LZ_NT>::total), c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p);
       } else {
         auto k = lz77_kernel<1, LZ_NT>;
-        MTS_LAUNCH(k, dim3(grid), dim3(LZ_NT), (LzSmem<1, LZ_NT>::total), c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p, c->lz);
+        MTS_LAUNCH(k, dim3(grid), dim3(LZ_NT), (LzSmem<1, LZ_NT>::total), c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p);
       }
       CKL();
       c->launches++;

@@ -42,12 +42,6 @@ static const int HIST_STRIDE = 320;          // u32 per segment: [0,286) lit/len
 static const int HDR_WORDS = 192;            // dynamic header capacity (u32) per segment
 static const int CODE_STRIDE = 320;          // u32 per segment: code | len<<16, same layout as the histogram
 
-struct LzParams {
-  int max_chain;    // entries of a 6-byte-hash bucket examined per position (1 or 2)
-  int s_ways;       // entries of a 4-byte-hash bucket examined per position (1 or 2)
-  int nice_len;     // a match this long ends the search of the remaining candidates
-  int lazy;         // 2: no match search at all (Huffman only; development aid)
-};
 
 __device__ __forceinline__ void len_symbol(unsigned len, unsigned& sym, unsigned& nb, unsigned& ev) {
   unsigned l = len - 3;
@@ -105,9 +99,7 @@ template <int STRIDE, int NT> struct LzSmem {
   static const size_t ring_off = 0;
   static const size_t headl_off = LZ_RING + LZ_MIRROR;     // multiple of 16
   static const size_t heads_off = headl_off + ((size_t)4 << HL_BITS);
-  static const size_t mlen_off = heads_off + ((size_t)4 << HS_BITS);
-  static const size_t mdist_off = mlen_off + (size_t)(NT + 8) * 2;       // per unit: match length | back-extension flag
-  static const size_t xe_off = (mdist_off + (size_t)(NT + 8) * 2 + 3) & ~(size_t)3;
+  static const size_t xe_off = heads_off + ((size_t)4 << HS_BITS);
   static const size_t hist_off = (xe_off + (size_t)(NT + 8) * 4 + 15) & ~(size_t)15;
   static const size_t misc_off = hist_off + (size_t)HIST_STRIDE * 4;     // [0..31] element base of each stretch, [32..63] entries, [64],[65] carry, [66] step total
   static const size_t mbar_off = misc_off + 72 * 4;                      // 8-byte aligned
@@ -156,28 +148,6 @@ __device__ __forceinline__ unsigned lz_hash6(unsigned w0, unsigned w1, int bits)
   return ((w0 * 0x9E3779B1u) ^ ((w1 & 0xffffu) * 0x85EBCA6Bu)) >> (32 - bits);
 }
 
-// Length of the match between the position whose first 16 bytes are w0..w3 (ring offset pm) and the candidate at ring
-// offset qm (both < LZ_RING), up to lim.  All reads run forward without wrapping (mirror).
-__device__ __forceinline__ unsigned lz_match_len(const unsigned char* ring, unsigned pm, unsigned qm, unsigned lim,
-                                                 unsigned w0, unsigned w1, unsigned w2, unsigned w3) {
-  const unsigned* qw = (const unsigned*)(ring + (qm & ~3u));
-  const unsigned sh = qm << 3;
-  unsigned len = 0;
-  unsigned t0 = qw[0], t1 = qw[1];
-  unsigned x = __funnelshift_r(t0, t1, sh) ^ w0;
-  if (!x) { len = 4; t0 = qw[2]; x = __funnelshift_r(t1, t0, sh) ^ w1;
-    if (!x) { len = 8; t1 = qw[3]; x = __funnelshift_r(t0, t1, sh) ^ w2;
-      if (!x) { len = 12; t0 = qw[4]; x = __funnelshift_r(t1, t0, sh) ^ w3;
-        if (!x) { len = 16;
-          while (len < lim) {
-            x = ring_load4(ring, (pm + len) & (LZ_RING - 1)) ^ ring_load4(ring, (qm + len) & (LZ_RING - 1));
-            if (x) break;
-            len += 4;
-          } } } } }
-  if (x) len += (unsigned)(__ffs((int)x) - 1) >> 3;
-  return min(len, lim);
-}
-
 #if defined(MTS_LZ_PROFILE) && !defined(MTSCOMP_EMU)
 // development instrumentation: cycles per phase (thread 0 of CTA 0), summed over steps
 // [0] steps [1] lookup+compare [2] insert+parse stage 1 [3] settle+chain [4] emit [5] whole step
@@ -194,21 +164,21 @@ __global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1) lz77_kernel(const unsig
                                                                      const DeflateSeg* __restrict__ segs, int n_segs,
                                                                      unsigned short* __restrict__ tokens,
                                                                      unsigned* __restrict__ hist,
-                                                                     DeflateSegOut* __restrict__ so, LzParams prm) {
+                                                                     DeflateSegOut* __restrict__ so) {
   typedef LzSmem<STRIDE, NT> L;
   const unsigned SEG = L::SEG, NSW = L::NSW, RM = LZ_RING - 1;
   MTS_DYN_SMEM(sm);
   unsigned char* ring = sm + L::ring_off;
+  const unsigned* ringw = (const unsigned*)ring;
   unsigned* headL = (unsigned*)(sm + L::headl_off);
   unsigned* headS = (unsigned*)(sm + L::heads_off);
-  unsigned short* mlen = (unsigned short*)(sm + L::mlen_off);
-  unsigned short* mdist = (unsigned short*)(sm + L::mdist_off);
   unsigned* xe = (unsigned*)(sm + L::xe_off);                    // per unit: exit of its stretch | token elements << 16
   unsigned* shist = (unsigned*)(sm + L::hist_off);
   unsigned* misc = (unsigned*)(sm + L::misc_off);
   unsigned* ent = misc + 32;                                      // parse entry position of each stretch
   unsigned long long* mbar = (unsigned long long*)(sm + L::mbar_off);
   const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned lt = (1u << lane) - 1;
   unsigned phase = 0;                                             // mbarrier phases completed so far (uniform)
 
   if (tid == 0) mbar_init(mbar);
@@ -248,53 +218,62 @@ __global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1) lz77_kernel(const unsig
       // ---- (A) lookup + (C) compare
       const unsigned li = tid * STRIDE;                   // local position in the step
       const unsigned p = s0 + li;
-      const unsigned u = p / STRIDE;
-      const unsigned ub = (u + LZ_BIAS) & 0xffffu;
-      unsigned best = 0, bdist = 0, hs = 0, hl = 0, cwl = 0, cws = 0;
+      const unsigned ub = (p / STRIDE + LZ_BIAS) & 0xffffu;
+      unsigned mlen = 0, mdist = 0, hs = 0, hl = 0, cwl = 0, cws = 0, w0 = 0;
       bool vS = false, vL = false;
-      if (li < slen && p + 4 <= n) {
+      if (li < slen) {
         const unsigned lim = min(258u, n - p);
         const unsigned pr = (p + off0) & RM;              // ring offset of this unit
-        unsigned w0, w1, w2, w3;                          // the first 16 bytes at p stay in registers
+        unsigned w1;
         {
-          const unsigned* pw = (const unsigned*)(ring + (pr & ~3u));
+          const unsigned* pw = ringw + (pr >> 2);
           const unsigned sh = pr << 3;
-          const unsigned t0 = pw[0], t1 = pw[1], t2 = pw[2], t3 = pw[3], t4 = pw[4];
+          const unsigned t0 = pw[0], t1 = pw[1], t2 = pw[2];
           w0 = __funnelshift_r(t0, t1, sh); w1 = __funnelshift_r(t1, t2, sh);
-          w2 = __funnelshift_r(t2, t3, sh); w3 = __funnelshift_r(t3, t4, sh);
         }
-        hs = lz_hash4(w0, L::HS_BITS); vS = true; cws = headS[hs];
-        if (p + 6 <= n) { hl = lz_hash6(w0, w1, L::HL_BITS); vL = true; cwl = headL[hl]; }
-        if (prm.lazy != 2) {
-          // candidates in order of preference: L newest, L second newest, S newest (S second newest if s_ways == 2)
-          unsigned cand[4] = {cwl >> 16, cwl & 0xffffu, cws >> 16, cws & 0xffffu};
-          const bool use[4] = {vL, vL && prm.max_chain >= 2, true, prm.s_ways >= 2};
+        if (lim >= 4) {
+          hs = lz_hash4(w0, L::HS_BITS); vS = true; cws = headS[hs];
+          if (lim >= 6) { hl = lz_hash6(w0, w1, L::HL_BITS); vL = true; cwl = headL[hl]; }
+          // Candidates: S newest, L newest, L second newest.  Fast path over the first 8 bytes: key = matched length
+          // class << 16 | ~distance, so that the largest key is the longest match and, among equals, the nearest.
+          unsigned bestk = 0;
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const unsigned du = (ub - cand[k]) & 0xffffu;
-            if (use[k] && du - 1 < (unsigned)L::MAXD_UNITS && du <= u && best < (unsigned)prm.nice_len) {
-              const unsigned dist = du * STRIDE;
-              if (dist != bdist) {
-                const unsigned len = lz_match_len(ring, pr, (pr - dist) & RM, lim, w0, w1, w2, w3);
-                if (len >= 4 && (len > best || (len == best && dist < bdist))) { best = len; bdist = dist; }
-              }
+          for (int k = 0; k < 3; k++) {
+            const unsigned cand = k == 0 ? cws >> 16 : k == 1 ? cwl >> 16 : cwl & 0xffffu;
+            const unsigned du = (ub - cand) & 0xffffu;
+            if (du - 1 < (unsigned)L::MAXD_UNITS && (k == 0 || vL)) {
+              const unsigned q = (pr - du * STRIDE) & RM;
+              const unsigned* qw = ringw + (q >> 2);
+              const unsigned sh = q << 3;
+              const unsigned t0 = qw[0], t1 = qw[1], t2 = qw[2];
+              const unsigned x0 = __funnelshift_r(t0, t1, sh) ^ w0, x1 = __funnelshift_r(t1, t2, sh) ^ w1;
+              // length class: 4..7 matched bytes (STRIDE 2: 4 or 6), 8 = the first 8 bytes match (extended below)
+              unsigned lc = 0;
+              if (x0 == 0) lc = x1 == 0 ? 8u : STRIDE == 2 ? ((x1 & 0xffffu) ? 4u : 6u) : 4u + (((unsigned)__ffs((int)x1) - 1) >> 3);
+              const unsigned key = (lc << 16) | (0xffffu ^ du);
+              if (lc) bestk = max(bestk, key);
             }
           }
+          if (bestk) {
+            mlen = bestk >> 16;
+            const unsigned du = 0xffffu ^ (bestk & 0xffffu);
+            mdist = du * STRIDE;
+            if (mlen == 8) {
+              // rare: longer than 8 bytes, compare on (no wrap: the mirror covers pr + 258 + 8)
+              const unsigned q = (pr - mdist) & RM;
+              unsigned x = 0;
+              while (mlen < lim) {
+                x = ring_load4(ring, pr + mlen) ^ ring_load4(ring, q + mlen);
+                if (x) break;
+                mlen += 4;
+              }
+              if (x) mlen += (unsigned)(__ffs((int)x) - 1) >> 3;
+            }
+            mlen = min(mlen, lim);
+            if (STRIDE == 2) mlen &= ~1u;                 // matches cover whole units
+            if (mlen < 4) { mlen = 0; mdist = 0; }
+          }
         }
-      }
-      {
-        unsigned bext = 0;
-        if (STRIDE == 2 && bdist) {
-          // The parse works on units, so matches cover whole units (length truncated to even: a sample whose low byte
-          // matched nearly always matches in its high byte too).  Bit 15 = the match also covers the byte BEFORE this
-          // unit (the previous sample's high byte); used when the previous unit of the same stretch turns out to be a literal.
-          best &= ~1u;
-          const unsigned q = p - 1;
-          bext = (lane > 0 && best < 258 && q >= bdist &&
-                  ring[(q + off0) & RM] == ring[(q + off0 - bdist) & RM]) ? 0x8000u : 0u;
-        }
-        mlen[tid] = (unsigned short)(bdist ? (best | bext) : 0);
-        mdist[tid] = (unsigned short)bdist;
       }
       LZ_PROF_T(t_a);
       __syncthreads();                                    // #1: every lookup and compare of the step is done
@@ -312,34 +291,26 @@ __global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1) lz77_kernel(const unsig
       }
       // ---- (D) greedy parse over units, hierarchical; thread = unit, warp = stretch of 32 units.
       //      Stage 1 (registers, shuffles): pointer doubling gives every unit the exit of the token chain that starts
-      //      there (where it leaves the stretch), the token elements it emits on the way and the mask of units it visits.
+      //      there (where it leaves the stretch) and the mask of the units it visits (= its tokens).
       //      Stage 2: one warp chains the stretches from the carried start (entry + element base per stretch).
-      //      Stage 3: the warp picks the mask of its entry unit and emits those tokens (ballot prefix -> offsets).
+      //      Stage 3: the warp picks the mask of its entry unit and emits those tokens (mask prefix -> offsets).
+      //      A token is 2 elements (match: length, distance; STRIDE 2 literal: the unit's two bytes) or 1 (STRIDE 1 literal).
       const unsigned nu = (slen + STRIDE - 1) / STRIDE;   // units in this step
       const unsigned start = misc[64 + (step & 1)];       // local start unit carried from the previous step
       const unsigned sb = wid * 32, se = min(sb + 32, nu);
       const unsigned sel = se > sb ? se - sb : 0;          // valid lanes of this stretch
-      const unsigned m = tid < nu ? mlen[tid] : 0;
-      const unsigned mnext = tid + 1 < nu ? mlen[tid + 1] : 0;
-      const unsigned l = m & 0x7fffu;
-      unsigned el = 0;                                     // token elements of the token starting at this unit
-      if (tid < nu) {
-        if (l) el = 2;
-        else {
-          el = (STRIDE == 2 && s0 + tid * STRIDE + 1 < n) ? 2 : 1;       // a literal per byte ...
-          if (mnext & 0x8000u) el--;                                     // ... unless the next match takes the last one
-        }
-      }
+      const unsigned mm = __ballot_sync(0xffffffffu, mlen != 0);
       unsigned M = 1u << lane;
       {
-        unsigned v = (lane + (l ? l / STRIDE : 1u)) | (el << 16);   // next unit (stretch-local) | elements
+        unsigned v = lane + (mlen ? mlen / STRIDE : 1u);   // next unit (stretch-local)
+#pragma unroll
         for (unsigned r = 0; r < 5; r++) {
-          const unsigned j = v & 0xffffu;
-          const unsigned tv = __shfl_sync(0xffffffffu, v, j & 31);
-          const unsigned tM = __shfl_sync(0xffffffffu, M, j & 31);
-          if (j < sel) { v = (tv & 0xffffu) | ((v & 0xffff0000u) + (tv & 0xffff0000u)); M |= tM; }
+          const unsigned tv = __shfl_sync(0xffffffffu, v, v & 31);
+          const unsigned tM = __shfl_sync(0xffffffffu, M, v & 31);
+          if (v < sel) { v = tv; M |= tM; }
         }
-        xe[tid] = (sb + (v & 0xffffu)) | (v & 0xffff0000u);
+        const unsigned els = STRIDE == 2 ? 2 * __popc(M) : __popc(M) + __popc(M & mm);
+        xe[tid] = (sb + v) | (els << 16);
       }
       LZ_PROF_T(t_b);
       __syncthreads();                                    // #2: first-round stores and xe[] are visible
@@ -382,34 +353,25 @@ __global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1) lz77_kernel(const unsig
       const unsigned entry = ent[wid];
       if (start < nu && entry < se) {                     // warp-uniform
         const unsigned reach = __shfl_sync(0xffffffffu, M, entry - sb);
-        const bool isr = (reach >> lane) & 1u;
-        const unsigned mine = isr ? el : 0u;
-        const unsigned lt = (1u << lane) - 1;
-        const unsigned excl = __popc(__ballot_sync(0xffffffffu, mine & 1) & lt) +
-                              2 * __popc(__ballot_sync(0xffffffffu, mine & 2) & lt);
-        const unsigned pos = run_tok + misc[wid] + excl;
-        if (isr) {
-          if (l) {
-            const unsigned d = mdist[tid];
-            // back-extended over the last byte of the previous unit when that one is a (literal) token start
-            const unsigned le = l + ((m >> 15) & (reach >> ((lane + 31) & 31)) & 1u);
-            tok[pos] = (unsigned short)(0x8000u | le);
-            tok[pos + 1] = (unsigned short)(d - 1);
+        if ((reach >> lane) & 1u) {
+          const unsigned before = reach & lt;
+          const unsigned pos = run_tok + misc[wid] + (STRIDE == 2 ? 2 * __popc(before) : __popc(before) + __popc(before & mm));
+          if (mlen) {
+            if (STRIDE == 2) *(unsigned*)(tok + pos) = (0x8000u | mlen) | ((mdist - 1) << 16);
+            else { tok[pos] = (unsigned short)(0x8000u | mlen); tok[pos + 1] = (unsigned short)(mdist - 1); }
             unsigned sym, nb, ev;
-            len_symbol(le, sym, nb, ev);
+            len_symbol(mlen, sym, nb, ev);
             atomicAdd(&shist[sym], 1u);
-            dist_symbol(d, sym, nb, ev);
+            dist_symbol(mdist, sym, nb, ev);
             atomicAdd(&shist[288 + sym], 1u);
           } else {
-            const unsigned r0 = s0 + tid * STRIDE + off0;
-            const unsigned b0 = ring[r0 & RM];
-            tok[pos] = (unsigned short)b0;
+            const unsigned b0 = w0 & 0xffu;
             atomicAdd(&shist[b0], 1u);
-            if (mine == 2) {
-              const unsigned b1 = ring[(r0 + 1) & RM];
-              tok[pos + 1] = (unsigned short)b1;
+            if (STRIDE == 2) {
+              const unsigned b1 = (w0 >> 8) & 0xffu;
+              *(unsigned*)(tok + pos) = b0 | (b1 << 16);
               atomicAdd(&shist[b1], 1u);
-            }
+            } else tok[pos] = (unsigned short)b0;
           }
         }
       }
