@@ -679,28 +679,25 @@ int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_
     int r = launch_fwd(c, itemsize, raw, c->d_T.p, d_cd, nb, max_ns, nc, flags);
     if (r) return r;
     c->end();
-    c->begin(2);
-    MTS_LAUNCH(adler_partial_kernel, dim3(n_segs), dim3(256), 0, c->stream, (const uint8_t*)c->d_T.p, d_as, (uint32_t*)c->d_seg_adler.p);
-    CKL();
-    MTS_LAUNCH(adler_combine_kernel, dim3((nb + 127) / 128), dim3(128), 0, c->stream, d_as, (const uint32_t*)c->d_seg_adler.p, d_first, nb, (uint32_t*)c->d_chunk_adler.p);
-    CKL();
-    c->launches += 2;
-    c->end();
     c->begin(3);
     {
       int grid = std::min(n_segs, c->sm_count * c->lz_ctas_per_sm);
       if (itemsize == 2) {
         auto k = lz77_kernel<2, LZ_NT>;
-        MTS_LAUNCH(k, dim3(grid), dim3(LZ_NT), (LzSmem<2, LZ_NT>::total), c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p);
+        MTS_LAUNCH(k, dim3(grid), dim3(LZ_NT + 32), (LzSmem<2, LZ_NT>::total), c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p, (unsigned*)c->d_seg_adler.p);
       } else {
         auto k = lz77_kernel<1, LZ_NT>;
-        MTS_LAUNCH(k, dim3(grid), dim3(LZ_NT), (LzSmem<1, LZ_NT>::total), c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p);
+        MTS_LAUNCH(k, dim3(grid), dim3(LZ_NT + 32), (LzSmem<1, LZ_NT>::total), c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p, (unsigned*)c->d_seg_adler.p);
       }
       CKL();
       c->launches++;
     }
     c->end();
     c->begin(4);
+    // the match finder left each segment's adler32 (it streams every byte of T anyway): fold them per chunk
+    MTS_LAUNCH(adler_combine_kernel, dim3((nb + 127) / 128), dim3(128), 0, c->stream, d_as, (const uint32_t*)c->d_seg_adler.p, d_first, nb, (uint32_t*)c->d_chunk_adler.p);
+    CKL();
+    c->launches++;
     MTS_LAUNCH(huff_kernel, dim3(n_segs), dim3(32), 0, c->stream, d_seg, n_segs, (unsigned*)c->d_hist.p, (unsigned*)c->d_codes.p, (unsigned*)c->d_hdrs.p, (DeflateSegOut*)c->d_so.p);
     CKL();
     MTS_LAUNCH(scan_kernel, dim3(1), dim3(1024), 0, c->stream, d_seg, n_segs, (DeflateSegOut*)c->d_so.p, (long long*)c->d_chunk_off.p, nb, d_cd, (int)c->write_index);

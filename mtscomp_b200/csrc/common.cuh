@@ -35,6 +35,15 @@ __device__ __forceinline__ void named_barrier(int id, int count) {
 #endif
 }
 
+// Non-blocking arrival at the same kind of barrier (the other `count - 32k` threads use named_barrier on this id).
+__device__ __forceinline__ void named_barrier_arrive(int id, int count) {
+#ifdef MTSCOMP_EMU
+  __emu_named_barrier_arrive(id, count);
+#else
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ unsigned warp_id() { return threadIdx.x >> 5; }
 

@@ -100,33 +100,37 @@ template <int STRIDE, int NT> struct LzSmem {
   static const size_t headl_off = LZ_RING + LZ_MIRROR;     // multiple of 16
   static const size_t heads_off = headl_off + ((size_t)4 << HL_BITS);
   static const size_t xe_off = heads_off + ((size_t)4 << HS_BITS);
-  static const size_t hist_off = (xe_off + (size_t)(NT + 8) * 4 + 15) & ~(size_t)15;
-  static const size_t misc_off = hist_off + (size_t)HIST_STRIDE * 4;     // [0..31] element base of each stretch, [32..63] entries, [64],[65] carry, [66] step total
-  static const size_t mbar_off = misc_off + 72 * 4;                      // 8-byte aligned
+  static const size_t hist_off = (xe_off + (size_t)(2 * NT) * 4 + 15) & ~(size_t)15;
+  static const size_t misc_off = hist_off + (size_t)HIST_STRIDE * 4;     // two steps of [0..31] element base of each stretch, [32..63] entries, [64] step total
+  static const size_t mbar_off = misc_off + 2 * 72 * 4;                  // 8-byte aligned
   static const size_t total = mbar_off + 16;
 };
 
 #ifdef MTSCOMP_EMU
 // host emulation: the "asynchronous" copy completes at once
-__device__ __forceinline__ void mbar_init(unsigned long long* bar) { *bar = 0; }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long*, unsigned) {}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long*) { memcpy(dst, src, bytes); }
-__device__ __forceinline__ void mbar_wait(unsigned long long*, unsigned) {}
+typedef unsigned long long* mbar_t;
+__device__ __forceinline__ mbar_t mbar_addr(unsigned long long* bar) { return bar; }
+__device__ __forceinline__ void mbar_init(mbar_t bar) { *bar = 0; }
+__device__ __forceinline__ void mbar_expect_tx(mbar_t, unsigned) {}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, mbar_t) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void mbar_wait(mbar_t, unsigned) {}
 #else
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+typedef unsigned mbar_t;                         // shared-window address of an mbarrier
+__device__ __forceinline__ mbar_t mbar_addr(unsigned long long* bar) { return smem_u32(bar); }
+__device__ __forceinline__ void mbar_init(mbar_t bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(mbar_t bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // TMA bulk copy global -> shared (16-byte aligned addresses, size a multiple of 16); completes on the mbarrier
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, mbar_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+__device__ __forceinline__ void mbar_wait(mbar_t bar, unsigned parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -135,7 +139,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "@p bra LAB_DONE;\n"
       "bra LAB_WAIT;\n"
       "LAB_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 #endif
 
@@ -160,23 +164,24 @@ __device__ unsigned long long g_lz_prof[16];
 #endif
 
 template <int STRIDE, int NT>
-__global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1) lz77_kernel(const unsigned char* __restrict__ tbuf,
-                                                                     const DeflateSeg* __restrict__ segs, int n_segs,
-                                                                     unsigned short* __restrict__ tokens,
-                                                                     unsigned* __restrict__ hist,
-                                                                     DeflateSegOut* __restrict__ so) {
+__global__ void __launch_bounds__(NT + 32, NT <= 512 ? 2 : 1) lz77_kernel(const unsigned char* __restrict__ tbuf,
+                                                                          const DeflateSeg* __restrict__ segs, int n_segs,
+                                                                          unsigned short* __restrict__ tokens,
+                                                                          unsigned* __restrict__ hist,
+                                                                          DeflateSegOut* __restrict__ so,
+                                                                          unsigned* __restrict__ seg_adler) {
   typedef LzSmem<STRIDE, NT> L;
   const unsigned SEG = L::SEG, NSW = L::NSW, RM = LZ_RING - 1;
+  const int NALL = NT + 32;                                       // unit threads + the chain warp
   MTS_DYN_SMEM(sm);
   unsigned char* ring = sm + L::ring_off;
   const unsigned* ringw = (const unsigned*)ring;
   unsigned* headL = (unsigned*)(sm + L::headl_off);
   unsigned* headS = (unsigned*)(sm + L::heads_off);
-  unsigned* xe = (unsigned*)(sm + L::xe_off);                    // per unit: exit of its stretch | token elements << 16
+  unsigned* xe = (unsigned*)(sm + L::xe_off);                    // [step parity][unit]: exit of its stretch | token elements << 16
   unsigned* shist = (unsigned*)(sm + L::hist_off);
-  unsigned* misc = (unsigned*)(sm + L::misc_off);
-  unsigned* ent = misc + 32;                                      // parse entry position of each stretch
-  unsigned long long* mbar = (unsigned long long*)(sm + L::mbar_off);
+  unsigned* misc = (unsigned*)(sm + L::misc_off);                // [step parity][0..31 element base of each stretch, 32..63 entry, 64 step total]
+  const mbar_t mbar = mbar_addr((unsigned long long*)(sm + L::mbar_off));
   const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned lt = (1u << lane) - 1;
   unsigned phase = 0;                                             // mbarrier phases completed so far (uniform)
@@ -187,96 +192,170 @@ __global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1) lz77_kernel(const unsig
   for (int sidx = blockIdx.x; sidx < n_segs; sidx += gridDim.x) {
     const DeflateSeg sg = segs[sidx];
     const unsigned n = (unsigned)sg.in_len;
+    const unsigned n_steps = (n + SEG - 1) / SEG;
     const unsigned char* in = tbuf + sg.in_off;
     const unsigned off0 = (unsigned)((uintptr_t)in & 15);
     const unsigned char* in16 = in - off0;                   // 16-byte aligned; ring coordinate c holds in16[c]
     unsigned short* tok = tokens + sg.tok_off;
     const unsigned n_ring = n + off0;                        // ring coordinates [off0, n_ring) are real input
-    unsigned run_tok = 0;                                    // token elements emitted so far (uniform across threads)
+    unsigned run_tok = 0;                                    // token elements emitted so far (uniform across the unit threads)
+    unsigned ad_a = 0, ad_c = 0;                             // adler32 partial sums of this thread's units
+    unsigned long long ad_b = 0;
 
     // reset tables (headL and headS are contiguous); pieces 0 and 1 of the input
-    for (unsigned i = tid; i < (1u << L::HL_BITS) + (1u << L::HS_BITS); i += NT) headL[i] = 0;
-    for (unsigned i = tid; i < HIST_STRIDE; i += NT) shist[i] = 0;
+    for (unsigned i = tid; i < (1u << L::HL_BITS) + (1u << L::HS_BITS); i += NALL) headL[i] = 0;
+    for (unsigned i = tid; i < HIST_STRIDE; i += NALL) shist[i] = 0;
     if (tid == 0) {
-      misc[64] = 0; misc[65] = 0;
       const unsigned len = min(2 * SEG, (n_ring + 15) & ~15u), mir = min((unsigned)LZ_MIRROR, len);
       mbar_expect_tx(mbar, len + mir);
       bulk_g2s(ring, in16, len, mbar);
       bulk_g2s(ring + LZ_RING, in16, mir, mbar);
     }
     __syncthreads();
-    mbar_wait(mbar, phase & 1); phase++;
 
-    const unsigned n_steps = (n + SEG - 1) / SEG;
-    for (unsigned step = 0; step < n_steps; step++) {
-      const unsigned s0 = step * SEG;                    // first position of this step
-      const unsigned slen = min(SEG, n - s0);
-      LZ_PROF_T(t_step);
-      // piece step + 1 (issued during the previous step) must have landed: this step reads up to s0 + SEG + 294
-      if (step > 0 && (step + 1) * SEG < n_ring) { mbar_wait(mbar, phase & 1); phase++; }
-
-      // ---- (A) lookup + (C) compare
-      const unsigned li = tid * STRIDE;                   // local position in the step
-      const unsigned p = s0 + li;
-      const unsigned ub = (p / STRIDE + LZ_BIAS) & 0xffffu;
-      unsigned mlen = 0, mdist = 0, hs = 0, hl = 0, cwl = 0, cws = 0, w0 = 0;
-      bool vS = false, vL = false;
-      if (li < slen) {
-        const unsigned lim = min(258u, n - p);
-        const unsigned pr = (p + off0) & RM;              // ring offset of this unit
-        unsigned w1;
-        {
-          const unsigned* pw = ringw + (pr >> 2);
-          const unsigned sh = pr << 3;
-          const unsigned t0 = pw[0], t1 = pw[1], t2 = pw[2];
-          w0 = __funnelshift_r(t0, t1, sh); w1 = __funnelshift_r(t1, t2, sh);
+    if (wid == NSW) {
+      // ================= chain warp: stage 2 of the parse, one step behind the unit warps' stage 1 and one step ahead
+      // of their stage 3 (it works while they look up and compare the next step).  By relaxation (lane = stretch):
+      // every lane guesses that its stretch is entered at its first unit, looks up where that chain leaves, and hands
+      // the exit to the next lane as ITS entry; repeat until no entry changes.  Lane w is certainly right after w
+      // rounds, but greedy parses that start a few units apart merge almost at once, so the exits barely depend on
+      // the entries: 2-4 rounds instead of a serial walk.
+      unsigned start = 0;                                   // local start unit carried from the previous step
+      named_barrier_arrive(1, NALL);
+      for (unsigned step = 0; step < n_steps; step++) {
+        const unsigned nu = (min(SEG, n - step * SEG) + STRIDE - 1) / STRIDE;
+        const unsigned* xs = xe + (step & 1) * NT;
+        unsigned* ms = misc + (step & 1) * 72;
+        named_barrier(2, NALL);                             // xe[] of this step is complete
+        if (start < nu) {
+          const unsigned my_se = min((lane + 1) * 32, nu);
+          unsigned e = lane == 0 ? start : lane * 32, t = 0;
+          for (;;) {
+            t = (lane < NSW && e < my_se) ? xs[e] : e;              // exit | elements << 16 (entry beyond the stretch: pass)
+            unsigned ne = __shfl_up_sync(0xffffffffu, t & 0xffffu, 1);
+            if (lane == 0) ne = start;
+            const bool ch = lane < NSW && ne != e;
+            e = ne;
+            if (!__any_sync(0xffffffffu, ch)) break;
+          }
+          unsigned acc = lane < NSW ? t >> 16 : 0u;                  // elements emitted by my stretch; inclusive scan
+          for (int d = 1; d < 32; d <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, acc, d); if ((int)lane >= d) acc += v; }
+          if (lane < NSW) { ms[32 + lane] = e < my_se ? e : 0xffffffffu; ms[lane] = acc - (t >> 16); }
+          if (lane == NSW - 1) ms[64] = acc;                         // elements emitted by this step
+          start = __shfl_sync(0xffffffffu, t & 0xffffu, NSW - 1) - nu;   // >= 0: where the last token of this step ends
+        } else {
+          if (lane < NSW) ms[32 + lane] = 0xffffffffu;
+          if (lane == 0) ms[64] = 0;
+          start -= nu;
         }
-        if (lim >= 4) {
-          hs = lz_hash4(w0, L::HS_BITS); vS = true; cws = headS[hs];
-          if (lim >= 6) { hl = lz_hash6(w0, w1, L::HL_BITS); vL = true; cwl = headL[hl]; }
-          // Candidates: S newest, L newest, L second newest.  Fast path over the first 8 bytes: key = matched length
-          // class << 16 | ~distance, so that the largest key is the longest match and, among equals, the nearest.
-          unsigned bestk = 0;
+        named_barrier_arrive(1, NALL);                      // entries and bases of this step are published
+      }
+    } else {
+    // ================= unit warps
+    mbar_wait(mbar, phase & 1); phase++;
+    unsigned pM = 0, pmm = 0, ptok = 0;                      // previous step's stage-1 results (emitted one step later)
+    for (unsigned step = 0; step <= n_steps; step++) {
+      unsigned M = 0, mm = 0, tokw = 0, hs = 0, hl = 0, cwl = 0, cws = 0, ub = 0;
+      bool vS = false, vL = false;
+      LZ_PROF_T(t_step);
+      if (step < n_steps) {
+        const unsigned s0 = step * SEG;                    // first position of this step
+        const unsigned slen = min(SEG, n - s0);
+        // piece step + 1 (issued during the previous step) must have landed: this step reads up to s0 + SEG + 294
+        if (step > 0 && (step + 1) * SEG < n_ring) { mbar_wait(mbar, phase & 1); phase++; }
+
+        // ---- (A) lookup + (C) compare
+        const unsigned li = tid * STRIDE;                   // local position in the step
+        const unsigned p = s0 + li;
+        ub = (p / STRIDE + LZ_BIAS) & 0xffffu;
+        unsigned mlen = 0, mdist = 0;
+        if (li < slen) {
+          const unsigned lim = min(258u, n - p);
+          const unsigned pr = (p + off0) & RM;              // ring offset of this unit
+          unsigned w0, w1;
+          {
+            const unsigned* pw = ringw + (pr >> 2);
+            const unsigned sh = pr << 3;
+            const unsigned t0 = pw[0], t1 = pw[1], t2 = pw[2];
+            w0 = __funnelshift_r(t0, t1, sh); w1 = __funnelshift_r(t1, t2, sh);
+          }
+          tokw = STRIDE == 2 ? __byte_perm(w0, 0, 0x4140) : (w0 & 0xffu);   // literal token: the unit's bytes, one per element
+          // adler32 of the segment: a = sum of bytes, b = sum of (n - position) * byte
+          {
+            const unsigned b1 = STRIDE == 2 ? tokw >> 16 : 0u, sum = (tokw & 0xffu) + b1;
+            ad_a += sum; ad_c += b1;
+            ad_b += (unsigned long long)(n - p) * sum;
+          }
+          if (lim >= 4) {
+            hs = lz_hash4(w0, L::HS_BITS); vS = true; cws = headS[hs];
+            vL = lim >= 6;
+            hl = vL ? lz_hash6(w0, w1, L::HL_BITS) : 0u; cwl = headL[hl];
+            // Candidates: S newest, L newest, L second newest, evaluated without branches so that their loads are in
+            // flight together (an unusable candidate compares the unit with itself and is masked).  Fast path over
+            // the first 8 bytes: key = matched length class << 16 | ~distance, so that the largest key is the longest
+            // match and, among equals, the nearest.
+            unsigned bestk = 0;
 #pragma unroll
-          for (int k = 0; k < 3; k++) {
-            const unsigned cand = k == 0 ? cws >> 16 : k == 1 ? cwl >> 16 : cwl & 0xffffu;
-            const unsigned du = (ub - cand) & 0xffffu;
-            if (du - 1 < (unsigned)L::MAXD_UNITS && (k == 0 || vL)) {
+            for (int k = 0; k < 3; k++) {
+              const unsigned cand = k == 0 ? cws >> 16 : k == 1 ? cwl >> 16 : cwl & 0xffffu;
+              const unsigned du = (ub - cand) & 0xffffu;          // any value: q below always lies inside the ring
+              const bool ok = du - 1 < (unsigned)L::MAXD_UNITS && (k == 0 || vL);
               const unsigned q = (pr - du * STRIDE) & RM;
               const unsigned* qw = ringw + (q >> 2);
               const unsigned sh = q << 3;
               const unsigned t0 = qw[0], t1 = qw[1], t2 = qw[2];
-              const unsigned x0 = __funnelshift_r(t0, t1, sh) ^ w0, x1 = __funnelshift_r(t1, t2, sh) ^ w1;
-              // length class: 4..7 matched bytes (STRIDE 2: 4 or 6), 8 = the first 8 bytes match (extended below)
-              unsigned lc = 0;
-              if (x0 == 0) lc = x1 == 0 ? 8u : STRIDE == 2 ? ((x1 & 0xffffu) ? 4u : 6u) : 4u + (((unsigned)__ffs((int)x1) - 1) >> 3);
+              const unsigned c0 = __funnelshift_r(t0, t1, sh), x1 = __funnelshift_r(t1, t2, sh) ^ w1;
+              // length class: 4..8 matched bytes (STRIDE 2: 4, 6, 8) from the trailing zeros of the second word's
+              // difference; 8 = the first 8 bytes match (extended below)
+              const unsigned tz = (unsigned)__clz((int)__brev(x1));   // 32 when x1 == 0
+              const unsigned lc = STRIDE == 2 ? 4u + 2u * (tz >> 4) : 4u + (tz >> 3);
               const unsigned key = (lc << 16) | (0xffffu ^ du);
-              if (lc) bestk = max(bestk, key);
+              bestk = max(bestk, (ok && c0 == w0) ? key : 0u);
             }
-          }
-          if (bestk) {
             mlen = bestk >> 16;
-            const unsigned du = 0xffffu ^ (bestk & 0xffffu);
-            mdist = du * STRIDE;
-            if (mlen == 8) {
-              // rare: longer than 8 bytes, compare on (no wrap: the mirror covers pr + 258 + 8)
-              const unsigned q = (pr - mdist) & RM;
-              unsigned x = 0;
-              while (mlen < lim) {
-                x = ring_load4(ring, pr + mlen) ^ ring_load4(ring, q + mlen);
-                if (x) break;
-                mlen += 4;
+            if (mlen) {
+              mdist = (0xffffu ^ (bestk & 0xffffu)) * STRIDE;
+              if (mlen == 8) {
+                // rare: longer than 8 bytes, compare on (no wrap: the mirror covers pr + 258 + 8)
+                const unsigned q = (pr - mdist) & RM;
+                unsigned x = 0;
+                while (mlen < lim) {
+                  x = ring_load4(ring, pr + mlen) ^ ring_load4(ring, q + mlen);
+                  if (x) break;
+                  mlen += 4;
+                }
+                if (x) mlen += (unsigned)(__ffs((int)x) - 1) >> 3;
               }
-              if (x) mlen += (unsigned)(__ffs((int)x) - 1) >> 3;
+              mlen = min(mlen, lim);
+              if (STRIDE == 2) mlen &= ~1u;                 // matches cover whole units
+              if (mlen < 4) mlen = 0;
+              else tokw = (0x8000u | mlen) | ((mdist - 1) << 16);
             }
-            mlen = min(mlen, lim);
-            if (STRIDE == 2) mlen &= ~1u;                 // matches cover whole units
-            if (mlen < 4) { mlen = 0; mdist = 0; }
           }
         }
+        // ---- (D) greedy parse over units, hierarchical; thread = unit, warp = stretch of 32 units.
+        //      Stage 1 (registers, shuffles; here): pointer doubling gives every unit the exit of the token chain that
+        //      starts there (where it leaves the stretch) and the mask of the units it visits (= its tokens).
+        //      Stage 2 (chain warp): chains the stretches from the carried start (entry + element base per stretch).
+        //      Stage 3 (one step later): the warp picks the mask of its entry unit and emits those tokens.
+        //      A token is 2 elements (match: length, distance; STRIDE 2 literal: the unit's two bytes) or 1 (STRIDE 1 literal).
+        const unsigned nu = (slen + STRIDE - 1) / STRIDE;   // units in this step
+        const unsigned sb = wid * 32;
+        const unsigned sel = min(sb + 32, nu) > sb ? min(sb + 32, nu) - sb : 0;   // valid lanes of this stretch
+        mm = __ballot_sync(0xffffffffu, mlen != 0);
+        M = 1u << lane;
+        unsigned v = lane + (mlen ? mlen / STRIDE : 1u);   // next unit (stretch-local)
+#pragma unroll
+        for (unsigned r = 0; r < 5; r++) {
+          const unsigned tv = __shfl_sync(0xffffffffu, v, v & 31);
+          const unsigned tM = __shfl_sync(0xffffffffu, M, v & 31);
+          if (v < sel) { v = tv; M |= tM; }
+        }
+        const unsigned els = STRIDE == 2 ? 2 * __popc(M) : __popc(M) + __popc(M & mm);
+        xe[(step & 1) * NT + tid] = (sb + v) | (els << 16);
       }
       LZ_PROF_T(t_a);
-      __syncthreads();                                    // #1: every lookup and compare of the step is done
+      named_barrier(1, NALL);                             // #1: every lookup of this step is done; stage 2 of the previous step too
 
       // ---- (B) insert, first round: any unit of the step becomes the bucket's newest; the next piece of input
       const unsigned myL = (ub << 16) | (cwl >> 16), myS = (ub << 16) | (cws >> 16);
@@ -289,103 +368,66 @@ __global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1) lz77_kernel(const unsig
         bulk_g2s(ring + o, in16 + c0, len, mbar);
         if (mir) bulk_g2s(ring + LZ_RING, in16 + c0, mir, mbar);
       }
-      // ---- (D) greedy parse over units, hierarchical; thread = unit, warp = stretch of 32 units.
-      //      Stage 1 (registers, shuffles): pointer doubling gives every unit the exit of the token chain that starts
-      //      there (where it leaves the stretch) and the mask of the units it visits (= its tokens).
-      //      Stage 2: one warp chains the stretches from the carried start (entry + element base per stretch).
-      //      Stage 3: the warp picks the mask of its entry unit and emits those tokens (mask prefix -> offsets).
-      //      A token is 2 elements (match: length, distance; STRIDE 2 literal: the unit's two bytes) or 1 (STRIDE 1 literal).
-      const unsigned nu = (slen + STRIDE - 1) / STRIDE;   // units in this step
-      const unsigned start = misc[64 + (step & 1)];       // local start unit carried from the previous step
-      const unsigned sb = wid * 32, se = min(sb + 32, nu);
-      const unsigned sel = se > sb ? se - sb : 0;          // valid lanes of this stretch
-      const unsigned mm = __ballot_sync(0xffffffffu, mlen != 0);
-      unsigned M = 1u << lane;
-      {
-        unsigned v = lane + (mlen ? mlen / STRIDE : 1u);   // next unit (stretch-local)
-#pragma unroll
-        for (unsigned r = 0; r < 5; r++) {
-          const unsigned tv = __shfl_sync(0xffffffffu, v, v & 31);
-          const unsigned tM = __shfl_sync(0xffffffffu, M, v & 31);
-          if (v < sel) { v = tv; M |= tM; }
+      // ---- stage 3 of the previous step: emit
+      if (step > 0) {
+        const unsigned* ms = misc + ((step - 1) & 1) * 72;
+        const unsigned entry = ms[32 + wid];
+        if (entry != 0xffffffffu) {                         // warp-uniform
+          const unsigned reach = __shfl_sync(0xffffffffu, pM, entry & 31);
+          if ((reach >> lane) & 1u) {
+            const unsigned before = reach & lt;
+            const unsigned pos = run_tok + ms[wid] + (STRIDE == 2 ? 2 * __popc(before) : __popc(before) + __popc(before & pmm));
+            if (ptok & 0x8000u) {
+              if (STRIDE == 2) *(unsigned*)(tok + pos) = ptok;
+              else { tok[pos] = (unsigned short)ptok; tok[pos + 1] = (unsigned short)(ptok >> 16); }
+              unsigned sym, nb, ev;
+              len_symbol(ptok & 0x1ffu, sym, nb, ev);
+              atomicAdd(&shist[sym], 1u);
+              dist_symbol((ptok >> 16) + 1, sym, nb, ev);
+              atomicAdd(&shist[288 + sym], 1u);
+            } else {
+              atomicAdd(&shist[ptok & 0xffu], 1u);
+              if (STRIDE == 2) {
+                *(unsigned*)(tok + pos) = ptok;
+                atomicAdd(&shist[ptok >> 16], 1u);
+              } else tok[pos] = (unsigned short)ptok;
+            }
+          }
         }
-        const unsigned els = STRIDE == 2 ? 2 * __popc(M) : __popc(M) + __popc(M & mm);
-        xe[tid] = (sb + v) | (els << 16);
+        run_tok += ms[64];
       }
+      if (step == n_steps) break;
+      pM = M; pmm = mm; ptok = tokw;
       LZ_PROF_T(t_b);
-      __syncthreads();                                    // #2: first-round stores and xe[] are visible
+      named_barrier(2, NALL);                             // #2: first-round stores are visible (and xe[] to the chain warp)
 
       // ---- (B) insert, second round: a lower unit of this step in my bucket gives way
       if (vL) { const unsigned d = (ub - (headL[hl] >> 16)) & 0xffffu; if (d - 1 < NT - 1) atomicMax(&headL[hl], myL); }
       if (vS) { const unsigned d = (ub - (headS[hs] >> 16)) & 0xffffu; if (d - 1 < NT - 1) atomicMax(&headS[hs], myS); }
-      if (wid == 0) {
-        // Stage 2, by relaxation (lane = stretch): every lane guesses that its stretch is entered at its first unit,
-        // looks up where that chain leaves, and hands the exit to the next lane as ITS entry; repeat until no entry
-        // changes.  Lane w is certainly right after w rounds, but greedy parses that start a few units apart merge
-        // almost at once, so the exits barely depend on the entries: 2-4 rounds instead of a serial walk.
-        if (start < nu) {
-          const unsigned my_se = min((lane + 1) * 32, nu);
-          unsigned e = lane == 0 ? start : lane * 32, t = 0;
-          for (;;) {
-            t = (lane < NSW && e < my_se) ? xe[e] : e;              // exit | elements << 16 (entry beyond the stretch: pass)
-            unsigned ne = __shfl_up_sync(0xffffffffu, t & 0xffffu, 1);
-            if (lane == 0) ne = start;
-            const bool ch = lane < NSW && ne != e;
-            e = ne;
-            if (!__any_sync(0xffffffffu, ch)) break;
-          }
-          unsigned acc = lane < NSW ? t >> 16 : 0u;                  // elements emitted by my stretch; inclusive scan
-          for (int d = 1; d < 32; d <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, acc, d); if ((int)lane >= d) acc += v; }
-          if (lane < NSW) { ent[lane] = e; misc[lane] = acc - (t >> 16); }
-          if (lane == NSW - 1) {
-            misc[66] = acc;                                         // elements emitted by this step
-            misc[64 + ((step + 1) & 1)] = (t & 0xffffu) - nu;       // >= 0: where the last token of this step ends
-          }
-        } else if (lane == 0) {
-          misc[66] = 0;
-          misc[64 + ((step + 1) & 1)] = start - nu;
-        }
-      }
       LZ_PROF_T(t_c);
-      __syncthreads();                                    // #3: buckets settled; entries and bases of the stretches known
-
-      // ---- stage 3: emit
-      const unsigned entry = ent[wid];
-      if (start < nu && entry < se) {                     // warp-uniform
-        const unsigned reach = __shfl_sync(0xffffffffu, M, entry - sb);
-        if ((reach >> lane) & 1u) {
-          const unsigned before = reach & lt;
-          const unsigned pos = run_tok + misc[wid] + (STRIDE == 2 ? 2 * __popc(before) : __popc(before) + __popc(before & mm));
-          if (mlen) {
-            if (STRIDE == 2) *(unsigned*)(tok + pos) = (0x8000u | mlen) | ((mdist - 1) << 16);
-            else { tok[pos] = (unsigned short)(0x8000u | mlen); tok[pos + 1] = (unsigned short)(mdist - 1); }
-            unsigned sym, nb, ev;
-            len_symbol(mlen, sym, nb, ev);
-            atomicAdd(&shist[sym], 1u);
-            dist_symbol(mdist, sym, nb, ev);
-            atomicAdd(&shist[288 + sym], 1u);
-          } else {
-            const unsigned b0 = w0 & 0xffu;
-            atomicAdd(&shist[b0], 1u);
-            if (STRIDE == 2) {
-              const unsigned b1 = (w0 >> 8) & 0xffu;
-              *(unsigned*)(tok + pos) = b0 | (b1 << 16);
-              atomicAdd(&shist[b1], 1u);
-            } else tok[pos] = (unsigned short)b0;
-          }
-        }
-      }
-      run_tok += misc[66];
-      LZ_PROF_T(t_d);
-      LZ_PROF_ADD(0, 1); LZ_PROF_ADD(1, t_a - t_step); LZ_PROF_ADD(2, t_b - t_a); LZ_PROF_ADD(3, t_c - t_b);
-      LZ_PROF_ADD(4, t_d - t_c); LZ_PROF_ADD(5, t_d - t_step);
+      named_barrier(3, NT);                               // #3: buckets settled
+      LZ_PROF_ADD(0, 1); LZ_PROF_ADD(1, t_a - t_step); LZ_PROF_ADD(2, t_b - t_a); LZ_PROF_ADD(3, t_c - t_b); LZ_PROF_ADD(5, t_c - t_step);
+    }
     }
 
     // ---- segment done: publish histogram + token count (the barrier also keeps the next segment's table reset and
     //      input pieces away from threads still emitting)
+    //      adler32 of the segment's bytes (standalone, from adler = 1; folded per chunk by adler_combine_kernel)
+    {
+      unsigned long long a = ad_a, b = (ad_b - ad_c) % ADLER_BASE;
+      a = warp_sum(a); b = warp_sum(b);
+      unsigned long long* red = (unsigned long long*)xe;
+      if (lane == 0) { red[2 * wid] = a; red[2 * wid + 1] = b; }
+    }
     __syncthreads();
-    for (unsigned i = tid; i < HIST_STRIDE; i += NT) hist[(size_t)sidx * HIST_STRIDE + i] = shist[i];
-    if (tid == 0) so[sidx].n_tok = run_tok;
+    for (unsigned i = tid; i < HIST_STRIDE; i += NALL) hist[(size_t)sidx * HIST_STRIDE + i] = shist[i];
+    if (tid == 0) {
+      so[sidx].n_tok = run_tok;
+      const unsigned long long* red = (const unsigned long long*)xe;
+      unsigned long long ta = 0, tb = 0;
+      for (unsigned w = 0; w < NSW; w++) { ta += red[2 * w]; tb += red[2 * w + 1]; }
+      seg_adler[sidx] = ((unsigned)((n % ADLER_BASE + tb) % ADLER_BASE) << 16) | (unsigned)((1 + ta) % ADLER_BASE);
+    }
     __syncthreads();
   }
 }

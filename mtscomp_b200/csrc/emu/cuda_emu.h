@@ -123,6 +123,10 @@ static inline void __emu_named_barrier(int id, int count) {
   if (++b->nb_count[id] == count) { b->nb_count[id] = 0; b->nb_gen[id]++; }
   else while (b->nb_gen[id] == g) emu::yield();
 }
+static inline void __emu_named_barrier_arrive(int id, int count) {
+  emu::Block* b = emu::g_blk;
+  if (++b->nb_count[id] == count) { b->nb_count[id] = 0; b->nb_gen[id]++; }
+}
 static inline unsigned __emu_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }
 static inline emu::Warp& __emu_warp() { return emu::g_blk->warps[__emu_tid() >> 5]; }
 static inline void __emu_wbar(unsigned mask) {

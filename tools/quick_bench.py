@@ -48,7 +48,7 @@ def main():
         buf = (C.c_ulonglong * 16)()
         lib.mtsb_debug_lz_profile(buf)
         v = list(buf); st = max(v[0], 1)
-        print('lz profile (cycles/step, thread 0 of CTA 0): steps %d  lookup+compare %.0f  insert+stage1 %.0f  settle+chain %.0f  emit %.0f  whole step %.0f' % (v[0], v[1] / st, v[2] / st, v[3] / st, v[4] / st, v[5] / st), flush=True)
+        print('lz profile (cycles/step, thread 0 of CTA 0): steps %d  lookup+compare+stage1 %.0f  insert+emit %.0f  settle %.0f  whole step %.0f' % (v[0], v[1] / st, v[2] / st, v[3] / st, v[5] / st), flush=True)
     csize = int(offs[-1])
     comp = np.empty(csize, dtype=np.uint8)
     lib.mtsb_memcpy(cd.ctx, comp.ctypes.data, d_comp, csize, 2)
