@@ -316,15 +316,20 @@ __global__ void __launch_bounds__(NT + 32, NT <= 512 ? 2 : 1) lz77_kernel(const 
             if (mlen) {
               mdist = (0xffffu ^ (bestk & 0xffffu)) * STRIDE;
               if (mlen == 8) {
-                // rare: longer than 8 bytes, compare on (no wrap: the mirror covers pr + 258 + 8)
+                // the first 8 bytes match: check the next two bytes, which ends it for most; the few matches that go
+                // on are compared word by word (no wrap: the mirror covers pr + 258 + 8)
                 const unsigned q = (pr - mdist) & RM;
-                unsigned x = 0;
-                while (mlen < lim) {
-                  x = ring_load4(ring, pr + mlen) ^ ring_load4(ring, q + mlen);
-                  if (x) break;
-                  mlen += 4;
+                const bool more = STRIDE == 2 ? *(const unsigned short*)(ring + pr + 8) == *(const unsigned short*)(ring + q + 8)
+                                              : ring[pr + 8] == ring[q + 8];
+                if (more) {
+                  unsigned x = 0;
+                  while (mlen < lim) {
+                    x = ring_load4(ring, pr + mlen) ^ ring_load4(ring, q + mlen);
+                    if (x) break;
+                    mlen += 4;
+                  }
+                  if (x) mlen += (unsigned)(__ffs((int)x) - 1) >> 3;
                 }
-                if (x) mlen += (unsigned)(__ffs((int)x) - 1) >> 3;
               }
               mlen = min(mlen, lim);
               if (STRIDE == 2) mlen &= ~1u;                 // matches cover whole units
