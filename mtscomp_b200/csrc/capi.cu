@@ -148,6 +148,12 @@ int set_attrs(mtsb_ctx* c) {
   CK(cudaFuncSetAttribute(fwd_transform_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
   CK(cudaFuncSetAttribute(fwd_transform_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
   CK(cudaFuncSetAttribute(fwd_transform_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+  CK(cudaFuncSetAttribute(fwd_tile_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  CK(cudaFuncSetAttribute(fwd_tile_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  CK(cudaFuncSetAttribute(fwd_tile_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  CK(cudaFuncSetAttribute(fwd_tile_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  CK(cudaFuncSetAttribute(fwd_tile_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  CK(cudaFuncSetAttribute(fwd_tile_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
   CK(cudaFuncSetAttribute(inv_apply_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
   CK(cudaFuncSetAttribute(inv_apply_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
   CK(cudaFuncSetAttribute(inv_apply_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
@@ -181,15 +187,21 @@ int small_copy(mtsb_ctx* c, void* dst, const void* src, size_t bytes) {
 template <class T>
 int launch_fwd_t(mtsb_ctx* c, const void* raw, void* tbuf, const ChunkDesc* d_cd, int n_chunks, int max_ns, int nc,
                  int flags) {
-  if (!(flags & (FLAG_ORDER_C | FLAG_SPATIAL_DIFF))) {
-    // default layout: register-only kernel, one 32-byte channel run per thread
+  if (!(flags & FLAG_ORDER_C)) {
+    // channel-major output: TMA-staged tile of TT rows (a multiple of the 32-byte run), about 56 KB of shared memory
     const int R = ColRun<T>::R;
-    dim3 grid((nc + 31) / 32, (max_ns + 4 * R - 1) / (4 * R), n_chunks);
-    auto k = fwd_cols_kernel<T>;
-    MTS_LAUNCH(k, grid, dim3(128), 0, c->stream, (const T*)raw, (T*)tbuf, d_cd, nc, flags);
-    c->launches++;
-    CKL();
-    return 0;
+    long long tt = (56 * 1024) / ((long long)nc * (long long)sizeof(T)) - 1;
+    tt = std::min<long long>(64, tt / R * R);
+    if (tt >= R) {
+      const int TT = (int)tt;
+      const size_t smem = 16 + (size_t)(TT + 1) * nc * sizeof(T) + 32;
+      dim3 grid((max_ns + TT - 1) / TT, n_chunks);
+      auto k = fwd_tile_kernel<T>;
+      MTS_LAUNCH(k, grid, dim3(FWD_TILE_THREADS), smem, c->stream, (const T*)raw, (T*)tbuf, d_cd, nc, TT, flags);
+      c->launches++;
+      CKL();
+      return 0;
+    }
   }
   int TT = tile_rows(nc, sizeof(T), 1);
   if (TT < 1) return fail(c, MTSB_E_ARG, "n_channels=%d too large for the transform tile", nc);
@@ -705,7 +717,8 @@ int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_
     c->launches += 2;
     c->end();
     c->begin(5);
-    MTS_LAUNCH(encode_kernel, dim3(n_segs), dim3(ENC_THREADS), 0, c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (const unsigned short*)c->d_tok.p, (const unsigned*)c->d_codes.p, (const unsigned*)c->d_hdrs.p, (const DeflateSegOut*)c->d_so.p, (const unsigned*)c->d_chunk_adler.p, outp, d_cd, (int)c->write_index);
+    auto ek = itemsize == 2 ? encode_kernel<true> : encode_kernel<false>;
+    MTS_LAUNCH(ek, dim3(n_segs), dim3(ENC_THREADS), 0, c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (const unsigned short*)c->d_tok.p, (const unsigned*)c->d_codes.p, (const unsigned*)c->d_hdrs.p, (const DeflateSegOut*)c->d_so.p, (const unsigned*)c->d_chunk_adler.p, outp, d_cd, (int)c->write_index);
     CKL();
     c->launches++;
     c->end();

@@ -44,6 +44,56 @@ __device__ __forceinline__ void named_barrier_arrive(int id, int count) {
 #endif
 }
 
+// ---- TMA bulk copies (cp.async.bulk) completing on an mbarrier: one elected thread arms the barrier with the byte
+//      count and issues the copy, every consumer waits for the phase.
+#ifdef MTSCOMP_EMU
+// host emulation: the "asynchronous" copy completes at once
+typedef unsigned long long* mbar_t;
+__device__ __forceinline__ mbar_t mbar_addr(unsigned long long* bar) { return bar; }
+__device__ __forceinline__ void mbar_init(mbar_t bar) { *bar = 0; }
+__device__ __forceinline__ void mbar_expect_tx(mbar_t, unsigned) {}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, mbar_t) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void mbar_wait(mbar_t, unsigned) {}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void bulk_s2g_wait() {}
+__device__ __forceinline__ void fence_async_smem() {}
+#else
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+typedef unsigned mbar_t;                         // shared-window address of an mbarrier
+__device__ __forceinline__ mbar_t mbar_addr(unsigned long long* bar) { return smem_u32(bar); }
+__device__ __forceinline__ void mbar_init(mbar_t bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(mbar_t bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (16-byte aligned addresses, size a multiple of 16); completes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, mbar_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(mbar_t bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// TMA bulk copy shared -> global (same alignment rules); bulk_s2g_wait() returns when the sources may be reused.
+// Shared memory written by ordinary stores must be fenced (fence_async_smem) before the copy engine reads it.
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_s2g_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ unsigned warp_id() { return threadIdx.x >> 5; }
 

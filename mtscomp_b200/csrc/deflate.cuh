@@ -106,43 +106,6 @@ template <int STRIDE, int NT> struct LzSmem {
   static const size_t total = mbar_off + 16;
 };
 
-#ifdef MTSCOMP_EMU
-// host emulation: the "asynchronous" copy completes at once
-typedef unsigned long long* mbar_t;
-__device__ __forceinline__ mbar_t mbar_addr(unsigned long long* bar) { return bar; }
-__device__ __forceinline__ void mbar_init(mbar_t bar) { *bar = 0; }
-__device__ __forceinline__ void mbar_expect_tx(mbar_t, unsigned) {}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, mbar_t) { memcpy(dst, src, bytes); }
-__device__ __forceinline__ void mbar_wait(mbar_t, unsigned) {}
-#else
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-typedef unsigned mbar_t;                         // shared-window address of an mbarrier
-__device__ __forceinline__ mbar_t mbar_addr(unsigned long long* bar) { return smem_u32(bar); }
-__device__ __forceinline__ void mbar_init(mbar_t bar) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(mbar_t bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// TMA bulk copy global -> shared (16-byte aligned addresses, size a multiple of 16); completes on the mbarrier
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, mbar_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(mbar_t bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra LAB_DONE;\n"
-      "bra LAB_WAIT;\n"
-      "LAB_DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-#endif
-
 __device__ __forceinline__ unsigned ring_load4(const unsigned char* ring, unsigned m) {   // m < LZ_RING
   const unsigned* w = (const unsigned*)(ring + (m & ~3u));
   return __funnelshift_r(w[0], w[1], m << 3);              // w[1] may lie in the mirror
@@ -719,6 +682,7 @@ __device__ __forceinline__ void stage_flush(const unsigned* stage, unsigned nwor
   }
 }
 
+template <bool PAIRS>
 __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char* __restrict__ tbuf,
                                                              const DeflateSeg* __restrict__ segs, int n_segs,
                                                              const unsigned short* __restrict__ tokens,
@@ -805,38 +769,74 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
     cur &= 31;
     __syncthreads();
   }
+  // Each thread turns 8 token elements into 8 codes of <= 28 bits (PAIRS: the elements come as 4 aligned 32-bit tokens
+  // -- length | distance << 16, or two literal bytes -- so there is no dependence on the previous element), the block
+  // prefix sum of the bit counts places them, and the thread strings its codes together in a 64-bit register: whole
+  // words go to the staging window with plain stores, only the first and the last (shared with the neighbours) by atomicOr.
   const unsigned short* tok = tokens + sg.tok_off;
   const unsigned ntok = o.n_tok;
   for (unsigned base = 0; base < ntok; base += ENC_TILE) {
     unsigned v[ENC_PER], nb[ENC_PER], mine = 0;
-    unsigned i0 = base + tid * ENC_PER;
-    unsigned prev_el = (i0 > 0 && i0 <= ntok) ? tok[i0 - 1] : 0;
-    for (int j = 0; j < ENC_PER; j++) {
-      unsigned i = i0 + j;
-      v[j] = 0; nb[j] = 0;
-      if (i < ntok) {
-        unsigned e = tok[i];
-        if (prev_el & 0x8000u) {            // distance element (follows a length element)
-          unsigned sym, xb, ev;
-          dist_symbol(e + 1, sym, xb, ev);
-          unsigned c = code[288 + sym];
-          v[j] = (c & 0xffff) | (ev << (c >> 16));
-          nb[j] = (c >> 16) + xb;
-          prev_el = 0;
-        } else if (e & 0x8000u) {           // length element
-          unsigned sym, xb, ev;
-          len_symbol(e & 0x1ff, sym, xb, ev);
-          unsigned c = code[sym];
-          v[j] = (c & 0xffff) | (ev << (c >> 16));
-          nb[j] = (c >> 16) + xb;
-          prev_el = e;
-        } else {                            // literal
-          unsigned c = code[e];
-          v[j] = c & 0xffff;
-          nb[j] = c >> 16;
-          prev_el = e;
+    const unsigned i0 = base + tid * ENC_PER;
+    if (PAIRS) {
+      uint4 t4 = make_uint4(0, 0, 0, 0);
+      if (i0 + ENC_PER <= ntok && !((uintptr_t)(tok + i0) & 15)) t4 = *(const uint4*)(tok + i0);
+      else {
+        const unsigned* tw = (const unsigned*)(tok + i0);
+        if (i0 < ntok) t4.x = tw[0];
+        if (i0 + 2 < ntok) t4.y = tw[1];
+        if (i0 + 4 < ntok) t4.z = tw[2];
+        if (i0 + 6 < ntok) t4.w = tw[3];
+      }
+      const unsigned tk[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const unsigned e = tk[j];
+        unsigned c0, c1, x0 = 0, x1 = 0, e0 = 0, e1 = 0;
+        if (e & 0x8000u) {                  // match: length element, distance element
+          unsigned sym;
+          len_symbol(e & 0x1ffu, sym, x0, e0);
+          c0 = code[sym];
+          dist_symbol((e >> 16) + 1, sym, x1, e1);
+          c1 = code[288 + sym];
+        } else { c0 = code[e & 0xffu]; c1 = code[e >> 16]; }
+        const bool on = i0 + 2 * j < ntok;
+        v[2 * j] = (c0 & 0xffffu) | (e0 << (c0 >> 16));
+        nb[2 * j] = on ? (c0 >> 16) + x0 : 0u;
+        v[2 * j + 1] = (c1 & 0xffffu) | (e1 << (c1 >> 16));
+        nb[2 * j + 1] = on ? (c1 >> 16) + x1 : 0u;
+        mine += nb[2 * j] + nb[2 * j + 1];
+      }
+    } else {
+      unsigned prev_el = (i0 > 0 && i0 <= ntok) ? tok[i0 - 1] : 0;
+      // bit 15 marks a length element (distance elements are <= 32767), and what follows a length is its distance
+      for (int j = 0; j < ENC_PER; j++) {
+        unsigned i = i0 + j;
+        v[j] = 0; nb[j] = 0;
+        if (i < ntok) {
+          unsigned e = tok[i];
+          if (prev_el & 0x8000u) {            // distance element (follows a length element)
+            unsigned sym, xb, ev;
+            dist_symbol(e + 1, sym, xb, ev);
+            unsigned c = code[288 + sym];
+            v[j] = (c & 0xffff) | (ev << (c >> 16));
+            nb[j] = (c >> 16) + xb;
+            prev_el = 0;
+          } else if (e & 0x8000u) {           // length element
+            unsigned sym, xb, ev;
+            len_symbol(e & 0x1ff, sym, xb, ev);
+            unsigned c = code[sym];
+            v[j] = (c & 0xffff) | (ev << (c >> 16));
+            nb[j] = (c >> 16) + xb;
+            prev_el = e;
+          } else {                            // literal
+            unsigned c = code[e];
+            v[j] = c & 0xffff;
+            nb[j] = c >> 16;
+            prev_el = e;
+          }
+          mine += nb[j];
         }
-        mine += nb[j];
       }
     }
     unsigned incl = warp_incl_scan(mine);
@@ -848,8 +848,22 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
       tile_bits = run;
     }
     __syncthreads();
-    unsigned bp = cur + wtot[wid] + incl - mine;
-    for (int j = 0; j < ENC_PER; j++) { stage_or(stage, bp, v[j], nb[j]); bp += nb[j]; }
+    if (mine) {
+      const unsigned bp = cur + wtot[wid] + incl - mine;
+      unsigned wi = bp >> 5, fill = bp & 31;
+      unsigned long long acc = 0;
+      bool first = true;
+#pragma unroll
+      for (int j = 0; j < ENC_PER; j++) {
+        acc |= (unsigned long long)v[j] << fill;
+        fill += nb[j];
+        if (fill >= 32) {
+          if (first) { atomicOr(&stage[wi], (unsigned)acc); first = false; } else stage[wi] = (unsigned)acc;
+          wi++; acc >>= 32; fill -= 32;
+        }
+      }
+      if (fill) atomicOr(&stage[wi], (unsigned)acc);
+    }
     __syncthreads();
     cur += tile_bits;
     unsigned nw = cur >> 5;

@@ -203,40 +203,95 @@ __global__ void __launch_bounds__(512) inv_apply_kernel(const T* __restrict__ in
 }
 
 // ------------------------------------------------------------------------------------------------ fast paths
-// Default layout ('F' order, time diff only, the reference's defaults): no shared memory at all.  A thread owns one
-// channel and a run of R = 32 / sizeof(T) consecutive samples, i.e. one 32-byte sector of the channel-major side.
-// On the row-major side the 32 lanes of a warp touch 32 consecutive channels of a row (contiguous bytes).
+// Channel-major layouts ('F' order, the reference's default).  The unit of work is one channel x R = 32 / sizeof(T)
+// consecutive samples, i.e. one 32-byte sector of the channel-major side.
 template <class T> struct ColRun { static const int R = 32 / sizeof(T); };
 
-template <class T>
-__global__ void __launch_bounds__(128) fwd_cols_kernel(const T* __restrict__ src, T* __restrict__ dst,
-                                                       const ChunkDesc* __restrict__ chunks, int nc, int flags) {
-  const int R = ColRun<T>::R;
-  const ChunkDesc cd = chunks[blockIdx.z];
-  const int ns = cd.ns;
-  const int c = blockIdx.x * 32 + (int)lane_id();
-  const int t0 = (blockIdx.y * 4 + (int)warp_id()) * R;
-  if (t0 >= ns || c >= nc) return;
-  const T* x = src + cd.elem_off;
-  T* y = dst + cd.elem_off + (long long)c * ns + t0;
-  const bool td = (flags & FLAG_TIME_DIFF) != 0;
-  const int rows = min(R, ns - t0);
-  T v[R];
-  T prev = (td && t0 > 0) ? x[(long long)(t0 - 1) * nc + c] : (T)0;
+// Forward transform for the channel-major ('F') layouts, time and/or spatial differences.  A CTA takes a tile of TT
+// consecutive rows x all channels, which is ONE contiguous span of the row-major side: it is staged in shared memory by
+// a TMA bulk copy (the 16-byte aligned interior; the ragged ends by ordinary loads), together with the row above as
+// halo.  A work item is one channel x R rows = one 32-byte sector of the channel-major side: the lanes of a warp take
+// consecutive channels, so the shared-memory reads are conflict-free at any row pitch (385 or 384 channels alike),
+// and every item leaves as two 128-bit stores.
+// A full run of R elements (32 bytes) leaves with the widest stores its address allows (channel runs of an odd number
+// of samples are only 8-, 4- or 2-byte aligned); a short run element by element.
+template <class T> __device__ __forceinline__ void store_run(T* y, const T (&v)[32 / sizeof(T)], int nr) {
+  const int R = 32 / sizeof(T);
+  const uintptr_t a = (uintptr_t)y;
+  if (nr == R && !(a & 15)) {
+    uint4 q[2];
+    memcpy(q, v, 32);
+    ((uint4*)y)[0] = q[0]; ((uint4*)y)[1] = q[1];
+  } else if (nr == R && !(a & 7)) {
+    uint2 q[4];
+    memcpy(q, v, 32);
 #pragma unroll
-  for (int r = 0; r < R; r++) {
-    T cur = (r < rows) ? x[(long long)(t0 + r) * nc + c] : (T)0;
-    v[r] = td ? (T)(cur - prev) : cur;
-    prev = cur;
-  }
-  if (rows == R && ((uintptr_t)y & 15) == 0) {
-    uint4 a, b;
-    memcpy(&a, &v[0], 16);
-    memcpy(&b, &v[R / 2], 16);
-    ((uint4*)y)[0] = a;
-    ((uint4*)y)[1] = b;
+    for (int i = 0; i < 4; i++) ((uint2*)y)[i] = q[i];
+  } else if (nr == R && !(a & 3)) {
+    unsigned q[8];
+    memcpy(q, v, 32);
+#pragma unroll
+    for (int i = 0; i < 8; i++) ((unsigned*)y)[i] = q[i];
   } else {
-    for (int r = 0; r < rows; r++) y[r] = v[r];
+#pragma unroll
+    for (int r = 0; r < R; r++) if (r < nr) y[r] = v[r];
+  }
+}
+
+static const int FWD_TILE_THREADS = 256;
+template <class T>
+__global__ void __launch_bounds__(FWD_TILE_THREADS) fwd_tile_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                                    const ChunkDesc* __restrict__ chunks, int nc, int TT,
+                                                                    int flags) {
+  const int R = ColRun<T>::R;
+  MTS_DYN_SMEM(sm);                                    // [0,16) mbarrier, [16, ...) the span (16-byte aligned)
+  const ChunkDesc cd = chunks[blockIdx.y];
+  const int ns = cd.ns;
+  const int t0 = blockIdx.x * TT;
+  if (t0 >= ns) return;
+  const int rows = min(TT, ns - t0);
+  const int halo = t0 > 0 ? 1 : 0;
+  const unsigned char* x = (const unsigned char*)(src + cd.elem_off + (long long)(t0 - halo) * nc);
+  const unsigned span = (unsigned)((rows + halo) * nc) * (unsigned)sizeof(T);
+  const unsigned off0 = (unsigned)((uintptr_t)x & 15);
+  unsigned char* data = sm + 16;                       // data[off0 + i] = x[i]
+  const unsigned head = min(span, (16 - off0) & 15);   // bytes before the aligned interior
+  const unsigned mid = (span - head) & ~15u;
+  const mbar_t mbar = mbar_addr((unsigned long long*)sm);
+  if (threadIdx.x == 0) {
+    mbar_init(mbar);
+    if (mid) { mbar_expect_tx(mbar, mid); bulk_g2s(data + off0 + head, x + head, mid, mbar); }
+  }
+  for (unsigned i = threadIdx.x; i < head; i += blockDim.x) data[off0 + i] = x[i];
+  for (unsigned i = head + mid + threadIdx.x; i < span; i += blockDim.x) data[off0 + i] = x[i];
+  __syncthreads();                                     // barrier initialised, ragged ends in place
+  if (mid) mbar_wait(mbar, 0);
+
+  const T* s = (const T*)(data + off0) + (long long)halo * nc;     // s[r * nc + c] = sample t0 + r, channel c
+  const bool td = (flags & FLAG_TIME_DIFF) != 0, sd = (flags & FLAG_SPATIAL_DIFF) != 0;
+  T* ychunk = dst + cd.elem_off;
+  const int groups = (rows + R - 1) / R;
+  for (int it = threadIdx.x; it < groups * nc; it += blockDim.x) {
+    const int g = it / nc, c = it - g * nc;
+    const int r0 = g * R, nr = min(R, rows - r0);
+    const T* p = s + (long long)r0 * nc + c;
+    const bool left = sd && c > 0;
+    // in the reference's order (it matters for floating point): time difference of each column first, then the
+    // difference between the two columns (mtscomp.py:381-394)
+    T prev = 0, prevl = 0;
+    if (td && (r0 > 0 || halo)) { prev = p[-nc]; if (left) prevl = p[-nc - 1]; }
+    T v[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      T cur = 0, curl = 0;
+      if (r < nr) { cur = p[r * nc]; if (left) curl = p[r * nc - 1]; }
+      T a = td ? (T)(cur - prev) : cur;
+      if (left) a = (T)(a - (td ? (T)(curl - prevl) : curl));
+      v[r] = a;
+      prev = cur; prevl = curl;
+    }
+    T* y = ychunk + (long long)c * ns + t0 + r0;
+    store_run<T>(y, v, nr);
   }
 }
 
