@@ -45,13 +45,28 @@ def parse():
     ap.add_argument('--chunks', type=int, default=600, help='chunks per GPU per step (600 = 10 min of AP data)')
     ap.add_argument('--distinct', type=int, default=8, help='distinct synthetic chunks tiled to --chunks')
     ap.add_argument('--cpu-sample', type=int, default=0, help='chunks in the CPU baseline sample (0 = auto)')
+    ap.add_argument('--no-legs', action='store_true', help='skip the configs[2..4] legs (sharded file, LFP, latency)')
+    ap.add_argument('--shard-chunks', type=int, default=24, help='configs[2] leg: chunks per rank of the one-file recording')
+    ap.add_argument('--lfp-chunks', type=int, default=1200, help='configs[3] leg: 1 s LFP chunks (N=1 only)')
+    ap.add_argument('--lfp-small-chunks', type=int, default=12000, help='configs[3] leg: 0.1 s LFP chunks (N=1 only)')
+    ap.add_argument('--latency-chunks', type=int, default=16, help='configs[4] leg: chunks of the 384-channel files (N=1 only)')
     return ap.parse_args()
 
 
 def workload_config(n_chunks, n_distinct):
+    """The same dict for both arms (--impl b200 / reference): what is measured, not how."""
     return {'workload': 'BASELINE configs[1] shape: 10 min AP, 385ch x 30kHz int16, %d chunks of 1 s (23.1 MB) '
                         'per GPU, chunk_order F, time diff; compress AND decompress' % n_chunks,
-            'chunks_per_gpu': n_chunks, 'n_distinct_chunks': n_distinct, 'raw_bytes_per_gpu': n_chunks * CHUNK_BYTES}
+            'chunks_per_gpu': n_chunks, 'n_distinct_chunks': n_distinct, 'raw_bytes_per_gpu': n_chunks * CHUNK_BYTES,
+            'l2': 'inputs larger than L2 (%.0f MB distinct raw per GPU, %.1f GB per step)' % (
+                n_distinct * CHUNK_BYTES / 1e6, n_chunks * CHUNK_BYTES / 1e9),
+            'sharding': 'contiguous chunk ranges per GPU, no collective on the data path'}
+
+
+def lz77_profile():
+    """Figures of the committed ncu capture of the dominant kernel (profiles/r02_lz77_ncu.json)."""
+    tp = ROOT / 'profiles' / 'r02_lz77_ncu.json'
+    return json.loads(tp.read_text()) if tp.exists() else {}
 
 
 def host_threads():
@@ -146,7 +161,7 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': n_sample * CHUNK_BYTES / v / 1e6, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int16', 'data': 'synthetic',
-        'config': dict(workload_config(args.chunks, min(args.distinct, args.chunks)), sample=sample),
+        'config': workload_config(args.chunks, min(args.distinct, args.chunks)),
         'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample,
                          'decompress_value': float(np.mean(vals_d))},
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -303,6 +318,21 @@ def run_b200(args):
     mean_ms = np.array([np.mean([r[k] for r in rec]) for k in keys])
     mx = max_over_ranks(mean_ms)          # max over ranks of the per-step means
     gbps = {k: world * (e2e_bytes if k in ('ce', 're') else raw_bytes) / (mx[i] / 1e3) / 1e9 for i, k in enumerate(keys)}
+    # ---- copy-only ceiling of the host link with all ranks copying at once, and the extra legs
+    sys.path.insert(0, str(ROOT / 'tools'))
+    import bench_legs
+    del h_comp_t, h_out_t, h_ref_t
+    ceil_bytes = min(e2e_bytes, 4 << 30)
+    h2d_s, d2h_s = max_over_ranks(bench_legs.copy_ceiling(ceil_bytes, barrier))
+    legs = {}
+    if not args.no_legs:
+        del d_raw, d_comp, d_out, d_ref, h_raw_t
+        torch.cuda.empty_cache()
+        legs['sharded_file'] = bench_legs.sharded_leg(rank, world, args.shard_chunks)
+        if world == 1:
+            legs['lfp_1s_chunks'] = bench_legs.lfp_leg(cd, args.lfp_chunks, 2500, threads)
+            legs['lfp_0.1s_chunks'] = bench_legs.lfp_leg(cd, args.lfp_small_chunks, 250, threads)
+            legs['latency'] = bench_legs.latency_leg(threads, n_chunks=args.latency_chunks)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -314,21 +344,21 @@ def run_b200(args):
     lz_ms = float(np.mean([r['tm'][3] for r in rec]))
     alg_bytes = raw_bytes + csize               # read raw + write compressed = (1 + r) B per raw byte
     achieved = alg_bytes / (lz_ms / 1e3) / 1e9
-    traffic = None
-    tp = ROOT / 'profiles' / 'lz77_traffic.json'
-    if tp.exists():
-        traffic = json.loads(tp.read_text()).get('dram_bytes_per_raw_byte')
-        traffic = traffic * raw_bytes if traffic else None
+    prof = lz77_profile()
+    traffic = prof.get('dram_bytes_per_raw_byte')
+    traffic = traffic * raw_bytes if traffic else None
     inf_ms = float(np.mean([r['tm_r'][2] for r in rec]))
     # the HBM-bound stages of the path against the same measured peak (algorithmic bytes: transform reads and writes
     # every byte once; adler32 reads it once; the inverse reads T twice (tile sums + apply) and writes once)
     def hbm_stage(ms, bytes_per_raw):
         a = bytes_per_raw * raw_bytes / (ms / 1e3) / 1e9
         return {'ms': ms, 'achieved': a, 'frac': a / hbm, 'bytes_per_raw_byte': bytes_per_raw}
-    tr_ms = float(np.mean([r['tm'][1] for r in rec])); ad_ms = float(np.mean([r['tm'][2] for r in rec]))
+    tr_ms = float(np.mean([r['tm'][1] for r in rec]))
     inv_ms = float(np.mean([r['tm_r'][4] for r in rec]))
-    hbm_stages = {'fwd_cols_kernel': hbm_stage(tr_ms, 2), 'adler_partial_kernel': hbm_stage(ad_ms, 1),
-                  'inv_tile_sums+inv_cols_kernel': hbm_stage(inv_ms, 3)}
+    hbm_stages = {'fwd_tile_kernel': hbm_stage(tr_ms, 2), 'inverse kernels': hbm_stage(inv_ms, 3)}
+    ad_ms = float(np.mean([r['tm_r'][3] for r in rec]))
+    if ad_ms > 0:
+        hbm_stages['adler_partial_kernel (decode)'] = hbm_stage(ad_ms, 1)
     dec_names = ['h2d', 'plan', 'inflate', 'adler', 'inverse', 'd2h', '-', 'total']
     stage_r = {k: float(np.mean([r['tm_r'][i] for r in rec])) for i, k in enumerate(dec_names) if k != '-'}
     stage_g = {k: float(np.mean([r['tm_g'][i] for r in rec])) for i, k in enumerate(dec_names) if k != '-'}
@@ -336,24 +366,36 @@ def run_b200(args):
         'metric': METRIC, 'value': gbps['c'], 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': float(mx[0]), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'int16', 'data': 'synthetic',
-        'config': dict(workload_config(n_chunks, n_distinct),
-                   l2='inputs larger than L2 (%.0f MB distinct raw per GPU, %.1f GB per step)' % (
-                       n_distinct * CHUNK_BYTES / 1e6, raw_bytes / 1e9),
-                   sharding='contiguous chunk ranges per GPU, no collective on the data path',
-                   seg_bytes=cd.get_param('seg_bytes'), 
-                   e2e_chunks_per_gpu=n_e2e),
+        'config': workload_config(n_chunks, n_distinct),
+        'run': {'seg_bytes': cd.get_param('seg_bytes'), 'e2e_chunks_per_gpu': n_e2e,
+                'lz_ctas_per_sm': cd.get_param('lz_ctas_per_sm')},
         'e2e': {'value': gbps['ce'], 'unit': UNIT, 'h2d_bytes_per_step': e2e_bytes, 'd2h_bytes_per_step': rec[-1]['csize_e']},
+        'e2e_ceiling': {
+            'h2d_GBps_all_ranks': world * ceil_bytes / h2d_s / 1e9, 'd2h_GBps_all_ranks': world * ceil_bytes / d2h_s / 1e9,
+            'compress_GBps': world * ceil_bytes / max(h2d_s, d2h_s * rec[-1]['csize_e'] / e2e_bytes) / 1e9,
+            'decompress_GBps': world * ceil_bytes / max(d2h_s, h2d_s * rec[-1]['csize_e'] / e2e_bytes) / 1e9,
+            'note': 'copy-only pinned-memory transfers of %.1f GB per rank, all ranks at once (max over ranks): what the '
+                    'host link alone allows for raw-in/compressed-out and compressed-in/raw-out' % (ceil_bytes / 1e9)},
+        'configs': legs,
         'decompress': {
+            'roofline': {'kernel': 'block-parallel inflate (par_find/validate/block/lz), reference-written streams',
+                         'bound': 'issue', 'achieved': (raw_bytes + ref_total) / (inf_ms / 1e3) / 1e9, 'peak': hbm,
+                         'unit': 'GB/s', 'frac': (raw_bytes + ref_total) / (inf_ms / 1e3) / 1e9 / hbm,
+                         'note': 'algorithmic bytes = compressed read + raw written per step, over the inflate stage'},
             'reference_written': {'value': gbps['r'], 'unit': UNIT, 'e2e_value': gbps['re'], 'inflate_ms': inf_ms,
                                   'streams': n_chunks, 'stage_ms': stage_r,
                                   'note': 'index-less zlib streams (what the reference Writer emits): block-parallel decoder'},
             'gpu_written': {'value': gbps['g'], 'unit': UNIT, 'stage_ms': stage_g, 'note': 'in-band segment index: every segment is one known block for the block kernels'}},
         'ratio': {'gpu_comp_over_raw': csize / raw_bytes, 'zlib6_comp_over_raw': ref_total / raw_bytes,
                   'gpu_size_over_zlib': csize / ref_total, 'north_star_limit': 1.031},
-        'roofline': {'kernel': 'lz77_kernel<2>', 'bound': 'hbm', 'achieved': achieved, 'peak': hbm, 'unit': 'GB/s',
+        'roofline': {'kernel': 'lz77_kernel<2,512>', 'bound': 'issue', 'achieved': achieved, 'peak': hbm, 'unit': 'GB/s',
                      'frac': achieved / hbm, 'traffic': traffic, 'peak_source': how,
-                     'note': 'algorithmic bytes = raw + compressed per step; the match finder is shared-memory '
-                             'latency bound, not HBM bound (see DESIGN.md)',
+                     'issue_slot_frac': prof.get('issue_slot_frac'), 'alu_pipe_frac': prof.get('alu_pipe_frac'),
+                     'warp_inst_per_raw_byte': prof.get('warp_inst_per_raw_byte'),
+                     'note': 'frac = algorithmic bytes (raw + compressed per step) / kernel time / measured HBM peak, as '
+                             'the contract defines it; the kernel is bound by instruction issue (integer ALU pipe), '
+                             'not by HBM: issue_slot_frac / alu_pipe_frac are from the committed ncu capture '
+                             '(profiles/r02_lz77_ncu.json)',
                      'hbm_bound_stages': hbm_stages,
                      'stage_ms': dict(zip(['h2d', 'transform', 'adler', 'lz77', 'huffman_scan', 'encode', 'd2h', 'total'],
                                           [float(np.mean([r['tm'][i] for r in rec])) for i in range(8)]))},

@@ -76,6 +76,30 @@ def _declare(lib):
     return lib
 
 
+class HostBuffer:
+    """Pinned host memory from mtsb_host_alloc, visible as a NumPy uint8 array (`.array`) and a raw pointer (`.ptr`).
+    Views of `.array` must not outlive the buffer."""
+
+    def __init__(self, lib, nbytes):
+        self.lib, self.nbytes = lib, int(nbytes)
+        self.ptr = lib.mtsb_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError('mtsb_host_alloc(%d) failed' % self.nbytes)
+        self.array = np.ctypeslib.as_array((C.c_ubyte * self.nbytes).from_address(self.ptr))
+
+    def release(self):
+        if self.ptr:
+            self.array = None
+            self.lib.mtsb_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
 _lib = None
 _lib_lock = threading.Lock()
 
@@ -116,6 +140,8 @@ class Codec:
             raise NativeUnavailable('mtsb_create failed: %s' % self.lib.mtsb_last_error(None).decode())
         self.device = int(device)
         self.lock = threading.Lock()
+        self.stage_lock = threading.RLock()     # guards the named staging buffers below (one user at a time)
+        self._staging = {}
         # tunables for experiments without touching code: MTSCOMP_B200_PARAMS="par_batch_bytes=4294967296,max_chain=8"
         for kv in filter(None, os.environ.get('MTSCOMP_B200_PARAMS', '').split(',')):
             k, v = kv.split('=')
@@ -123,8 +149,37 @@ class Codec:
 
     def close(self):
         if getattr(self, 'ctx', None):
+            for b in self._staging.values():
+                b.release()
+            self._staging.clear()
             self.lib.mtsb_destroy(self.ctx)
             self.ctx = None
+
+    # -- pinned staging and device memory (the Python layer's I/O buffers)
+    def host_buffer(self, name, nbytes):
+        """Named pinned buffer of at least `nbytes`, kept for reuse and grown on demand (hold `stage_lock` while the
+        contents matter)."""
+        b = self._staging.get(name)
+        if b is None or b.nbytes < nbytes:
+            if b is not None:
+                b.release()
+            b = self._staging[name] = HostBuffer(self.lib, max(int(nbytes) + (int(nbytes) >> 3), 1 << 16))
+        return b
+
+    def device_alloc(self, nbytes):
+        p = self.lib.mtsb_device_alloc(self.ctx, int(nbytes))
+        if not p:
+            raise MemoryError('mtsb_device_alloc(%d) failed' % nbytes)
+        return p
+
+    def device_free(self, ptr):
+        if getattr(self, 'ctx', None) and ptr:
+            self.lib.mtsb_device_free(self.ctx, C.c_void_p(ptr))
+
+    def memcpy(self, dst, src, nbytes, kind):
+        """kind 1: host -> device, 2: device -> host, 3: device -> device (synchronous)."""
+        with self.lock:
+            self._check(self.lib.mtsb_memcpy(self.ctx, C.c_void_p(dst), C.c_void_p(src), int(nbytes), int(kind)))
 
     def __del__(self):
         try:

@@ -13,6 +13,7 @@ ignores trailing bytes), which lets the GPU Reader decode a chunk's segments in 
 """
 
 import bisect
+from collections import OrderedDict
 from functools import lru_cache
 import hashlib
 import json
@@ -31,7 +32,9 @@ from .rawio import load_raw_data
 
 _seek_lock = Lock()
 CRITICAL_ERROR_URL = "https://github.com/int-brain-lab/mtscomp/issues/new?title=Critical+error"
-GPU_BATCH_CHUNKS = 64  # chunks handed to the GPU per call by Writer.write / Reader.tofile
+GPU_BATCH_CHUNKS = 64        # chunks handed to the GPU per call by Writer.write / Reader.tofile ...
+GPU_BATCH_BYTES = 1 << 30    # ... and at most this many raw bytes (long chunks: the host staging stays bounded)
+MAX_CHUNK_BYTES = 0x7fffffff  # the kernels index a chunk with 32 bits
 
 
 def _require_integer_dtype(dtype):
@@ -39,6 +42,8 @@ def _require_integer_dtype(dtype):
     float64 (IEEE differences, sequential sums in np.cumsum's order: the decoded values equal the reference Reader's
     bit for bit, which — as in the reference — are close to, not identical with, what was written)."""
     dtype = np.dtype(dtype)
+    if dtype.byteorder not in ('=', '|', '<' if np.little_endian else '>'):
+        raise NotImplementedError("mtscomp_b200 works on native-endian data; dtype %s is not supported." % dtype.str)
     ok_int = np.issubdtype(dtype, np.integer) and dtype.itemsize in (1, 2, 4, 8)
     ok_float = dtype.kind == 'f' and dtype.itemsize in (4, 8)
     if not (ok_int or ok_float):
@@ -51,6 +56,26 @@ def _require_integer_dtype(dtype):
 def _codec_for(config):
     dev = config.get('device', None)
     return _native.default_codec(dev)
+
+
+def _batch_ranges(bounds, row_bytes, first, last):
+    """[lo, hi) chunk ranges covering [first, last): at most GPU_BATCH_CHUNKS chunks and GPU_BATCH_BYTES raw bytes each
+    (a single chunk larger than that forms its own batch)."""
+    lo = first
+    while lo < last:
+        hi = lo + 1
+        while hi < last and hi - lo < GPU_BATCH_CHUNKS and (bounds[hi + 1] - bounds[lo]) * row_bytes <= GPU_BATCH_BYTES:
+            hi += 1
+        yield lo, hi
+        lo = hi
+
+
+def _check_chunk_limits(bounds, n_channels, itemsize):
+    big = max(bounds[i + 1] - bounds[i] for i in range(len(bounds) - 1)) * n_channels * itemsize
+    if big > MAX_CHUNK_BYTES:
+        raise NotImplementedError(
+            "a chunk of %d bytes exceeds the %d bytes the CUDA codec handles per chunk; use a shorter chunk_duration."
+            % (big, MAX_CHUNK_BYTES))
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -138,6 +163,7 @@ class Writer:
         logger.info("Opening %s, duration %.1fs, %d channels.", data_path,
                     self.n_samples / self.sample_rate, self.n_channels)
         self._compute_chunk_bounds()
+        _check_chunk_limits(self.chunk_bounds, self.n_channels, np.dtype(self.dtype).itemsize)
         self.sha1_compressed = hashlib.sha1()
         self.sha1_uncompressed = hashlib.sha1()
 
@@ -207,37 +233,44 @@ class Writer:
         if not outmeta:
             outmeta = self.data_path.with_suffix('.ch')
         Path(out).parent.mkdir(exist_ok=True, parents=True)
-        offset = 0
         self.chunk_offsets = [0]
         logger.info("Starting compression on the GPU.")
-        step = max(int(self.batch_size), GPU_BATCH_CHUNKS)
-        # The two SHA-1 digests of the .ch format run at ~1 GB/s per core, far below the GPU: each digest gets its own
-        # worker (one thread each keeps the update order; hashlib releases the GIL) and works on batch k while the
-        # GPU compresses batch k+1.  The file is written by the worker that hashes the compressed bytes.
-        def _hash_raw(batch):
-            for idx in sorted(batch.keys()):
-                self.sha1_uncompressed.update(batch[idx][0])
+        dtype = _require_integer_dtype(self.dtype)
+        codec = _codec_for(self.config)
+        flags = _native._fl(self._flags(), dtype)
+        nc, isz, b = self.n_channels, dtype.itemsize, self.chunk_bounds
+        ranges = list(_batch_ranges(b, nc * isz, 0, self.n_chunks))
+        caps = [sum(codec.compress_bound(b[i + 1] - b[i], nc, isz, flags) for i in range(lo, hi)) for lo, hi in ranges]
+        # Batches go through two pairs of PINNED staging buffers: the memory map is read straight into one (no
+        # intermediate copy), the codec fills the other with the packed streams, and while the GPU works on batch k+1 two
+        # workers finish batch k: one feeds the raw bytes to its SHA-1, the other writes and hashes the compressed bytes.
+        # The two digests the .ch format demands run at 1-2 GB/s per core and are the ceiling of this method.
+        def _write_and_hash(fb, comp):
+            fb.write(comp)
+            self.sha1_compressed.update(comp)
 
-        def _write_and_hash(fb, batch):
-            for idx in sorted(batch.keys()):
-                cbytes = batch[idx][1]
-                fb.write(cbytes)
-                self.sha1_compressed.update(cbytes)
-
-        with open(out, 'wb') as fb, ThreadPoolExecutor(1) as raw_worker, ThreadPoolExecutor(1) as out_worker:
-            pending = []
-            for first in tqdm(range(0, self.n_chunks, step), desc='Compressing', disable=self.quiet):
-                last = min(first + step, self.n_chunks)
-                batch = self.compress_batch(first, last)
-                assert set(batch.keys()) <= set(range(first, last))
-                for idx in sorted(batch.keys()):
-                    offset += len(batch[idx][1])
-                    self.chunk_offsets.append(offset)
-                for f in pending:                      # at most one batch in flight per worker: bounded memory
+        with codec.stage_lock, open(out, 'wb') as fb, \
+                ThreadPoolExecutor(1) as raw_worker, ThreadPoolExecutor(1) as out_worker:
+            raw_bufs = [codec.host_buffer('w_raw%d' % i, max((b[hi] - b[lo]) * nc * isz for lo, hi in ranges)) for i in (0, 1)]
+            comp_bufs = [codec.host_buffer('w_comp%d' % i, max(caps)) for i in (0, 1)]
+            pending = [[], []]
+            for k, (lo, hi) in enumerate(tqdm(ranges, desc='Compressing', disable=self.quiet)):
+                slot = k & 1
+                for f in pending[slot]:                # the slot's previous batch has been hashed and written
                     f.result()
-                pending = [raw_worker.submit(_hash_raw, batch), out_worker.submit(_write_and_hash, fb, batch)]
-            for f in pending:
-                f.result()
+                n_raw = (b[hi] - b[lo]) * nc * isz
+                raw = raw_bufs[slot].array[:n_raw]
+                np.copyto(raw.view(dtype).reshape(-1, nc), self.data[b[lo]:b[hi], :])
+                rows = np.asarray(b[lo:hi + 1], dtype=np.int64) - b[lo]
+                offs = codec.compress_ptr(raw_bufs[slot].ptr, 0, rows, nc, isz, flags, comp_bufs[slot].ptr, 0, caps[k])
+                base = self.chunk_offsets[-1]
+                self.chunk_offsets.extend(int(base + o) for o in offs[1:])
+                comp = comp_bufs[slot].array[:int(offs[-1])]
+                pending[slot] = [raw_worker.submit(self.sha1_uncompressed.update, raw),
+                                 out_worker.submit(_write_and_hash, fb, comp)]
+            for fs in pending:
+                for f in fs:
+                    f.result()
             csize = fb.tell()
         assert self.chunk_offsets[-1] == csize
         ratio = csize / self.file_size
@@ -278,6 +311,45 @@ class _SerialPool:
         pass
 
 
+class _DeviceBlock:
+    """Device memory holding the decoded rows of one or more consecutive chunks."""
+
+    def __init__(self, codec, nbytes):
+        self.codec, self.nbytes = codec, int(nbytes)
+        self.ptr = codec.device_alloc(self.nbytes)
+
+    def __del__(self):
+        try:
+            self.codec.device_free(self.ptr)
+        except Exception:  # pragma: no cover
+            pass
+
+
+class _DeviceChunkCache:
+    """LRU of decoded chunks kept IN DEVICE MEMORY (the reference keeps host arrays, mtscomp.py:582-588): a repeated or
+    overlapping read costs one device-to-host copy of the rows asked for instead of a decode.
+    Entry: chunk_idx -> (block, byte offset of the chunk in the block, bytes)."""
+
+    def __init__(self, capacity):
+        self.capacity = max(int(capacity), 1)
+        self.entries = OrderedDict()
+
+    def get(self, idx):
+        e = self.entries.get(idx)
+        if e is not None:
+            self.entries.move_to_end(idx)
+        return e
+
+    def put(self, idx, entry):
+        self.entries[idx] = entry
+        self.entries.move_to_end(idx)
+        while len(self.entries) > self.capacity:
+            self.entries.popitem(last=False)
+
+    def clear(self):
+        self.entries.clear()
+
+
 class Reader:
     """Random-access reader of `.cbin` + `.ch` (reference mtscomp.py:514-859), decoding on the GPU."""
 
@@ -315,6 +387,12 @@ class Reader:
                 logger.error("File to decompress has unexpected extension %s.", Path(cdata).suffix)
             cdata = open(cdata, 'rb')
         self.cdata = cdata
+        try:
+            self._fd = cdata.fileno()
+        except Exception:
+            self._fd = None
+        _check_chunk_limits(self.chunk_bounds, self.n_channels, self.dtype.itemsize)
+        self._dev_cache = _DeviceChunkCache(self.cache_size)
         self.set_cache_size()
 
     def set_cache_size(self, cache_size=None):
@@ -324,6 +402,8 @@ class Reader:
             assert cache_size > 0
             self.read_chunk = lru_cache(maxsize=cache_size)(self.read_chunk)
             self.cache_size = cache_size
+            if getattr(self, '_dev_cache', None) is not None:
+                self._dev_cache.capacity = cache_size
 
     def iter_chunks(self, first_chunk=0, last_chunk=None):
         """Yield (chunk_idx, chunk_start, chunk_length) (reference mtscomp.py:590-600)."""
@@ -337,8 +417,8 @@ class Reader:
         return _native.flags_of(self.cmeta.do_time_diff, self.cmeta.do_spatial_diff, self.chunk_order)
 
     def _pread(self, length, start):
-        if hasattr(os, 'pread'):
-            buf = os.pread(self.cdata.fileno(), length, start)
+        if self._fd is not None and hasattr(os, 'pread'):
+            buf = os.pread(self._fd, length, start)
         else:  # pragma: no cover
             with _seek_lock:
                 self.cdata.seek(start)
@@ -346,28 +426,118 @@ class Reader:
         assert len(buf) == length
         return buf
 
-    def _decode_block(self, chunk_ids, spans):
-        """Decode several chunks in one GPU call -> (array of all their rows, row offsets).
-        spans: [(start, length)] in the .cbin; consecutive chunks are fetched with a single read."""
-        _require_integer_dtype(self.dtype)
-        lengths = [length for _, length in spans]
-        offs = np.concatenate(([0], np.cumsum(lengths))).astype(np.int64)
-        if all(spans[k][0] + spans[k][1] == spans[k + 1][0] for k in range(len(spans) - 1)):
-            blob = self._pread(int(offs[-1]), spans[0][0])
+    def _pread_into(self, view, start):
+        """Fill the uint8 array `view` (pinned staging) from the .cbin at `start`, without intermediate bytes objects."""
+        n = view.shape[0]
+        if self._fd is not None and hasattr(os, 'preadv'):
+            mv = memoryview(view)
+            got = 0
+            while got < n:
+                k = os.preadv(self._fd, [mv[got:]], start + got)
+                assert k > 0, "unexpected end of the compressed file"
+                got += k
         else:
-            blob = b''.join(self._pread(length, start) for start, length in spans)
+            view[:] = np.frombuffer(self._pread(n, start), dtype=np.uint8)
+
+    def _stage_compressed(self, codec, spans):
+        """Read the .cbin ranges `spans` [(start, length)] back to back into the pinned 'r_comp' buffer (one read per
+        run of adjacent ranges) -> (buffer, offsets)."""
+        offs = np.concatenate(([0], np.cumsum([length for _, length in spans]))).astype(np.int64)
+        buf = codec.host_buffer('r_comp', int(offs[-1]) + 64)
+        k = 0
+        while k < len(spans):
+            j = k
+            while j + 1 < len(spans) and spans[j][0] + spans[j][1] == spans[j + 1][0]:
+                j += 1
+            self._pread_into(buf.array[int(offs[k]):int(offs[j + 1])], spans[k][0])
+            k = j + 1
+        return buf, offs
+
+    def _rows_of(self, chunk_ids):
         sizes = [self.chunk_bounds[i + 1] - self.chunk_bounds[i] for i in chunk_ids]
-        rows = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
-        out, status = _codec_for(self.config).decompress(blob, offs, rows, self.n_channels, self.dtype, self._flags())
+        return np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
+
+    def _raise_if_corrupt(self, status, chunk_ids):
         bad = np.flatnonzero(status)
         if len(bad):
             raise IOError("Compressed chunk #%d is corrupted." % chunk_ids[int(bad[0])])
+
+    def _decode_into(self, chunk_ids, spans, dst_ptr, dst_is_device):
+        """One GPU call: chunks `chunk_ids` (compressed bytes at `spans`) decoded back to back at `dst_ptr`."""
+        dtype = _require_integer_dtype(self.dtype)
+        codec = _codec_for(self.config)
+        with codec.stage_lock:
+            buf, offs = self._stage_compressed(codec, spans)
+            rows = self._rows_of(chunk_ids)
+            status = codec.decompress_ptr(buf.ptr, 0, offs, rows, self.n_channels, dtype.itemsize,
+                                          _native._fl(self._flags(), dtype), dst_ptr, int(dst_is_device))
+        self._raise_if_corrupt(status, chunk_ids)
+        return rows
+
+    def _decode_block(self, chunk_ids, spans):
+        """Decode several chunks in one GPU call -> (fresh host array of all their rows, row offsets)."""
+        rows = self._rows_of(chunk_ids)
+        out = np.empty((int(rows[-1]), self.n_channels), dtype=self.dtype)
+        self._decode_into(chunk_ids, spans, out.ctypes.data, False)
         return out, rows
 
     def _decode(self, chunk_ids, spans):
         """Decode several chunks in one GPU call -> list of per-chunk arrays (views of one block)."""
         out, rows = self._decode_block(chunk_ids, spans)
         return [out[rows[k]:rows[k + 1]] for k in range(len(chunk_ids))]
+
+    def _span(self, idx):
+        return self.chunk_offsets[idx], self.chunk_offsets[idx + 1] - self.chunk_offsets[idx]
+
+    def _device_chunks(self, first, last):
+        """Make chunks first..last resident in device memory (decoding the missing ones, a run of consecutive misses
+        per GPU call) and yield (chunk_idx, device pointer of its first row)."""
+        codec = _codec_for(self.config)
+        row_bytes = self.n_channels * self.dtype.itemsize
+        idx = first
+        while idx <= last:
+            e = self._dev_cache.get(idx)
+            if e is not None:
+                yield idx, e[0].ptr + e[1], e
+                idx += 1
+                continue
+            hi = idx + 1
+            while hi <= last and hi - idx < GPU_BATCH_CHUNKS and self._dev_cache.entries.get(hi) is None and \
+                    (self.chunk_bounds[hi + 1] - self.chunk_bounds[idx]) * row_bytes <= GPU_BATCH_BYTES:
+                hi += 1
+            ids = list(range(idx, hi))
+            block = _DeviceBlock(codec, (self.chunk_bounds[hi] - self.chunk_bounds[idx]) * row_bytes + 256)
+            rows = self._decode_into(ids, [self._span(i) for i in ids], block.ptr, True)
+            for k, i in enumerate(ids):
+                e = (block, int(rows[k]) * row_bytes, int(rows[k + 1] - rows[k]) * row_bytes)
+                self._dev_cache.put(i, e)
+                yield i, block.ptr + e[1], e
+            idx = hi
+
+    def _read_rows(self, i0, i1):
+        """Rows [i0, i1) as a fresh C-contiguous host array: the chunks they touch are decoded into (or found in) the
+        device-side cache and only the rows asked for cross the bus."""
+        codec = _codec_for(self.config)
+        row_bytes = self.n_channels * self.dtype.itemsize
+        out = np.empty((i1 - i0, self.n_channels), dtype=self.dtype)
+        first, last = self._chunks_for_interval(i0, i1)
+        # consecutive chunks of one device block are fetched with a single copy
+        run_ptr = run_dst = run_len = None
+        for idx, ptr, _keep in self._device_chunks(first, last):
+            c0, c1 = self.chunk_bounds[idx], self.chunk_bounds[idx + 1]
+            a, b = max(i0, c0), min(i1, c1)
+            if b <= a:
+                continue
+            src, dst, n = ptr + (a - c0) * row_bytes, (a - i0) * row_bytes, (b - a) * row_bytes
+            if run_ptr is not None and run_ptr + run_len == src and run_dst + run_len == dst:
+                run_len += n
+                continue
+            if run_ptr is not None:
+                codec.memcpy(out.ctypes.data + run_dst, run_ptr, run_len, 2)
+            run_ptr, run_dst, run_len = src, dst, n
+        if run_ptr is not None:
+            codec.memcpy(out.ctypes.data + run_dst, run_ptr, run_len, 2)
+        return out
 
     def read_chunk(self, chunk_idx, chunk_start, chunk_length):
         """Read + decode one chunk -> C-contiguous (n_samples_chunk, n_channels) (reference mtscomp.py:602-635)."""
@@ -427,25 +597,10 @@ class Reader:
             i1 = self._validate_index(item.stop, self.n_samples)
             if i1 <= i0:
                 return empty
-            first, last = self._chunks_for_interval(i0, i1)
-            if first == last:
-                chunks = [self.read_chunk(idx, start, length) for idx, start, length in self.iter_chunks(first, last)]
-            else:
-                # several chunks: batched GPU calls (the reference decodes them one by one, mtscomp.py:826-829); a
-                # single batch is returned as is, without the concatenation copy
-                todo = list(self.iter_chunks(first, last))
-                chunks = []
-                for g in range(0, len(todo), GPU_BATCH_CHUNKS):
-                    part = todo[g:g + GPU_BATCH_CHUNKS]
-                    chunks.append(self._decode_block([idx for idx, _, _ in part],
-                                                     [(start, length) for _, start, length in part])[0])
-            if not chunks:  # pragma: no cover
-                return empty
-            arr = chunks[0] if len(chunks) == 1 else np.concatenate(chunks)
-            assert arr.shape == (self.chunk_bounds[last + 1] - self.chunk_bounds[first], self.n_channels)
-            a, b = i0 - self.chunk_bounds[first], i1 - self.chunk_bounds[first]
-            assert 0 <= a <= b <= arr.shape[0]
-            out = arr[a:b:item.step, :]
+            # the chunks the slice touches are decoded into (or found in) the device-side LRU and only rows i0..i1
+            # are copied to the host (the reference decodes and concatenates whole chunks, mtscomp.py:810-856)
+            arr = self._read_rows(i0, i1)
+            out = arr[::item.step, :] if item.step not in (None, 1) else arr
             assert out.shape[0] == len(range(i0, i1, item.step or 1))
             return out
         if isinstance(item, tuple):
@@ -479,13 +634,25 @@ class Reader:
                 "The output file %s already exists, use --overwrite or specify another output path." % out)
         elif overwrite and out.exists():
             out.unlink()
-        step = max(int(self.batch_size), GPU_BATCH_CHUNKS)
-        with open(out, 'wb') as fb:
-            for first in tqdm(range(0, self.n_chunks, step), desc='Decompressing', disable=self.quiet):
-                last = min(first + step, self.n_chunks)
-                chunks = self.decompress_chunks(range(first, last))
-                for idx in sorted(chunks.keys()):
-                    fb.write(chunks[idx])
+        dtype = _require_integer_dtype(self.dtype)
+        codec = _codec_for(self.config)
+        row_bytes = self.n_channels * dtype.itemsize
+        ranges = list(_batch_ranges(self.chunk_bounds, row_bytes, 0, self.n_chunks))
+        # two pinned output buffers: the GPU decodes batch k+1 into one while a worker writes batch k from the other
+        with codec.stage_lock, open(out, 'wb') as fb, ThreadPoolExecutor(1) as writer:
+            n_max = max((self.chunk_bounds[hi] - self.chunk_bounds[lo]) * row_bytes for lo, hi in ranges)
+            bufs = [codec.host_buffer('r_out%d' % i, n_max) for i in (0, 1)]
+            pending = [None, None]
+            for k, (lo, hi) in enumerate(tqdm(ranges, desc='Decompressing', disable=self.quiet)):
+                slot = k & 1
+                if pending[slot] is not None:
+                    pending[slot].result()
+                ids = list(range(lo, hi))
+                rows = self._decode_into(ids, [self._span(i) for i in ids], bufs[slot].ptr, False)
+                pending[slot] = writer.submit(fb.write, bufs[slot].array[:int(rows[-1]) * row_bytes])
+            for f in pending:
+                if f is not None:
+                    f.result()
             dsize = fb.tell()
         assert dsize == self.chunk_bounds[-1] * self.n_channels * self.dtype.itemsize
         logger.info("Wrote %s (%.1f GB).", out, dsize / 1024 ** 3)
@@ -495,6 +662,8 @@ class Reader:
             logger.debug("Automatic integrity check after decompression PASSED.")
 
     def close(self):
+        if getattr(self, '_dev_cache', None) is not None:
+            self._dev_cache.clear()
         if self.cdata:
             self.cdata.close()
 
@@ -543,20 +712,22 @@ def check(data, out, outmeta):
     """Decode every chunk and compare with `data` (reference mtscomp.py:866-888); AssertionError on mismatch."""
     unc = decompress(out, outmeta)
     try:
-        step = GPU_BATCH_CHUNKS
-        for first in tqdm(range(0, unc.n_chunks, step), desc='Checking'):
-            last = min(first + step, unc.n_chunks)
-            chunks = unc.decompress_chunks(range(first, last))
-            for idx in range(first, last):
-                i0, i1 = unc.chunk_bounds[idx], unc.chunk_bounds[idx + 1]
-                expected = data[i0:i1]
-                chunk = chunks[idx]
-                assert chunk.dtype == expected.dtype
-                assert chunk.shape == expected.shape
-                if np.issubdtype(chunk.dtype, np.integer):
-                    assert np.array_equal(chunk, expected)
-                else:  # pragma: no cover
-                    assert np.allclose(chunk, expected, atol=CHECK_ATOL)
+        dtype = _require_integer_dtype(unc.dtype)
+        codec = _codec_for(unc.config)
+        row_bytes = unc.n_channels * dtype.itemsize
+        assert tuple(data.shape) == tuple(unc.shape) and data.dtype == dtype
+        with codec.stage_lock:
+            for lo, hi in tqdm(list(_batch_ranges(unc.chunk_bounds, row_bytes, 0, unc.n_chunks)), desc='Checking'):
+                ids = list(range(lo, hi))
+                buf = codec.host_buffer('r_out0', (unc.chunk_bounds[hi] - unc.chunk_bounds[lo]) * row_bytes)
+                rows = unc._decode_into(ids, [unc._span(i) for i in ids], buf.ptr, False)
+                got = buf.array[:int(rows[-1]) * row_bytes].view(dtype).reshape(-1, unc.n_channels)
+                expected = data[unc.chunk_bounds[lo]:unc.chunk_bounds[hi]]
+                assert got.shape == expected.shape
+                if np.issubdtype(dtype, np.integer):
+                    assert np.array_equal(got, expected)
+                else:
+                    assert np.allclose(got, expected, atol=CHECK_ATOL)
     finally:
         unc.close()
 

@@ -66,3 +66,22 @@ def test_cross_compatibility(ref, emulated_default_codec, tmp_path, kw):
             assert mg[k] == mr[k], k
     # ratio: within the north star's 3 % of the reference's zlib
     assert (tmp_path / 'g.cbin').stat().st_size <= 1.031 * (tmp_path / 'r.cbin').stat().st_size + 64 * len(mg['chunk_bounds'])
+
+
+def test_port_reader_equals_reference_reader(ref, tmp_path):
+    """oracle/reader.PortReader (the CPU baseline of the latency measurement) returns what the unmodified reference
+    Reader returns, slice for slice, including its cache behaviour at cache_size 1."""
+    from oracle.reader import PortReader
+    rng = np.random.default_rng(0)
+    x = np.cumsum(rng.integers(-5, 6, (7000, 13)), axis=0).astype(np.int16)
+    x.tofile(tmp_path / 'a.bin')
+    ref.compress(tmp_path / 'a.bin', tmp_path / 'a.cbin', tmp_path / 'a.ch', sample_rate=1000., n_channels=13,
+                 dtype=np.int16, quiet=True, check_after_compress=False, n_threads=1)
+    r = ref.decompress(tmp_path / 'a.cbin', tmp_path / 'a.ch')
+    p = PortReader(tmp_path / 'a.cbin', tmp_path / 'a.ch', cache_size=1)
+    for a, b, c in [(0, 10, None), (990, 1010, None), (500, 6500, 3), (6990, 7000, None), (-5, None, None),
+                    (None, None, None), (3000, 2000, None), (999, 1000, None), (1000, 1001, None)]:
+        assert np.array_equal(r[a:b:c], p[a:b:c]), (a, b, c)
+        assert p.chunks_for_interval(a or 0, b or 7000) == r._chunks_for_interval(a or 0, b or 7000)
+    r.close()
+    p.close()

@@ -61,3 +61,41 @@ def test_two_ranks_reassemble_the_sequential_file(tmp_path):
     assert offsets.tolist() == woffs.tolist()
     assert bases == [0, len(parts[0])]
     assert np.array_equal(np.concatenate(parts), want)
+
+
+def _file_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import mtscomp_b200 as M
+    M.CONFIG_PATH = os.path.join(tmp, '.mtscomp')
+    sharding.write_sharded(os.path.join(tmp, 'data.bin'), os.path.join(tmp, 'data.cbin'), os.path.join(tmp, 'data.ch'),
+                           rank, world, sample_rate=1000., n_channels=12, dtype=np.int16, codec=_OracleCodec())
+    dist.destroy_process_group()
+
+
+def test_two_ranks_write_one_file(tmp_path):
+    """write_sharded at world size 2 (host logic only: offsets, pwrite at the rank bases, digests, .ch) gives the file
+    a sequential writer gives, and the reference's own Reader semantics hold for it (zlib per chunk, SHA-1s)."""
+    import hashlib
+    import json
+    import zlib
+    import torch.multiprocessing as mp
+    from oracle import codec as ora
+    rng = np.random.default_rng(3)
+    data = np.cumsum(rng.integers(-9, 10, (7300, 12)), axis=0).astype(np.int16)
+    data.tofile(tmp_path / 'data.bin')
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_file_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    meta = json.loads((tmp_path / 'data.ch').read_text())
+    blob = (tmp_path / 'data.cbin').read_bytes()
+    b, o = meta['chunk_bounds'], meta['chunk_offsets']
+    assert b == list(range(0, 7300, 1000)) + [7300] and o[-1] == len(blob)
+    assert meta['sha1_compressed'] == hashlib.sha1(blob).hexdigest()
+    assert meta['sha1_uncompressed'] == hashlib.sha1(data.tobytes()).hexdigest()
+    for i in range(len(b) - 1):
+        assert zlib.decompress(blob[o[i]:o[i + 1]]) == ora.transform_chunk(data[b[i]:b[i + 1]])
