@@ -523,7 +523,9 @@ class Reader:
         first, last = self._chunks_for_interval(i0, i1)
         # consecutive chunks of one device block are fetched with a single copy
         run_ptr = run_dst = run_len = None
-        for idx, ptr, _keep in self._device_chunks(first, last):
+        keep = []                                     # the blocks stay alive until their rows have been copied
+        for idx, ptr, entry in self._device_chunks(first, last):
+            keep.append(entry)
             c0, c1 = self.chunk_bounds[idx], self.chunk_bounds[idx + 1]
             a, b = max(i0, c0), min(i1, c1)
             if b <= a:

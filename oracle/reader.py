@@ -52,7 +52,9 @@ class PortReader:
         last = clip(bisect.bisect_right(self.bounds, i1, lo=first) - 1, 0, self.n_chunks - 1)
         return first, last
 
-    def __getitem__(self, item):                                 # mtscomp.py:798-856, slices only
+    def __getitem__(self, item):                                 # mtscomp.py:798-856: slices, (slice, columns)
+        if isinstance(item, tuple):
+            return self[item[0]] if len(item) == 1 else self[item[0]][:, item[1]]
         assert isinstance(item, slice)
         i0 = 0 if item.start is None else int(item.start)
         i1 = self.n_samples if item.stop is None else int(item.stop)

@@ -93,14 +93,14 @@ def write_reference_style(arr, sample_rate, cbin, ch, threads):
     Path(ch).write_text(json.dumps(meta, indent=2, sort_keys=True))
 
 
-def latency_leg(threads, n_chunks=16, n_gpu=(40, 40, 30, 12), n_cpu=(10, 10, 6, 3), seed=11):
+def latency_leg(threads, n_chunks=16, n_gpu=(40, 40, 30, 12), n_cpu=(10, 10, 6, 3), seed=11, ns=30000, nc=384):
     """p50 / p99 of `r[t0:t1, :]` for 10 ms, 100 ms, 1 s and 10 s windows at random t0 on 384-channel 30 kHz data
     (23.04 MB chunks), cache_size = 1: the GPU Reader on a reference-written and on a GPU-written file, and the oracle
     port of the reference Reader on the reference-written file, all on this box, files on tmpfs."""
     import mtscomp_b200 as M
     from mtscomp_b200 import synth
     from oracle.reader import PortReader
-    ns, nc, sr = 30000, 384, 30000.
+    sr = float(ns)
     d = scratch_dir('lat')
     try:
         M.CONFIG_PATH = d / '.mtscomp'
@@ -110,7 +110,7 @@ def latency_leg(threads, n_chunks=16, n_gpu=(40, 40, 30, 12), n_cpu=(10, 10, 6, 
         write_reference_style(arr, sr, d / 'ref.cbin', d / 'ref.ch', threads)
         M.compress(d / 'np2.bin', d / 'gpu.cbin', d / 'gpu.ch', sample_rate=sr, n_channels=nc, dtype=np.int16,
                    quiet=True, check_after_compress=False)
-        windows = [('10ms', 300), ('100ms', 3000), ('1s', 30000), ('10s', 300000)]
+        windows = [('10ms', ns // 100), ('100ms', ns // 10), ('1s', ns), ('10s', 10 * ns)]
         readers = [('gpu_reader_reference_written', lambda: M.decompress(d / 'ref.cbin', d / 'ref.ch', cache_size=1), n_gpu),
                    ('gpu_reader_gpu_written', lambda: M.decompress(d / 'gpu.cbin', d / 'gpu.ch', cache_size=1), n_gpu),
                    ('cpu_port_reader_reference_written', lambda: PortReader(d / 'ref.cbin', d / 'ref.ch', cache_size=1), n_cpu)]
