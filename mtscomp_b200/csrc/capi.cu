@@ -63,7 +63,7 @@ struct mtsb_ctx {
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_done = nullptr;
   int lz_ctas_per_sm = 2;
   // device scratch
-  Buf d_pstreams, d_surv, d_cand, d_pcount, d_tokens, d_cells, d_ptab, d_plist, d_pbad, d_boff, d_subs, d_subidx;   // block-parallel inflate scratch
+  Buf d_pstreams, d_surv, d_cand, d_pcount, d_tokens, d_cells, d_ptab, d_plist, d_pbad;   // block-parallel inflate scratch
   Buf d_raw, d_raw2, d_out2, d_comp2, d_T, d_tok, d_hist, d_codes, d_hdrs, d_tab, d_so, d_seg_adler, d_chunk_adler, d_chunk_off, d_out,
       d_partial, d_comp, d_status, d_tadler, d_gather;
   Buf h_tab, h_small;
@@ -368,7 +368,6 @@ void mtsb_destroy(mtsb_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   Buf* bufs[] = {&c->d_pstreams, &c->d_surv, &c->d_cand, &c->d_pcount, &c->d_tokens, &c->d_cells, &c->d_ptab, &c->d_plist, &c->d_pbad,
-                 &c->d_boff, &c->d_subs, &c->d_subidx,
                  &c->d_raw, &c->d_raw2, &c->d_out2, &c->d_comp2, &c->d_T, &c->d_tok, &c->d_hist, &c->d_codes, &c->d_hdrs, &c->d_tab, &c->d_so,
                  &c->d_seg_adler, &c->d_chunk_adler, &c->d_chunk_off, &c->d_out, &c->d_partial, &c->d_comp,
                  &c->d_status, &c->d_tadler, &c->d_gather, &c->h_tab, &c->h_small};
@@ -802,16 +801,13 @@ static int par_decode(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Infla
   const size_t surv_cap = (size_t)std::max<long long>(1 << 20, in_total * 8 / 300);
   // token slots: one per 6 bits of input (typical streams spend 9..15 bits per token); if that is not enough the blocks
   // that do not fit end the chain of their stream (serial decode of the rest)
-  const long long tok_total = in_total * 8 / 6 + 4096 + 32ll * (long long)n_slots;   // (every block's slots are rounded up to 32)
+  const long long tok_total = in_total * 8 / 6 + 4096;
   const size_t o_keys = ((size_t)ns * 4 + 255) & ~(size_t)255;      // d_cand: [bucket fill counts | bucket keys]
   NEED(c->d_pstreams, (size_t)ns * sizeof(ParStream));
   NEED(c->d_pcount, 256);
   NEED(c->d_pbad, (size_t)ns * sizeof(ParRes) + 64);
   NEED(c->d_plist, n_slots * sizeof(ParBlk));
   NEED(c->d_tokens, (size_t)tok_total * 4 + 64);
-  NEED(c->d_boff, (size_t)(tok_total / 32 + 64) * 4);
-  NEED(c->d_subs, n_slots * sizeof(ResSub) + 64);
-  NEED(c->d_subidx, (size_t)ns * 8 + 64);                          // [first run of each stream | number of runs]
   const size_t o_blk = ((size_t)ns * sizeof(ParStream) + 255) & ~(size_t)255;   // host staging: [streams | blocks]
   NEED(c->h_tab, o_blk + (blks ? n_slots * sizeof(ParBlk) : 0) + 64);
   NEED(c->h_small, 4096 + (size_t)ns * (sizeof(ParRes) + 4) + 64);
@@ -842,7 +838,7 @@ static int par_decode(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Infla
   }
   MTS_LAUNCH(par_block_kernel, dim3((unsigned)((n_slots + PAR_BLK_WARPS - 1) / PAR_BLK_WARPS)), dim3(PAR_BLK_WARPS * 32), 0, c->stream,
              dcomp, d_ps, (ParBlk*)c->d_plist.p, (unsigned)n_slots, (unsigned*)c->d_tokens.p,
-             (unsigned long long*)((char*)c->d_pcount.p + 16), (unsigned long long)tok_total, (unsigned*)c->d_boff.p);
+             (unsigned long long*)((char*)c->d_pcount.p + 16), (unsigned long long)tok_total);
   CKL();
   // measured (ms of inflate, chain of tiles / cells): 1 stream 23.4 / 4.1, 8 streams 25.4 / 9.6, 64 streams 35 / 48,
   // 600 streams 180 / 415 -> the cells path is the low-latency path for a handful of streams only
@@ -853,7 +849,7 @@ static int par_decode(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Infla
     for (int i = 1; i < ns; i++) { lo = std::min(lo, ps[i].out_off); hi = std::max(hi, ps[i].out_off + ps[i].out_len); }
     NEED(c->d_cells, (size_t)(hi - lo) * 2 + 64);
     MTS_LAUNCH(par_chain_kernel, dim3((ns + 63) / 64), dim3(64), 0, c->stream, d_ps, (ParBlk*)c->d_plist.p, bcap, (unsigned)ns,
-               (ParRes*)c->d_pbad.p, (ResSub*)nullptr, (unsigned*)nullptr);
+               (ParRes*)c->d_pbad.p);
     CKL();
     auto k = par_lzc_kernel<256, 4096>;
     MTS_LAUNCH(k, dim3((unsigned)n_slots), dim3(256), 0, c->stream, d_ps, (ParBlk*)c->d_plist.p, (const unsigned*)c->d_tokens.p,
@@ -863,35 +859,18 @@ static int par_decode(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Infla
                (const unsigned short*)c->d_cells.p, lo, dT, (ParRes*)c->d_pbad.p);
     CKL();
     c->launches += 3;
+  } else if (c->par_lz_wide < 0 ? ns <= 2 * c->sm_count : c->par_lz_wide == 1) {
+    auto k = par_lz_kernel<1024, 16384>;
+    MTS_LAUNCH(k, dim3(ns), dim3(1024), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p, bcap, (const unsigned*)c->d_tokens.p, dT,
+               (ParRes*)c->d_pbad.p);
+    CKL();
+    c->launches++;
   } else {
-    // chain walk -> runs of tokens per stream -> pipelined resolve (CTA per stream; more warps per stream when there
-    // are few streams, since a stream's batches can only overlap inside its own CTA)
-    unsigned* d_sfirst = (unsigned*)c->d_subidx.p;
-    unsigned* d_scount = d_sfirst + ns;
-    {
-      std::vector<unsigned> sf(ns);
-      for (int i = 0; i < ns; i++) sf[i] = (unsigned)i * bcap;
-      NEED(c->h_tab, o_blk + (blks ? n_slots * sizeof(ParBlk) : 0) + (size_t)ns * 4 + 64);
-      char* hf = (char*)c->h_tab.p + o_blk + (blks ? n_slots * sizeof(ParBlk) : 0);
-      hf = (char*)(((uintptr_t)hf + 15) & ~(uintptr_t)15);
-      memcpy(hf, sf.data(), (size_t)ns * 4);
-      int r = small_copy(c, d_sfirst, hf, (size_t)ns * 4); if (r) return r;
-    }
-    MTS_LAUNCH(par_chain_kernel, dim3((ns + 63) / 64), dim3(64), 0, c->stream, d_ps, (ParBlk*)c->d_plist.p, bcap, (unsigned)ns,
-               (ParRes*)c->d_pbad.p, (ResSub*)c->d_subs.p, d_scount);
+    auto k = par_lz_kernel<256, 4096>;
+    MTS_LAUNCH(k, dim3(ns), dim3(256), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p, bcap, (const unsigned*)c->d_tokens.p, dT,
+               (ParRes*)c->d_pbad.p);
     CKL();
-    const bool wide = c->par_lz_wide < 0 ? ns <= 6 * c->sm_count : c->par_lz_wide == 1;
-    if (wide) {
-      auto k = lz_resolve_kernel<16>;
-      MTS_LAUNCH(k, dim3(ns), dim3(16 * 32), 0, c->stream, d_ps, (const ResSub*)c->d_subs.p, (const unsigned*)d_sfirst,
-                 (const unsigned*)d_scount, (const unsigned*)c->d_tokens.p, (const unsigned*)c->d_boff.p, dT, (ParRes*)c->d_pbad.p);
-    } else {
-      auto k = lz_resolve_kernel<2>;
-      MTS_LAUNCH(k, dim3(ns), dim3(2 * 32), 0, c->stream, d_ps, (const ResSub*)c->d_subs.p, (const unsigned*)d_sfirst,
-                 (const unsigned*)d_scount, (const unsigned*)c->d_tokens.p, (const unsigned*)c->d_boff.p, dT, (ParRes*)c->d_pbad.p);
-    }
-    CKL();
-    c->launches += 2;
+    c->launches++;
   }
   c->launches++;
   char* hs = (char*)c->h_small.p;

@@ -260,7 +260,6 @@ static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
 }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
-template <class T> static inline T __ldcg(const T* p) { return *(const volatile T*)p; }
 using std::max;
 using std::min;
 static inline unsigned min(unsigned a, int b) { return a < (unsigned)b ? a : (unsigned)b; }

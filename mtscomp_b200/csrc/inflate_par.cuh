@@ -10,9 +10,8 @@
 //   (host)                 sort the candidates (stream, bit); a block's bit range ends at the next candidate
 //   3 par_block_kernel     WARP per candidate: tables in shared memory, the 32 lanes decode 32 sub-chunks of the block
 //                          in parallel (self-synchronising Huffman decoding) into 32-bit tokens (literal / length+distance)
-//   4 par_chain_kernel     thread per stream: follows the chain of blocks (each must start where the previous one ended)
-//     lz_resolve_kernel    CTA per stream: turns the tokens of the chained blocks into bytes, 32 tokens per warp at a
-//                          time, the warps of the CTA running ahead of each other behind an in-order watermark
+//   4 par_lz_kernel        CTA per stream: follows the chain of blocks (each must start where the previous one ended) and
+//                          turns their tokens into bytes, a tile of 256 tokens at a time, staged in shared memory
 //   5 (inflate.cuh)        one warp per stream decodes the tail serially (usually nothing or the final small block)
 // Anything unexpected (no chain, overflow of a list, bad data) falls back to the serial decoder, which also produces
 // the error status; this path never decides that a stream is corrupt by itself.
@@ -41,7 +40,7 @@ struct ParBlk {          // a candidate block in stream order (host-sorted), fil
   long long tok_off;     // OUT: first slot in the token buffer
 };
 
-struct ParRes {          // per stream, written by par_chain_kernel / lz_resolve_kernel
+struct ParRes {          // per stream, written by par_lz_kernel
   unsigned tail_bit;     // bit offset where the serial decoder has to resume
   unsigned tail_out;     // output bytes produced so far
   unsigned n_done;       // blocks resolved
@@ -391,13 +390,10 @@ struct SpanRes { unsigned end, ntok, nout, flags; };   // flags: 1 end-of-block 
 // let them drift apart until every lane runs alone (measured: 2.5 active lanes per instruction with a branchy loop).
 // Called by ALL lanes of the warp (run = false: nothing to decode, r is left alone).  Every iteration starts with a
 // warp vote, which makes the lanes reconverge once per symbol; finished lanes idle until the last one is done.
-// EMIT: tok points at the lane's first token slot, which is token gi0 of the block; the block's batch table gets
-// boff_blk[i] = output offset (o0 = the lane's) before token 32 * i.
 template <bool EMIT>
 __device__ __forceinline__ void blk_span(bool run, const unsigned char* in, unsigned in_len, unsigned start,
                                          unsigned bound, const BlkTabs& T, const unsigned short* lenx,
-                                         const unsigned* distx, unsigned* tok, SpanRes& r, unsigned gi0 = 0,
-                                         unsigned o0 = 0, unsigned* boff_blk = nullptr) {
+                                         const unsigned* distx, unsigned* tok, SpanRes& r) {
   const unsigned in_bits = in_len * 8;
   TBits br;
   br.init(in, in_len, run ? start : 0u);
@@ -437,10 +433,7 @@ __device__ __forceinline__ void blk_span(bool run, const unsigned char* in, unsi
     const unsigned xb2 = dx >> 16;
     const unsigned dist = (dx & 0xffffu) + ((win2 >> cl2) & ((1u << xb2) - 1));
     br.drop(isl ? cl2 + xb2 : 0u);
-    if (EMIT) {
-      tok[ntok] = isl ? (0x80000000u | (len << 16) | (dist - 1)) : val;
-      if (((gi0 + ntok) & 31u) == 0) boff_blk[(gi0 + ntok) >> 5] = o0 + nout;
-    }
+    if (EMIT) tok[ntok] = isl ? (0x80000000u | (len << 16) | (dist - 1)) : val;
     ntok++;
     nout += isl ? len : 1u;
   }
@@ -522,8 +515,7 @@ __global__ void __launch_bounds__(PAR_BLK_WARPS * 32) par_block_kernel(const uns
                                                                        ParBlk* __restrict__ blks, unsigned n,
                                                                        unsigned* __restrict__ tokens,
                                                                        unsigned long long* __restrict__ tok_cursor,
-                                                                       unsigned long long tok_capacity,
-                                                                       unsigned* __restrict__ boff) {
+                                                                       unsigned long long tok_capacity) {
   __shared__ BlkTabs tabs[PAR_BLK_WARPS];
   __shared__ unsigned short lenx[32];
   __shared__ unsigned distx[32];
@@ -593,27 +585,26 @@ __global__ void __launch_bounds__(PAR_BLK_WARPS * 32) par_block_kernel(const uns
     // ---- totals and token offsets
     const unsigned bad = __ballot_sync(0xffffffffu, (r.flags & 2) != 0);
     const unsigned eob = __shfl_sync(0xffffffffu, r.flags, 31) & 1;
-    unsigned pre = r.ntok, pre_out = r.nout;
+    unsigned pre = r.ntok, sum_out = r.nout;
     for (int d = 1; d < 32; d <<= 1) {
-      const unsigned v = __shfl_up_sync(0xffffffffu, pre, d), vo = __shfl_up_sync(0xffffffffu, pre_out, d);
-      if ((int)lane >= d) { pre += v; pre_out += vo; }
+      const unsigned v = __shfl_up_sync(0xffffffffu, pre, d);
+      if ((int)lane >= d) pre += v;
     }
+    for (int d = 16; d >= 1; d >>= 1) sum_out += __shfl_xor_sync(0xffffffffu, sum_out, d);
     total_tok = __shfl_sync(0xffffffffu, pre, 31);
-    total_out = __shfl_sync(0xffffffffu, pre_out, 31);
+    total_out = sum_out;
     ok = !bad && eob;
-    // token slots are handed out from one cursor once the count is known (false candidates take some too), in
-    // multiples of 32: the block's batch table then lives at boff[tok_off / 32]
+    // token slots are handed out from one cursor once the count is known (false candidates take some too)
     unsigned long long toff = 0;
-    if (ok && lane == 0) toff = atomicAdd(tok_cursor, (unsigned long long)((total_tok + 31) & ~31u));
+    if (ok && lane == 0) toff = atomicAdd(tok_cursor, (unsigned long long)total_tok);
     toff = __shfl_sync(0xffffffffu, toff, 0);
-    if (toff + ((total_tok + 31) & ~31u) > tok_capacity) ok = false;
+    if (toff + total_tok > tok_capacity) ok = false;
     blk.tok_off = (long long)toff;
     {
       const bool emit = ok && !(r.flags & 4) && r.ntok;
       if (__any_sync(0xffffffffu, emit)) {
         SpanRes r2 = r;
-        blk_span<true>(emit, in, in_len, start, bound, T, lenx, distx, tokens + blk.tok_off + (pre - r.ntok), r2,
-                       pre - r.ntok, pre_out - r.nout, boff + (blk.tok_off >> 5));
+        blk_span<true>(emit, in, in_len, start, bound, T, lenx, distx, tokens + blk.tok_off + (pre - r.ntok), r2);
         if (emit && (r2.ntok != r.ntok || r2.end != r.end)) ok = false;           // cannot happen
       }
     }
@@ -629,6 +620,14 @@ __global__ void __launch_bounds__(PAR_BLK_WARPS * 32) par_block_kernel(const uns
   }
 }
 
+// 5. Tokens -> bytes: one CTA per stream walks the stream's tokens in order, one tile of up to PAR_LZ_THREADS tokens /
+//    PAR_LZ_CAP output bytes at a time (thread = token).  A block-wide scan of the token lengths gives every token its
+//    position; the tile's output is assembled in shared memory and then stored coalesced.  Literals and the bytes that
+//    matches copy from before the tile (global memory, written by earlier tiles) are placed at once; bytes copied from
+//    inside the tile wait, without block barriers, until the PENDING bitmap (one bit per staged byte, set by the
+//    matches that still have to produce it) is clear over their source range.
+// Two shapes: 256 threads / 4 KB (up to 8 CTAs per SM: many streams) and 1024 threads / 16 KB (few streams: a stream
+// is a serial chain of tiles, so its latency is what counts).
 __device__ __forceinline__ unsigned par_bits(unsigned a, unsigned b, unsigned w) {   // bits of [a, b) that fall in word w
   const unsigned lo = max(a, w * 32), hi = min(b, w * 32 + 32);
   if (hi <= lo) return 0;
@@ -655,170 +654,152 @@ __device__ __forceinline__ bool par_range(unsigned* bm, unsigned a, unsigned b) 
   }
   return hit;
 }
-// 5. Tokens -> bytes: lz_resolve_kernel, one CTA of W warps per stream.  The stream's tokens come as RUNS (ResSub: one
-//    per decoded block, or per indexed sub-block of a GPU-written segment) with a table of the output offset before
-//    every 32nd token, so a BATCH of 32 tokens knows where it writes without looking at its predecessors.  The warps
-//    take the batches of the stream round-robin and run AHEAD of each other: a token is a literal run of 1..3 bytes
-//    (stored at once) or a match, which is copied by its lane as soon as the WATERMARK -- the output position up to
-//    which every earlier batch has been committed, in order -- has passed the end of its source; matches that read what
-//    their own batch writes are copied afterwards by the whole warp, one after the other.  Completed batches raise
-//    a flag in a small ring; whoever completes a batch commits every consecutive flagged batch and raises the
-//    watermark.  No block barrier in the loop, no staging in shared memory, every byte is written once.
-struct ResSub {            // a run of tokens, in stream order
-  long long tok_off;       // first token slot (a multiple of 32); the run's batch table starts at boff[tok_off / 32]
-  unsigned n_tok;
-  unsigned out_base;       // output offset of the run inside its stream
-};
-
-__device__ __forceinline__ void spin_pause() {
-#ifdef MTSCOMP_EMU
-  emu::yield();
-#else
-  __nanosleep(20);
-#endif
-}
-__device__ __forceinline__ unsigned vol_ld(const unsigned* p) { return *(const volatile unsigned*)p; }
-
-static const int RES_RING = 64;              // batches between the oldest uncommitted and the newest admitted one
-static const int RES_MAX_SUBS = 2048;        // runs per stream (more: the stream is left to the serial decoder)
-static const unsigned RES_SPIN_LIMIT = 1u << 26;
-
-template <int W>
-__global__ void __launch_bounds__(W * 32) lz_resolve_kernel(const ParStream* __restrict__ streams,
-                                                            const ResSub* __restrict__ subs,
-                                                            const unsigned* __restrict__ sub_first,
-                                                            const unsigned* __restrict__ sub_count,
-                                                            const unsigned* __restrict__ tokens,
-                                                            const unsigned* __restrict__ boff,
-                                                            unsigned char* out_base, ParRes* __restrict__ res) {
-  __shared__ unsigned s_pre[RES_MAX_SUBS + 1];                     // batches before run i
-  __shared__ unsigned s_flag[RES_RING], s_fend[RES_RING];
-  __shared__ unsigned s_wm, s_next, s_fail;
-  const unsigned sidx = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const ParStream st = streams[sidx];
-  const unsigned first = sub_first[sidx], n_sub = sub_count[sidx];
-  const unsigned total_out = res[sidx].tail_out;                   // bytes the runs produce (set by whoever built them)
+template <int PAR_LZ_THREADS, int PAR_LZ_CAP>
+__global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream* __restrict__ streams,
+                                                                const ParBlk* __restrict__ blks,
+                                                                unsigned bstride,
+                                                                const unsigned* __restrict__ tokens,
+                                                                unsigned char* out_base, ParRes* __restrict__ res) {
+  const int NT = PAR_LZ_THREADS;
+  __shared__ unsigned ob_w[PAR_LZ_CAP / 4 + 1];
+  __shared__ unsigned pend_w[PAR_LZ_CAP / 32 + 1];
+  __shared__ unsigned wsum[NT / 32];
+  __shared__ unsigned s_total;
+  unsigned char* ob = (unsigned char*)ob_w;
+  const ParStream st = streams[blockIdx.x];
   unsigned char* out = out_base + st.out_off;
-  if (n_sub == 0) return;
-  if (tid == 0) { s_wm = 0; s_next = 0; s_fail = n_sub > (unsigned)RES_MAX_SUBS ? 1u : 0u; }
-  for (unsigned i = tid; i < (unsigned)RES_RING; i += W * 32) s_flag[i] = 0;
-  if (wid == 0 && n_sub <= (unsigned)RES_MAX_SUBS) {
-    unsigned carry = 0;
-    for (unsigned i0 = 0; i0 < n_sub; i0 += 32) {
-      const unsigned i = i0 + lane;
-      unsigned v = i < n_sub ? (subs[first + i].n_tok + 31) >> 5 : 0u, incl = v;
-      for (int d = 1; d < 32; d <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += u; }
-      if (i < n_sub) s_pre[i] = carry + incl - v;
-      carry += __shfl_sync(0xffffffffu, incl, 31);
+  const unsigned out_cap = (unsigned)st.out_len;
+  const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (unsigned i = tid; i < PAR_LZ_CAP / 32 + 1; i += NT) pend_w[i] = 0;
+  unsigned obase = 0;
+  bool fail = false;
+  // ---- walk the chain of blocks: the first block starts right after the zlib header, every next one where its
+  //      predecessor ended; the walk stops at the first block that is missing or was not decoded cleanly
+  unsigned cur_bit = st.first_bit, n_done = 0, fin = 0;
+  unsigned bj = blockIdx.x * bstride;                        // this stream's blocks: [bj, bend), unused slots have bit ~0
+  const unsigned bend = bj + bstride;
+  for (;;) {
+    while (bj < bend && blks[bj].bit < cur_bit) bj++;
+    if (bj >= bend) break;
+    const ParBlk blk = blks[bj];
+    if (blk.bit != cur_bit || !(blk.flags & 1) || blk.end_bit <= cur_bit || (unsigned long long)obase + blk.out_len > out_cap) break;
+    const unsigned* tk = tokens + blk.tok_off;
+    const unsigned T = blk.n_tok;
+    const unsigned block_end = obase + blk.out_len;
+  unsigned t0 = 0;
+  unsigned nxt = tid < T ? tk[tid] : 0;
+  while (t0 < T) {
+    const unsigned t = nxt;
+    const bool has = t0 + tid < T;
+    if (t0 + NT + tid < T) nxt = tk[t0 + NT + tid];                 // assumes that the whole tile fits (the usual case)
+    const bool isM = has && (t >> 31);
+    const unsigned L = has ? (isM ? (t >> 16) & 0x1ffu : 1u) : 0u;
+    unsigned incl = L;
+    for (int d = 1; d < 32; d <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += v; }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();                                                // also orders the previous tile's stores before the loads below
+    unsigned ws = lane < (unsigned)(NT / 32) ? wsum[lane] : 0u;     // every warp scans the warp totals itself
+    for (int d = 1; d < NT / 32; d <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, ws, d); if ((int)lane >= d) ws += v; }
+    const unsigned woff = __shfl_sync(0xffffffffu, ws, (wid + 31) & 31) * (wid > 0);
+    const unsigned rel = woff + incl - L;                           // position inside the tile
+    const bool fits = has && rel + L <= (unsigned)PAR_LZ_CAP;       // monotone: the tile is the longest fitting prefix
+    const unsigned ncut = (unsigned)__syncthreads_count(fits);
+    if (fits && tid + 1 == ncut) s_total = rel + L;
+    const unsigned dist = (t & 0x7fffu) + 1;
+    bool m = fits && isM;
+    if (m && dist > obase + rel) { fail = true; m = false; }
+    if (fits && obase + rel + L > block_end) { fail = true; m = false; }
+    else if (fits && !isM) ob[rel] = (unsigned char)t;
+    const int srel = (int)rel - (int)dist;                          // source position inside the tile (negative: before it)
+    unsigned n_old = 0;
+    if (m) {
+      n_old = srel < 0 ? min(L, (unsigned)(-srel)) : 0u;
+      if (n_old < L) {                                              // has an in-tile part: its bytes are pending
+        par_range<0>(pend_w, rel, rel + L);
+      }
+      // bytes from before the tile: aligned 32-bit loads (the output buffer is 4-byte aligned and padded), 8 bytes a turn
+      const unsigned char* sp = out + obase + srel;
+      const unsigned mis = (unsigned)((uintptr_t)sp & 3);
+      const unsigned* sw = (const unsigned*)(sp - mis);
+      for (unsigned j0 = 0; j0 < n_old; j0 += 8) {
+        const unsigned w0 = sw[0], w1 = (mis + n_old - j0 > 4) ? sw[1] : 0u, w2 = (mis + n_old - j0 > 8) ? sw[2] : 0u;
+        unsigned v0 = __funnelshift_r(w0, w1, mis * 8), v1 = __funnelshift_r(w1, w2, mis * 8);
+        unsigned char* dp = ob + rel + j0;
+#pragma unroll
+        for (unsigned j = 0; j < 4; j++) { if (j0 + j < n_old) dp[j] = (unsigned char)v0; v0 >>= 8; }
+#pragma unroll
+        for (unsigned j = 4; j < 8; j++) { if (j0 + j < n_old) dp[j] = (unsigned char)v1; v1 >>= 8; }
+        sw += 2;
+      }
+      if (n_old == L) m = false;
     }
-    if (lane == 0) s_pre[n_sub] = carry;
-  }
-  __syncthreads();
-  if (!vol_ld(&s_fail)) {
-    const unsigned total = s_pre[n_sub];
-    unsigned cur = 0;
-    ResSub sb = subs[first];
-    for (unsigned g = wid; g < total; g += W) {
-      if (g >= s_pre[cur + 1]) {
-        do { cur++; } while (g >= s_pre[cur + 1]);
-        sb = subs[first + cur];
-      }
-      const unsigned k = g - s_pre[cur];
-      // admission: the flag ring holds RES_RING batches
-      if (lane == 0) {
-        unsigned spins = 0;
-        while (g >= vol_ld(&s_next) + (unsigned)RES_RING && !vol_ld(&s_fail)) { spin_pause(); if (++spins > RES_SPIN_LIMIT) atomicOr(&s_fail, 1u); }
-      }
-      __syncwarp();
-      if (vol_ld(&s_fail)) break;
-      const unsigned idx = 32 * k + lane;
-      const bool has = idx < sb.n_tok;
-      const unsigned t = has ? tokens[sb.tok_off + idx] : 0u;
-      const unsigned ob = sb.out_base + boff[(sb.tok_off >> 5) + k];
-      const bool isM = has && (t >> 31);
-      const unsigned L = has ? (isM ? (t >> 16) & 0x1ffu : ((t >> 24) & 3u) + 1u) : 0u;
-      const unsigned dist = (t & 0x7fffu) + 1;
-      unsigned incl = L;
-      for (int d = 1; d < 32; d <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += v; }
-      const unsigned p = ob + incl - L;
-      const unsigned end = ob + __shfl_sync(0xffffffffu, incl, 31);
-      bool bad = has && (p + L > total_out || (isM && (dist > p || L < 3)));
-      // the last batch of a run must end where the next run begins (or where the stream's resolved part ends)
-      if (lane == 0 && 32 * k + 32 >= sb.n_tok && end != (cur + 1 < n_sub ? subs[first + cur + 1].out_base : total_out)) bad = true;
-      if (__any_sync(0xffffffffu, bad)) { if (lane == 0) atomicOr(&s_fail, 1u); break; }
-      if (has && !isM) {
-        out[p] = (unsigned char)t;
-        if (L > 1) out[p + 1] = (unsigned char)(t >> 8);
-        if (L > 2) out[p + 2] = (unsigned char)(t >> 16);
-      }
-      const unsigned src = p - dist;
-      const bool ext = isM && src + min(L, dist) <= ob;            // reads nothing that this batch writes
-      if (ext) {
-        const unsigned need = src + min(L, dist);
-        unsigned spins = 0;
-        while (vol_ld(&s_wm) < need && !vol_ld(&s_fail)) { spin_pause(); if (++spins > RES_SPIN_LIMIT) atomicOr(&s_fail, 1u); }
-        if (!vol_ld(&s_fail)) {
-          // the source repeats with period dist when it runs into the lane's own output: wrap instead of re-reading
-          if (((p | src | L) & 1u) == 0) {
-            const unsigned short* sp = (const unsigned short*)(out + src);
-            unsigned short* dp = (unsigned short*)(out + p);
-            const unsigned n2 = L >> 1, per = dist >> 1;
-            for (unsigned i = 0, j = 0; i < n2; i++) { dp[i] = __ldcg(sp + j); if (++j == per) j = 0; }
-          } else {
-            for (unsigned i = 0, j = 0; i < L; i++) { out[p + i] = __ldcg(out + src + j); if (++j == dist) j = 0; }
-          }
+    __syncthreads();                                                // literals, old bytes, pending bits and s_total are visible
+    const unsigned a = (unsigned)max(srel, 0), b = min((unsigned)(srel + (int)L), rel);   // in-tile source bytes outside my own output
+    while (__any_sync(0xffffffffu, m)) {
+      if (m) {
+        const bool clear = !(b > a && par_range<2>(pend_w, a, b));
+        if (clear) {
+          __threadfence_block();
+          for (unsigned j = n_old; j < L; j++) ob[rel + j] = ob[(unsigned)(srel + (int)j)];   // in order: may read my own bytes
+          __threadfence_block();
+          par_range<1>(pend_w, rel, rel + L);
+          m = false;
         }
       }
-      __syncwarp();
-      unsigned dep = __ballot_sync(0xffffffffu, isM && !ext);
-      if (dep) {
-        // (their sources may begin before the batch: everything before it has to be there)
-        if (lane == 0) {
-          unsigned spins = 0;
-          while (vol_ld(&s_wm) < ob && !vol_ld(&s_fail)) { spin_pause(); if (++spins > RES_SPIN_LIMIT) atomicOr(&s_fail, 1u); }
-        }
-        __syncwarp();
-        if (vol_ld(&s_fail)) break;
-        while (dep) {
-          const int m = __ffs((int)dep) - 1;
-          dep &= dep - 1;
-          const unsigned pm = __shfl_sync(0xffffffffu, p, m), Lm = __shfl_sync(0xffffffffu, L, m), dm = __shfl_sync(0xffffffffu, dist, m);
-          for (unsigned i = lane; i < Lm; i += 32) out[pm + i] = __ldcg(out + pm - dm + (dm < Lm ? i % dm : i));
-          __syncwarp();
-        }
-      }
-      // commit: flag this batch, then every consecutive flagged batch in order
-      if (lane == 0) {
-        __threadfence();
-        s_fend[g % RES_RING] = end;
-        __threadfence_block();
-        *(volatile unsigned*)&s_flag[g % RES_RING] = g + 1;
-        for (;;) {
-          const unsigned n = vol_ld(&s_next);
-          if (vol_ld(&s_flag[n % RES_RING]) != n + 1) break;
-          const unsigned e = vol_ld(&s_fend[n % RES_RING]);
-          if (atomicCAS(&s_next, n, n + 1) == n) atomicMax(&s_wm, e);
-        }
-      }
-      __syncwarp();
     }
+    __syncthreads();
+    const unsigned total = s_total;
+    {
+      // coalesced store of the tile: bytes up to the first 16-byte boundary, 16-byte vectors (assembled from the
+      // staging words, whose alignment differs), bytes of the rest
+      unsigned char* gp = out + obase;
+      const unsigned head = min(total, (unsigned)((16 - ((uintptr_t)gp & 15)) & 15));
+      if (tid < head) gp[tid] = ob[tid];
+      const unsigned nvec = (total - head) >> 4;
+      for (unsigned v = tid; v < nvec; v += NT) {
+        const unsigned o = head + v * 16;
+        const unsigned* ww = ob_w + (o >> 2);
+        const unsigned sh = (o & 3) * 8;
+        const unsigned a0 = ww[0], a1 = ww[1], a2 = ww[2], a3 = ww[3], a4 = sh ? ww[4] : 0u;
+        uint4 val;
+        val.x = __funnelshift_r(a0, a1, sh); val.y = __funnelshift_r(a1, a2, sh);
+        val.z = __funnelshift_r(a2, a3, sh); val.w = __funnelshift_r(a3, a4, sh);
+        *(uint4*)(gp + o) = val;
+      }
+      const unsigned rest = head + nvec * 16;
+      if (rest + tid < total) gp[rest + tid] = ob[rest + tid];
+    }
+    obase += total;
+    t0 += ncut;
+    if (ncut != (unsigned)NT && t0 < T) nxt = t0 + tid < T ? tk[t0 + tid] : 0;   // the tile was cut short: reload
   }
-  __syncthreads();
-  if (tid == 0 && vol_ld(&s_fail)) res[sidx].flags |= 2u;
+    if (__syncthreads_or(fail || obase != block_end)) { fail = true; break; }
+    cur_bit = blk.end_bit;
+    n_done++;
+    fin = (blk.flags >> 1) & 1;
+    bj++;
+    if (fin) break;
+  }
+  if (tid == 0) {
+    ParRes r;
+    r.tail_bit = cur_bit; r.tail_out = obase; r.n_done = n_done; r.flags = fin | (fail ? 2u : 0u);
+    res[blockIdx.x] = r;
+  }
 }
+
 
 // ---------------------------------------------------------------------------------------------- few streams: low latency
-// With few streams the blocks of a stream are resolved IN PARALLEL instead, one CTA per block, into 16-bit cells: a byte, or a
+// par_lz_kernel makes every stream a serial chain of tiles (~20 ms for a 23 MB chunk, whatever the batch size).  With
+// few streams the blocks of a stream are resolved IN PARALLEL instead, one CTA per block, into 16-bit cells: a byte, or a
 // MARKER 0x8000 | index into the 32 KB before the block for what is copied from there (markers are copied like data, so
 // every cell ends up as a byte or as a direct reference to the window).  A last, fully parallel pass turns the cells
 // into bytes.
-//   par_chain_kernel  thread per stream: follow the chain, give every chained block its output
+//   par_chain_kernel  thread per stream: follow the chain (as par_lz_kernel does), give every chained block its output
 //                     offset (kept in ParBlk::limit, which nobody needs any more) and flag 4, write the stream's result
-//   par_lzc_kernel    CTA per block slot: tokens -> cells, a tile of tokens at a time staged in shared memory
+//   par_lzc_kernel    CTA per block slot: tokens -> cells, same tile scheme as par_lz_kernel
 //   par_cells_kernel  CTA per block: cells -> bytes, markers chased back through the cells of the earlier blocks
 __global__ void __launch_bounds__(64) par_chain_kernel(const ParStream* __restrict__ streams, ParBlk* __restrict__ blks,
-                                                       unsigned bstride, unsigned ns, ParRes* __restrict__ res,
-                                                       ResSub* __restrict__ subs, unsigned* __restrict__ sub_count) {
+                                                       unsigned bstride, unsigned ns, ParRes* __restrict__ res) {
   const unsigned sidx = blockIdx.x * blockDim.x + threadIdx.x;
   if (sidx >= ns) return;
   const ParStream st = streams[sidx];
@@ -833,7 +814,6 @@ __global__ void __launch_bounds__(64) par_chain_kernel(const ParStream* __restri
         (unsigned long long)obase + blk.out_len > (unsigned)st.out_len) break;
     blks[bj].limit = obase;
     blks[bj].flags = blk.flags | 4;
-    if (subs) { ResSub u; u.tok_off = blk.tok_off; u.n_tok = blk.n_tok; u.out_base = obase; subs[(size_t)sidx * bstride + n_done] = u; }
     obase += blk.out_len;
     cur_bit = blk.end_bit;
     n_done++;
@@ -844,7 +824,6 @@ __global__ void __launch_bounds__(64) par_chain_kernel(const ParStream* __restri
   ParRes r;
   r.tail_bit = cur_bit; r.tail_out = obase; r.n_done = n_done; r.flags = fin;
   res[sidx] = r;
-  if (sub_count) sub_count[sidx] = n_done;
 }
 
 template <int NT, int CAP>
