@@ -13,6 +13,7 @@
 #include "deflate.cuh"
 #include "inflate.cuh"
 #include "inflate_par.cuh"
+#include "inflate_seg.cuh"
 #include "transform.cuh"
 
 using namespace mts;
@@ -40,8 +41,8 @@ struct Buf {
   }
 };
 
-static const uint32_t INDEX_MAGIC = 0x4253544Du;   // "MTSB"
-static const int INDEX_TAIL = 16;
+static const int INDEX_TAIL = 16;                  // {segment bytes, k, magic, sum}: the end of both index formats (deflate.cuh)
+static const int INDEX_TAIL_V2 = 24;               // the second format has {sub-block bytes, step bytes} before it
 
 }  // namespace
 
@@ -64,8 +65,10 @@ struct mtsb_ctx {
   int lz_ctas_per_sm = 2;
   // device scratch
   Buf d_pstreams, d_surv, d_cand, d_pcount, d_tokens, d_cells, d_ptab, d_plist, d_pbad;   // block-parallel inflate scratch
+  Buf d_segv2, d_btab, d_subout;                                                          // indexed (second format) segments
+  long long seg_v2 = 1;         // indexed segments of the second format go through seg_tokens / seg_resolve
   Buf d_raw, d_raw2, d_out2, d_comp2, d_T, d_tok, d_hist, d_codes, d_hdrs, d_tab, d_so, d_seg_adler, d_chunk_adler, d_chunk_off, d_out,
-      d_partial, d_comp, d_status, d_tadler, d_gather;
+      d_partial, d_comp, d_status, d_tadler, d_gather, d_subabs;
   Buf h_tab, h_small;
   // timings
   std::vector<cudaEvent_t> ev_pool;
@@ -163,6 +166,7 @@ int set_attrs(mtsb_ctx* c) {
   CK(cudaFuncSetAttribute(lz77_kernel<1, LZ_NT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(lz77_kernel<2, LZ_NT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(par_block_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(seg_resolve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   c->attr_set = true;
   return 0;
 }
@@ -308,7 +312,7 @@ long long stored_bound(long long m) { return m + 5 * ((m + 65534) / 65535); }
 long long chunk_bound(const mtsb_ctx* c, long long raw, long long seg) {
   long long k = (raw + seg - 1) / seg, full = raw / seg, rem = raw - full * seg;
   long long b = 2 + full * stored_bound(seg) + (rem ? stored_bound(rem) : 0) + 6;
-  if (c->write_index) b += 4 * k + INDEX_TAIL;
+  if (c->write_index) b += 4 * (full * idx_n_sub(seg) + (rem ? idx_n_sub(rem) : 0)) + 4 * k + INDEX_TAIL_V2;
   return b;
 }
 
@@ -368,9 +372,10 @@ void mtsb_destroy(mtsb_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   Buf* bufs[] = {&c->d_pstreams, &c->d_surv, &c->d_cand, &c->d_pcount, &c->d_tokens, &c->d_cells, &c->d_ptab, &c->d_plist, &c->d_pbad,
+                 &c->d_segv2, &c->d_btab, &c->d_subout,
                  &c->d_raw, &c->d_raw2, &c->d_out2, &c->d_comp2, &c->d_T, &c->d_tok, &c->d_hist, &c->d_codes, &c->d_hdrs, &c->d_tab, &c->d_so,
                  &c->d_seg_adler, &c->d_chunk_adler, &c->d_chunk_off, &c->d_out, &c->d_partial, &c->d_comp,
-                 &c->d_status, &c->d_tadler, &c->d_gather, &c->h_tab, &c->h_small};
+                 &c->d_status, &c->d_tadler, &c->d_gather, &c->d_subabs, &c->h_tab, &c->h_small};
   for (Buf* b : bufs) b->release();
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   for (int i = 0; i < 2; i++) { if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]); if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]); }
@@ -398,6 +403,7 @@ int mtsb_set_param(mtsb_ctx* c, const char* name, long long v) {
   else if (s == "write_index") c->write_index = v ? 1 : 0;
   else if (s == "par_inflate") c->par_inflate = v ? 1 : 0;
   else if (s == "par_indexed") c->par_indexed = v ? 1 : 0;
+  else if (s == "seg_v2") c->seg_v2 = v ? 1 : 0;
   else if (s == "par_cells") c->par_cells = v < 0 ? -1 : (v ? 1 : 0);
   else if (s == "par_lz_wide") c->par_lz_wide = v < 0 ? -1 : (v ? 1 : 0);
   else if (s == "par_batch_bytes") { if (v < (1 << 20)) return fail(c, MTSB_E_ARG, "par_batch_bytes too small"); c->par_batch_bytes = v; }
@@ -417,6 +423,7 @@ long long mtsb_get_param(mtsb_ctx* c, const char* name) {
   if (s == "par_lz_wide") return c->par_lz_wide;
   if (s == "par_cells") return c->par_cells;
   if (s == "par_indexed") return c->par_indexed;
+  if (s == "seg_v2") return c->seg_v2;
   if (s == "par_batch_bytes") return c->par_batch_bytes;
   if (s == "par_survivors") return c->par_stats[0];
   if (s == "par_candidates") return c->par_stats[1];
@@ -606,7 +613,7 @@ int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_
     std::vector<ChunkDesc> cds(nb);
     std::vector<DeflateSeg> segs;
     std::vector<int> first(nb + 1);
-    int max_ns = 0;
+    int max_ns = 0, n_subs = 0;
     long long bound = 0;
     for (int i = 0; i < nb; i++) {
       long long ns = chunk_rows[c0 + i + 1] - chunk_rows[c0 + i];
@@ -628,7 +635,8 @@ int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_
         s.in_len = (int)std::min<long long>(seg, raw - (long long)j * seg);
         s.chunk = i;
         s.flags = (j == 0 ? SEG_FIRST : 0) | (j == k - 1 ? SEG_LAST : 0);
-        s.pad_ = 0;
+        s.sub_first = n_subs;
+        n_subs += idx_n_sub(s.in_len);
         segs.push_back(s);
       }
       bound += chunk_bound(c, raw, seg);
@@ -658,6 +666,7 @@ int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_
     NEED(c->d_seg_adler, (size_t)n_segs * 4);
     NEED(c->d_chunk_adler, (size_t)nb * 4);
     NEED(c->d_chunk_off, (size_t)(nb + 1) * 8);
+    NEED(c->d_subabs, (size_t)n_subs * 8 + 64);
     NEED(c->h_small, (size_t)(nb + 1) * 8);
     const char* d = (const char*)c->d_tab.p;
     const ChunkDesc* d_cd = (const ChunkDesc*)(d + o_cd);
@@ -718,9 +727,16 @@ int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_
     c->end();
     c->begin(5);
     auto ek = itemsize == 2 ? encode_kernel<true> : encode_kernel<false>;
-    MTS_LAUNCH(ek, dim3(n_segs), dim3(ENC_THREADS), 0, c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (const unsigned short*)c->d_tok.p, (const unsigned*)c->d_codes.p, (const unsigned*)c->d_hdrs.p, (const DeflateSegOut*)c->d_so.p, (const unsigned*)c->d_chunk_adler.p, outp, d_cd, (int)c->write_index);
+    MTS_LAUNCH(ek, dim3(n_segs), dim3(ENC_THREADS), 0, c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (const unsigned short*)c->d_tok.p, (const unsigned*)c->d_codes.p, (const unsigned*)c->d_hdrs.p, (const DeflateSegOut*)c->d_so.p, (const unsigned*)c->d_chunk_adler.p, outp, c->write_index ? (unsigned long long*)c->d_subabs.p : (unsigned long long*)nullptr);
     CKL();
     c->launches++;
+    if (c->write_index) {
+      MTS_LAUNCH(trailer_kernel, dim3(nb), dim3(128), 0, c->stream, d_seg, (const DeflateSegOut*)c->d_so.p, d_cd,
+                 (const long long*)c->d_chunk_off.p, (const unsigned long long*)c->d_subabs.p, outp,
+                 (unsigned)(LZ_NT * (itemsize == 2 ? 2 : 1)));
+      CKL();
+      c->launches++;
+    }
     c->end();
     { int rc_ = small_copy(c, c->h_small.p, c->d_chunk_off.p, (size_t)(nb + 1) * 8); if (rc_) return rc_; }
     CK(cudaStreamSynchronize(c->stream));
@@ -920,6 +936,55 @@ static int par_phase_indexed(mtsb_ctx* c, const unsigned char* dcomp, std::vecto
   return par_decode(c, dcomp, segs, ids, ps, &blks, in_total, max_in, dT, 0);
 }
 
+// The indexed segments of chunks with the second index format: `ids` index into segs, v2[i] describes segs[ids[i]].
+// seg_tokens_kernel (lane per indexed sub-block) + seg_resolve_kernel (all tokens of a step at once); segments that
+// pass become INF_RESUME tails (the serial kernel then only checks the empty stored block behind them), the others
+// are decoded serially from their start.
+static int par_phase_v2(mtsb_ctx* c, const unsigned char* dcomp, std::vector<InflateSeg>& segs, const std::vector<int>& ids,
+                        std::vector<SegV2>& v2, unsigned char* dT) {
+  const size_t SMEM = SEG_RING + (SEG_MAX_STEPS + 1) * 4;
+  const long long GROUP_SUBS = (4ll << 30) / IDX_SUB_BYTES;     // sub-blocks per launch pair: bounds the token scratch (~9 GB)
+  size_t a = 0;
+  while (a < ids.size()) {
+    size_t b = a;
+    long long subs = 0;
+    while (b < ids.size() && (b == a || subs + idx_n_sub(v2[b].out_len) <= GROUP_SUBS)) { v2[b].sub_first = (int)subs; subs += idx_n_sub(v2[b].out_len); b++; }
+    const int ns = (int)(b - a);
+    NEED(c->d_segv2, (size_t)ns * sizeof(SegV2));
+    NEED(c->d_tokens, (size_t)subs * SEG_TOK_STRIDE * 4 + 64);
+    NEED(c->d_btab, (size_t)subs * SEG_BATCHES * sizeof(uint2) + 64);
+    NEED(c->d_subout, (size_t)subs * sizeof(SubOut) + 64);
+    NEED(c->d_pbad, (size_t)ns * sizeof(ParRes) + 64);
+    NEED(c->h_tab, (size_t)ns * sizeof(SegV2) + 64);
+    NEED(c->h_small, 4096 + (size_t)ns * sizeof(ParRes) + 64);
+    memcpy(c->h_tab.p, v2.data() + a, (size_t)ns * sizeof(SegV2));
+    { int r = small_copy(c, c->d_segv2.p, c->h_tab.p, (size_t)ns * sizeof(SegV2)); if (r) return r; }
+    MTS_LAUNCH(seg_tokens_kernel, dim3(ns), dim3(32), 0, c->stream, dcomp, (const SegV2*)c->d_segv2.p, (unsigned*)c->d_tokens.p,
+               (uint2*)c->d_btab.p, (SubOut*)c->d_subout.p, (ParRes*)c->d_pbad.p);
+    CKL();
+    MTS_LAUNCH(seg_resolve_kernel, dim3(ns), dim3(SEG_RES_WARPS * 32), SMEM, c->stream, (const SegV2*)c->d_segv2.p,
+               (const unsigned*)c->d_tokens.p, (const uint2*)c->d_btab.p, (const SubOut*)c->d_subout.p, dT, (ParRes*)c->d_pbad.p);
+    CKL();
+    c->launches += 2;
+    char* hs = (char*)c->h_small.p;
+    { int r = small_copy(c, hs + 4096, c->d_pbad.p, (size_t)ns * sizeof(ParRes)); if (r) return r; }
+    CK(cudaStreamSynchronize(c->stream));
+    const ParRes* res = (const ParRes*)(hs + 4096);
+    for (int i = 0; i < ns; i++) {
+      const ParRes& r = res[i];
+      c->par_stats[2] += r.n_done;
+      if (r.n_done == 0 || (r.flags & 2)) continue;             // full serial decode of this segment
+      InflateSeg& sg = segs[ids[a + i]];
+      sg.flags = INF_RESUME;
+      sg.start_bit = r.tail_bit;
+      sg.opos0 = r.tail_out;
+      c->par_stats[3]++;
+    }
+    a = b;
+  }
+  return 0;
+}
+
 // Block-parallel decode of the whole-stream segments `whole` (indices into segs): plain zlib streams.
 static int par_phase(mtsb_ctx* c, const unsigned char* dcomp, std::vector<InflateSeg>& segs, const std::vector<int>& whole,
                      unsigned char* dT) {
@@ -955,7 +1020,9 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
   // ---- plan: look for the segment index after each chunk's zlib stream
   c->begin(1);
   std::vector<int> nseg(n_chunks, 0);
-  std::vector<long long> segb(n_chunks, 0);
+  std::vector<long long> segb(n_chunks, 0), idx_extra(n_chunks, 0);
+  std::vector<char> idx_v2(n_chunks, 0);
+  std::vector<unsigned> idx_step(n_chunks, 0);
   std::vector<unsigned char> tails, idx;
   std::vector<long long> tpos, ipos;
   {
@@ -978,12 +1045,18 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
       long long l = comp_offsets[i + 1] - comp_offsets[i];
       long long raw = (chunk_rows[i + 1] - chunk_rows[i]) * row_bytes;
       uint32_t sb = rd32(t), k = rd32(t + 4), magic = rd32(t + 8);
-      if (magic != INDEX_MAGIC || sb == 0 || k == 0) continue;
+      if ((magic != IDX_MAGIC_V1 && magic != IDX_MAGIC_V2) || sb == 0 || k == 0) continue;
       if ((long long)k != (raw + sb - 1) / sb) continue;
-      if (8 + 4ll * k + INDEX_TAIL >= l) continue;
-      nseg[i] = (int)k; segb[i] = sb;
-      off2.push_back(comp_offsets[i + 1] - INDEX_TAIL - 4ll * k - 4);   // adler32 + k lengths
-      len2.push_back((int)(4 * k + 4));
+      // second format: {sub-block bytes, step bytes} and the sub-block table lie before the k lengths
+      long long extra = 0;
+      if (magic == IDX_MAGIC_V2) {
+        long long full = raw / sb, rem = raw - full * sb;
+        extra = 8 + 4 * (full * idx_n_sub(sb) + (rem ? idx_n_sub(rem) : 0));
+      }
+      if (8 + 4ll * k + INDEX_TAIL + extra >= l) continue;
+      nseg[i] = (int)k; segb[i] = sb; idx_extra[i] = extra; idx_v2[i] = magic == IDX_MAGIC_V2;
+      off2.push_back(comp_offsets[i + 1] - INDEX_TAIL - 4ll * k - extra - 4);   // adler32 | [sub table] | k lengths | [2 words]
+      len2.push_back((int)(4 * k + 4 + extra));
       who2.push_back(i);
     }
     r = fetch_ranges(c, comp, comp_is_device, off2, len2, idx, ipos);
@@ -997,8 +1070,15 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
       long long l = comp_offsets[i + 1] - comp_offsets[i];
       unsigned long long sum = 0;
       bool ok = true;
-      for (int q = 0; q < nseg[i]; q++) { uint32_t v = rd32(p + 4 + 4 * q); if (v == 0) ok = false; sum += v; }
-      if (!ok || (long long)sum != l - 8 - 4ll * nseg[i] - INDEX_TAIL || (uint32_t)sum != rd32(t + 12)) { nseg[i] = 0; continue; }
+      const unsigned char* lens = p + 4 + (idx_v2[i] ? idx_extra[i] - 8 : 0);    // after the adler32 and the sub-block table
+      for (int q = 0; q < nseg[i]; q++) { uint32_t v = rd32(lens + 4 * q); if (v == 0) ok = false; sum += v; }
+      if (!ok || (long long)sum != l - 8 - 4ll * nseg[i] - INDEX_TAIL - idx_extra[i] || (uint32_t)sum != rd32(t + 12)) { nseg[i] = 0; continue; }
+      if (idx_v2[i]) {
+        // the fast path needs the sub-block size this build uses and a sane step size; otherwise only the segment lengths are used
+        const uint32_t subb = rd32(lens + 4 * nseg[i]), stepb = rd32(lens + 4 * nseg[i] + 4);
+        const bool fast = subb == (uint32_t)IDX_SUB_BYTES && stepb >= 256 && stepb <= (uint32_t)IDX_SUB_BYTES && (stepb & (stepb - 1)) == 0;
+        idx_step[i] = fast ? stepb : 0;
+      }
       ipos_by_chunk[i] = ipos[j];
     }
     for (int i = 0; i < n_chunks; i++) if (nseg[i] && ipos_by_chunk[i] < 0) nseg[i] = 0;
@@ -1066,7 +1146,8 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
     std::vector<ChunkDesc> cds(nb);
     std::vector<InflateSeg> segs;
     std::vector<AdlerSeg> as;
-    std::vector<int> first(nb + 1), first_inf(nb + 1), whole;
+    std::vector<int> first(nb + 1), first_inf(nb + 1), whole, v2_ids;
+    std::vector<SegV2> v2;
     std::vector<uint32_t> want_adler(nb, 0);
     int max_ns = 0;
     const int ASEG = 1 << 16;
@@ -1082,13 +1163,23 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
       if (nseg[g]) {
         const unsigned char* p = idx.data() + tpos[g];
         want_adler[i] = ((uint32_t)p[0] << 24) | (p[1] << 16) | (p[2] << 8) | p[3];
+        const unsigned char* lens = p + 4 + (idx_v2[g] ? idx_extra[g] - 8 : 0);
         long long pos = cbase + 2;
+        long long tab = cbase + clen - INDEX_TAIL - 4ll * nseg[g] - idx_extra[g];   // the chunk's sub-block table (second format)
         for (int j = 0; j < nseg[g]; j++) {
           InflateSeg s;
-          s.in_off = pos; s.in_len = (int)rd32(p + 4 + 4 * j);
+          s.in_off = pos; s.in_len = (int)rd32(lens + 4 * j);
           s.out_off = tbase + (long long)j * segb[g];
           s.out_len = (int)std::min<long long>(segb[g], raw - (long long)j * segb[g]);
           s.flags = 0; s.start_bit = 0; s.opos0 = 0; s.pad_ = 0;
+          if (idx_step[g] && c->seg_v2 && c->par_inflate && s.in_len < (1 << 28)) {
+            SegV2 v;
+            v.in_off = s.in_off; v.out_off = s.out_off; v.tab_off = tab; v.in_len = s.in_len; v.out_len = s.out_len;
+            v.sub_first = 0; v.step_bytes = idx_step[g];
+            v2.push_back(v);
+            v2_ids.push_back((int)segs.size());
+          }
+          tab += 4ll * idx_n_sub(s.out_len);
           pos += s.in_len;
           segs.push_back(s);
         }
@@ -1132,11 +1223,13 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
       for (int w : whole) if (segs[w].in_len < PAR_MAX_IN) { whole_in += segs[w].in_len; fit.push_back(w); }
       if (whole_in >= 65536) { int r = par_phase(c, dcomp, segs, fit, (unsigned char*)c->d_T.p); if (r) return r; }
     }
+    if (!v2_ids.empty()) { int r = par_phase_v2(c, dcomp, segs, v2_ids, v2, (unsigned char*)c->d_T.p); if (r) return r; }
     if (c->par_inflate && c->par_indexed && (int)whole.size() < n_segs) {
       std::vector<int> ids;
-      size_t wi = 0;
+      size_t wi = 0, vi = 0;
       for (int j = 0; j < n_segs; j++) {
         if (wi < whole.size() && whole[wi] == j) { wi++; continue; }
+        if (vi < v2_ids.size() && v2_ids[vi] == j) { vi++; if (segs[j].flags & INF_RESUME) continue; }   // done by the second-format kernels
         if (segs[j].in_len < PAR_MAX_IN) ids.push_back(j);
       }
       int r = par_phase_indexed(c, dcomp, segs, ids, (unsigned char*)c->d_T.p);

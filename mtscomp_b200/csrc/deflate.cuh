@@ -24,9 +24,21 @@ struct DeflateSeg {
   int in_len;           // input bytes (> 0)
   int chunk;            // owning chunk (index within the batch)
   int flags;            // SEG_FIRST | SEG_LAST
-  int pad_;
+  int sub_first;        // index of the segment's first sub-block in the batch's sub-block table
 };
 enum { SEG_FIRST = 1, SEG_LAST = 2 };
+// In-band index written after each chunk's zlib stream (zlib.decompress ignores trailing bytes), all
+// little-endian u32:
+//   [sub-block table: for every segment, one entry per IDX_SUB_BYTES of its input | k segment body lengths |
+//    sub-block bytes, step bytes | segment bytes, k, magic "MTS2", sum of the lengths]
+// Sub-block j of a segment begins with the first token whose output starts at or after j * IDX_SUB_BYTES; its entry is
+// (bits from the previous sub-block's first token to its own; for j = 0 from the segment's first bit) | overshoot << 17,
+// overshoot = output offset of that token - j * IDX_SUB_BYTES (< 258).  "step bytes" states the encoder's STEP RULE: no
+// match reads output at or after the beginning of the step (of that many bytes, counted from the segment's start) that
+// the match itself starts in.  Files of the first format ("MTSB": k lengths | segment bytes, k, magic, sum) still decode.
+static const unsigned IDX_MAGIC_V1 = 0x4253544Du, IDX_MAGIC_V2 = 0x3253544Du;
+static const int IDX_SUB_BYTES = 8192;
+__host__ __device__ inline int idx_n_sub(long long seg_len) { return (int)((seg_len + IDX_SUB_BYTES - 1) / IDX_SUB_BYTES); }
 enum { MODE_STORED = 0, MODE_DYNAMIC = 1, MODE_FIXED = 2 };
 
 struct DeflateSegOut {   // written by huff_kernel / scan_kernel, read by encode_kernel
@@ -262,7 +274,11 @@ __global__ void __launch_bounds__(NT + 32, NT <= 512 ? 2 : 1) lz77_kernel(const 
             for (int k = 0; k < 3; k++) {
               const unsigned cand = k == 0 ? cws >> 16 : k == 1 ? cwl >> 16 : cwl & 0xffffu;
               const unsigned du = (ub - cand) & 0xffffu;          // any value: q below always lies inside the ring
-              const bool ok = du - 1 < (unsigned)L::MAXD_UNITS && (k == 0 || vL);
+              // STEP RULE: a match must not read what its own step writes -- its source ends at or before the step's
+              // first byte, so cap = dist - li bytes are usable (candidates are units of earlier steps: dist > li).
+              // The decoder relies on it: all the tokens of a step can be resolved at once (seg_resolve_kernel).
+              const unsigned cap = du * STRIDE - li;
+              const bool ok = du - 1 < (unsigned)L::MAXD_UNITS && (k == 0 || vL) && du * STRIDE >= li + 4;
               const unsigned q = (pr - du * STRIDE) & RM;
               const unsigned* qw = ringw + (q >> 2);
               const unsigned sh = q << 3;
@@ -271,14 +287,15 @@ __global__ void __launch_bounds__(NT + 32, NT <= 512 ? 2 : 1) lz77_kernel(const 
               // length class: 4..8 matched bytes (STRIDE 2: 4, 6, 8) from the trailing zeros of the second word's
               // difference; 8 = the first 8 bytes match (extended below)
               const unsigned tz = (unsigned)__clz((int)__brev(x1));   // 32 when x1 == 0
-              const unsigned lc = STRIDE == 2 ? 4u + 2u * (tz >> 4) : 4u + (tz >> 3);
+              const unsigned lc = min(STRIDE == 2 ? 4u + 2u * (tz >> 4) : 4u + (tz >> 3), cap);
               const unsigned key = (lc << 16) | (0xffffu ^ du);
               bestk = max(bestk, (ok && c0 == w0) ? key : 0u);
             }
             mlen = bestk >> 16;
             if (mlen) {
               mdist = (0xffffu ^ (bestk & 0xffffu)) * STRIDE;
-              if (mlen == 8) {
+              const unsigned lim2 = min(lim, mdist - li);             // (step rule)
+              if (mlen == 8 && lim2 > 8) {
                 // the first 8 bytes match: check the next two bytes, which ends it for most; the few matches that go
                 // on are compared word by word (no wrap: the mirror covers pr + 258 + 8)
                 const unsigned q = (pr - mdist) & RM;
@@ -286,7 +303,7 @@ __global__ void __launch_bounds__(NT + 32, NT <= 512 ? 2 : 1) lz77_kernel(const 
                                               : ring[pr + 8] == ring[q + 8];
                 if (more) {
                   unsigned x = 0;
-                  while (mlen < lim) {
+                  while (mlen < lim2) {
                     x = ring_load4(ring, pr + mlen) ^ ring_load4(ring, q + mlen);
                     if (x) break;
                     mlen += 4;
@@ -294,7 +311,7 @@ __global__ void __launch_bounds__(NT + 32, NT <= 512 ? 2 : 1) lz77_kernel(const 
                   if (x) mlen += (unsigned)(__ffs((int)x) - 1) >> 3;
                 }
               }
-              mlen = min(mlen, lim);
+              mlen = min(mlen, lim2);
               if (STRIDE == 2) mlen &= ~1u;                 // matches cover whole units
               if (mlen < 4) mlen = 0;
               else tokw = (0x8000u | mlen) | ((mdist - 1) << 16);
@@ -631,7 +648,11 @@ __global__ void __launch_bounds__(1024) scan_kernel(const DeflateSeg* __restrict
     if (i < n_segs) {
       fl = segs[i].flags;
       sz = so[i].body_bytes + ((fl & SEG_FIRST) ? 2 : 0) + ((fl & SEG_LAST) ? 6 : 0);
-      if ((fl & SEG_LAST) && write_index) sz += 4ull * (unsigned)chunks[segs[i].chunk].n_seg + 16;
+      if ((fl & SEG_LAST) && write_index) {
+        const ChunkDesc cd = chunks[segs[i].chunk];
+        const unsigned subs = (unsigned)(segs[i].sub_first + idx_n_sub(segs[i].in_len) - segs[cd.first_seg].sub_first);
+        sz += 4ull * subs + 4ull * (unsigned)cd.n_seg + 24;
+      }
     }
     unsigned long long incl = warp_incl_scan(sz);
     if (lane_id() == 31) wsum[warp_id()] = incl;
@@ -691,11 +712,11 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
                                                              const DeflateSegOut* __restrict__ so,
                                                              const unsigned* __restrict__ chunk_adler,
                                                              unsigned char* __restrict__ dst,
-                                                             const ChunkDesc* __restrict__ chunks, int write_index) {
+                                                             unsigned long long* __restrict__ sub_abs) {
   __shared__ unsigned stage[ENC_STAGE_WORDS];
   __shared__ unsigned code[CODE_STRIDE];
-  __shared__ unsigned wtot[ENC_THREADS / 32];
-  __shared__ unsigned tile_bits;
+  __shared__ unsigned long long wtot64[ENC_THREADS / 32];
+  __shared__ unsigned tile_bits, tile_out;
   const int sidx = blockIdx.x;
   if (sidx >= n_segs) return;
   const DeflateSeg sg = segs[sidx];
@@ -715,23 +736,12 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
     unsigned char t[6] = {0x03, 0x00, (unsigned char)(a >> 24), (unsigned char)(a >> 16), (unsigned char)(a >> 8), (unsigned char)a};
     body_end[tid] = t[tid];
   }
-  if ((sg.flags & SEG_LAST) && write_index) {
-    // segment index after the zlib stream (zlib.decompress ignores trailing bytes): k compressed segment
-    // lengths, then {segment bytes, k, magic "MTSB", sum of the lengths}, all little-endian u32
-    const ChunkDesc cd = chunks[sg.chunk];
-    unsigned char* ix = body_end + 6;
-    const unsigned k = (unsigned)cd.n_seg;
-    unsigned sum = 0;
-    for (unsigned j = tid; j < k; j += blockDim.x) {
-      unsigned v = so[cd.first_seg + j].body_bytes;
-      for (int b = 0; b < 4; b++) ix[4 * j + b] = (unsigned char)(v >> (8 * b));
-    }
-    if (tid == 0) {
-      for (unsigned j = 0; j < k; j++) sum += so[cd.first_seg + j].body_bytes;
-      unsigned tail[4] = {(unsigned)cd.pad_, k, 0x4253544Du, sum};
-      for (int q = 0; q < 4; q++)
-        for (int b = 0; b < 4; b++) ix[4 * k + 4 * q + b] = (unsigned char)(tail[q] >> (8 * b));
-    }
+  // sub-block table of this segment (absolute: bit of the sub-block's first token << 9 | output overshoot): entry 0
+  // here, the others by the thread whose token reaches the boundary; zero for a stored segment
+  const int n_sub = idx_n_sub(sg.in_len);
+  if (sub_abs) {
+    if (o.mode == MODE_STORED) { for (int j = tid; j < n_sub; j += blockDim.x) sub_abs[sg.sub_first + j] = 0; }
+    else if (tid == 0) sub_abs[sg.sub_first] = (unsigned long long)o.hdr_bits << 9;
   }
   const unsigned char* in = tbuf + sg.in_off;
   if (o.mode == MODE_STORED) {
@@ -775,8 +785,9 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
   // words go to the staging window with plain stores, only the first and the last (shared with the neighbours) by atomicOr.
   const unsigned short* tok = tokens + sg.tok_off;
   const unsigned ntok = o.n_tok;
+  unsigned seg_bits = o.hdr_bits, seg_out = 0;      // bits / output bytes of the segment before the tile
   for (unsigned base = 0; base < ntok; base += ENC_TILE) {
-    unsigned v[ENC_PER], nb[ENC_PER], mine = 0;
+    unsigned v[ENC_PER], nb[ENC_PER], ol[ENC_PER], mine = 0, mine_out = 0;
     const unsigned i0 = base + tid * ENC_PER;
     if (PAIRS) {
       uint4 t4 = make_uint4(0, 0, 0, 0);
@@ -805,22 +816,26 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
         nb[2 * j] = on ? (c0 >> 16) + x0 : 0u;
         v[2 * j + 1] = (c1 & 0xffffu) | (e1 << (c1 >> 16));
         nb[2 * j + 1] = on ? (c1 >> 16) + x1 : 0u;
+        ol[2 * j] = 0;                                       // the token's output is credited to its second code
+        ol[2 * j + 1] = on ? ((e & 0x8000u) ? (e & 0x1ffu) : 2u) : 0u;
         mine += nb[2 * j] + nb[2 * j + 1];
+        mine_out += ol[2 * j + 1];
       }
     } else {
       unsigned prev_el = (i0 > 0 && i0 <= ntok) ? tok[i0 - 1] : 0;
       // bit 15 marks a length element (distance elements are <= 32767), and what follows a length is its distance
       for (int j = 0; j < ENC_PER; j++) {
         unsigned i = i0 + j;
-        v[j] = 0; nb[j] = 0;
+        v[j] = 0; nb[j] = 0; ol[j] = 0;
         if (i < ntok) {
           unsigned e = tok[i];
-          if (prev_el & 0x8000u) {            // distance element (follows a length element)
+          if (prev_el & 0x8000u) {            // distance element (follows a length element): closes the match
             unsigned sym, xb, ev;
             dist_symbol(e + 1, sym, xb, ev);
             unsigned c = code[288 + sym];
             v[j] = (c & 0xffff) | (ev << (c >> 16));
             nb[j] = (c >> 16) + xb;
+            ol[j] = prev_el & 0x1ffu;
             prev_el = 0;
           } else if (e & 0x8000u) {           // length element
             unsigned sym, xb, ev;
@@ -833,23 +848,43 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
             unsigned c = code[e];
             v[j] = c & 0xffff;
             nb[j] = c >> 16;
+            ol[j] = 1;
             prev_el = e;
           }
           mine += nb[j];
+          mine_out += ol[j];
         }
       }
     }
-    unsigned incl = warp_incl_scan(mine);
-    if (lane == 31) wtot[wid] = incl;
+    // one scan for both: bits in the low word, output bytes in the high word
+    const unsigned long long incl64 = warp_incl_scan((unsigned long long)mine | ((unsigned long long)mine_out << 32));
+    const unsigned incl = (unsigned)incl64;
+    if (lane == 31) wtot64[wid] = incl64;
     __syncthreads();
     if (tid == 0) {
-      unsigned run = 0;
-      for (int w = 0; w < ENC_THREADS / 32; w++) { unsigned t = wtot[w]; wtot[w] = run; run += t; }
-      tile_bits = run;
+      unsigned long long run = 0;
+      for (int w = 0; w < ENC_THREADS / 32; w++) { unsigned long long t = wtot64[w]; wtot64[w] = run; run += t; }
+      tile_bits = (unsigned)run;
+      tile_out = (unsigned)(run >> 32);
     }
     __syncthreads();
+    const unsigned wbits = (unsigned)wtot64[wid], wout = (unsigned)(wtot64[wid] >> 32);
+    if (sub_abs && mine_out) {
+      // a token that reaches the next multiple of IDX_SUB_BYTES makes its successor the first token of that sub-block
+      unsigned bit = seg_bits + wbits + incl - mine, op = seg_out + wout + (unsigned)(incl64 >> 32) - mine_out;
+#pragma unroll
+      for (int j = 0; j < ENC_PER; j++) {
+        bit += nb[j];
+        const unsigned oe = op + ol[j];
+        if (ol[j] && (oe / IDX_SUB_BYTES) != (op / IDX_SUB_BYTES)) {
+          const unsigned jn = oe / IDX_SUB_BYTES;
+          if ((int)jn < n_sub) sub_abs[sg.sub_first + jn] = ((unsigned long long)bit << 9) | (oe - jn * IDX_SUB_BYTES);
+        }
+        op = oe;
+      }
+    }
     if (mine) {
-      const unsigned bp = cur + wtot[wid] + incl - mine;
+      const unsigned bp = cur + wbits + incl - mine;
       unsigned wi = bp >> 5, fill = bp & 31;
       unsigned long long acc = 0;
       bool first = true;
@@ -866,6 +901,8 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
     }
     __syncthreads();
     cur += tile_bits;
+    seg_bits += tile_bits;
+    seg_out += tile_out;
     unsigned nw = cur >> 5;
     stage_flush(stage, nw, gw, out, out_end);
     __syncthreads();
@@ -890,6 +927,39 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
   __syncthreads();
   unsigned endbits = tile_bits;
   stage_flush(stage, (endbits + 31) >> 5, gw, out, body_end);
+}
+
+// ------------------------------------------------------------------------------------------------ trailer_kernel
+// One CTA per chunk, after encode_kernel: the in-band index (layout at IDX_MAGIC_V2 above) behind the chunk's zlib stream.
+__device__ __forceinline__ void put32(unsigned char* p, unsigned v) {
+  p[0] = (unsigned char)v; p[1] = (unsigned char)(v >> 8); p[2] = (unsigned char)(v >> 16); p[3] = (unsigned char)(v >> 24);
+}
+__global__ void __launch_bounds__(128) trailer_kernel(const DeflateSeg* __restrict__ segs, const DeflateSegOut* __restrict__ so,
+                                                      const ChunkDesc* __restrict__ chunks, const long long* __restrict__ chunk_off,
+                                                      const unsigned long long* __restrict__ sub_abs,
+                                                      unsigned char* __restrict__ dst, unsigned step_bytes) {
+  const ChunkDesc cd = chunks[blockIdx.x];
+  const unsigned k = (unsigned)cd.n_seg;
+  const DeflateSeg s0 = segs[cd.first_seg], s1 = segs[cd.first_seg + k - 1];
+  const unsigned n_subs = (unsigned)(s1.sub_first + idx_n_sub(s1.in_len) - s0.sub_first);
+  unsigned char* ix = dst + chunk_off[blockIdx.x + 1] - (4ull * n_subs + 4ull * k + 24);
+  for (unsigned q = threadIdx.x; q < k; q += blockDim.x) {
+    const DeflateSeg sg = segs[cd.first_seg + q];
+    const int ns = idx_n_sub(sg.in_len);
+    for (int j = 0; j < ns; j++) {
+      const unsigned long long a = sub_abs[sg.sub_first + j], b = j ? sub_abs[sg.sub_first + j - 1] : 0ull;
+      const unsigned delta = (unsigned)((a >> 9) - (b >> 9));
+      put32(ix + 4ull * (unsigned)(sg.sub_first - s0.sub_first + j), (delta & 0x1ffffu) | ((unsigned)(a & 511u) << 17));
+    }
+    put32(ix + 4ull * n_subs + 4ull * q, so[cd.first_seg + q].body_bytes);
+  }
+  if (threadIdx.x == 0) {
+    unsigned sum = 0;
+    for (unsigned q = 0; q < k; q++) sum += so[cd.first_seg + q].body_bytes;
+    unsigned char* t = ix + 4ull * n_subs + 4ull * k;
+    put32(t, IDX_SUB_BYTES); put32(t + 4, step_bytes);
+    put32(t + 8, (unsigned)cd.pad_); put32(t + 12, k); put32(t + 16, IDX_MAGIC_V2); put32(t + 20, sum);
+  }
 }
 
 }  // namespace mts
