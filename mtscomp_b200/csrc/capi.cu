@@ -941,7 +941,9 @@ static int par_phase_indexed(mtsb_ctx* c, const unsigned char* dcomp, std::vecto
 // pass become INF_RESUME tails (the serial kernel then only checks the empty stored block behind them), the others
 // are decoded serially from their start.
 static int par_phase_v2(mtsb_ctx* c, const unsigned char* dcomp, std::vector<InflateSeg>& segs, const std::vector<int>& ids,
-                        std::vector<SegV2>& v2, unsigned char* dT) {
+                        std::vector<SegV2>& v2, unsigned char* dT, std::vector<uint32_t>& seg_ad, std::vector<char>& seg_ok) {
+  seg_ad.assign(ids.size(), 0);
+  seg_ok.assign(ids.size(), 0);
   const size_t SMEM = SEG_RING + (SEG_MAX_STEPS + 1) * 4;
   const long long GROUP_SUBS = (4ll << 30) / IDX_SUB_BYTES;     // sub-blocks per launch pair: bounds the token scratch (~9 GB)
   size_t a = 0;
@@ -955,25 +957,31 @@ static int par_phase_v2(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Inf
     NEED(c->d_btab, (size_t)subs * SEG_BATCHES * sizeof(uint2) + 64);
     NEED(c->d_subout, (size_t)subs * sizeof(SubOut) + 64);
     NEED(c->d_pbad, (size_t)ns * sizeof(ParRes) + 64);
+    NEED(c->d_tadler, (size_t)ns * 4 + 64);
     NEED(c->h_tab, (size_t)ns * sizeof(SegV2) + 64);
-    NEED(c->h_small, 4096 + (size_t)ns * sizeof(ParRes) + 64);
+    NEED(c->h_small, 4096 + (size_t)ns * (sizeof(ParRes) + 4) + 128);
     memcpy(c->h_tab.p, v2.data() + a, (size_t)ns * sizeof(SegV2));
     { int r = small_copy(c, c->d_segv2.p, c->h_tab.p, (size_t)ns * sizeof(SegV2)); if (r) return r; }
     MTS_LAUNCH(seg_tokens_kernel, dim3(ns), dim3(32), 0, c->stream, dcomp, (const SegV2*)c->d_segv2.p, (unsigned*)c->d_tokens.p,
                (uint2*)c->d_btab.p, (SubOut*)c->d_subout.p, (ParRes*)c->d_pbad.p);
     CKL();
     MTS_LAUNCH(seg_resolve_kernel, dim3(ns), dim3(SEG_RES_WARPS * 32), SMEM, c->stream, (const SegV2*)c->d_segv2.p,
-               (const unsigned*)c->d_tokens.p, (const uint2*)c->d_btab.p, (const SubOut*)c->d_subout.p, dT, (ParRes*)c->d_pbad.p);
+               (const unsigned*)c->d_tokens.p, (const uint2*)c->d_btab.p, (const SubOut*)c->d_subout.p, dT, (ParRes*)c->d_pbad.p,
+               (unsigned*)c->d_tadler.p);
     CKL();
     c->launches += 2;
     char* hs = (char*)c->h_small.p;
+    const size_t o_ad = 4096 + (((size_t)ns * sizeof(ParRes) + 15) & ~(size_t)15);
     { int r = small_copy(c, hs + 4096, c->d_pbad.p, (size_t)ns * sizeof(ParRes)); if (r) return r; }
+    { int r = small_copy(c, hs + o_ad, c->d_tadler.p, (size_t)ns * 4); if (r) return r; }
     CK(cudaStreamSynchronize(c->stream));
     const ParRes* res = (const ParRes*)(hs + 4096);
     for (int i = 0; i < ns; i++) {
       const ParRes& r = res[i];
       c->par_stats[2] += r.n_done;
       if (r.n_done == 0 || (r.flags & 2)) continue;             // full serial decode of this segment
+      seg_ok[a + i] = 1;
+      seg_ad[a + i] = ((const uint32_t*)(hs + o_ad))[i];
       InflateSeg& sg = segs[ids[a + i]];
       sg.flags = INF_RESUME;
       sg.start_bit = r.tail_bit;
@@ -1190,16 +1198,9 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
         whole.push_back((int)segs.size());
         segs.push_back(s);
       }
-      first[i] = (int)as.size();
-      for (long long o = 0; o < raw; o += ASEG) as.push_back(AdlerSeg{tbase + o, (int)std::min<long long>(ASEG, raw - o), 0});
     }
-    first[nb] = (int)as.size();
     first_inf[nb] = (int)segs.size();
-    const int n_segs = (int)segs.size(), n_as = (int)as.size();
-    size_t o_cd = 0, o_seg = (o_cd + nb * sizeof(ChunkDesc) + 255) & ~(size_t)255;
-    size_t o_as = (o_seg + n_segs * sizeof(InflateSeg) + 255) & ~(size_t)255;
-    size_t o_first = (o_as + n_as * sizeof(AdlerSeg) + 255) & ~(size_t)255;
-    size_t tab_bytes = o_first + (nb + 1) * sizeof(int);
+    const int n_segs = (int)segs.size();
     NEED(c->d_T, (size_t)bbytes + 16384);
     c->begin(0);
     if (!comp_is_device && k + 1 < n_sb) {
@@ -1223,7 +1224,9 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
       for (int w : whole) if (segs[w].in_len < PAR_MAX_IN) { whole_in += segs[w].in_len; fit.push_back(w); }
       if (whole_in >= 65536) { int r = par_phase(c, dcomp, segs, fit, (unsigned char*)c->d_T.p); if (r) return r; }
     }
-    if (!v2_ids.empty()) { int r = par_phase_v2(c, dcomp, segs, v2_ids, v2, (unsigned char*)c->d_T.p); if (r) return r; }
+    std::vector<uint32_t> v2_ad;
+    std::vector<char> v2_ok;
+    if (!v2_ids.empty()) { int r = par_phase_v2(c, dcomp, segs, v2_ids, v2, (unsigned char*)c->d_T.p, v2_ad, v2_ok); if (r) return r; }
     if (c->par_inflate && c->par_indexed && (int)whole.size() < n_segs) {
       std::vector<int> ids;
       size_t wi = 0, vi = 0;
@@ -1235,6 +1238,37 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
       int r = par_phase_indexed(c, dcomp, segs, ids, (unsigned char*)c->d_T.p);
       if (r) return r;
     }
+    // adler32 of each chunk's transformed bytes: folded on the host from the segments' sums where the second-format
+    // kernels produced every segment of the chunk, computed by the adler kernels otherwise
+    std::vector<uint32_t> host_adler(nb, 0);
+    std::vector<char> have_adler(nb, 0);
+    {
+      size_t vi = 0;
+      for (int i = 0; i < nb; i++) {
+        bool all = first_inf[i + 1] > first_inf[i];
+        uint32_t a = 1;
+        for (int j = first_inf[i]; j < first_inf[i + 1]; j++) {
+          while (vi < v2_ids.size() && v2_ids[vi] < j) vi++;
+          if (vi < v2_ids.size() && v2_ids[vi] == j && v2_ok[vi]) {
+            const uint32_t a2 = v2_ad[vi], len2 = (uint32_t)segs[j].out_len;
+            const uint32_t s1a = a & 0xffff, s2a = a >> 16, s1b = a2 & 0xffff, s2b = a2 >> 16;
+            const uint32_t s1 = (s1a + s1b + ADLER_BASE - 1) % ADLER_BASE;
+            const unsigned long long t = (unsigned long long)(len2 % ADLER_BASE) * ((s1a + ADLER_BASE - 1) % ADLER_BASE);
+            a = ((uint32_t)((s2a + s2b + t) % ADLER_BASE) << 16) | s1;
+          } else { all = false; break; }
+        }
+        if (all) { have_adler[i] = 1; host_adler[i] = a; }
+        const long long raw = (long long)cds[i].ns * row_bytes, tbase = cds[i].elem_off * itemsize;
+        first[i] = (int)as.size();
+        if (!all) for (long long o = 0; o < raw; o += ASEG) as.push_back(AdlerSeg{tbase + o, (int)std::min<long long>(ASEG, raw - o), 0});
+      }
+      first[nb] = (int)as.size();
+    }
+    const int n_as = (int)as.size();
+    size_t o_cd = 0, o_seg = (o_cd + nb * sizeof(ChunkDesc) + 255) & ~(size_t)255;
+    size_t o_as = (o_seg + n_segs * sizeof(InflateSeg) + 255) & ~(size_t)255;
+    size_t o_first = (o_as + n_as * sizeof(AdlerSeg) + 255) & ~(size_t)255;
+    size_t tab_bytes = o_first + (nb + 1) * sizeof(int);
     NEED(c->h_tab, tab_bytes);
     NEED(c->d_tab, tab_bytes);
     char* h = (char*)c->h_tab.p;
@@ -1244,7 +1278,7 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
     memcpy(h + o_first, first.data(), (nb + 1) * sizeof(int));
     NEED(c->d_status, (size_t)n_segs * 4);
     NEED(c->d_tadler, (size_t)n_segs * 4);
-    NEED(c->d_seg_adler, (size_t)n_as * 4);
+    NEED(c->d_seg_adler, (size_t)n_as * 4 + 64);
     NEED(c->d_chunk_adler, (size_t)nb * 4);
     NEED(c->h_small, (size_t)n_segs * 8 + (size_t)nb * 4 + 128);
     const char* d = (const char*)c->d_tab.p;
@@ -1263,8 +1297,10 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
     c->launches++;
     c->end();
     c->begin(3);
-    MTS_LAUNCH(adler_partial_kernel, dim3(n_as), dim3(256), 0, c->stream, (const uint8_t*)c->d_T.p, (const AdlerSeg*)(d + o_as), (uint32_t*)c->d_seg_adler.p);
-    CKL();
+    if (n_as) {
+      MTS_LAUNCH(adler_partial_kernel, dim3(n_as), dim3(256), 0, c->stream, (const uint8_t*)c->d_T.p, (const AdlerSeg*)(d + o_as), (uint32_t*)c->d_seg_adler.p);
+      CKL();
+    }
     MTS_LAUNCH(adler_combine_kernel, dim3((nb + 127) / 128), dim3(128), 0, c->stream, (const AdlerSeg*)(d + o_as), (const uint32_t*)c->d_seg_adler.p, (const int*)(d + o_first), nb, (uint32_t*)c->d_chunk_adler.p);
     CKL();
     c->launches += 2;
@@ -1297,7 +1333,7 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
       for (int j = first_inf[i]; j < first_inf[i + 1] && !s; j++) s = st[j];
       if (!s) {
         uint32_t want = nseg[c0 + i] ? want_adler[i] : ta[first_inf[i]];
-        if (want != ca[i]) s = INF_BAD_ADLER;
+        if (want != (have_adler[i] ? host_adler[i] : ca[i])) s = INF_BAD_ADLER;
       }
       if (s) any_bad = true;
       if (chunk_status) chunk_status[c0 + i] = s;

@@ -869,14 +869,16 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
     }
     __syncthreads();
     const unsigned wbits = (unsigned)wtot64[wid], wout = (unsigned)(wtot64[wid] >> 32);
-    if (sub_abs && mine_out) {
-      // a token that reaches the next multiple of IDX_SUB_BYTES makes its successor the first token of that sub-block
-      unsigned bit = seg_bits + wbits + incl - mine, op = seg_out + wout + (unsigned)(incl64 >> 32) - mine_out;
+    const unsigned op0 = seg_out + wout + (unsigned)(incl64 >> 32) - mine_out;
+    if (sub_abs && (op0 + mine_out) / IDX_SUB_BYTES != op0 / IDX_SUB_BYTES) {
+      // (rare: once per IDX_SUB_BYTES of output) one of this thread's tokens reaches the next multiple of
+      // IDX_SUB_BYTES, which makes its successor the first token of that sub-block
+      unsigned bit = seg_bits + wbits + incl - mine, op = op0;
 #pragma unroll
       for (int j = 0; j < ENC_PER; j++) {
         bit += nb[j];
         const unsigned oe = op + ol[j];
-        if (ol[j] && (oe / IDX_SUB_BYTES) != (op / IDX_SUB_BYTES)) {
+        if (oe / IDX_SUB_BYTES != op / IDX_SUB_BYTES) {
           const unsigned jn = oe / IDX_SUB_BYTES;
           if ((int)jn < n_sub) sub_abs[sg.sub_first + jn] = ((unsigned long long)bit << 9) | (oe - jn * IDX_SUB_BYTES);
         }

@@ -46,10 +46,10 @@ struct TokSink {            // a lane's token writer
   unsigned* tok;            // the sub-block's slots
   uint2* btab;              // per batch: {output offset before it, tokens in it}
   unsigned* stepb;
-  unsigned n, step0, cur_step, step_shift, out0;
+  unsigned n, bpos, step0, cur_step, step_shift;
   bool over;
   __device__ __forceinline__ void open(unsigned* t, uint2* b, unsigned* sb, unsigned first_pos, unsigned shift, unsigned sub_pos) {
-    tok = t; btab = b; stepb = sb; n = 0; step_shift = shift; out0 = sub_pos;
+    tok = t; btab = b; stepb = sb; n = 0; bpos = first_pos; step_shift = shift;
     step0 = sub_pos >> shift; cur_step = first_pos >> shift; over = false;
     for (unsigned q = 0; q <= cur_step - step0 && q < (unsigned)SEG_MAX_SPS; q++) stepb[q] = 0;
   }
@@ -57,20 +57,54 @@ struct TokSink {            // a lane's token writer
   __device__ __forceinline__ void put(unsigned word, unsigned pos) {
     const unsigned st = pos >> step_shift;
     if (st != cur_step) {                                  // a new step begins: close the batch, note where the step starts
-      if (n & 31u) { btab[n >> 5].y = n & 31u; n = (n + 31u) & ~31u; }
+      if (n & 31u) { btab[n >> 5] = make_uint2(bpos, n & 31u); n = (n + 31u) & ~31u; }
       for (unsigned q = cur_step + 1; q <= st; q++) if (q - step0 < (unsigned)SEG_MAX_SPS) stepb[q - step0] = n >> 5;
       cur_step = st;
     }
-    if (n >= (unsigned)SEG_TOK_STRIDE) { over = true; return; }
-    if ((n & 31u) == 0) btab[n >> 5].x = pos;
-    tok[n] = word;
+    if ((n & 31u) == 0) bpos = pos;
+    if (n < (unsigned)SEG_TOK_STRIDE) tok[n] = word; else over = true;
     n++;
-    if ((n & 31u) == 0) btab[(n >> 5) - 1].y = 32u;
+    if ((n & 31u) == 0 && !over) btab[(n >> 5) - 1] = make_uint2(bpos, 32u);
   }
   __device__ __forceinline__ void close(unsigned n_steps_sub) {
-    if (n & 31u) { btab[n >> 5].y = n & 31u; n = (n + 31u) & ~31u; }
+    if ((n & 31u) && !over) { btab[n >> 5] = make_uint2(bpos, n & 31u); n = (n + 31u) & ~31u; }
     for (unsigned q = cur_step - step0 + 1; q < n_steps_sub && q < (unsigned)SEG_MAX_SPS; q++) stepb[q] = n >> 5;
   }
+};
+
+// Bit reader of one lane: 64 stream bits in (lo, hi), cursor pos < 32 after fill().  fill() has no branch (the lanes of a
+// warp read 32 different streams and must not drift apart): it shifts in the next word when the cursor has passed 32.
+struct LaneBits {
+  const unsigned* w;     // 4-byte aligned base of the stream
+  unsigned sh, kmax, k, raw, ahead, lo, hi, pos, base_bit;
+  __device__ __forceinline__ void init(const unsigned char* in, unsigned in_len, unsigned bit) {
+    const unsigned mis = (unsigned)((uintptr_t)in & 3);
+    w = (const unsigned*)(in - mis);
+    sh = mis * 8;
+    kmax = (mis + max(in_len, 1u) - 1) >> 2;
+    const unsigned word = bit >> 5;
+    k = word;
+    raw = w[min(k, kmax)]; k++;
+    ahead = w[min(k, kmax)];
+    lo = __funnelshift_r(raw, ahead, sh); raw = ahead; k++; ahead = w[min(k, kmax)];
+    hi = __funnelshift_r(raw, ahead, sh); raw = ahead; k++; ahead = w[min(k, kmax)];
+    pos = bit & 31;
+    base_bit = word << 5;
+  }
+  __device__ __forceinline__ void fill() {
+    const bool need = pos >= 32;
+    const unsigned nw = __funnelshift_r(raw, ahead, sh);
+    lo = need ? hi : lo;
+    hi = need ? nw : hi;
+    raw = need ? ahead : raw;
+    pos -= need ? 32u : 0u;
+    base_bit += need ? 32u : 0u;
+    k += need ? 1u : 0u;
+    if (need) ahead = w[min(k, kmax)];
+  }
+  __device__ __forceinline__ unsigned window() const { return __funnelshift_r(lo, hi, pos); }
+  __device__ __forceinline__ void drop(unsigned n) { pos += n; }
+  __device__ __forceinline__ unsigned bit_pos() const { return base_bit + pos; }
 };
 
 __device__ __forceinline__ unsigned rd32u(const unsigned char* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((unsigned)p[3] << 24); }
@@ -126,51 +160,62 @@ __global__ void __launch_bounds__(32) seg_tokens_kernel(const unsigned char* __r
     const size_t sub = (size_t)sg.sub_first + j;
     SubOut* so = subs + sub;
     if (act) sink.open(tokens + sub * SEG_TOK_STRIDE, btab + sub * SEG_BATCHES, so->stepb, pos0, step_shift, j * IDX_SUB_BYTES);
-    TBits br;
+    LaneBits br;
     br.init(in, in_len, (act && good) ? start : 0u);
-    unsigned pos = pos0, plit = 0, np = 0, pstart = pos0, flags = 0;
+    // One symbol per iteration, at most one token written: the token in hand (`pend`: a run of 1..3 literals, or a
+    // match) is written when the next symbol cannot join it.
+    unsigned pos = pos0, pend = 0, ppos = pos0, np = 0, flags = 0;      // np: literals in hand (0: pend is a match or nothing)
+    bool have = false;
     bool active = act && good;
     while (__any_sync(0xffffffffu, active)) {
-      if (!active) continue;
-      br.refill();
-      if (br.bit_pos() >= bound) { active = false; continue; }
-      const unsigned win = br.window();
-      const unsigned en = T.ltab[win & ((1u << PAR_LBITS) - 1)];
-      unsigned cl = en & 15, kind = (en >> 4) & 3, val = en >> 6;
-      if (cl == 0) {                                                          // rare: a code longer than the table
-        unsigned sym;
-        if (!blk_long<PAR_LBITS>(win, T.llong, T.lsorted, sym, cl)) { flags = 2; active = false; continue; }
-        kind = sym < 256 ? (unsigned)K_LIT : sym == 256 ? (unsigned)K_EOB : sym < 286 ? (unsigned)K_LEN : (unsigned)K_BAD;
-        val = sym < 256 ? sym : sym > 256 ? sym - 257 : 0;
+      if (active) {
+        br.fill();
+        const bool past = br.bit_pos() >= bound;
+        const unsigned win = br.window();
+        const unsigned en = T.ltab[win & ((1u << PAR_LBITS) - 1)];
+        unsigned cl = en & 15, kind = (en >> 4) & 3, val = en >> 6;
+        if (cl == 0 && !past) {                                               // rare: a code longer than the table
+          unsigned sym;
+          if (!blk_long<PAR_LBITS>(win, T.llong, T.lsorted, sym, cl)) { kind = K_BAD; cl = 1; }
+          else {
+            kind = sym < 256 ? (unsigned)K_LIT : sym == 256 ? (unsigned)K_EOB : sym < 286 ? (unsigned)K_LEN : (unsigned)K_BAD;
+            val = sym < 256 ? sym : sym > 256 ? sym - 257 : 0;
+          }
+        }
+        const bool stop = past || kind >= (unsigned)K_EOB;
+        const bool isl = kind == K_LEN;
+        const unsigned lx = lenx[isl ? val : 0u];
+        const unsigned xb = isl ? lx >> 12 : 0u;
+        const unsigned len = (lx & 0xfffu) + ((win >> cl) & ((1u << xb) - 1));
+        br.drop(past ? 0u : cl + xb);
+        br.fill();
+        const unsigned win2 = br.window();
+        const unsigned e2 = T.dtab[win2 & ((1u << PAR_DBITS) - 1)];
+        unsigned cl2 = e2 & 15, dsym = e2 >> 4;
+        bool dbad = false;
+        if (isl && cl2 == 0 && !stop) dbad = !blk_long<PAR_DBITS>(win2, T.dlong, T.dsorted, dsym, cl2);
+        const unsigned dx = distx[dsym & 31];
+        dbad = dbad || (isl && dx == 0);
+        const unsigned xb2 = dx >> 16;
+        const unsigned dist = (dx & 0xffffu) + ((win2 >> cl2) & ((1u << xb2) - 1));
+        br.drop((isl && !stop) ? cl2 + xb2 : 0u);
+        if (stop || dbad) {
+          flags = (!past && kind == K_EOB) ? 1u : (past ? 0u : 2u);
+          if (dbad) flags = 2;
+          active = false;
+        } else {
+          const bool join = !isl && have && np > 0 && np < 3;                 // a literal joins the literals in hand
+          if (have && !join) sink.put(pend, ppos);
+          if (join) { pend |= val << (8 * np); np++; pend = (pend & 0x00ffffffu) | ((np - 1) << 24); }
+          else if (isl) { pend = TOK_MATCH | (len << 16) | (dist - 1); ppos = pos; np = 0; }
+          else { pend = val; ppos = pos; np = 1; }
+          have = true;
+          pos += isl ? len : 1u;
+        }
       }
-      if (kind >= (unsigned)K_EOB) {
-        br.drop(cl);
-        flags = kind == K_EOB ? 1u : 2u;
-        active = false;
-        continue;
-      }
-      const bool isl = kind == K_LEN;
-      const unsigned lx = lenx[isl ? val : 0u];
-      const unsigned xb = isl ? lx >> 12 : 0u;
-      const unsigned len = (lx & 0xfffu) + ((win >> cl) & ((1u << xb) - 1));
-      br.drop(cl + xb);
-      br.refill();
-      const unsigned win2 = br.window();
-      const unsigned e2 = T.dtab[win2 & ((1u << PAR_DBITS) - 1)];
-      unsigned cl2 = e2 & 15, dsym = e2 >> 4;
-      if (isl && cl2 == 0 && !blk_long<PAR_DBITS>(win2, T.dlong, T.dsorted, dsym, cl2)) { flags = 2; active = false; continue; }
-      const unsigned dx = distx[dsym & 31];
-      if (isl && dx == 0) { flags = 2; active = false; continue; }
-      const unsigned xb2 = dx >> 16;
-      const unsigned dist = (dx & 0xffffu) + ((win2 >> cl2) & ((1u << xb2) - 1));
-      br.drop(isl ? cl2 + xb2 : 0u);
-      // pending literals leave before a match and when three are waiting
-      if (np && (isl || np == 3)) { sink.put(((np - 1) << 24) | plit, pstart); np = 0; plit = 0; }
-      if (isl) { sink.put(TOK_MATCH | (len << 16) | (dist - 1), pos); pos += len; }
-      else { if (!np) pstart = pos; plit |= val << (8 * np); np++; pos++; }
     }
     if (act && good) {
-      if (np) sink.put(((np - 1) << 24) | plit, pstart);
+      if (have) sink.put(pend, ppos);
       sink.close(min(sps, (out_len - j * IDX_SUB_BYTES + sg.step_bytes - 1) >> step_shift));
       // the sub-block must end exactly where the next one begins (bits and bytes); the last one with the end-of-block code
       good = !(flags & 2) && !sink.over && pos == pos1 && br.bit_pos() <= in_bits &&
@@ -188,17 +233,20 @@ __global__ void __launch_bounds__(32) seg_tokens_kernel(const unsigned char* __r
 }
 
 // ---------------------------------------------------------------------------------------------- seg_resolve_kernel
+// Also leaves the segment's standalone adler32 (seg_adler, as the encoder's lz77_kernel does): the bytes pass through
+// the flushing threads' registers anyway.
 __global__ void __launch_bounds__(SEG_RES_WARPS * 32) seg_resolve_kernel(const SegV2* __restrict__ segs,
                                                                          const unsigned* __restrict__ tokens,
                                                                          const uint2* __restrict__ btab,
                                                                          const SubOut* __restrict__ subs,
-                                                                         unsigned char* out_base, ParRes* __restrict__ res) {
-  MTS_DYN_SMEM(sm);                                             // [ring SEG_RING][first batch of each step + 1]
+                                                                         unsigned char* out_base, ParRes* __restrict__ res,
+                                                                         unsigned* __restrict__ seg_adler) {
+  MTS_DYN_SMEM(sm);                                             // [ring SEG_RING][per step: first batch | batches << 24]
   unsigned char* ring = sm;
   unsigned short* ring16 = (unsigned short*)sm;
   const unsigned* ring32 = (const unsigned*)sm;
-  unsigned* s_first = (unsigned*)(sm + SEG_RING);               // absolute batch index where step s starts; [n_steps] = end
-  __shared__ unsigned s_fail;
+  unsigned* s_step = (unsigned*)(sm + SEG_RING);                // first batch (relative to the segment's) | batches << 24
+  __shared__ unsigned long long s_red[2 * SEG_RES_WARPS];
   const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned W = SEG_RES_WARPS, NT = SEG_RES_WARPS * 32, RM = SEG_RING - 1;
   const SegV2 sg = segs[blockIdx.x];
@@ -210,39 +258,39 @@ __global__ void __launch_bounds__(SEG_RES_WARPS * 32) seg_resolve_kernel(const S
   const unsigned n_steps = (out_len + DS - 1) >> step_shift;
   unsigned char* out = out_base + sg.out_off;
   const bool al4 = ((uintptr_t)out & 3) == 0;
-  if (tid == 0) s_fail = n_steps > (unsigned)SEG_MAX_STEPS ? 1u : 0u;
-  __syncthreads();
-  if (s_fail) { if (tid == 0) res[blockIdx.x].flags |= 2u; return; }
+  if (n_steps > (unsigned)SEG_MAX_STEPS) { if (tid == 0) res[blockIdx.x].flags |= 2u; return; }
   // batches of a step: from its first batch to the next step's (the steps of a sub-block are consecutive in its token
   // area; the last step of a sub-block ends with the sub-block's slots)
   for (unsigned s = tid; s < n_steps; s += NT) {
     const unsigned j = s / sps, ls = s - j * sps;
-    s_first[s] = (sg.sub_first + j) * SEG_BATCHES + subs[(size_t)sg.sub_first + j].stepb[ls];
+    const SubOut* so = subs + (size_t)sg.sub_first + j;
+    const unsigned b0 = so->stepb[ls];
+    const unsigned b1 = (ls + 1 < sps && s + 1 < n_steps) ? so->stepb[ls + 1] : (so->n_slots + 31) >> 5;
+    s_step[s] = (j * SEG_BATCHES + b0) | (min(b1 > b0 ? b1 - b0 : 0u, 255u) << 24);
   }
   __syncthreads();
   const unsigned max_dist = SEG_RING - DS - 320;                // what the ring still holds while a step is being written
-  // software pipeline: the tokens of a warp's first batch of step s + 1 are fetched while step s is resolved
+  const size_t bat0 = (size_t)sg.sub_first * SEG_BATCHES;
+  // software pipeline: a warp's first batch of step s + 1 is fetched while step s is resolved (slots beyond a batch's
+  // token count hold stale words: the count masks them)
   unsigned t_nx = 0;
   uint2 bt_nx = make_uint2(0, 0);
-  auto step_end = [&](unsigned s) -> unsigned {                // one past the last batch of step s
-    const unsigned j = s / sps;
-    if (s + 1 < n_steps && (s + 1) / sps == j) return s_first[s + 1];
-    return (sg.sub_first + j) * SEG_BATCHES + ((subs[(size_t)sg.sub_first + j].n_slots + 31) >> 5);
-  };
   auto fetch = [&](unsigned s) {
     if (s >= n_steps) return;
-    const unsigned b = s_first[s] + wid;
-    if (b < step_end(s)) { bt_nx = btab[b]; t_nx = lane < bt_nx.y ? tokens[(size_t)b * 32 + lane] : 0u; }
+    const unsigned e = s_step[s];
+    if (wid < (e >> 24)) { const size_t b = bat0 + (e & 0xffffffu) + wid; bt_nx = btab[b]; t_nx = tokens[b * 32 + lane]; }
   };
   fetch(0);
   bool bad = false;
+  unsigned ad_a = 0;
+  unsigned long long ad_b = 0;
   for (unsigned s = 0; s < n_steps; s++) {
-    const unsigned b0 = s_first[s], b1 = step_end(s), s_start = s << step_shift;
+    const unsigned e = s_step[s], nb = e >> 24, s_start = s << step_shift;
     unsigned t = t_nx;
     uint2 bt = bt_nx;
     fetch(s + 1);
-    for (unsigned b = b0 + wid; b < b1; b += W) {
-      if (b != b0 + wid) { bt = btab[b]; t = lane < bt.y ? tokens[(size_t)b * 32 + lane] : 0u; }
+    for (unsigned q = wid; q < nb; q += W) {
+      if (q != wid) { const size_t b = bat0 + (e & 0xffffffu) + q; bt = btab[b]; t = tokens[b * 32 + lane]; }
       const bool has = lane < bt.y;
       const bool isM = has && (t >> 31);
       const unsigned L = has ? (isM ? (t >> 16) & 0x1ffu : ((t >> 24) & 3u) + 1u) : 0u;
@@ -260,7 +308,15 @@ __global__ void __launch_bounds__(SEG_RES_WARPS * 32) seg_resolve_kernel(const S
           if (L > 2) ring[(p + 2) & RM] = (unsigned char)(t >> 16);
         } else if (((p | dist | L) & 1u) == 0) {
           const unsigned p2 = p >> 1, s2 = (p - dist) >> 1, n2 = L >> 1, M2 = RM >> 1;
-          for (unsigned i = 0; i < n2; i++) ring16[(p2 + i) & M2] = ring16[(s2 + i) & M2];
+          // the first 8 bytes without a loop (most matches), the rest of a longer one in a loop
+          unsigned short v0 = ring16[s2 & M2], v1 = ring16[(s2 + 1) & M2], v2 = 0, v3 = 0;
+          if (n2 > 2) v2 = ring16[(s2 + 2) & M2];
+          if (n2 > 3) v3 = ring16[(s2 + 3) & M2];
+          ring16[p2 & M2] = v0;
+          ring16[(p2 + 1) & M2] = v1;
+          if (n2 > 2) ring16[(p2 + 2) & M2] = v2;
+          if (n2 > 3) ring16[(p2 + 3) & M2] = v3;
+          for (unsigned i = 4; i < n2; i++) ring16[(p2 + i) & M2] = ring16[(s2 + i) & M2];
         } else {
           for (unsigned i = 0; i < L; i++) ring[(p + i) & RM] = ring[(p - dist + i) & RM];
         }
@@ -268,15 +324,40 @@ __global__ void __launch_bounds__(SEG_RES_WARPS * 32) seg_resolve_kernel(const S
     }
     if (__syncthreads_or(bad)) { bad = true; break; }
     // the step's bytes are complete (matches of earlier steps may have spilled into it): ring -> global, coalesced
-    const unsigned e = min(s_start + DS, out_len);
+    const unsigned end = min(s_start + DS, out_len);
     if (al4) {
-      for (unsigned i = s_start + 4 * tid; i + 4 <= e; i += 4 * NT) *(unsigned*)(out + i) = ring32[(i & RM) >> 2];
-      if (tid < (e & 3u)) out[(e & ~3u) + tid] = ring[((e & ~3u) + tid) & RM];
+      for (unsigned i = s_start + 4 * tid; i + 4 <= end; i += 4 * NT) {
+        const unsigned w = ring32[(i & RM) >> 2];
+        *(unsigned*)(out + i) = w;
+        const unsigned sum = (w & 0xffu) + ((w >> 8) & 0xffu) + ((w >> 16) & 0xffu) + (w >> 24);
+        ad_a += sum;
+        ad_b += (unsigned long long)(out_len - i) * sum - (((w >> 8) & 0xffu) + 2 * ((w >> 16) & 0xffu) + 3 * (w >> 24));
+      }
+      if (tid < (end & 3u)) {
+        const unsigned i = (end & ~3u) + tid, v = ring[i & RM];
+        out[i] = (unsigned char)v;
+        ad_a += v; ad_b += (unsigned long long)(out_len - i) * v;
+      }
     } else {
-      for (unsigned i = s_start + tid; i < e; i += NT) out[i] = ring[i & RM];
+      for (unsigned i = s_start + tid; i < end; i += NT) {
+        const unsigned v = ring[i & RM];
+        out[i] = (unsigned char)v;
+        ad_a += v; ad_b += (unsigned long long)(out_len - i) * v;
+      }
     }
   }
-  if (bad && tid == 0) res[blockIdx.x].flags |= 2u;
+  if (bad) { if (tid == 0) res[blockIdx.x].flags |= 2u; return; }
+  {
+    unsigned long long a = ad_a, b = ad_b % ADLER_BASE;
+    a = warp_sum(a); b = warp_sum(b);
+    if (lane == 0) { s_red[2 * wid] = a; s_red[2 * wid + 1] = b; }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long ta = 0, tb = 0;
+      for (unsigned w = 0; w < W; w++) { ta += s_red[2 * w]; tb += s_red[2 * w + 1]; }
+      seg_adler[blockIdx.x] = ((unsigned)((out_len % ADLER_BASE + tb) % ADLER_BASE) << 16) | (unsigned)((1 + ta) % ADLER_BASE);
+    }
+  }
 }
 
 }  // namespace mts

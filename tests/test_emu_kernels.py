@@ -111,8 +111,9 @@ def test_emulated_marker_chains(emu):
 
 
 def test_emulated_indexed_segments_both_decoders(emu):
-    """GPU-written chunk (kernel logic under emulation): the indexed segments through the block kernels and through
-    the serial warp decoder give the same bytes; a segment stored uncompressed stays with the serial decoder."""
+    """GPU-written chunk (kernel logic under emulation): the indexed segments through the second-format kernels
+    (seg_tokens / seg_resolve), through the block kernels and through the serial warp decoder give the same bytes; a
+    segment stored uncompressed stays with the serial decoder."""
     from mtscomp_b200 import _native, synth
     rng = np.random.default_rng(2)
     x = np.concatenate([synth.ap_chunk(ns=4000, nc=48, seed=11),
@@ -122,15 +123,17 @@ def test_emulated_indexed_segments_both_decoders(emu):
         emu.set_param('seg_bytes', 65536)
         comp, offs = emu.compress(x, rows, _native.TIME_DIFF)
         outs = []
-        for indexed in (1, 0):
+        for v2, indexed in ((1, 0), (0, 1), (0, 0)):
+            emu.set_param('seg_v2', v2)
             emu.set_param('par_indexed', indexed)
             out, st = emu.decompress(comp, offs, rows, 48, np.int16, _native.TIME_DIFF)
             assert not st.any() and np.array_equal(out, x)
             outs.append(emu.get_param('par_resumed'))
-        assert outs[0] >= 4 and outs[1] == 0
+        assert outs[0] >= 4 and outs[1] >= 4 and outs[2] == 0
     finally:
         emu.set_param('seg_bytes', 262144)
         emu.set_param('par_indexed', 1)
+        emu.set_param('seg_v2', 1)
 
 
 @pytest.mark.parametrize('name', sorted(json.loads((GOLDEN / 'manifest.json').read_text()).get('float_cases', {})))

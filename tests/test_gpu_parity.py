@@ -270,8 +270,9 @@ def test_block_parallel_skips_a_false_candidate(codec):
 
 
 def test_indexed_segments_block_kernels_match_serial(codec):
-    """GPU-written chunks: the indexed segments decode through the block kernels (default) or through the serial warp
-    decoder (par_indexed = 0); both must give the input back, including chunks with segments stored uncompressed."""
+    """GPU-written chunks: the indexed segments decode through the second-format kernels (seg_tokens / seg_resolve, the
+    default), through the block kernels (seg_v2 = 0) or through the serial warp decoder (par_indexed = 0 as well); all
+    must give the input back, including chunks with segments stored uncompressed."""
     from mtscomp_b200 import synth
     rng = np.random.default_rng(12)
     x = np.concatenate([synth.ap_chunk(ns=20000, nc=64, seed=70),
@@ -280,6 +281,10 @@ def test_indexed_segments_block_kernels_match_serial(codec):
     rows = [0, 20000, 40000, 60000]
     comp, offs = codec.compress(x, rows, F())
     try:
+        codec.set_param('par_indexed', 0)
+        out2, st2 = codec.decompress(comp, offs, rows, 64, np.int16, F())
+        resumed2 = codec.get_param('par_resumed')
+        codec.set_param('seg_v2', 0)
         codec.set_param('par_indexed', 1)
         out1, st1 = codec.decompress(comp, offs, rows, 64, np.int16, F())
         resumed = codec.get_param('par_resumed')
@@ -288,9 +293,10 @@ def test_indexed_segments_block_kernels_match_serial(codec):
         assert codec.get_param('par_resumed') == 0
     finally:
         codec.set_param('par_indexed', 1)
-    assert not st1.any() and not st0.any()
-    assert np.array_equal(out1, x) and np.array_equal(out0, x)
-    assert resumed >= 10                        # the segments of the two compressible chunks went through the block kernels
+        codec.set_param('seg_v2', 1)
+    assert not st1.any() and not st0.any() and not st2.any()
+    assert np.array_equal(out1, x) and np.array_equal(out0, x) and np.array_equal(out2, x)
+    assert resumed >= 10 and resumed2 >= 10     # the segments of the two compressible chunks went through the parallel kernels
     bad = bytearray(comp)
     bad[offs[0] + (offs[1] - offs[0]) // 2] ^= 0x11
     _, st = codec.decompress(bytes(bad), offs, rows, 64, np.int16, F())
