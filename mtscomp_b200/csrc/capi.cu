@@ -1084,7 +1084,7 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
       if (idx_v2[i]) {
         // the fast path needs the sub-block size this build uses and a sane step size; otherwise only the segment lengths are used
         const uint32_t subb = rd32(lens + 4 * nseg[i]), stepb = rd32(lens + 4 * nseg[i] + 4);
-        const bool fast = subb == (uint32_t)IDX_SUB_BYTES && stepb >= 256 && stepb <= (uint32_t)IDX_SUB_BYTES && (stepb & (stepb - 1)) == 0;
+        const bool fast = subb == (uint32_t)IDX_SUB_BYTES && stepb >= 256 && stepb <= (uint32_t)IDX_SUB_BYTES / 2 && (stepb & (stepb - 1)) == 0;
         idx_step[i] = fast ? stepb : 0;
       }
       ipos_by_chunk[i] = ipos[j];

@@ -29,16 +29,22 @@ struct DeflateSeg {
 enum { SEG_FIRST = 1, SEG_LAST = 2 };
 // In-band index written after each chunk's zlib stream (zlib.decompress ignores trailing bytes), all
 // little-endian u32:
-//   [sub-block table: for every segment, one entry per IDX_SUB_BYTES of its input | k segment body lengths |
+//   [sub-block table: for every segment, one entry per sub-block of its input | k segment body lengths |
 //    sub-block bytes, step bytes | segment bytes, k, magic "MTS2", sum of the lengths]
-// Sub-block j of a segment begins with the first token whose output starts at or after j * IDX_SUB_BYTES; its entry is
-// (bits from the previous sub-block's first token to its own; for j = 0 from the segment's first bit) | overshoot << 17,
-// overshoot = output offset of that token - j * IDX_SUB_BYTES (< 258).  "step bytes" states the encoder's STEP RULE: no
+// The sub-blocks of a segment begin at the output offsets idx_bound(j) = 0, S/2, S, 2S, 3S, ... (S = IDX_SUB_BYTES; the
+// first S bytes, which are mostly literals because the window is still empty, count as two sub-blocks so that all of
+// them hold about the same number of codes).  Sub-block j starts with the first token whose output begins at or after
+// idx_bound(j); its entry is (bits from the previous sub-block's first token to its own; for j = 0 from the segment's
+// first bit) | overshoot << 17, overshoot = output offset of that token - idx_bound(j) (< 258).  "step bytes" states the encoder's STEP RULE: no
 // match reads output at or after the beginning of the step (of that many bytes, counted from the segment's start) that
 // the match itself starts in.  Files of the first format ("MTSB": k lengths | segment bytes, k, magic, sum) still decode.
 static const unsigned IDX_MAGIC_V1 = 0x4253544Du, IDX_MAGIC_V2 = 0x3253544Du;
 static const int IDX_SUB_BYTES = 8192;
-__host__ __device__ inline int idx_n_sub(long long seg_len) { return (int)((seg_len + IDX_SUB_BYTES - 1) / IDX_SUB_BYTES); }
+__host__ __device__ inline int idx_n_sub(long long seg_len) {
+  return (int)((seg_len + IDX_SUB_BYTES - 1) / IDX_SUB_BYTES) + (seg_len > IDX_SUB_BYTES / 2 ? 1 : 0);
+}
+__host__ __device__ inline unsigned idx_bound(unsigned j) { return j == 0 ? 0u : j == 1 ? IDX_SUB_BYTES / 2u : (j - 1) * (unsigned)IDX_SUB_BYTES; }
+__host__ __device__ inline unsigned idx_item(unsigned pos) { return (pos >= IDX_SUB_BYTES / 2u ? 1u : 0u) + pos / (unsigned)IDX_SUB_BYTES; }   // sub-block that holds pos
 enum { MODE_STORED = 0, MODE_DYNAMIC = 1, MODE_FIXED = 2 };
 
 struct DeflateSegOut {   // written by huff_kernel / scan_kernel, read by encode_kernel
@@ -870,18 +876,16 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
     __syncthreads();
     const unsigned wbits = (unsigned)wtot64[wid], wout = (unsigned)(wtot64[wid] >> 32);
     const unsigned op0 = seg_out + wout + (unsigned)(incl64 >> 32) - mine_out;
-    if (sub_abs && (op0 + mine_out) / IDX_SUB_BYTES != op0 / IDX_SUB_BYTES) {
-      // (rare: once per IDX_SUB_BYTES of output) one of this thread's tokens reaches the next multiple of
-      // IDX_SUB_BYTES, which makes its successor the first token of that sub-block
+    if (sub_abs && idx_item(op0 + mine_out) != idx_item(op0)) {
+      // (rare: once per sub-block of output) one of this thread's tokens reaches the next sub-block boundary, which
+      // makes its successor the first token of that sub-block
       unsigned bit = seg_bits + wbits + incl - mine, op = op0;
 #pragma unroll
       for (int j = 0; j < ENC_PER; j++) {
         bit += nb[j];
         const unsigned oe = op + ol[j];
-        if (oe / IDX_SUB_BYTES != op / IDX_SUB_BYTES) {
-          const unsigned jn = oe / IDX_SUB_BYTES;
-          if ((int)jn < n_sub) sub_abs[sg.sub_first + jn] = ((unsigned long long)bit << 9) | (oe - jn * IDX_SUB_BYTES);
-        }
+        const unsigned jn = idx_item(oe);
+        if (jn != idx_item(op) && (int)jn < n_sub) sub_abs[sg.sub_first + jn] = ((unsigned long long)bit << 9) | (oe - idx_bound(jn));
         op = oe;
       }
     }

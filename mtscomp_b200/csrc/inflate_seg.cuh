@@ -3,7 +3,8 @@
 // Such a segment is ONE dynamic-Huffman block whose sub-blocks (every IDX_SUB_BYTES of output) are indexed by bit offset,
 // and whose matches obey the STEP RULE: a match never reads output at or after the beginning of the step (step_bytes of
 // output, counted from the segment's start) in which it starts.  That removes both serial chains of inflate:
-//   seg_tokens_kernel   warp per segment, LANE per sub-block: every lane decodes its sub-block's Huffman codes once, from
+//   seg_tokens_kernel   warp per segment, LANE per sub-block (the first one, mostly literals behind an empty window, is
+//                       indexed as two halves so that the lanes have equal work): every lane decodes its codes once, from
 //                       its indexed bit offset, into 32-bit tokens (runs of up to 3 literals packed into one; batches of
 //                       32 token slots never straddle a step) + the output offset before every batch
 //   seg_resolve_kernel  CTA per segment: step after step, ALL the tokens of a step are resolved at once (their sources
@@ -137,7 +138,6 @@ __global__ void __launch_bounds__(32) seg_tokens_kernel(const unsigned char* __r
   ok = ok && blk_build<2>(T.lens + nl, nd, T.dtab, PAR_DBITS, T.dlong, T.dsorted, T.code, lane);
   unsigned step_shift = 0;
   while ((1u << step_shift) < sg.step_bytes) step_shift++;
-  const unsigned sps = (unsigned)IDX_SUB_BYTES >> step_shift;                 // steps per sub-block
   const unsigned n_sub = (unsigned)idx_n_sub(out_len);
   const unsigned char* tab = comp + sg.tab_off;
   unsigned carry = 0, end_bit = 0;
@@ -151,15 +151,15 @@ __global__ void __launch_bounds__(32) seg_tokens_kernel(const unsigned char* __r
     carry += __shfl_sync(0xffffffffu, incl, 31);
     const bool last = j + 1 == n_sub;
     const unsigned bound = last ? in_bits : start + (e1 & 0x1ffffu);
-    const unsigned pos0 = j * IDX_SUB_BYTES + ((e >> 17) & 511u);             // output offset of its first token
-    const unsigned pos1 = last ? out_len : (j + 1) * IDX_SUB_BYTES + ((e1 >> 17) & 511u);
+    const unsigned pos0 = idx_bound(j) + ((e >> 17) & 511u);                  // output offset of its first token
+    const unsigned pos1 = last ? out_len : idx_bound(j + 1) + ((e1 >> 17) & 511u);
     bool good = !act || (start < in_bits && bound <= in_bits && bound > start && pos0 < pos1 && pos1 <= out_len &&
                          (j > 0 || (start == hdr_end && pos0 == 0)));
     // ---- the lane's sub-block: one pass over its codes (the loop of blk_span, with a token sink)
     TokSink sink;
     const size_t sub = (size_t)sg.sub_first + j;
     SubOut* so = subs + sub;
-    if (act) sink.open(tokens + sub * SEG_TOK_STRIDE, btab + sub * SEG_BATCHES, so->stepb, pos0, step_shift, j * IDX_SUB_BYTES);
+    if (act) sink.open(tokens + sub * SEG_TOK_STRIDE, btab + sub * SEG_BATCHES, so->stepb, pos0, step_shift, idx_bound(j));
     LaneBits br;
     br.init(in, in_len, (act && good) ? start : 0u);
     // One symbol per iteration, at most one token written: the token in hand (`pend`: a run of 1..3 literals, or a
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(32) seg_tokens_kernel(const unsigned char* __r
     }
     if (act && good) {
       if (have) sink.put(pend, ppos);
-      sink.close(min(sps, (out_len - j * IDX_SUB_BYTES + sg.step_bytes - 1) >> step_shift));
+      sink.close(((last ? out_len : idx_bound(j + 1)) - idx_bound(j) + sg.step_bytes - 1) >> step_shift);
       // the sub-block must end exactly where the next one begins (bits and bytes); the last one with the end-of-block code
       good = !(flags & 2) && !sink.over && pos == pos1 && br.bit_pos() <= in_bits &&
              (last ? (flags & 1) != 0 : (br.bit_pos() == bound && !(flags & 1)));
@@ -254,7 +254,6 @@ __global__ void __launch_bounds__(SEG_RES_WARPS * 32) seg_resolve_kernel(const S
   const unsigned out_len = (unsigned)sg.out_len, DS = sg.step_bytes;
   unsigned step_shift = 0;
   while ((1u << step_shift) < DS) step_shift++;
-  const unsigned sps = (unsigned)IDX_SUB_BYTES >> step_shift;
   const unsigned n_steps = (out_len + DS - 1) >> step_shift;
   unsigned char* out = out_base + sg.out_off;
   const bool al4 = ((uintptr_t)out & 3) == 0;
@@ -262,10 +261,10 @@ __global__ void __launch_bounds__(SEG_RES_WARPS * 32) seg_resolve_kernel(const S
   // batches of a step: from its first batch to the next step's (the steps of a sub-block are consecutive in its token
   // area; the last step of a sub-block ends with the sub-block's slots)
   for (unsigned s = tid; s < n_steps; s += NT) {
-    const unsigned j = s / sps, ls = s - j * sps;
+    const unsigned j = idx_item(s << step_shift), ls = s - (idx_bound(j) >> step_shift);
     const SubOut* so = subs + (size_t)sg.sub_first + j;
     const unsigned b0 = so->stepb[ls];
-    const unsigned b1 = (ls + 1 < sps && s + 1 < n_steps) ? so->stepb[ls + 1] : (so->n_slots + 31) >> 5;
+    const unsigned b1 = (s + 1 < n_steps && idx_item((s + 1) << step_shift) == j) ? so->stepb[ls + 1] : (so->n_slots + 31) >> 5;
     s_step[s] = (j * SEG_BATCHES + b0) | (min(b1 > b0 ? b1 - b0 : 0u, 255u) << 24);
   }
   __syncthreads();
