@@ -67,6 +67,7 @@ struct mtsb_ctx {
   Buf d_pstreams, d_surv, d_cand, d_pcount, d_tokens, d_cells, d_ptab, d_plist, d_pbad;   // block-parallel inflate scratch
   Buf d_segv2, d_btab, d_subout;                                                          // indexed (second format) segments
   long long seg_v2 = 1;         // indexed segments of the second format go through seg_tokens / seg_resolve
+  bool ignore_index = false;    // (internal) decode every chunk as a plain zlib stream: the retry of chunks whose index misled
   Buf d_raw, d_raw2, d_out2, d_comp2, d_T, d_tok, d_hist, d_codes, d_hdrs, d_tab, d_so, d_seg_adler, d_chunk_adler, d_chunk_off, d_out,
       d_partial, d_comp, d_status, d_tadler, d_gather, d_subabs;
   Buf h_tab, h_small;
@@ -1039,7 +1040,7 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
     std::vector<int> who;
     for (int i = 0; i < n_chunks; i++) {
       long long l = comp_offsets[i + 1] - comp_offsets[i];
-      if (l >= 2 + 6 + 4 + INDEX_TAIL) { off.push_back(comp_offsets[i + 1] - INDEX_TAIL); len.push_back(INDEX_TAIL); who.push_back(i); }
+      if (l >= 2 + 6 + 4 + INDEX_TAIL && !c->ignore_index) { off.push_back(comp_offsets[i + 1] - INDEX_TAIL); len.push_back(INDEX_TAIL); who.push_back(i); }
     }
     int r = fetch_ranges(c, comp, comp_is_device, off, len, tails, tpos);
     if (r) return r;
@@ -1341,6 +1342,25 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
   }
   if (!dst_is_device) CK(cudaStreamSynchronize(c->copy_out));
   c->collect_timing();
+  if (any_bad && chunk_status && !c->ignore_index) {
+    // A chunk that carries something that looks like an index but does not decode with it (bytes after a foreign zlib
+    // stream that happen to pass the index checks) is still a valid chunk for zlib, which ignores what follows the
+    // stream: decode it again as a plain stream before calling it corrupt.
+    any_bad = false;
+    for (int i = 0; i < n_chunks; i++) {
+      if (!chunk_status[i]) continue;
+      if (!nseg[i]) { any_bad = true; continue; }
+      const long long one_off[2] = {0, comp_offsets[i + 1] - comp_offsets[i]}, one_rows[2] = {0, chunk_rows[i + 1] - chunk_rows[i]};
+      int st = 0;
+      c->ignore_index = true;
+      const int rc = mtsb_decompress_chunks(c, comp + comp_offsets[i], comp_is_device, one_off, 1, one_rows, nc, itemsize, flags,
+                                            (char*)dst + chunk_rows[i] * row_bytes, dst_is_device, &st);
+      c->ignore_index = false;
+      if (rc != 0 && rc != MTSB_E_CORRUPT) return rc;
+      chunk_status[i] = st;
+      if (st) any_bad = true;
+    }
+  }
   if (any_bad) return fail(c, MTSB_E_CORRUPT, "at least one compressed chunk is corrupted");
   return 0;
 }

@@ -1,5 +1,5 @@
 timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 600 python tools/quick_bench.py 600 8 > gpurun_out/r2m_qb600.log 2>&1
-grep -h "compress \|ratio\|decompress\|exact" gpurun_out/r2m_qb600.log
-timeout 300 python tools/quick_bench.py 1 1 > gpurun_out/r2m_qb1.log 2>&1
-grep -h "decompress\|exact" gpurun_out/r2m_qb1.log
+timeout 600 python tools/quick_bench.py 600 8 > gpurun_out/r2o_qb600.log 2>&1
+grep -h "compress \|ratio\|decompress\|exact" gpurun_out/r2o_qb600.log
+timeout 300 python tools/quick_bench.py 1 1 > gpurun_out/r2o_qb1.log 2>&1
+grep -h "decompress\|exact" gpurun_out/r2o_qb1.log
