@@ -255,7 +255,7 @@ int launch_inv_t(mtsb_ctx* c, const void* tbuf, void* out, const ChunkDesc* d_cd
   }
   if (fast) {
     auto k3 = inv_cols_kernel<T>;
-    MTS_LAUNCH(k3, dim3((nc + 127) / 128, max_tiles, n_chunks), dim3(128), 0, c->stream, (const T*)tbuf, (T*)out, (const T*)partial, d_cd, nc, TT, max_tiles, flags);
+    MTS_LAUNCH(k3, dim3(max_tiles, (nc + 127) / 128, n_chunks), dim3(128), 0, c->stream, (const T*)tbuf, (T*)out, (const T*)partial, d_cd, nc, TT, max_tiles, flags);
   } else {
     auto k3 = inv_apply_kernel<T>;
     MTS_LAUNCH(k3, grid, dim3(512), tile_smem(nc, sizeof(T), TT), c->stream, (const T*)tbuf, (T*)out, (const T*)partial, d_cd, nc, TT, max_tiles, flags);

@@ -304,13 +304,13 @@ __global__ void __launch_bounds__(128) inv_cols_kernel(const T* __restrict__ in,
   const int R = ColRun<T>::R;
   const ChunkDesc cd = chunks[blockIdx.z];
   const int ns = cd.ns;
-  const int c = blockIdx.x * 128 + (int)threadIdx.x;
-  const int t0 = blockIdx.y * TT;
+  const int c = blockIdx.y * 128 + (int)threadIdx.x;        // (tiles on x: a long chunk has more than 65535 of them)
+  const int t0 = blockIdx.x * TT;
   if (t0 >= ns || c >= nc) return;
   const T* x = in + cd.elem_off + (long long)c * ns;
   T* y = out + cd.elem_off;
   const bool td = (flags & FLAG_TIME_DIFF) != 0;
-  T run = td ? partial[((long long)blockIdx.z * max_tiles + blockIdx.y) * nc + c] : (T)0;
+  T run = td ? partial[((long long)blockIdx.z * max_tiles + blockIdx.x) * nc + c] : (T)0;
   const int tend = min(t0 + TT, ns);
   for (int t = t0; t < tend; t += R) {
     const int rows = min(R, tend - t);

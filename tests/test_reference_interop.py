@@ -98,3 +98,26 @@ def test_reference_suite_subset_against_this_package(tmp_path):
                         'test_low or test_high or test_chop or test_check_fail or test_comp_decomp or test_3d'],
                        cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+GPU_WRITTEN = Path(__file__).resolve().parent / 'golden' / 'gpu_written'
+
+
+@pytest.mark.parametrize('name', sorted(json.loads((GPU_WRITTEN / 'manifest.json').read_text())))
+def test_files_written_on_the_b200_open_in_the_reference_reader(ref, tmp_path, name):
+    """tests/golden/gpu_written/*: .cbin/.ch written by this package's Writer ON THE B200 (tools/make_gpu_golden.py,
+    CUDA library, in-band index and all).  The unmodified reference Reader must return the source array, its own
+    check() must pass, and decompress-to-file must reproduce the raw bytes."""
+    import hashlib
+    raw = (GPU_WRITTEN / (name + '.bin')).read_bytes()
+    meta = json.loads((GPU_WRITTEN / (name + '.ch')).read_text())
+    arr = np.frombuffer(raw, dtype=meta['dtype']).reshape(-1, meta['n_channels'])
+    r = ref.decompress(GPU_WRITTEN / (name + '.cbin'), GPU_WRITTEN / (name + '.ch'))
+    assert np.array_equal(r[:], arr)
+    assert np.array_equal(r[17:1203:5, 1:], arr[17:1203:5, 1:])
+    r.close()
+    ref.check(arr, GPU_WRITTEN / (name + '.cbin'), GPU_WRITTEN / (name + '.ch'))
+    ref.decompress(GPU_WRITTEN / (name + '.cbin'), GPU_WRITTEN / (name + '.ch'), tmp_path / 'back.bin', quiet=True).close()
+    assert (tmp_path / 'back.bin').read_bytes() == raw
+    assert meta['sha1_uncompressed'] == hashlib.sha1(raw).hexdigest()
+    assert meta['sha1_compressed'] == hashlib.sha1((GPU_WRITTEN / (name + '.cbin')).read_bytes()).hexdigest()
