@@ -96,8 +96,18 @@ struct TBits {
     pos = bit & 31;
     base_bit = word << 5;
   }
+  // no branch: the lanes of a warp read different streams and must not drift apart (ncu: with `if (pos >= 32)` as a
+  // branch the refill was 57 % of the warp instructions of the symbol loops)
   __device__ __forceinline__ void refill() {
-    if (pos >= 32) { lo = hi; hi = next_word(); pos -= 32; base_bit += 32; }
+    const bool need = pos >= 32;
+    const unsigned nw = __funnelshift_r(raw, ahead, sh);
+    lo = need ? hi : lo;
+    hi = need ? nw : hi;
+    raw = need ? ahead : raw;
+    pos -= need ? 32u : 0u;
+    base_bit += need ? 32u : 0u;
+    k += need ? 1u : 0u;
+    if (need) ahead = w[min(k, kmax)];
   }
   __device__ __forceinline__ unsigned window() const { return __funnelshift_r(lo, hi, pos); }
   __device__ __forceinline__ void drop(unsigned n) { pos += n; }

@@ -73,41 +73,6 @@ struct TokSink {            // a lane's token writer
   }
 };
 
-// Bit reader of one lane: 64 stream bits in (lo, hi), cursor pos < 32 after fill().  fill() has no branch (the lanes of a
-// warp read 32 different streams and must not drift apart): it shifts in the next word when the cursor has passed 32.
-struct LaneBits {
-  const unsigned* w;     // 4-byte aligned base of the stream
-  unsigned sh, kmax, k, raw, ahead, lo, hi, pos, base_bit;
-  __device__ __forceinline__ void init(const unsigned char* in, unsigned in_len, unsigned bit) {
-    const unsigned mis = (unsigned)((uintptr_t)in & 3);
-    w = (const unsigned*)(in - mis);
-    sh = mis * 8;
-    kmax = (mis + max(in_len, 1u) - 1) >> 2;
-    const unsigned word = bit >> 5;
-    k = word;
-    raw = w[min(k, kmax)]; k++;
-    ahead = w[min(k, kmax)];
-    lo = __funnelshift_r(raw, ahead, sh); raw = ahead; k++; ahead = w[min(k, kmax)];
-    hi = __funnelshift_r(raw, ahead, sh); raw = ahead; k++; ahead = w[min(k, kmax)];
-    pos = bit & 31;
-    base_bit = word << 5;
-  }
-  __device__ __forceinline__ void fill() {
-    const bool need = pos >= 32;
-    const unsigned nw = __funnelshift_r(raw, ahead, sh);
-    lo = need ? hi : lo;
-    hi = need ? nw : hi;
-    raw = need ? ahead : raw;
-    pos -= need ? 32u : 0u;
-    base_bit += need ? 32u : 0u;
-    k += need ? 1u : 0u;
-    if (need) ahead = w[min(k, kmax)];
-  }
-  __device__ __forceinline__ unsigned window() const { return __funnelshift_r(lo, hi, pos); }
-  __device__ __forceinline__ void drop(unsigned n) { pos += n; }
-  __device__ __forceinline__ unsigned bit_pos() const { return base_bit + pos; }
-};
-
 __device__ __forceinline__ unsigned rd32u(const unsigned char* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((unsigned)p[3] << 24); }
 
 __global__ void __launch_bounds__(32) seg_tokens_kernel(const unsigned char* __restrict__ comp, const SegV2* __restrict__ segs,
@@ -160,7 +125,7 @@ __global__ void __launch_bounds__(32) seg_tokens_kernel(const unsigned char* __r
     const size_t sub = (size_t)sg.sub_first + j;
     SubOut* so = subs + sub;
     if (act) sink.open(tokens + sub * SEG_TOK_STRIDE, btab + sub * SEG_BATCHES, so->stepb, pos0, step_shift, idx_bound(j));
-    LaneBits br;
+    TBits br;
     br.init(in, in_len, (act && good) ? start : 0u);
     // One symbol per iteration, at most one token written: the token in hand (`pend`: a run of 1..3 literals, or a
     // match) is written when the next symbol cannot join it.
@@ -169,7 +134,7 @@ __global__ void __launch_bounds__(32) seg_tokens_kernel(const unsigned char* __r
     bool active = act && good;
     while (__any_sync(0xffffffffu, active)) {
       if (active) {
-        br.fill();
+        br.refill();
         const bool past = br.bit_pos() >= bound;
         const unsigned win = br.window();
         const unsigned en = T.ltab[win & ((1u << PAR_LBITS) - 1)];
@@ -188,7 +153,7 @@ __global__ void __launch_bounds__(32) seg_tokens_kernel(const unsigned char* __r
         const unsigned xb = isl ? lx >> 12 : 0u;
         const unsigned len = (lx & 0xfffu) + ((win >> cl) & ((1u << xb) - 1));
         br.drop(past ? 0u : cl + xb);
-        br.fill();
+        br.refill();
         const unsigned win2 = br.window();
         const unsigned e2 = T.dtab[win2 & ((1u << PAR_DBITS) - 1)];
         unsigned cl2 = e2 & 15, dsym = e2 >> 4;
