@@ -333,6 +333,7 @@ def run_b200(args):
             legs['lfp_1s_chunks'] = bench_legs.lfp_leg(cd, args.lfp_chunks, 2500, threads)
             legs['lfp_0.1s_chunks'] = bench_legs.lfp_leg(cd, args.lfp_small_chunks, 250, threads)
             legs['latency'] = bench_legs.latency_leg(threads, n_chunks=args.latency_chunks)
+            legs['file_to_file'] = bench_legs.file_leg()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -69,7 +69,8 @@ struct mtsb_ctx {
   long long seg_v2 = 1;         // indexed segments of the second format go through seg_tokens / seg_resolve
   bool ignore_index = false;    // (internal) decode every chunk as a plain zlib stream: the retry of chunks whose index misled
   Buf d_raw, d_raw2, d_out2, d_comp2, d_T, d_tok, d_hist, d_codes, d_hdrs, d_tab, d_so, d_seg_adler, d_chunk_adler, d_chunk_off, d_out,
-      d_partial, d_comp, d_status, d_tadler, d_gather, d_subabs;
+      d_partial, d_comp, d_status, d_tadler, d_gather, d_subabs, d_invstate;
+  long long inv_single_pass = 1;   // channel-major inverse transform in one pass (inv_tile_kernel); 0: tile sums + apply
   Buf h_tab, h_small;
   // timings
   std::vector<cudaEvent_t> ev_pool;
@@ -152,6 +153,10 @@ int set_attrs(mtsb_ctx* c) {
   CK(cudaFuncSetAttribute(fwd_transform_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
   CK(cudaFuncSetAttribute(fwd_transform_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
   CK(cudaFuncSetAttribute(fwd_transform_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+  CK(cudaFuncSetAttribute(inv_tile_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 73728));
+  CK(cudaFuncSetAttribute(inv_tile_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 73728));
+  CK(cudaFuncSetAttribute(inv_tile_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 73728));
+  CK(cudaFuncSetAttribute(inv_tile_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 73728));
   CK(cudaFuncSetAttribute(fwd_tile_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
   CK(cudaFuncSetAttribute(fwd_tile_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
   CK(cudaFuncSetAttribute(fwd_tile_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
@@ -236,6 +241,28 @@ int launch_fwd(mtsb_ctx* c, int isz, const void* raw, void* tbuf, const ChunkDes
 template <class T>
 int launch_inv_t(mtsb_ctx* c, const void* tbuf, void* out, const ChunkDesc* d_cd, int n_chunks, int max_ns, int nc,
                  int flags) {
+  if (!(flags & FLAG_ORDER_C) && c->inv_single_pass) {
+    // channel-major input: one pass, carries by decoupled look-back (about 56 KB of shared memory per tile)
+    const int R = ColRun<T>::R;
+    long long tt = (56 * 1024) / ((long long)nc * (long long)sizeof(T));
+    tt = std::min<long long>(64, tt / R * R);
+    if (tt >= R) {
+      const int TT = (int)tt, max_tiles = (max_ns + TT - 1) / TT, G = TT / R;
+      const size_t smem = 16 + 16 + (((size_t)TT * nc * sizeof(T) + 15) & ~(size_t)15) + (size_t)G * nc * sizeof(T) + 16;
+      const size_t n_tiles = (size_t)n_chunks * max_tiles;
+      const bool td = (flags & FLAG_TIME_DIFF) != 0;
+      NEED(c->d_partial, td ? 2 * n_tiles * nc * sizeof(T) + 256 : 256);
+      NEED(c->d_invstate, n_tiles * 4 + 64);
+      CK(cudaMemsetAsync(c->d_invstate.p, 0, n_tiles * 4 + 64, c->stream));
+      T* agg = (T*)c->d_partial.p;
+      auto k = inv_tile_kernel<T>;
+      MTS_LAUNCH(k, dim3((unsigned)n_tiles), dim3(INV_TILE_THREADS), smem, c->stream, (const T*)tbuf, (T*)out, d_cd, n_chunks, nc, TT,
+                 max_tiles, flags, agg, agg + n_tiles * nc, (unsigned*)c->d_invstate.p, (unsigned*)c->d_invstate.p + n_tiles);
+      c->launches++;
+      CKL();
+      return 0;
+    }
+  }
   const bool fast = !(flags & (FLAG_ORDER_C | FLAG_SPATIAL_DIFF));
   int TT = fast ? 256 : tile_rows(nc, sizeof(T), 0);
   if (TT < 1) return fail(c, MTSB_E_ARG, "n_channels=%d too large for the transform tile", nc);
@@ -376,7 +403,7 @@ void mtsb_destroy(mtsb_ctx* c) {
                  &c->d_segv2, &c->d_btab, &c->d_subout,
                  &c->d_raw, &c->d_raw2, &c->d_out2, &c->d_comp2, &c->d_T, &c->d_tok, &c->d_hist, &c->d_codes, &c->d_hdrs, &c->d_tab, &c->d_so,
                  &c->d_seg_adler, &c->d_chunk_adler, &c->d_chunk_off, &c->d_out, &c->d_partial, &c->d_comp,
-                 &c->d_status, &c->d_tadler, &c->d_gather, &c->d_subabs, &c->h_tab, &c->h_small};
+                 &c->d_status, &c->d_tadler, &c->d_gather, &c->d_subabs, &c->d_invstate, &c->h_tab, &c->h_small};
   for (Buf* b : bufs) b->release();
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   for (int i = 0; i < 2; i++) { if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]); if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]); }
@@ -405,6 +432,7 @@ int mtsb_set_param(mtsb_ctx* c, const char* name, long long v) {
   else if (s == "par_inflate") c->par_inflate = v ? 1 : 0;
   else if (s == "par_indexed") c->par_indexed = v ? 1 : 0;
   else if (s == "seg_v2") c->seg_v2 = v ? 1 : 0;
+  else if (s == "inv_single_pass") c->inv_single_pass = v ? 1 : 0;
   else if (s == "par_cells") c->par_cells = v < 0 ? -1 : (v ? 1 : 0);
   else if (s == "par_lz_wide") c->par_lz_wide = v < 0 ? -1 : (v ? 1 : 0);
   else if (s == "par_batch_bytes") { if (v < (1 << 20)) return fail(c, MTSB_E_ARG, "par_batch_bytes too small"); c->par_batch_bytes = v; }
@@ -425,6 +453,7 @@ long long mtsb_get_param(mtsb_ctx* c, const char* name) {
   if (s == "par_cells") return c->par_cells;
   if (s == "par_indexed") return c->par_indexed;
   if (s == "seg_v2") return c->seg_v2;
+  if (s == "inv_single_pass") return c->inv_single_pass;
   if (s == "par_batch_bytes") return c->par_batch_bytes;
   if (s == "par_survivors") return c->par_stats[0];
   if (s == "par_candidates") return c->par_stats[1];

@@ -295,6 +295,132 @@ __global__ void __launch_bounds__(FWD_TILE_THREADS) fwd_tile_kernel(const T* __r
   }
 }
 
+// Inverse transform for the channel-major layouts in ONE pass over the data (read T once, write the output once): a CTA
+// takes a tile of TT rows x all channels.  Within the tile the running sums are local (registers + a few group totals in
+// shared memory); across the tiles of a chunk each channel's carry travels by decoupled look-back: a tile publishes its
+// per-channel AGGREGATE as soon as it has it, then adds up the aggregates of its predecessors until it meets one that
+// has already published its INCLUSIVE prefix, and publishes its own.  Tiles are handed out by a ticket counter in
+// tile-major order over the chunks of the batch (tile t of every chunk before tile t + 1 of any): with many chunks the
+// predecessor finished a whole generation earlier and the look-back is one step; a waiting tile only ever waits for
+// tickets below its own, which are running or done.  The finished rows leave shared memory as one contiguous span
+// (TMA bulk store of the aligned interior).
+static const int INV_TILE_THREADS = 256;
+template <class T>
+__global__ void __launch_bounds__(INV_TILE_THREADS) inv_tile_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                                    const ChunkDesc* __restrict__ chunks, int n_chunks,
+                                                                    int nc, int TT, int max_tiles, int flags,
+                                                                    T* agg, T* incl, unsigned* state, unsigned* ticket) {
+  const int R = ColRun<T>::R;
+  MTS_DYN_SMEM(sm);                                    // [16 bytes][tile: data at offset off0, rows x nc][group totals G x nc]
+  __shared__ unsigned s_ticket;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const unsigned tk = s_ticket;
+  const int tl = (int)(tk / (unsigned)n_chunks), ci = (int)(tk % (unsigned)n_chunks);
+  const ChunkDesc cd = chunks[ci];
+  const int ns = cd.ns;
+  const int t0 = tl * TT;
+  if (t0 >= ns) return;
+  const int rows = min(TT, ns - t0);
+  const bool td = (flags & FLAG_TIME_DIFF) != 0, sd = (flags & FLAG_SPATIAL_DIFF) != 0;
+  unsigned char* gout = (unsigned char*)(out + cd.elem_off + (long long)t0 * nc);
+  const unsigned off0 = (unsigned)((uintptr_t)gout & 15);
+  T* s = (T*)(sm + 16 + off0);                         // s[r * nc + c]; 16-byte aligned exactly where the output is
+  const int G = (TT + R - 1) / R;
+  T* tot = (T*)(sm + 16 + 16 + (((size_t)TT * nc * sizeof(T) + 15) & ~(size_t)15));   // tot[g * nc + c]
+  const T* x = in + cd.elem_off;
+  const int groups = (rows + R - 1) / R;
+  // ---- load + running sums inside every run of R rows
+  for (int it = threadIdx.x; it < groups * nc; it += blockDim.x) {
+    const int g = it / nc, c = it - g * nc;
+    const int r0 = g * R, nr = min(R, rows - r0);
+    const T* p = x + (long long)c * ns + t0 + r0;
+    T v[R];
+    if (nr == R && ((uintptr_t)p & 15) == 0) {
+      uint4 q[2];
+      q[0] = ((const uint4*)p)[0]; q[1] = ((const uint4*)p)[1];
+      memcpy(v, q, 32);
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; r++) v[r] = r < nr ? p[r] : (T)0;
+    }
+    T run = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      if (td) { run = (T)(run + v[r]); v[r] = run; }
+      if (r < nr) s[(r0 + r) * nc + c] = v[r];
+    }
+    tot[g * nc + c] = run;
+  }
+  __syncthreads();
+  if (td) {
+    T* my_agg = agg + ((long long)ci * max_tiles + tl) * nc;
+    T* my_incl = incl + ((long long)ci * max_tiles + tl) * nc;
+    unsigned* st = state + (long long)ci * max_tiles;
+    // ---- aggregate of the tile, published at once
+    for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+      T a = 0;
+      for (int g = 0; g < groups; g++) a = (T)(a + tot[g * nc + c]);
+      my_agg[c] = a;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *(volatile unsigned*)&st[tl] = 1u;
+    // ---- look-back + carries into the tile
+    for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+      T carry = 0;
+      for (int i = tl - 1; i >= 0; i--) {
+        unsigned f;
+        while ((f = *(volatile unsigned*)&st[i]) == 0u) {
+#ifdef MTSCOMP_EMU
+          emu::yield();
+#endif
+        }
+        __threadfence();
+        if (f == 2u) { carry = (T)(carry + ((volatile T*)(incl + ((long long)ci * max_tiles + i) * nc))[c]); break; }
+        carry = (T)(carry + ((volatile T*)(agg + ((long long)ci * max_tiles + i) * nc))[c]);
+      }
+      T a = carry;
+      for (int g = 0; g < groups; g++) {
+        const T t = tot[g * nc + c];
+        const int r1 = min(g * R + R, rows);
+        for (int r = g * R; r < r1; r++) s[r * nc + c] = (T)(s[r * nc + c] + a);
+        a = (T)(a + t);
+      }
+      my_incl[c] = a;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *(volatile unsigned*)&st[tl] = 2u;
+  }
+  if (sd) {
+    // per-row running sum over the channels (after the time sums: the two commute in modular arithmetic)
+    const int nw = blockDim.x >> 5;
+    for (int r = warp_id(); r < rows; r += nw) {
+      T carry = 0;
+      for (int c0 = 0; c0 < nc; c0 += 32) {
+        const int c = c0 + lane_id();
+        T v = (c < nc) ? s[r * nc + c] : (T)0;
+        v = (T)(warp_incl_scan(v) + carry);
+        if (c < nc) s[r * nc + c] = v;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- rows -> global: one contiguous span; 16-byte aligned interior by TMA bulk store, the ragged ends by threads
+  const unsigned span = (unsigned)(rows * nc) * (unsigned)sizeof(T);
+  const unsigned head = min(span, (16 - off0) & 15), mid = (span - head) & ~15u;
+  const unsigned char* sb = (const unsigned char*)s;
+  for (unsigned i = threadIdx.x; i < head; i += blockDim.x) gout[i] = sb[i];
+  for (unsigned i = head + mid + threadIdx.x; i < span; i += blockDim.x) gout[i] = sb[i];
+  if (mid) {
+    fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) { bulk_s2g(gout + head, sb + head, mid); bulk_s2g_wait(); }
+  }
+}
+
 // Inverse of the above: per-channel running sum seeded by the scanned tile sums (tile = TT rows, TT % R == 0).
 template <class T>
 __global__ void __launch_bounds__(128) inv_cols_kernel(const T* __restrict__ in, T* __restrict__ out,

@@ -135,6 +135,49 @@ def latency_leg(threads, n_chunks=16, n_gpu=(40, 40, 30, 12), n_cpu=(10, 10, 6, 
         shutil.rmtree(d, ignore_errors=True)
 
 
+# ---------------------------------------------------------------------------------------------------- file to file through the API
+def file_leg(n_chunks=48):
+    """Writer.write and Reader.tofile through the drop-in API, files on tmpfs, against the format's own ceiling: the .ch
+    records two SHA-1 digests, sequential passes at hashlib speed (measured here on the same bytes)."""
+    import mtscomp_b200 as M
+    from mtscomp_b200 import synth
+    ns, nc, sr = 30000, 385, 30000.
+    d = scratch_dir('file')
+    try:
+        M.CONFIG_PATH = d / '.mtscomp'
+        base = [synth.ap_chunk(ns, nc, seed=700 + i) for i in range(4)]
+        with open(d / 'rec.bin', 'wb') as f:
+            for i in range(n_chunks):
+                f.write(base[i % 4].tobytes())
+        raw_bytes = n_chunks * ns * nc * 2
+        # warm-up on a short file (context, staging buffers), then the timed runs
+        base[0].tofile(d / 'w.bin')
+        M.compress(d / 'w.bin', d / 'w.cbin', d / 'w.ch', sample_rate=sr, n_channels=nc, dtype=np.int16, quiet=True, check_after_compress=False)
+        t = time.perf_counter()
+        M.compress(d / 'rec.bin', d / 'rec.cbin', d / 'rec.ch', sample_rate=sr, n_channels=nc, dtype=np.int16, quiet=True,
+                   check_after_compress=False)
+        t_w = time.perf_counter() - t
+        t = time.perf_counter()
+        M.decompress(d / 'rec.cbin', d / 'rec.ch', d / 'back.bin', quiet=True, check_after_decompress=False).close()
+        t_r = time.perf_counter() - t
+        mm = np.memmap(d / 'rec.bin', dtype=np.uint8, mode='r')
+        t = time.perf_counter()
+        h = hashlib.sha1()
+        for o in range(0, raw_bytes, 64 << 20):
+            h.update(mm[o:o + (64 << 20)])
+        t_h = time.perf_counter() - t
+        meta = json.loads((d / 'rec.ch').read_text())
+        assert meta['sha1_uncompressed'] == h.hexdigest()
+        assert (d / 'back.bin').read_bytes() == bytes(mm)
+        del mm
+        return {'chunks': n_chunks, 'raw_GB': raw_bytes / 1e9, 'writer_write_GBps': raw_bytes / t_w / 1e9,
+                'hashlib_sha1_GBps': raw_bytes / t_h / 1e9, 'writer_fraction_of_sha1': t_h / t_w,
+                'reader_tofile_GBps': raw_bytes / t_r / 1e9, 'files': 'tmpfs' if str(d).startswith('/dev/shm') else 'tmp',
+                'note': 'compress() / decompress(out=...) of the package, checks off; sha1_uncompressed verified, output file == input'}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 # ---------------------------------------------------------------------------------------------------- configs[2]: one file, N ranks
 def sharded_leg(rank, world, chunks_per_rank, group=None, zlib_sample=4):
     """A synthetic AP recording of world x chunks_per_rank one-second chunks on tmpfs, compressed by all ranks into ONE
