@@ -163,7 +163,8 @@ class Codec:
         if b is None or b.nbytes < nbytes:
             if b is not None:
                 b.release()
-            b = self._staging[name] = HostBuffer(self.lib, max(int(nbytes) + (int(nbytes) >> 3), 1 << 16))
+            # (pinning is slow: grow in large steps so that a Reader asked for ever wider windows re-pins rarely)
+            b = self._staging[name] = HostBuffer(self.lib, max(2 * int(nbytes), 1 << 20))
         return b
 
     def device_alloc(self, nbytes):

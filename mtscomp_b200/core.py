@@ -33,7 +33,8 @@ from .rawio import load_raw_data
 _seek_lock = Lock()
 CRITICAL_ERROR_URL = "https://github.com/int-brain-lab/mtscomp/issues/new?title=Critical+error"
 GPU_BATCH_CHUNKS = 64        # chunks handed to the GPU per call by Writer.write / Reader.tofile ...
-GPU_BATCH_BYTES = 1 << 30    # ... and at most this many raw bytes (long chunks: the host staging stays bounded)
+GPU_BATCH_BYTES = 256 << 20  # ... and at most this many raw bytes: the pinned staging (two raw + two compressed buffers in
+                             # the Writer) stays near 1 GB -- pinning host memory costs about 0.7 s per GB on the B200 box
 MAX_CHUNK_BYTES = 0x7fffffff  # the kernels index a chunk with 32 bits
 
 

@@ -69,7 +69,7 @@ struct mtsb_ctx {
   long long seg_v2 = 1;         // indexed segments of the second format go through seg_tokens / seg_resolve
   bool ignore_index = false;    // (internal) decode every chunk as a plain zlib stream: the retry of chunks whose index misled
   Buf d_raw, d_raw2, d_out2, d_comp2, d_T, d_tok, d_hist, d_codes, d_hdrs, d_tab, d_so, d_seg_adler, d_chunk_adler, d_chunk_off, d_out,
-      d_partial, d_comp, d_status, d_tadler, d_gather, d_subabs, d_invstate;
+      d_partial, d_comp, d_status, d_tadler, d_gather, d_subabs, d_subtok, d_invstate;
   long long inv_single_pass = 1;   // channel-major inverse transform in one pass (inv_tile_kernel); 0: tile sums + apply
   Buf h_tab, h_small;
   // timings
@@ -403,7 +403,7 @@ void mtsb_destroy(mtsb_ctx* c) {
                  &c->d_segv2, &c->d_btab, &c->d_subout,
                  &c->d_raw, &c->d_raw2, &c->d_out2, &c->d_comp2, &c->d_T, &c->d_tok, &c->d_hist, &c->d_codes, &c->d_hdrs, &c->d_tab, &c->d_so,
                  &c->d_seg_adler, &c->d_chunk_adler, &c->d_chunk_off, &c->d_out, &c->d_partial, &c->d_comp,
-                 &c->d_status, &c->d_tadler, &c->d_gather, &c->d_subabs, &c->d_invstate, &c->h_tab, &c->h_small};
+                 &c->d_status, &c->d_tadler, &c->d_gather, &c->d_subabs, &c->d_subtok, &c->d_invstate, &c->h_tab, &c->h_small};
   for (Buf* b : bufs) b->release();
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   for (int i = 0; i < 2; i++) { if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]); if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]); }
@@ -697,6 +697,7 @@ int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_
     NEED(c->d_chunk_adler, (size_t)nb * 4);
     NEED(c->d_chunk_off, (size_t)(nb + 1) * 8);
     NEED(c->d_subabs, (size_t)n_subs * 8 + 64);
+    NEED(c->d_subtok, (size_t)n_subs * 8 + 64);
     NEED(c->h_small, (size_t)(nb + 1) * 8);
     const char* d = (const char*)c->d_tab.p;
     const ChunkDesc* d_cd = (const ChunkDesc*)(d + o_cd);
@@ -735,10 +736,10 @@ int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_
       int grid = std::min(n_segs, c->sm_count * c->lz_ctas_per_sm);
       if (itemsize == 2) {
         auto k = lz77_kernel<2, LZ_NT>;
-        MTS_LAUNCH(k, dim3(grid), dim3(LZ_NT + 32), (LzSmem<2, LZ_NT>::total), c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p, (unsigned*)c->d_seg_adler.p);
+        MTS_LAUNCH(k, dim3(grid), dim3(LZ_NT + 32), (LzSmem<2, LZ_NT>::total), c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p, (unsigned*)c->d_seg_adler.p, c->write_index ? (unsigned long long*)c->d_subtok.p : (unsigned long long*)nullptr);
       } else {
         auto k = lz77_kernel<1, LZ_NT>;
-        MTS_LAUNCH(k, dim3(grid), dim3(LZ_NT + 32), (LzSmem<1, LZ_NT>::total), c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p, (unsigned*)c->d_seg_adler.p);
+        MTS_LAUNCH(k, dim3(grid), dim3(LZ_NT + 32), (LzSmem<1, LZ_NT>::total), c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p, (unsigned*)c->d_seg_adler.p, c->write_index ? (unsigned long long*)c->d_subtok.p : (unsigned long long*)nullptr);
       }
       CKL();
       c->launches++;
@@ -757,7 +758,7 @@ int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_
     c->end();
     c->begin(5);
     auto ek = itemsize == 2 ? encode_kernel<true> : encode_kernel<false>;
-    MTS_LAUNCH(ek, dim3(n_segs), dim3(ENC_THREADS), 0, c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (const unsigned short*)c->d_tok.p, (const unsigned*)c->d_codes.p, (const unsigned*)c->d_hdrs.p, (const DeflateSegOut*)c->d_so.p, (const unsigned*)c->d_chunk_adler.p, outp, c->write_index ? (unsigned long long*)c->d_subabs.p : (unsigned long long*)nullptr);
+    MTS_LAUNCH(ek, dim3(n_segs), dim3(ENC_THREADS), 0, c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (const unsigned short*)c->d_tok.p, (const unsigned*)c->d_codes.p, (const unsigned*)c->d_hdrs.p, (const DeflateSegOut*)c->d_so.p, (const unsigned*)c->d_chunk_adler.p, outp, (const unsigned long long*)c->d_subtok.p, c->write_index ? (unsigned long long*)c->d_subabs.p : (unsigned long long*)nullptr);
     CKL();
     c->launches++;
     if (c->write_index) {

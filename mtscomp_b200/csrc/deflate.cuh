@@ -150,7 +150,8 @@ __global__ void __launch_bounds__(NT + 32, NT <= 512 ? 2 : 1) lz77_kernel(const 
                                                                           unsigned short* __restrict__ tokens,
                                                                           unsigned* __restrict__ hist,
                                                                           DeflateSegOut* __restrict__ so,
-                                                                          unsigned* __restrict__ seg_adler) {
+                                                                          unsigned* __restrict__ seg_adler,
+                                                                          unsigned long long* __restrict__ sub_tok) {
   typedef LzSmem<STRIDE, NT> L;
   const unsigned SEG = L::SEG, NSW = L::NSW, RM = LZ_RING - 1;
   const int NALL = NT + 32;                                       // unit threads + the chain warp
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(NT + 32, NT <= 512 ? 2 : 1) lz77_kernel(const 
     unsigned short* tok = tokens + sg.tok_off;
     const unsigned n_ring = n + off0;                        // ring coordinates [off0, n_ring) are real input
     unsigned run_tok = 0;                                    // token elements emitted so far (uniform across the unit threads)
+    const unsigned n_sub = sub_tok ? (unsigned)idx_n_sub(n) : 0u;   // index entries of the segment (0: no index wanted)
     unsigned ad_a = 0, ad_c = 0;                             // adler32 partial sums of this thread's units
     unsigned long long ad_b = 0;
 
@@ -368,6 +370,16 @@ __global__ void __launch_bounds__(NT + 32, NT <= 512 ? 2 : 1) lz77_kernel(const 
           if ((reach >> lane) & 1u) {
             const unsigned before = reach & lt;
             const unsigned pos = run_tok + ms[wid] + (STRIDE == 2 ? 2 * __popc(before) : __popc(before) + __popc(before & pmm));
+            {
+              // in-band index: a token whose output reaches the next sub-block boundary makes its successor the first
+              // token of that sub-block; noted as (token element index of the successor) << 9 | output overshoot, the
+              // encode kernel turns the element index into a bit offset
+              const unsigned pp = (step - 1) * SEG + tid * STRIDE;
+              const unsigned pl = (ptok & 0x8000u) ? (ptok & 0x1ffu) : (STRIDE == 2 ? 2u : 1u);
+              const unsigned jn = idx_item(pp + pl);
+              if (jn != idx_item(pp) && jn < n_sub)
+                sub_tok[sg.sub_first + jn] = ((unsigned long long)(pos + ((ptok & 0x8000u) || STRIDE == 2 ? 2u : 1u)) << 9) | (pp + pl - idx_bound(jn));
+            }
             if (ptok & 0x8000u) {
               if (STRIDE == 2) *(unsigned*)(tok + pos) = ptok;
               else { tok[pos] = (unsigned short)ptok; tok[pos + 1] = (unsigned short)(ptok >> 16); }
@@ -718,11 +730,12 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
                                                              const DeflateSegOut* __restrict__ so,
                                                              const unsigned* __restrict__ chunk_adler,
                                                              unsigned char* __restrict__ dst,
-                                                             unsigned long long* __restrict__ sub_abs) {
+                                                             const unsigned long long* __restrict__ sub_tok,   // lz77's notes
+                                                             unsigned long long* __restrict__ sub_abs) {         // bit offsets
   __shared__ unsigned stage[ENC_STAGE_WORDS];
   __shared__ unsigned code[CODE_STRIDE];
-  __shared__ unsigned long long wtot64[ENC_THREADS / 32];
-  __shared__ unsigned tile_bits, tile_out;
+  __shared__ unsigned wtot[ENC_THREADS / 32];
+  __shared__ unsigned tile_bits;
   const int sidx = blockIdx.x;
   if (sidx >= n_segs) return;
   const DeflateSeg sg = segs[sidx];
@@ -742,13 +755,11 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
     unsigned char t[6] = {0x03, 0x00, (unsigned char)(a >> 24), (unsigned char)(a >> 16), (unsigned char)(a >> 8), (unsigned char)a};
     body_end[tid] = t[tid];
   }
-  // sub-block table of this segment (absolute: bit of the sub-block's first token << 9 | output overshoot): entry 0
-  // here, the others by the thread whose token reaches the boundary; zero for a stored segment
+  // sub-block table of this segment: lz77_kernel left (token element index << 9 | output overshoot) for the entries 1..,
+  // this kernel replaces the element index by the bit offset of that element (entry 0: the first token); all zero for
+  // a stored segment
   const int n_sub = idx_n_sub(sg.in_len);
-  if (sub_abs) {
-    if (o.mode == MODE_STORED) { for (int j = tid; j < n_sub; j += blockDim.x) sub_abs[sg.sub_first + j] = 0; }
-    else if (tid == 0) sub_abs[sg.sub_first] = (unsigned long long)o.hdr_bits << 9;
-  }
+  if (sub_abs && o.mode == MODE_STORED) for (int j = tid; j < n_sub; j += blockDim.x) sub_abs[sg.sub_first + j] = 0;
   const unsigned char* in = tbuf + sg.in_off;
   if (o.mode == MODE_STORED) {
     unsigned n = (unsigned)sg.in_len;
@@ -791,9 +802,11 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
   // words go to the staging window with plain stores, only the first and the last (shared with the neighbours) by atomicOr.
   const unsigned short* tok = tokens + sg.tok_off;
   const unsigned ntok = o.n_tok;
-  unsigned seg_bits = o.hdr_bits, seg_out = 0;      // bits / output bytes of the segment before the tile
+  unsigned seg_bits = o.hdr_bits;                   // bits of the segment before the tile
+  int sub_cur = 1;                                  // next entry of the sub-block table to resolve (uniform)
+  if (sub_abs && tid == 0) sub_abs[sg.sub_first] = (unsigned long long)o.hdr_bits << 9;
   for (unsigned base = 0; base < ntok; base += ENC_TILE) {
-    unsigned v[ENC_PER], nb[ENC_PER], ol[ENC_PER], mine = 0, mine_out = 0;
+    unsigned v[ENC_PER], nb[ENC_PER], mine = 0;
     const unsigned i0 = base + tid * ENC_PER;
     if (PAIRS) {
       uint4 t4 = make_uint4(0, 0, 0, 0);
@@ -822,17 +835,14 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
         nb[2 * j] = on ? (c0 >> 16) + x0 : 0u;
         v[2 * j + 1] = (c1 & 0xffffu) | (e1 << (c1 >> 16));
         nb[2 * j + 1] = on ? (c1 >> 16) + x1 : 0u;
-        ol[2 * j] = 0;                                       // the token's output is credited to its second code
-        ol[2 * j + 1] = on ? ((e & 0x8000u) ? (e & 0x1ffu) : 2u) : 0u;
         mine += nb[2 * j] + nb[2 * j + 1];
-        mine_out += ol[2 * j + 1];
       }
     } else {
       unsigned prev_el = (i0 > 0 && i0 <= ntok) ? tok[i0 - 1] : 0;
       // bit 15 marks a length element (distance elements are <= 32767), and what follows a length is its distance
       for (int j = 0; j < ENC_PER; j++) {
         unsigned i = i0 + j;
-        v[j] = 0; nb[j] = 0; ol[j] = 0;
+        v[j] = 0; nb[j] = 0;
         if (i < ntok) {
           unsigned e = tok[i];
           if (prev_el & 0x8000u) {            // distance element (follows a length element): closes the match
@@ -841,7 +851,6 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
             unsigned c = code[288 + sym];
             v[j] = (c & 0xffff) | (ev << (c >> 16));
             nb[j] = (c >> 16) + xb;
-            ol[j] = prev_el & 0x1ffu;
             prev_el = 0;
           } else if (e & 0x8000u) {           // length element
             unsigned sym, xb, ev;
@@ -854,40 +863,33 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
             unsigned c = code[e];
             v[j] = c & 0xffff;
             nb[j] = c >> 16;
-            ol[j] = 1;
             prev_el = e;
           }
           mine += nb[j];
-          mine_out += ol[j];
         }
       }
     }
-    // one scan for both: bits in the low word, output bytes in the high word
-    const unsigned long long incl64 = warp_incl_scan((unsigned long long)mine | ((unsigned long long)mine_out << 32));
-    const unsigned incl = (unsigned)incl64;
-    if (lane == 31) wtot64[wid] = incl64;
+    unsigned incl = warp_incl_scan(mine);
+    if (lane == 31) wtot[wid] = incl;
     __syncthreads();
     if (tid == 0) {
-      unsigned long long run = 0;
-      for (int w = 0; w < ENC_THREADS / 32; w++) { unsigned long long t = wtot64[w]; wtot64[w] = run; run += t; }
-      tile_bits = (unsigned)run;
-      tile_out = (unsigned)(run >> 32);
+      unsigned run = 0;
+      for (int w = 0; w < ENC_THREADS / 32; w++) { unsigned t = wtot[w]; wtot[w] = run; run += t; }
+      tile_bits = run;
     }
     __syncthreads();
-    const unsigned wbits = (unsigned)wtot64[wid], wout = (unsigned)(wtot64[wid] >> 32);
-    const unsigned op0 = seg_out + wout + (unsigned)(incl64 >> 32) - mine_out;
-    if (sub_abs && idx_item(op0 + mine_out) != idx_item(op0)) {
-      // (rare: once per sub-block of output) one of this thread's tokens reaches the next sub-block boundary, which
-      // makes its successor the first token of that sub-block
-      unsigned bit = seg_bits + wbits + incl - mine, op = op0;
-#pragma unroll
-      for (int j = 0; j < ENC_PER; j++) {
-        bit += nb[j];
-        const unsigned oe = op + ol[j];
-        const unsigned jn = idx_item(oe);
-        if (jn != idx_item(op) && (int)jn < n_sub) sub_abs[sg.sub_first + jn] = ((unsigned long long)bit << 9) | (oe - idx_bound(jn));
-        op = oe;
+    const unsigned wbits = wtot[wid];
+    // sub-block table: the noted token elements that fall into this tile get their bit offsets (usually none or one)
+    while (sub_abs && sub_cur < n_sub) {
+      const unsigned long long note = sub_tok[sg.sub_first + sub_cur];
+      const unsigned el = (unsigned)(note >> 9);
+      if (el >= base + ENC_TILE || el >= ntok) break;        // (el >= ntok cannot happen for a note of this segment)
+      if (el >= i0 && el < i0 + ENC_PER) {
+        unsigned bit = seg_bits + wbits + incl - mine;
+        for (unsigned j = 0; j < el - i0; j++) bit += nb[j];
+        sub_abs[sg.sub_first + sub_cur] = ((unsigned long long)bit << 9) | (note & 511u);
       }
+      sub_cur++;
     }
     if (mine) {
       const unsigned bp = cur + wbits + incl - mine;
@@ -908,7 +910,6 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
     __syncthreads();
     cur += tile_bits;
     seg_bits += tile_bits;
-    seg_out += tile_out;
     unsigned nw = cur >> 5;
     stage_flush(stage, nw, gw, out, out_end);
     __syncthreads();

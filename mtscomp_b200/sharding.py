@@ -143,7 +143,7 @@ def write_sharded(data_path, out, outmeta, rank, world, sample_rate=None, n_chan
         w.chunk_offsets = offsets
         meta = w.get_cmeta()
         meta['sha1_compressed'] = h.hexdigest()
-        meta['sha1_uncompressed'] = raw_sha.result() if raw_sha is not None else None
+        meta['sha1_uncompressed'] = raw_sha.result() if raw_sha is not None else None   # (None: as after a chop)
         with open(outmeta, 'w') as f:
             json.dump(meta, f, indent=2, sort_keys=True)
     pool.shutdown()

@@ -136,7 +136,7 @@ def latency_leg(threads, n_chunks=16, n_gpu=(40, 40, 30, 12), n_cpu=(10, 10, 6, 
 
 
 # ---------------------------------------------------------------------------------------------------- file to file through the API
-def file_leg(n_chunks=48):
+def file_leg(n_chunks=128):
     """Writer.write and Reader.tofile through the drop-in API, files on tmpfs, against the format's own ceiling: the .ch
     records two SHA-1 digests, sequential passes at hashlib speed (measured here on the same bytes)."""
     import mtscomp_b200 as M
@@ -150,9 +150,14 @@ def file_leg(n_chunks=48):
             for i in range(n_chunks):
                 f.write(base[i % 4].tobytes())
         raw_bytes = n_chunks * ns * nc * 2
-        # warm-up on a short file (context, staging buffers), then the timed runs
-        base[0].tofile(d / 'w.bin')
+        # warm-up on a file of two batches (context, pinned staging buffers of the final size), then the timed runs
+        with open(d / 'w.bin', 'wb') as f:
+            for i in range(24):
+                f.write(base[i % 4].tobytes())
         M.compress(d / 'w.bin', d / 'w.cbin', d / 'w.ch', sample_rate=sr, n_channels=nc, dtype=np.int16, quiet=True, check_after_compress=False)
+        M.decompress(d / 'w.cbin', d / 'w.ch', d / 'w_back.bin', quiet=True, check_after_decompress=False).close()
+        for p in ('w.bin', 'w.cbin', 'w.ch', 'w_back.bin'):
+            (d / p).unlink()
         t = time.perf_counter()
         M.compress(d / 'rec.bin', d / 'rec.cbin', d / 'rec.ch', sample_rate=sr, n_channels=nc, dtype=np.int16, quiet=True,
                    check_after_compress=False)
@@ -210,6 +215,10 @@ def sharded_leg(rank, world, chunks_per_rank, group=None, zlib_sample=4):
     for i in range(first, last):
         os.pwrite(fd, base[i % 4].tobytes(), i * cb)
     os.close(fd)
+    sharding._barrier(group)
+    # (first call: context and pinned staging buffers; the second one is timed)
+    sharding.write_sharded(raw_path, d / 'warm.cbin', d / 'warm.ch', rank, world, sample_rate=sr, n_channels=nc, dtype=np.int16,
+                           group=group, hash_raw=False)
     sharding._barrier(group)
     t = time.perf_counter()
     offsets, secs = sharding.write_sharded(raw_path, d / 'rec.cbin', d / 'rec.ch', rank, world, sample_rate=sr,

@@ -1,0 +1,6 @@
+set -x
+ncu --set full --clock-control none --import-source on -k regex:lz77 -s 1 -c 1 -o gpurun_out/r02_lz77 python tools/quick_bench.py 16 8 > gpurun_out/r02_ncu_lz77.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"seg_|fwd_tile|inv_tile|encode_kernel" -c 12 -o gpurun_out/r02_others python tools/quick_bench.py 16 8 > gpurun_out/r02_ncu_others.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches_bench120.csv python bench.py --chunks 120 --steps 1 --warmup 1 --no-legs > gpurun_out/r02_bench120_under_ncu.log 2>&1
+timeout 1500 python bench.py > gpurun_out/r02_bench.log 2>&1
+tail -c 3000 gpurun_out/r02_bench.log
