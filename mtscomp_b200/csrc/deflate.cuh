@@ -365,12 +365,15 @@ __global__ void __launch_bounds__(NT + 32, NT <= 512 ? 2 : 1) lz77_kernel(const 
       if (step > 0) {
         const unsigned* ms = misc + ((step - 1) & 1) * 72;
         const unsigned entry = ms[32 + wid];
+        // (sub-block boundaries are multiples of IDX_SUB_BYTES / 2: only a step that reaches one can hold such a token)
+        const unsigned ps = (step - 1) * SEG;
+        const bool idx_near = n_sub && ((ps + SEG + 258) / (IDX_SUB_BYTES / 2)) != (ps / (IDX_SUB_BYTES / 2));
         if (entry != 0xffffffffu) {                         // warp-uniform
           const unsigned reach = __shfl_sync(0xffffffffu, pM, entry & 31);
           if ((reach >> lane) & 1u) {
             const unsigned before = reach & lt;
             const unsigned pos = run_tok + ms[wid] + (STRIDE == 2 ? 2 * __popc(before) : __popc(before) + __popc(before & pmm));
-            {
+            if (idx_near) {
               // in-band index: a token whose output reaches the next sub-block boundary makes its successor the first
               // token of that sub-block; noted as (token element index of the successor) << 9 | output overshoot, the
               // encode kernel turns the element index into a bit offset
@@ -732,10 +735,11 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
                                                              unsigned char* __restrict__ dst,
                                                              const unsigned long long* __restrict__ sub_tok,   // lz77's notes
                                                              unsigned long long* __restrict__ sub_abs) {         // bit offsets
-  __shared__ unsigned stage[ENC_STAGE_WORDS];
+  __shared__ unsigned stage_mem[2 * ENC_STAGE_WORDS];
   __shared__ unsigned code[CODE_STRIDE];
-  __shared__ unsigned wtot[ENC_THREADS / 32];
+  __shared__ unsigned wtot[2 * (ENC_THREADS / 32)];
   __shared__ unsigned tile_bits;
+  unsigned* stage = stage_mem;
   const int sidx = blockIdx.x;
   if (sidx >= n_segs) return;
   const DeflateSeg sg = segs[sidx];
@@ -773,7 +777,7 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
   }
   // ---- dynamic block
   for (unsigned i = tid; i < CODE_STRIDE; i += blockDim.x) code[i] = codes[(size_t)sidx * CODE_STRIDE + i];
-  for (unsigned i = tid; i < ENC_STAGE_WORDS; i += blockDim.x) stage[i] = 0;
+  for (unsigned i = tid; i < 2 * ENC_STAGE_WORDS; i += blockDim.x) stage[i] = 0;
   __syncthreads();
   unsigned char* gw = (unsigned char*)((uintptr_t)out & ~(uintptr_t)3);   // global address of stage word 0
   unsigned cur = 8 * (unsigned)((uintptr_t)out & 3);                       // bit cursor inside the stage
@@ -803,8 +807,15 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
   const unsigned short* tok = tokens + sg.tok_off;
   const unsigned ntok = o.n_tok;
   unsigned seg_bits = o.hdr_bits;                   // bits of the segment before the tile
-  int sub_cur = 1;                                  // next entry of the sub-block table to resolve (uniform)
+  int sub_cur = 1;                                  // next entry of the sub-block table to resolve (uniform) ...
+  unsigned note_el = 0xffffffffu, note_ov = 0;      // ... its token element index and overshoot, as lz77_kernel noted them
+  if (sub_abs && n_sub > 1) {
+    const unsigned long long note = sub_tok[sg.sub_first + 1];
+    note_el = (unsigned)(note >> 9); note_ov = (unsigned)(note & 511u);
+  }
+  if (!sub_abs) sub_cur = n_sub;
   if (sub_abs && tid == 0) sub_abs[sg.sub_first] = (unsigned long long)o.hdr_bits << 9;
+  unsigned tile = 0;
   for (unsigned base = 0; base < ntok; base += ENC_TILE) {
     unsigned v[ENC_PER], nb[ENC_PER], mine = 0;
     const unsigned i0 = base + tid * ENC_PER;
@@ -869,27 +880,31 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
         }
       }
     }
-    unsigned incl = warp_incl_scan(mine);
-    if (lane == 31) wtot[wid] = incl;
-    __syncthreads();
-    if (tid == 0) {
-      unsigned run = 0;
-      for (int w = 0; w < ENC_THREADS / 32; w++) { unsigned t = wtot[w]; wtot[w] = run; run += t; }
-      tile_bits = run;
+    // Two staging windows take turns: while the threads string tile t into one, the other (flushed and cleared during
+    // tile t - 1) is ready for tile t + 1; two block barriers per tile.
+    unsigned* const stg = stage + (tile & 1u) * ENC_STAGE_WORDS;
+    unsigned* const oth = stage + ((tile & 1u) ^ 1u) * ENC_STAGE_WORDS;
+    const unsigned incl = warp_incl_scan(mine);
+    if (lane == 31) wtot[(tile & 1u) * (ENC_THREADS / 32) + wid] = incl;
+    __syncthreads();                                            // #1: warp totals; the previous tile's flush is done
+    unsigned wbits = 0, tbits = 0;
+    {
+      const unsigned* wt = wtot + (tile & 1u) * (ENC_THREADS / 32);
+#pragma unroll
+      for (unsigned w = 0; w < ENC_THREADS / 32; w++) { const unsigned t = wt[w]; wbits += w < wid ? t : 0u; tbits += t; }
     }
-    __syncthreads();
-    const unsigned wbits = wtot[wid];
-    // sub-block table: the noted token elements that fall into this tile get their bit offsets (usually none or one)
-    while (sub_abs && sub_cur < n_sub) {
-      const unsigned long long note = sub_tok[sg.sub_first + sub_cur];
-      const unsigned el = (unsigned)(note >> 9);
-      if (el >= base + ENC_TILE || el >= ntok) break;        // (el >= ntok cannot happen for a note of this segment)
-      if (el >= i0 && el < i0 + ENC_PER) {
+    // sub-block table: the noted token element that falls into this tile gets its bit offset (usually none, at most a few)
+    while (note_el < base + ENC_TILE && note_el < ntok) {
+      if (note_el >= i0 && note_el < i0 + ENC_PER) {
         unsigned bit = seg_bits + wbits + incl - mine;
-        for (unsigned j = 0; j < el - i0; j++) bit += nb[j];
-        sub_abs[sg.sub_first + sub_cur] = ((unsigned long long)bit << 9) | (note & 511u);
+#pragma unroll
+        for (unsigned j = 0; j < (unsigned)ENC_PER; j++) bit += j < note_el - i0 ? nb[j] : 0u;
+        sub_abs[sg.sub_first + sub_cur] = ((unsigned long long)bit << 9) | note_ov;
       }
       sub_cur++;
+      const unsigned long long note = sub_cur < n_sub ? sub_tok[sg.sub_first + sub_cur] : ~0ull;
+      note_el = sub_cur < n_sub ? (unsigned)(note >> 9) : 0xffffffffu;
+      note_ov = (unsigned)(note & 511u);
     }
     if (mine) {
       const unsigned bp = cur + wbits + incl - mine;
@@ -901,27 +916,27 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
         acc |= (unsigned long long)v[j] << fill;
         fill += nb[j];
         if (fill >= 32) {
-          if (first) { atomicOr(&stage[wi], (unsigned)acc); first = false; } else stage[wi] = (unsigned)acc;
+          if (first) { atomicOr(&stg[wi], (unsigned)acc); first = false; } else stg[wi] = (unsigned)acc;
           wi++; acc >>= 32; fill -= 32;
         }
       }
-      if (fill) atomicOr(&stage[wi], (unsigned)acc);
+      if (fill) atomicOr(&stg[wi], (unsigned)acc);
     }
-    __syncthreads();
-    cur += tile_bits;
-    seg_bits += tile_bits;
-    unsigned nw = cur >> 5;
-    stage_flush(stage, nw, gw, out, out_end);
-    __syncthreads();
-    unsigned keep = stage[nw];
-    __syncthreads();
-    for (unsigned i = tid; i <= nw + 1; i += blockDim.x) stage[i] = 0;
-    __syncthreads();
-    if (tid == 0) stage[0] = keep;
+    __syncthreads();                                            // #2: the tile's bits are in the window
+    cur += tbits;
+    seg_bits += tbits;
+    const unsigned nw = cur >> 5;
+    stage_flush(stg, nw, gw, out, out_end);
+    // every thread clears the words it has just flushed; the last, partial word moves to the head of the other window
+    // (clean since the tile before the last), which the next tile strings its bits into after its first barrier
+    for (unsigned i = tid; i < nw; i += blockDim.x) stg[i] = 0;
+    if (tid == 0) { oth[0] = stg[nw]; stg[nw] = 0; stg[nw + 1] = 0; }
     gw += 4 * (size_t)nw;
     cur &= 31;
-    __syncthreads();
+    tile++;
   }
+  stage = stage + (tile & 1u) * ENC_STAGE_WORDS;                 // the window that holds the tail
+  __syncthreads();
   // end-of-block, then the empty stored block: 3 zero bits, pad to a byte boundary, 00 00 FF FF
   if (tid == 0) {
     unsigned c = code[256];
