@@ -604,7 +604,9 @@ int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_
   long long total_out = 0;
   // sub-batches: bounded by batch_bytes; smaller when a host buffer is involved so that copies pipeline with kernels
   const bool host_io = !src_is_device || !dst_is_device;
-  const long long sb_limit = host_io ? std::min(c->batch_bytes, c->host_batch_bytes) : c->batch_bytes;
+  // device-resident calls have nothing to overlap with: one large sub-batch keeps the persistent match-finder CTAs
+  // busy to the end (measured on 600 chunks: 2 GiB 99.9, 4 GiB 100.6, one 13.9 GB batch 101.7 GB/s)
+  const long long sb_limit = host_io ? std::min(c->batch_bytes, c->host_batch_bytes) : std::max<long long>(c->batch_bytes, 16ll << 30);
   std::vector<int> sb_first;
   long long max_sb_bytes = 0, max_sb_bound = 0;
   for (int a = 0; a < n_chunks;) {
@@ -733,13 +735,15 @@ int mtsb_compress_chunks(mtsb_ctx* c, const void* src, int src_is_device, int n_
     c->end();
     c->begin(3);
     {
+      NEED(c->d_invstate, 256);
+      CK(cudaMemsetAsync(c->d_invstate.p, 0, 64, c->stream));    // the match finder's segment counter
       int grid = std::min(n_segs, c->sm_count * c->lz_ctas_per_sm);
       if (itemsize == 2) {
         auto k = lz77_kernel<2, LZ_NT>;
-        MTS_LAUNCH(k, dim3(grid), dim3(LZ_NT + 32), (LzSmem<2, LZ_NT>::total), c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p, (unsigned*)c->d_seg_adler.p, c->write_index ? (unsigned long long*)c->d_subtok.p : (unsigned long long*)nullptr);
+        MTS_LAUNCH(k, dim3(grid), dim3(LZ_NT + 32), (LzSmem<2, LZ_NT>::total), c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p, (unsigned*)c->d_seg_adler.p, c->write_index ? (unsigned long long*)c->d_subtok.p : (unsigned long long*)nullptr, (unsigned*)c->d_invstate.p);
       } else {
         auto k = lz77_kernel<1, LZ_NT>;
-        MTS_LAUNCH(k, dim3(grid), dim3(LZ_NT + 32), (LzSmem<1, LZ_NT>::total), c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p, (unsigned*)c->d_seg_adler.p, c->write_index ? (unsigned long long*)c->d_subtok.p : (unsigned long long*)nullptr);
+        MTS_LAUNCH(k, dim3(grid), dim3(LZ_NT + 32), (LzSmem<1, LZ_NT>::total), c->stream, (const unsigned char*)c->d_T.p, d_seg, n_segs, (unsigned short*)c->d_tok.p, (unsigned*)c->d_hist.p, (DeflateSegOut*)c->d_so.p, (unsigned*)c->d_seg_adler.p, c->write_index ? (unsigned long long*)c->d_subtok.p : (unsigned long long*)nullptr, (unsigned*)c->d_invstate.p);
       }
       CKL();
       c->launches++;

@@ -120,7 +120,7 @@ template <int STRIDE, int NT> struct LzSmem {
   static const size_t xe_off = heads_off + ((size_t)4 << HS_BITS);
   static const size_t hist_off = (xe_off + (size_t)(2 * NT) * 4 + 15) & ~(size_t)15;
   static const size_t misc_off = hist_off + (size_t)HIST_STRIDE * 4;     // two steps of [0..31] element base of each stretch, [32..63] entries, [64] step total
-  static const size_t mbar_off = misc_off + 2 * 72 * 4;                  // 8-byte aligned
+  static const size_t mbar_off = misc_off + 2 * 72 * 4 + 8;              // 8-byte aligned; [2 * 72]: the CTA's next segment
   static const size_t total = mbar_off + 16;
 };
 
@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(NT + 32, NT <= 512 ? 2 : 1) lz77_kernel(const 
                                                                           unsigned* __restrict__ hist,
                                                                           DeflateSegOut* __restrict__ so,
                                                                           unsigned* __restrict__ seg_adler,
-                                                                          unsigned long long* __restrict__ sub_tok) {
+                                                                          unsigned long long* __restrict__ sub_tok,
+                                                                          unsigned* __restrict__ next_seg) {
   typedef LzSmem<STRIDE, NT> L;
   const unsigned SEG = L::SEG, NSW = L::NSW, RM = LZ_RING - 1;
   const int NALL = NT + 32;                                       // unit threads + the chain warp
@@ -171,7 +172,8 @@ __global__ void __launch_bounds__(NT + 32, NT <= 512 ? 2 : 1) lz77_kernel(const 
   if (tid == 0) mbar_init(mbar);
   __syncthreads();
 
-  for (int sidx = blockIdx.x; sidx < n_segs; sidx += gridDim.x) {
+  // the first segment of a CTA is its block index, the following ones come from a counter (the CTAs drift apart)
+  for (int sidx = blockIdx.x; sidx < n_segs;) {
     const DeflateSeg sg = segs[sidx];
     const unsigned n = (unsigned)sg.in_len;
     const unsigned n_steps = (n + SEG - 1) / SEG;
@@ -282,11 +284,7 @@ __global__ void __launch_bounds__(NT + 32, NT <= 512 ? 2 : 1) lz77_kernel(const 
             for (int k = 0; k < 3; k++) {
               const unsigned cand = k == 0 ? cws >> 16 : k == 1 ? cwl >> 16 : cwl & 0xffffu;
               const unsigned du = (ub - cand) & 0xffffu;          // any value: q below always lies inside the ring
-              // STEP RULE: a match must not read what its own step writes -- its source ends at or before the step's
-              // first byte, so cap = dist - li bytes are usable (candidates are units of earlier steps: dist > li).
-              // The decoder relies on it: all the tokens of a step can be resolved at once (seg_resolve_kernel).
-              const unsigned cap = du * STRIDE - li;
-              const bool ok = du - 1 < (unsigned)L::MAXD_UNITS && (k == 0 || vL) && du * STRIDE >= li + 4;
+              const bool ok = du - 1 < (unsigned)L::MAXD_UNITS && (k == 0 || vL);
               const unsigned q = (pr - du * STRIDE) & RM;
               const unsigned* qw = ringw + (q >> 2);
               const unsigned sh = q << 3;
@@ -295,14 +293,18 @@ __global__ void __launch_bounds__(NT + 32, NT <= 512 ? 2 : 1) lz77_kernel(const 
               // length class: 4..8 matched bytes (STRIDE 2: 4, 6, 8) from the trailing zeros of the second word's
               // difference; 8 = the first 8 bytes match (extended below)
               const unsigned tz = (unsigned)__clz((int)__brev(x1));   // 32 when x1 == 0
-              const unsigned lc = min(STRIDE == 2 ? 4u + 2u * (tz >> 4) : 4u + (tz >> 3), cap);
+              const unsigned lc = STRIDE == 2 ? 4u + 2u * (tz >> 4) : 4u + (tz >> 3);
               const unsigned key = (lc << 16) | (0xffffu ^ du);
               bestk = max(bestk, (ok && c0 == w0) ? key : 0u);
             }
             mlen = bestk >> 16;
             if (mlen) {
               mdist = (0xffffu ^ (bestk & 0xffffu)) * STRIDE;
-              const unsigned lim2 = min(lim, mdist - li);             // (step rule)
+              // STEP RULE: a match must not read what its own step writes -- its source ends at or before the step's
+              // first byte, so mdist - li bytes are usable (candidates are units of earlier steps: mdist > li; a stale
+              // table entry that points into this step is cut to nothing).  The decoder relies on it: all the tokens
+              // of a step can be resolved at once (seg_resolve_kernel).  Applied to the winner only.
+              const unsigned lim2 = min(lim, mdist > li ? mdist - li : 0u);
               if (mlen == 8 && lim2 > 8) {
                 // the first 8 bytes match: check the next two bytes, which ends it for most; the few matches that go
                 // on are compared word by word (no wrap: the mirror covers pr + 258 + 8)
@@ -433,8 +435,10 @@ __global__ void __launch_bounds__(NT + 32, NT <= 512 ? 2 : 1) lz77_kernel(const 
       unsigned long long ta = 0, tb = 0;
       for (unsigned w = 0; w < NSW; w++) { ta += red[2 * w]; tb += red[2 * w + 1]; }
       seg_adler[sidx] = ((unsigned)((n % ADLER_BASE + tb) % ADLER_BASE) << 16) | (unsigned)((1 + ta) % ADLER_BASE);
+      misc[2 * 72] = gridDim.x + atomicAdd(next_seg, 1u);
     }
     __syncthreads();
+    sidx = (int)misc[2 * 72];
   }
 }
 
@@ -735,11 +739,10 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
                                                              unsigned char* __restrict__ dst,
                                                              const unsigned long long* __restrict__ sub_tok,   // lz77's notes
                                                              unsigned long long* __restrict__ sub_abs) {         // bit offsets
-  __shared__ unsigned stage_mem[2 * ENC_STAGE_WORDS];
+  __shared__ unsigned stage[ENC_STAGE_WORDS];
   __shared__ unsigned code[CODE_STRIDE];
-  __shared__ unsigned wtot[2 * (ENC_THREADS / 32)];
+  __shared__ unsigned wtot[ENC_THREADS / 32];
   __shared__ unsigned tile_bits;
-  unsigned* stage = stage_mem;
   const int sidx = blockIdx.x;
   if (sidx >= n_segs) return;
   const DeflateSeg sg = segs[sidx];
@@ -777,7 +780,7 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
   }
   // ---- dynamic block
   for (unsigned i = tid; i < CODE_STRIDE; i += blockDim.x) code[i] = codes[(size_t)sidx * CODE_STRIDE + i];
-  for (unsigned i = tid; i < 2 * ENC_STAGE_WORDS; i += blockDim.x) stage[i] = 0;
+  for (unsigned i = tid; i < ENC_STAGE_WORDS; i += blockDim.x) stage[i] = 0;
   __syncthreads();
   unsigned char* gw = (unsigned char*)((uintptr_t)out & ~(uintptr_t)3);   // global address of stage word 0
   unsigned cur = 8 * (unsigned)((uintptr_t)out & 3);                       // bit cursor inside the stage
@@ -815,7 +818,6 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
   }
   if (!sub_abs) sub_cur = n_sub;
   if (sub_abs && tid == 0) sub_abs[sg.sub_first] = (unsigned long long)o.hdr_bits << 9;
-  unsigned tile = 0;
   for (unsigned base = 0; base < ntok; base += ENC_TILE) {
     unsigned v[ENC_PER], nb[ENC_PER], mine = 0;
     const unsigned i0 = base + tid * ENC_PER;
@@ -880,23 +882,19 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
         }
       }
     }
-    // Two staging windows take turns: while the threads string tile t into one, the other (flushed and cleared during
-    // tile t - 1) is ready for tile t + 1; two block barriers per tile.
-    unsigned* const stg = stage + (tile & 1u) * ENC_STAGE_WORDS;
-    unsigned* const oth = stage + ((tile & 1u) ^ 1u) * ENC_STAGE_WORDS;
-    const unsigned incl = warp_incl_scan(mine);
-    if (lane == 31) wtot[(tile & 1u) * (ENC_THREADS / 32) + wid] = incl;
-    __syncthreads();                                            // #1: warp totals; the previous tile's flush is done
-    unsigned wbits = 0, tbits = 0;
-    {
-      const unsigned* wt = wtot + (tile & 1u) * (ENC_THREADS / 32);
-#pragma unroll
-      for (unsigned w = 0; w < ENC_THREADS / 32; w++) { const unsigned t = wt[w]; wbits += w < wid ? t : 0u; tbits += t; }
+    unsigned incl = warp_incl_scan(mine);
+    if (lane == 31) wtot[wid] = incl;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned run = 0;
+      for (int w = 0; w < ENC_THREADS / 32; w++) { unsigned t = wtot[w]; wtot[w] = run; run += t; }
+      tile_bits = run;
     }
+    __syncthreads();
     // sub-block table: the noted token element that falls into this tile gets its bit offset (usually none, at most a few)
     while (note_el < base + ENC_TILE && note_el < ntok) {
       if (note_el >= i0 && note_el < i0 + ENC_PER) {
-        unsigned bit = seg_bits + wbits + incl - mine;
+        unsigned bit = seg_bits + wtot[wid] + incl - mine;
 #pragma unroll
         for (unsigned j = 0; j < (unsigned)ENC_PER; j++) bit += j < note_el - i0 ? nb[j] : 0u;
         sub_abs[sg.sub_first + sub_cur] = ((unsigned long long)bit << 9) | note_ov;
@@ -907,7 +905,7 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
       note_ov = (unsigned)(note & 511u);
     }
     if (mine) {
-      const unsigned bp = cur + wbits + incl - mine;
+      const unsigned bp = cur + wtot[wid] + incl - mine;
       unsigned wi = bp >> 5, fill = bp & 31;
       unsigned long long acc = 0;
       bool first = true;
@@ -916,27 +914,27 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const unsigned char
         acc |= (unsigned long long)v[j] << fill;
         fill += nb[j];
         if (fill >= 32) {
-          if (first) { atomicOr(&stg[wi], (unsigned)acc); first = false; } else stg[wi] = (unsigned)acc;
+          if (first) { atomicOr(&stage[wi], (unsigned)acc); first = false; } else stage[wi] = (unsigned)acc;
           wi++; acc >>= 32; fill -= 32;
         }
       }
-      if (fill) atomicOr(&stg[wi], (unsigned)acc);
+      if (fill) atomicOr(&stage[wi], (unsigned)acc);
     }
-    __syncthreads();                                            // #2: the tile's bits are in the window
-    cur += tbits;
-    seg_bits += tbits;
-    const unsigned nw = cur >> 5;
-    stage_flush(stg, nw, gw, out, out_end);
-    // every thread clears the words it has just flushed; the last, partial word moves to the head of the other window
-    // (clean since the tile before the last), which the next tile strings its bits into after its first barrier
-    for (unsigned i = tid; i < nw; i += blockDim.x) stg[i] = 0;
-    if (tid == 0) { oth[0] = stg[nw]; stg[nw] = 0; stg[nw + 1] = 0; }
+    __syncthreads();
+    cur += tile_bits;
+    seg_bits += tile_bits;
+    unsigned nw = cur >> 5;
+    stage_flush(stage, nw, gw, out, out_end);
+    __syncthreads();
+    unsigned keep = stage[nw];
+    __syncthreads();
+    for (unsigned i = tid; i <= nw + 1; i += blockDim.x) stage[i] = 0;
+    __syncthreads();
+    if (tid == 0) stage[0] = keep;
     gw += 4 * (size_t)nw;
     cur &= 31;
-    tile++;
+    __syncthreads();
   }
-  stage = stage + (tile & 1u) * ENC_STAGE_WORDS;                 // the window that holds the tail
-  __syncthreads();
   // end-of-block, then the empty stored block: 3 zero bits, pad to a byte boundary, 00 00 FF FF
   if (tid == 0) {
     unsigned c = code[256];
