@@ -284,7 +284,13 @@ __global__ void __launch_bounds__(NT + 32, NT <= 512 ? 2 : 1) lz77_kernel(const 
             for (int k = 0; k < 3; k++) {
               const unsigned cand = k == 0 ? cws >> 16 : k == 1 ? cwl >> 16 : cwl & 0xffffu;
               const unsigned du = (ub - cand) & 0xffffu;          // any value: q below always lies inside the ring
-              const bool ok = du - 1 < (unsigned)L::MAXD_UNITS && (k == 0 || vL);
+              // STEP RULE: a match must not read what its own step writes -- its source ends at or before the step's
+              // first byte, so cap = dist - li bytes are usable (candidates are units of earlier steps: dist > li; a
+              // stale table entry that points into this step is refused).  The decoder relies on it: all the tokens of
+              // a step can be resolved at once (seg_resolve_kernel).  Per candidate, so that a long run still finds
+              // the older, uncapped candidate.
+              const unsigned dist_k = du * STRIDE, cap = dist_k - li;
+              const bool ok = du - 1 < (unsigned)L::MAXD_UNITS && (k == 0 || vL) && dist_k > li;
               const unsigned q = (pr - du * STRIDE) & RM;
               const unsigned* qw = ringw + (q >> 2);
               const unsigned sh = q << 3;
@@ -293,18 +299,14 @@ __global__ void __launch_bounds__(NT + 32, NT <= 512 ? 2 : 1) lz77_kernel(const 
               // length class: 4..8 matched bytes (STRIDE 2: 4, 6, 8) from the trailing zeros of the second word's
               // difference; 8 = the first 8 bytes match (extended below)
               const unsigned tz = (unsigned)__clz((int)__brev(x1));   // 32 when x1 == 0
-              const unsigned lc = STRIDE == 2 ? 4u + 2u * (tz >> 4) : 4u + (tz >> 3);
+              const unsigned lc = min(STRIDE == 2 ? 4u + 2u * (tz >> 4) : 4u + (tz >> 3), cap);
               const unsigned key = (lc << 16) | (0xffffu ^ du);
-              bestk = max(bestk, (ok && c0 == w0) ? key : 0u);
+              bestk = max(bestk, (ok && c0 == w0 && lc >= 4) ? key : 0u);
             }
             mlen = bestk >> 16;
             if (mlen) {
               mdist = (0xffffu ^ (bestk & 0xffffu)) * STRIDE;
-              // STEP RULE: a match must not read what its own step writes -- its source ends at or before the step's
-              // first byte, so mdist - li bytes are usable (candidates are units of earlier steps: mdist > li; a stale
-              // table entry that points into this step is cut to nothing).  The decoder relies on it: all the tokens
-              // of a step can be resolved at once (seg_resolve_kernel).  Applied to the winner only.
-              const unsigned lim2 = min(lim, mdist > li ? mdist - li : 0u);
+              const unsigned lim2 = min(lim, mdist - li);             // (step rule)
               if (mlen == 8 && lim2 > 8) {
                 // the first 8 bytes match: check the next two bytes, which ends it for most; the few matches that go
                 // on are compared word by word (no wrap: the mirror covers pr + 258 + 8)
