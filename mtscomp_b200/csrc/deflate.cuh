@@ -287,10 +287,11 @@ __global__ void __launch_bounds__(NT + 32, NT <= 512 ? 2 : 1) lz77_kernel(const 
               // STEP RULE: a match must not read what its own step writes -- its source ends at or before the step's
               // first byte, so cap = dist - li bytes are usable (candidates are units of earlier steps: dist > li; a
               // stale table entry that points into this step is refused).  The decoder relies on it: all the tokens of
-              // a step can be resolved at once (seg_resolve_kernel).  Per candidate, so that a long run still finds
-              // the older, uncapped candidate.
-              const unsigned dist_k = du * STRIDE, cap = dist_k - li;
-              const bool ok = du - 1 < (unsigned)L::MAXD_UNITS && (k == 0 || vL) && dist_k > li;
+              // a step can be resolved at once (seg_resolve_kernel).  A candidate with fewer than 8 usable bytes is not
+              // considered at all (so the 8-byte fast path needs no cap, and a long run finds the older candidate
+              // whose source is not cut short); the winner's extension is capped below.
+              const unsigned dist_k = du * STRIDE;
+              const bool ok = du - 1 < (unsigned)L::MAXD_UNITS && (k == 0 || vL) && dist_k >= li + 8;
               const unsigned q = (pr - du * STRIDE) & RM;
               const unsigned* qw = ringw + (q >> 2);
               const unsigned sh = q << 3;
@@ -299,9 +300,9 @@ __global__ void __launch_bounds__(NT + 32, NT <= 512 ? 2 : 1) lz77_kernel(const 
               // length class: 4..8 matched bytes (STRIDE 2: 4, 6, 8) from the trailing zeros of the second word's
               // difference; 8 = the first 8 bytes match (extended below)
               const unsigned tz = (unsigned)__clz((int)__brev(x1));   // 32 when x1 == 0
-              const unsigned lc = min(STRIDE == 2 ? 4u + 2u * (tz >> 4) : 4u + (tz >> 3), cap);
+              const unsigned lc = STRIDE == 2 ? 4u + 2u * (tz >> 4) : 4u + (tz >> 3);
               const unsigned key = (lc << 16) | (0xffffu ^ du);
-              bestk = max(bestk, (ok && c0 == w0 && lc >= 4) ? key : 0u);
+              bestk = max(bestk, (ok && c0 == w0) ? key : 0u);
             }
             mlen = bestk >> 16;
             if (mlen) {
