@@ -69,7 +69,9 @@ struct mtsb_ctx {
   long long seg_v2 = 1;         // indexed segments of the second format go through seg_tokens / seg_resolve
   bool ignore_index = false;    // (internal) decode every chunk as a plain zlib stream: the retry of chunks whose index misled
   Buf d_raw, d_raw2, d_out2, d_comp2, d_T, d_tok, d_hist, d_codes, d_hdrs, d_tab, d_so, d_seg_adler, d_chunk_adler, d_chunk_off, d_out,
-      d_partial, d_comp, d_status, d_tadler, d_gather, d_subabs, d_subtok, d_invstate;
+      d_partial, d_comp, d_status, d_tadler, d_gather, d_subabs, d_subtok, d_invstate, d_invcells;
+  unsigned inv_epoch = 0;          // epoch of the last inv_tile_kernel launch (tags its look-back cells)
+  long long inv_order_block = 2;   // inv_tile_kernel: consecutive tiles of a chunk that get consecutive tickets
   long long inv_single_pass = 1;   // channel-major inverse transform in one pass (inv_tile_kernel); 0: tile sums + apply
   Buf h_tab, h_small;
   // timings
@@ -153,16 +155,19 @@ int set_attrs(mtsb_ctx* c) {
   CK(cudaFuncSetAttribute(fwd_transform_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
   CK(cudaFuncSetAttribute(fwd_transform_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
   CK(cudaFuncSetAttribute(fwd_transform_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
-  CK(cudaFuncSetAttribute(inv_tile_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 73728));
-  CK(cudaFuncSetAttribute(inv_tile_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 73728));
-  CK(cudaFuncSetAttribute(inv_tile_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 73728));
-  CK(cudaFuncSetAttribute(inv_tile_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 73728));
-  CK(cudaFuncSetAttribute(fwd_tile_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-  CK(cudaFuncSetAttribute(fwd_tile_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-  CK(cudaFuncSetAttribute(fwd_tile_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-  CK(cudaFuncSetAttribute(fwd_tile_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-  CK(cudaFuncSetAttribute(fwd_tile_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-  CK(cudaFuncSetAttribute(fwd_tile_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+#define MTS_INV_ATTR(T) \
+  CK(cudaFuncSetAttribute((inv_tile_kernel<T, 4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 73728)); \
+  CK(cudaFuncSetAttribute((inv_tile_kernel<T, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 73728)); \
+  CK(cudaFuncSetAttribute((inv_tile_kernel<T, 1, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, 73728));
+  MTS_INV_ATTR(uint8_t) MTS_INV_ATTR(uint16_t) MTS_INV_ATTR(uint32_t) MTS_INV_ATTR(uint64_t)
+#undef MTS_INV_ATTR
+#define MTS_FWD_ATTR(T) \
+  CK(cudaFuncSetAttribute((fwd_tile_kernel<T, 4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 73728)); \
+  CK(cudaFuncSetAttribute((fwd_tile_kernel<T, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 73728)); \
+  CK(cudaFuncSetAttribute((fwd_tile_kernel<T, 1, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, 73728));
+  MTS_FWD_ATTR(uint8_t) MTS_FWD_ATTR(uint16_t) MTS_FWD_ATTR(uint32_t) MTS_FWD_ATTR(uint64_t)
+  MTS_FWD_ATTR(float) MTS_FWD_ATTR(double)
+#undef MTS_FWD_ATTR
   CK(cudaFuncSetAttribute(inv_apply_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
   CK(cudaFuncSetAttribute(inv_apply_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
   CK(cudaFuncSetAttribute(inv_apply_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
@@ -197,21 +202,20 @@ int small_copy(mtsb_ctx* c, void* dst, const void* src, size_t bytes) {
 template <class T>
 int launch_fwd_t(mtsb_ctx* c, const void* raw, void* tbuf, const ChunkDesc* d_cd, int n_chunks, int max_ns, int nc,
                  int flags) {
-  if (!(flags & FLAG_ORDER_C)) {
-    // channel-major output: TMA-staged tile of TT rows (a multiple of the 32-byte run), about 56 KB of shared memory
+  if (!(flags & FLAG_ORDER_C) && nc <= 4 * INV_TILE_MAXT) {
+    // channel-major output: TMA-staged tile of G runs of R rows (+ the row above), a thread owns J channels; at most
+    // 70 KB of shared memory
     const int R = ColRun<T>::R;
-    long long tt = (56 * 1024) / ((long long)nc * (long long)sizeof(T)) - 1;
-    tt = std::min<long long>(64, tt / R * R);
-    if (tt >= R) {
-      const int TT = (int)tt;
-      const size_t smem = 16 + (size_t)(TT + 1) * nc * sizeof(T) + 32;
-      dim3 grid((max_ns + TT - 1) / TT, n_chunks);
-      auto k = fwd_tile_kernel<T>;
-      MTS_LAUNCH(k, grid, dim3(FWD_TILE_THREADS), smem, c->stream, (const T*)raw, (T*)tbuf, d_cd, nc, TT, flags);
-      c->launches++;
-      CKL();
-      return 0;
-    }
+    const int J = nc <= INV_TILE_MAXT ? 1 : nc <= 2 * INV_TILE_MAXT ? 2 : 4, G = 4 / J;
+    const int TT = G * R;
+    const int threads = (((nc + J - 1) / J) + 31) / 32 * 32;
+    const size_t smem = 16 + (size_t)(TT + 1) * nc * sizeof(T) + 32;
+    dim3 grid((max_ns + TT - 1) / TT, n_chunks);
+    auto k = J == 1 ? fwd_tile_kernel<T, 4, 1> : J == 2 ? fwd_tile_kernel<T, 2, 2> : fwd_tile_kernel<T, 1, 4>;
+    MTS_LAUNCH(k, grid, dim3(threads), smem, c->stream, (const T*)raw, (T*)tbuf, d_cd, nc, flags);
+    c->launches++;
+    CKL();
+    return 0;
   }
   int TT = tile_rows(nc, sizeof(T), 1);
   if (TT < 1) return fail(c, MTSB_E_ARG, "n_channels=%d too large for the transform tile", nc);
@@ -241,27 +245,35 @@ int launch_fwd(mtsb_ctx* c, int isz, const void* raw, void* tbuf, const ChunkDes
 template <class T>
 int launch_inv_t(mtsb_ctx* c, const void* tbuf, void* out, const ChunkDesc* d_cd, int n_chunks, int max_ns, int nc,
                  int flags) {
-  if (!(flags & FLAG_ORDER_C) && c->inv_single_pass) {
-    // channel-major input: one pass, carries by decoupled look-back (about 56 KB of shared memory per tile)
+  if (!(flags & FLAG_ORDER_C) && c->inv_single_pass && nc <= 4 * INV_TILE_MAXT) {
+    // channel-major input: one pass, carries by decoupled look-back; a tile is G runs of R rows, a thread owns J
+    // channels (G * J = 4 runs of 32 bytes in its registers), at most 64 KB of shared memory per tile
     const int R = ColRun<T>::R;
-    long long tt = (56 * 1024) / ((long long)nc * (long long)sizeof(T));
-    tt = std::min<long long>(64, tt / R * R);
-    if (tt >= R) {
-      const int TT = (int)tt, max_tiles = (max_ns + TT - 1) / TT, G = TT / R;
-      const size_t smem = 16 + 16 + (((size_t)TT * nc * sizeof(T) + 15) & ~(size_t)15) + (size_t)G * nc * sizeof(T) + 16;
-      const size_t n_tiles = (size_t)n_chunks * max_tiles;
-      const bool td = (flags & FLAG_TIME_DIFF) != 0;
-      NEED(c->d_partial, td ? 2 * n_tiles * nc * sizeof(T) + 256 : 256);
-      NEED(c->d_invstate, n_tiles * 4 + 64);
-      CK(cudaMemsetAsync(c->d_invstate.p, 0, n_tiles * 4 + 64, c->stream));
-      T* agg = (T*)c->d_partial.p;
-      auto k = inv_tile_kernel<T>;
-      MTS_LAUNCH(k, dim3((unsigned)n_tiles), dim3(INV_TILE_THREADS), smem, c->stream, (const T*)tbuf, (T*)out, d_cd, n_chunks, nc, TT,
-                 max_tiles, flags, agg, agg + n_tiles * nc, (unsigned*)c->d_invstate.p, (unsigned*)c->d_invstate.p + n_tiles);
-      c->launches++;
-      CKL();
-      return 0;
+    const int J = nc <= INV_TILE_MAXT ? 1 : nc <= 2 * INV_TILE_MAXT ? 2 : 4, G = 4 / J;
+    const int ob = (int)std::max<long long>(1, c->inv_order_block);
+    const int TT = G * R, max_tiles = ((max_ns + TT - 1) / TT + ob - 1) / ob * ob;
+    const int threads = (((nc + J - 1) / J) + 31) / 32 * 32;
+    const size_t smem = 16 + 16 + (((size_t)TT * nc * sizeof(T) + 15) & ~(size_t)15) + 16;
+    const size_t n_tiles = (size_t)n_chunks * max_tiles;
+    const bool td = (flags & FLAG_TIME_DIFF) != 0;
+    // look-back cells: tagged with the launch's epoch, so they are only cleared when the buffer is new or the epochs
+    // are used up
+    const size_t cells_bytes = td ? n_tiles * nc * inv_state_bytes<T>() + 256 : 256;
+    const void* before = c->d_invcells.p;
+    NEED(c->d_invcells, cells_bytes);
+    if (c->d_invcells.p != before || c->inv_epoch >= INV_EPOCH_MAX) {
+      CK(cudaMemsetAsync(c->d_invcells.p, 0, c->d_invcells.cap, c->stream));
+      c->inv_epoch = 0;
     }
+    const unsigned epoch = ++c->inv_epoch;
+    NEED(c->d_invstate, 64);
+    CK(cudaMemsetAsync(c->d_invstate.p, 0, 64, c->stream));
+    auto k = J == 1 ? inv_tile_kernel<T, 4, 1> : J == 2 ? inv_tile_kernel<T, 2, 2> : inv_tile_kernel<T, 1, 4>;
+    MTS_LAUNCH(k, dim3((unsigned)n_tiles), dim3(threads), smem, c->stream, (const T*)tbuf, (T*)out, d_cd, n_chunks, nc,
+               max_tiles, flags, ob, c->d_invcells.p, epoch, (unsigned*)c->d_invstate.p);
+    c->launches++;
+    CKL();
+    return 0;
   }
   const bool fast = !(flags & (FLAG_ORDER_C | FLAG_SPATIAL_DIFF));
   int TT = fast ? 256 : tile_rows(nc, sizeof(T), 0);
@@ -403,7 +415,7 @@ void mtsb_destroy(mtsb_ctx* c) {
                  &c->d_segv2, &c->d_btab, &c->d_subout,
                  &c->d_raw, &c->d_raw2, &c->d_out2, &c->d_comp2, &c->d_T, &c->d_tok, &c->d_hist, &c->d_codes, &c->d_hdrs, &c->d_tab, &c->d_so,
                  &c->d_seg_adler, &c->d_chunk_adler, &c->d_chunk_off, &c->d_out, &c->d_partial, &c->d_comp,
-                 &c->d_status, &c->d_tadler, &c->d_gather, &c->d_subabs, &c->d_subtok, &c->d_invstate, &c->h_tab, &c->h_small};
+                 &c->d_status, &c->d_tadler, &c->d_gather, &c->d_subabs, &c->d_subtok, &c->d_invstate, &c->d_invcells, &c->h_tab, &c->h_small};
   for (Buf* b : bufs) b->release();
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   for (int i = 0; i < 2; i++) { if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]); if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]); }
@@ -433,6 +445,8 @@ int mtsb_set_param(mtsb_ctx* c, const char* name, long long v) {
   else if (s == "par_indexed") c->par_indexed = v ? 1 : 0;
   else if (s == "seg_v2") c->seg_v2 = v ? 1 : 0;
   else if (s == "inv_single_pass") c->inv_single_pass = v ? 1 : 0;
+  else if (s == "inv_epoch") c->inv_epoch = (unsigned)v;          // (tests: the wrap of the look-back epochs)
+  else if (s == "inv_order_block") c->inv_order_block = std::min<long long>(std::max<long long>(v, 1), 64);
   else if (s == "par_cells") c->par_cells = v < 0 ? -1 : (v ? 1 : 0);
   else if (s == "par_lz_wide") c->par_lz_wide = v < 0 ? -1 : (v ? 1 : 0);
   else if (s == "par_batch_bytes") { if (v < (1 << 20)) return fail(c, MTSB_E_ARG, "par_batch_bytes too small"); c->par_batch_bytes = v; }
@@ -454,6 +468,8 @@ long long mtsb_get_param(mtsb_ctx* c, const char* name) {
   if (s == "par_indexed") return c->par_indexed;
   if (s == "seg_v2") return c->seg_v2;
   if (s == "inv_single_pass") return c->inv_single_pass;
+  if (s == "inv_order_block") return c->inv_order_block;
+  if (s == "inv_epoch") return c->inv_epoch;
   if (s == "par_batch_bytes") return c->par_batch_bytes;
   if (s == "par_survivors") return c->par_stats[0];
   if (s == "par_candidates") return c->par_stats[1];
@@ -1319,17 +1335,24 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
     const char* d = (const char*)c->d_tab.p;
     const ChunkDesc* d_cd = (const ChunkDesc*)(d + o_cd);
     { int rc_ = small_copy(c, c->d_tab.p, h, tab_bytes); if (rc_) return rc_; }
-    if (n_segs >= 6 * c->sm_count) {
+    // segments the second-format kernels finished completely need nothing from the serial kernel
+    int n_serial = 0;
+    for (const InflateSeg& sg : segs)
+      if (!((sg.flags & INF_RESUME) && !(sg.flags & INF_ZLIB) && sg.opos0 >= (unsigned)sg.out_len)) n_serial++;
+    if (!n_serial) {
+      CK(cudaMemsetAsync(c->d_status.p, 0, (size_t)n_segs * 4, c->stream));
+    } else if (n_segs >= 6 * c->sm_count) {
       // many short streams: global-memory window, 2 warps per CTA, up to 64 warps per SM
       auto k = inflate_kernel<false, 2>;
       MTS_LAUNCH(k, dim3((n_segs + 1) / 2), dim3(64), 0, c->stream, dcomp, (const InflateSeg*)(d + o_seg), n_segs, (unsigned char*)c->d_T.p, (int*)c->d_status.p, (unsigned*)c->d_tadler.p);
+      c->launches++;
     } else {
       // few long streams: shared-memory window, one warp per CTA
       auto k = inflate_kernel<true, 1>;
       MTS_LAUNCH(k, dim3(n_segs), dim3(32), 0, c->stream, dcomp, (const InflateSeg*)(d + o_seg), n_segs, (unsigned char*)c->d_T.p, (int*)c->d_status.p, (unsigned*)c->d_tadler.p);
+      c->launches++;
     }
     CKL();
-    c->launches++;
     c->end();
     c->begin(3);
     if (n_as) {

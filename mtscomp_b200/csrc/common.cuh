@@ -57,6 +57,9 @@ __device__ __forceinline__ void mbar_wait(mbar_t, unsigned) {}
 __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) { memcpy(dst, src, bytes); }
 __device__ __forceinline__ void bulk_s2g_wait() {}
 __device__ __forceinline__ void fence_async_smem() {}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N> __device__ __forceinline__ void cp_async_wait() {}
 #else
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 typedef unsigned mbar_t;                         // shared-window address of an mbarrier
@@ -92,6 +95,13 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned by
 }
 __device__ __forceinline__ void bulk_s2g_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Per-thread asynchronous copies of 16 bytes global -> shared (no destination register, so nothing in the issuing warp
+// waits for the load until cp_async_wait<N>: all but the thread's N most recent groups are complete).
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }

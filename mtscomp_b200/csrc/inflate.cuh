@@ -234,6 +234,10 @@ __global__ void __launch_bounds__(32 * WPC) inflate_kernel(const unsigned char* 
   const InflateSeg sg = segs[sidx];
   unsigned char* out = out_base + sg.out_off;
   const unsigned out_len = (unsigned)sg.out_len;
+  if ((sg.flags & INF_RESUME) && !(sg.flags & INF_ZLIB) && sg.opos0 >= out_len) {   // an indexed segment, already complete
+    if (lane == 0) status[sidx] = INF_OK;
+    return;
+  }
   const unsigned char* in = comp + sg.in_off;
   const unsigned in_len = (unsigned)sg.in_len;
   const unsigned a0 = SMEM ? (unsigned)((uintptr_t)out & 3) : 0;

@@ -115,6 +115,55 @@ struct TBits {
   __device__ __forceinline__ unsigned bit_pos() const { return base_bit + pos; }
 };
 
+// The same reader for the symbol loops that all 32 lanes of a warp run on 32 different streams.  There the loads of
+// TBits hurt: a refill selects from `ahead` in every iteration, and the scoreboard of that register is the WARP's, so
+// every iteration waited for the global load some lane had issued one iteration earlier (ncu: half of the stall samples
+// of the token kernel on that select).  Here the stream words come from a per-lane ring of four 16-byte slots in shared
+// memory that cp.async fills two slots ahead: no load with a register destination touches global memory.
+// `ring` is the lane's slot 0; slot s lies at ring + 32 * s (slot-major over the lanes of the warp).
+struct SBits {
+  const uint4* g;        // 16-byte aligned base of the stream
+  const unsigned* rw;    // the lane's ring as words: slot s, word i at rw[128 * s + i]
+  uint4* ring;
+  unsigned bmax;         // last readable 16-byte block
+  unsigned k;            // index of the stream word (from g) held in `ahead`
+  unsigned ahead, lo, hi;
+  unsigned pos;          // cursor inside (lo, hi), < 32 after refill
+  unsigned base_bit;     // stream bit offset of bit 0 of lo
+  __device__ __forceinline__ void fetch(unsigned b) { cp_async16(ring + 32 * (b & 3), g + min(b, bmax)); cp_async_commit(); }
+  __device__ __forceinline__ unsigned word(unsigned i) const { return rw[128 * ((i >> 2) & 3) + (i & 3)]; }
+  __device__ __forceinline__ void init(const unsigned char* in, unsigned in_len, unsigned bit, uint4* lane_ring) {
+    const unsigned mis = (unsigned)((uintptr_t)in & 15);
+    g = (const uint4*)(in - mis);
+    ring = lane_ring; rw = (const unsigned*)lane_ring;
+    bmax = (mis + max(in_len, 1u) - 1) >> 4;
+    const unsigned ab = bit + 8 * mis, w0 = ab >> 5, b0 = w0 >> 2;
+    fetch(b0); fetch(b0 + 1); fetch(b0 + 2);
+    cp_async_wait<0>();
+    lo = word(w0); hi = word(w0 + 1); ahead = word(w0 + 2);
+    k = w0 + 2;
+    // blocks up to (k >> 2) + 2 must be under way
+    if ((k >> 2) != b0) fetch(b0 + 3);
+    pos = ab & 31;
+    base_bit = (w0 << 5) - 8 * mis;
+  }
+  __device__ __forceinline__ void refill() {
+    const bool need = pos >= 32;
+    lo = need ? hi : lo;
+    hi = need ? ahead : hi;
+    pos -= need ? 32u : 0u;
+    base_bit += need ? 32u : 0u;
+    if (need) {
+      k++;
+      if ((k & 3) == 0) { fetch((k >> 2) + 2); cp_async_wait<1>(); }     // entering a block: the next one is complete
+      ahead = word(k);
+    }
+  }
+  __device__ __forceinline__ unsigned window() const { return __funnelshift_r(lo, hi, pos); }
+  __device__ __forceinline__ void drop(unsigned n) { pos += n; }
+  __device__ __forceinline__ unsigned bit_pos() const { return base_bit + pos; }
+};
+
 // ---------------------------------------------------------------------------------------------- header parse
 // Canonical decode of one symbol of the 19-symbol code-length code from a 32-bit window (bit-serial, <= 7 bits).
 __device__ __forceinline__ int par_cl_decode(unsigned win, const unsigned char* count, const unsigned char* sorted,
@@ -403,10 +452,10 @@ struct SpanRes { unsigned end, ntok, nout, flags; };   // flags: 1 end-of-block 
 template <bool EMIT>
 __device__ __forceinline__ void blk_span(bool run, const unsigned char* in, unsigned in_len, unsigned start,
                                          unsigned bound, const BlkTabs& T, const unsigned short* lenx,
-                                         const unsigned* distx, unsigned* tok, SpanRes& r) {
+                                         const unsigned* distx, unsigned* tok, SpanRes& r, uint4* lane_ring) {
   const unsigned in_bits = in_len * 8;
-  TBits br;
-  br.init(in, in_len, run ? start : 0u);
+  SBits br;
+  br.init(in, in_len, run ? start : 0u, lane_ring);
   unsigned ntok = 0, nout = 0, flags = 0;
   bool active = run;
   while (__any_sync(0xffffffffu, active)) {
@@ -517,7 +566,7 @@ __device__ bool blk_parse_header(const unsigned char* in, unsigned in_len, unsig
   return true;
 }
 
-static const int PAR_BLK_WARPS = 8;
+static const int PAR_BLK_WARPS = 4;
 static const unsigned PAR_PREROLL_BITS = 768;       // see par_block_kernel
 static const unsigned PAR_RUN_ON_BITS = 1u << 20;   // how far past the next candidate the last lane may look for the end-of-block code
 __global__ void __launch_bounds__(PAR_BLK_WARPS * 32) par_block_kernel(const unsigned char* __restrict__ comp,
@@ -527,9 +576,11 @@ __global__ void __launch_bounds__(PAR_BLK_WARPS * 32) par_block_kernel(const uns
                                                                        unsigned long long* __restrict__ tok_cursor,
                                                                        unsigned long long tok_capacity) {
   __shared__ BlkTabs tabs[PAR_BLK_WARPS];
+  __shared__ uint4 rings[PAR_BLK_WARPS][4 * 32];              // SBits: four 16-byte slots per lane
   __shared__ unsigned short lenx[32];
   __shared__ unsigned distx[32];
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint4* lane_ring = &rings[wid][lane];
   if (threadIdx.x < 32) { lenx[lane] = (unsigned short)par_len_info(lane); distx[lane] = par_dist_info(lane); }
   __syncthreads();
   const unsigned bi = blockIdx.x * PAR_BLK_WARPS + wid;
@@ -573,10 +624,10 @@ __global__ void __launch_bounds__(PAR_BLK_WARPS * 32) par_block_kernel(const uns
       const unsigned back = min(guess - hdr_end, PAR_PREROLL_BITS);
       SpanRes pr;
       pr.end = guess; pr.ntok = 0; pr.nout = 0; pr.flags = 0;
-      blk_span<false>(lane > 0 && back > 0, in, in_len, guess - back, guess, T, lenx, distx, nullptr, pr);
+      blk_span<false>(lane > 0 && back > 0, in, in_len, guess - back, guess, T, lenx, distx, nullptr, pr, lane_ring);
       if (lane > 0 && pr.flags == 0 && pr.end >= guess && pr.end < bound) start = pr.end;
     }
-    blk_span<false>(true, in, in_len, start, bound, T, lenx, distx, nullptr, r);
+    blk_span<false>(true, in, in_len, start, bound, T, lenx, distx, nullptr, r, lane_ring);
     for (int it = 0; it < 34; it++) {
       const unsigned pe = __shfl_up_sync(0xffffffffu, r.end, 1), pf = __shfl_up_sync(0xffffffffu, r.flags, 1);
       bool ch = false, rerun = false;
@@ -589,7 +640,7 @@ __global__ void __launch_bounds__(PAR_BLK_WARPS * 32) par_block_kernel(const uns
           ch = true;
         }
       }
-      if (__any_sync(0xffffffffu, rerun)) blk_span<false>(rerun, in, in_len, start, bound, T, lenx, distx, nullptr, r);
+      if (__any_sync(0xffffffffu, rerun)) blk_span<false>(rerun, in, in_len, start, bound, T, lenx, distx, nullptr, r, lane_ring);
       if (!__any_sync(0xffffffffu, ch)) break;
     }
     // ---- totals and token offsets
@@ -614,7 +665,7 @@ __global__ void __launch_bounds__(PAR_BLK_WARPS * 32) par_block_kernel(const uns
       const bool emit = ok && !(r.flags & 4) && r.ntok;
       if (__any_sync(0xffffffffu, emit)) {
         SpanRes r2 = r;
-        blk_span<true>(emit, in, in_len, start, bound, T, lenx, distx, tokens + blk.tok_off + (pre - r.ntok), r2);
+        blk_span<true>(emit, in, in_len, start, bound, T, lenx, distx, tokens + blk.tok_off + (pre - r.ntok), r2, lane_ring);
         if (emit && (r2.ntok != r.ntok || r2.end != r.end)) ok = false;           // cannot happen
       }
     }

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(32) seg_tokens_kernel(const unsigned char* __r
                                                         unsigned* __restrict__ tokens, uint2* __restrict__ btab,
                                                         SubOut* __restrict__ subs, ParRes* __restrict__ res) {
   __shared__ BlkTabs T;
+  __shared__ uint4 ring[4 * 32];                                // SBits: four 16-byte slots per lane
   __shared__ unsigned short lenx[32];
   __shared__ unsigned distx[32];
   const unsigned lane = threadIdx.x;
@@ -125,8 +126,8 @@ __global__ void __launch_bounds__(32) seg_tokens_kernel(const unsigned char* __r
     const size_t sub = (size_t)sg.sub_first + j;
     SubOut* so = subs + sub;
     if (act) sink.open(tokens + sub * SEG_TOK_STRIDE, btab + sub * SEG_BATCHES, so->stepb, pos0, step_shift, idx_bound(j));
-    TBits br;
-    br.init(in, in_len, (act && good) ? start : 0u);
+    SBits br;
+    br.init(in, in_len, (act && good) ? start : 0u, ring + lane);
     // One symbol per iteration, at most one token written: the token in hand (`pend`: a run of 1..3 literals, or a
     // match) is written when the next symbol cannot join it.
     unsigned pos = pos0, pend = 0, ppos = pos0, np = 0, flags = 0;      // np: literals in hand (0: pend is a match or nothing)

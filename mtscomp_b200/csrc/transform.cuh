@@ -238,12 +238,12 @@ template <class T> __device__ __forceinline__ void store_run(T* y, const T (&v)[
   }
 }
 
-static const int FWD_TILE_THREADS = 256;
-template <class T>
-__global__ void __launch_bounds__(FWD_TILE_THREADS) fwd_tile_kernel(const T* __restrict__ src, T* __restrict__ dst,
-                                                                    const ChunkDesc* __restrict__ chunks, int nc, int TT,
+static const int INV_TILE_MAXT = 448;                 // most threads of a tile kernel (one channel per thread and pass)
+template <class T, int G, int J>
+__global__ void __launch_bounds__(INV_TILE_MAXT, 2) fwd_tile_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                                    const ChunkDesc* __restrict__ chunks, int nc,
                                                                     int flags) {
-  const int R = ColRun<T>::R;
+  const int R = ColRun<T>::R, TT = G * R;
   MTS_DYN_SMEM(sm);                                    // [0,16) mbarrier, [16, ...) the span (16-byte aligned)
   const ChunkDesc cd = chunks[blockIdx.y];
   const int ns = cd.ns;
@@ -269,54 +269,139 @@ __global__ void __launch_bounds__(FWD_TILE_THREADS) fwd_tile_kernel(const T* __r
 
   const T* s = (const T*)(data + off0) + (long long)halo * nc;     // s[r * nc + c] = sample t0 + r, channel c
   const bool td = (flags & FLAG_TIME_DIFF) != 0, sd = (flags & FLAG_SPATIAL_DIFF) != 0;
-  T* ychunk = dst + cd.elem_off;
-  const int groups = (rows + R - 1) / R;
-  for (int it = threadIdx.x; it < groups * nc; it += blockDim.x) {
-    const int g = it / nc, c = it - g * nc;
-    const int r0 = g * R, nr = min(R, rows - r0);
-    const T* p = s + (long long)r0 * nc + c;
+  T* ychunk = dst + cd.elem_off + t0;
+  // a thread owns J channels and walks down the G runs of each: no index arithmetic beyond a pointer step per row
+#pragma unroll
+  for (int j = 0; j < J; j++) {
+    const int c = threadIdx.x + j * blockDim.x;
+    if (c >= nc) continue;
+    const T* p = s + c;
     const bool left = sd && c > 0;
     // in the reference's order (it matters for floating point): time difference of each column first, then the
     // difference between the two columns (mtscomp.py:381-394)
     T prev = 0, prevl = 0;
-    if (td && (r0 > 0 || halo)) { prev = p[-nc]; if (left) prevl = p[-nc - 1]; }
-    T v[R];
+    if (td && halo) { prev = p[-nc]; if (left) prevl = p[-nc - 1]; }
+    T* y = ychunk + (long long)c * ns;
 #pragma unroll
-    for (int r = 0; r < R; r++) {
-      T cur = 0, curl = 0;
-      if (r < nr) { cur = p[r * nc]; if (left) curl = p[r * nc - 1]; }
-      T a = td ? (T)(cur - prev) : cur;
-      if (left) a = (T)(a - (td ? (T)(curl - prevl) : curl));
-      v[r] = a;
-      prev = cur; prevl = curl;
+    for (int g = 0; g < G; g++) {
+      const int nr = min(R, rows - g * R);
+      if (nr <= 0) break;
+      T v[R];
+      if (nr == R && !left) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const T cur = p[(long long)(g * R + r) * nc];
+          v[r] = td ? (T)(cur - prev) : cur;
+          prev = cur;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          T cur = 0, curl = 0;
+          if (r < nr) { cur = p[(long long)(g * R + r) * nc]; if (left) curl = p[(long long)(g * R + r) * nc - 1]; }
+          T a = td ? (T)(cur - prev) : cur;
+          if (left) a = (T)(a - (td ? (T)(curl - prevl) : curl));
+          v[r] = a;
+          prev = cur; prevl = curl;
+        }
+      }
+      store_run<T>(y + g * R, v, nr);
     }
-    T* y = ychunk + (long long)c * ns + t0 + r0;
-    store_run<T>(y, v, nr);
   }
 }
 
 // Inverse transform for the channel-major layouts in ONE pass over the data (read T once, write the output once): a CTA
-// takes a tile of TT rows x all channels.  Within the tile the running sums are local (registers + a few group totals in
-// shared memory); across the tiles of a chunk each channel's carry travels by decoupled look-back: a tile publishes its
-// per-channel AGGREGATE as soon as it has it, then adds up the aggregates of its predecessors until it meets one that
-// has already published its INCLUSIVE prefix, and publishes its own.  Tiles are handed out by a ticket counter in
-// tile-major order over the chunks of the batch (tile t of every chunk before tile t + 1 of any): with many chunks the
-// predecessor finished a whole generation earlier and the look-back is one step; a waiting tile only ever waits for
-// tickets below its own, which are running or done.  The finished rows leave shared memory as one contiguous span
-// (TMA bulk store of the aligned interior).
-static const int INV_TILE_THREADS = 256;
-template <class T>
-__global__ void __launch_bounds__(INV_TILE_THREADS) inv_tile_kernel(const T* __restrict__ in, T* __restrict__ out,
+// takes a tile of TT = G * R rows x all channels.  A thread owns J channels (c = threadIdx.x + j * blockDim.x) and, of
+// each, the G runs of R rows of the tile: 32 bytes per run, loaded up front (G * J * 2 128-bit loads in flight per
+// thread) and KEPT IN REGISTERS while the carry arrives; so the tile costs one shared-memory store per element (the
+// transposition into row order) and nothing else.  Across the tiles of a chunk each channel's carry travels by decoupled
+// look-back, channel by channel (no barrier, no fence): per (tile, channel) there is ONE word that holds a value, its
+// kind (AGGREGATE of the tile / INCLUSIVE prefix up to its end) and the launch's epoch, so it is written and read
+// atomically and words left by earlier launches read as "not there yet" (no clearing between launches).  A thread
+// publishes its aggregate as soon as it has it, adds up the aggregates of the predecessors until it meets an inclusive
+// one, and publishes its own inclusive value; the predecessor's word is requested before the tile's data, so with many
+// chunks in the batch (tiles are handed out by a ticket counter, tile t of every chunk before tile t + 1 of any) it has
+// arrived, inclusive, before the data has.  A waiting thread only ever waits for tickets below its own, which are
+// running or done.  64-bit elements do not fit a word with their tag: they use separate value and tag arrays and fences.
+// The finished rows leave shared memory as one contiguous span (TMA bulk store of the aligned interior).
+template <class T> __device__ __forceinline__ void load_run(uint4 (&q)[2], const T* p, int nr) {
+  const int R = 32 / sizeof(T);
+  const uintptr_t a = (uintptr_t)p;
+  if (nr == R && !(a & 15)) {
+    q[0] = ((const uint4*)p)[0]; q[1] = ((const uint4*)p)[1];
+  } else if (nr == R && !(a & 7)) {
+    uint2 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) h[i] = ((const uint2*)p)[i];
+    memcpy(q, h, 32);
+  } else if (nr == R && !(a & 3)) {
+    unsigned h[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) h[i] = ((const unsigned*)p)[i];
+    memcpy(q, h, 32);
+  } else {
+    T v[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) v[r] = r < nr ? p[r] : (T)0;
+    memcpy(q, v, 32);
+  }
+}
+
+static const unsigned INV_EPOCH_MAX = 0x3fffu;         // epochs 1..INV_EPOCH_MAX, then the host clears the words
+template <int SZ> struct InvWord { typedef unsigned type; };
+template <> struct InvWord<4> { typedef unsigned long long type; };
+template <> struct InvWord<8> { typedef unsigned long long type; };
+// bytes of look-back state per (tile, channel)
+template <class T> __host__ __device__ inline size_t inv_state_bytes() { return sizeof(T) == 8 ? 24 : sizeof(typename InvWord<sizeof(T)>::type); }
+
+// One channel's look-back cell of one tile.  kind: 0 nothing yet, 1 aggregate, 2 inclusive.
+template <class T> struct InvCell {
+  typedef typename InvWord<sizeof(T)>::type W;
+  static const int VB = 8 * sizeof(T);
+  __device__ static __forceinline__ void put(void* base, size_t n_cells, size_t i, unsigned epoch, unsigned kind, T v) {
+    if (sizeof(T) == 8) {
+      unsigned long long* val = (unsigned long long*)base + (kind == 2 ? n_cells : 0);
+      volatile unsigned* tag = (volatile unsigned*)((unsigned long long*)base + 2 * n_cells);
+      ((volatile unsigned long long*)val)[i] = (unsigned long long)v;
+      __threadfence();
+      tag[i] = (epoch << 2) | kind;
+    } else {
+      ((volatile W*)base)[i] = (W)v | ((W)kind << VB) | ((W)epoch << (VB + 2));
+    }
+  }
+  // kind of the cell in this launch (0: not there yet) and its value
+  __device__ static __forceinline__ unsigned get(const void* base, size_t n_cells, size_t i, unsigned epoch, T& v) {
+    if (sizeof(T) == 8) {
+      const volatile unsigned* tag = (const volatile unsigned*)((const unsigned long long*)base + 2 * n_cells);
+      const unsigned t = tag[i];
+      if ((t >> 2) != epoch || !(t & 3)) return 0;
+      __threadfence();
+      v = (T)((const volatile unsigned long long*)base)[((t & 3) == 2 ? n_cells : 0) + i];
+      return t & 3;
+    } else {
+      const W w = ((const volatile W*)base)[i];
+      if ((unsigned)(w >> (VB + 2)) != epoch) return 0;
+      v = (T)w;
+      return (unsigned)(w >> VB) & 3u;
+    }
+  }
+};
+
+template <class T, int G, int J>
+__global__ void __launch_bounds__(INV_TILE_MAXT, 2) inv_tile_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                                     const ChunkDesc* __restrict__ chunks, int n_chunks,
-                                                                    int nc, int TT, int max_tiles, int flags,
-                                                                    T* agg, T* incl, unsigned* state, unsigned* ticket) {
-  const int R = ColRun<T>::R;
-  MTS_DYN_SMEM(sm);                                    // [16 bytes][tile: data at offset off0, rows x nc][group totals G x nc]
+                                                                    int nc, int max_tiles, int flags, int order_block,
+                                                                    void* cells, unsigned epoch, unsigned* ticket) {
+  const int R = ColRun<T>::R, TT = G * R;
+  MTS_DYN_SMEM(sm);                                    // [16 bytes][tile: data at offset off0, rows x nc]
   __shared__ unsigned s_ticket;
   if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
   __syncthreads();
   const unsigned tk = s_ticket;
-  const int tl = (int)(tk / (unsigned)n_chunks), ci = (int)(tk % (unsigned)n_chunks);
+  // order_block consecutive tiles of a chunk have consecutive tickets (they run at the same time and read neighbouring
+  // pieces of every channel run), then the same tiles of the next chunk, ...
+  const unsigned per = (unsigned)order_block * (unsigned)n_chunks, rem = tk % per;
+  const int ci = (int)(rem / (unsigned)order_block), tl = (int)(tk / per) * order_block + (int)(rem % (unsigned)order_block);
   const ChunkDesc cd = chunks[ci];
   const int ns = cd.ns;
   const int t0 = tl * TT;
@@ -326,84 +411,95 @@ __global__ void __launch_bounds__(INV_TILE_THREADS) inv_tile_kernel(const T* __r
   unsigned char* gout = (unsigned char*)(out + cd.elem_off + (long long)t0 * nc);
   const unsigned off0 = (unsigned)((uintptr_t)gout & 15);
   T* s = (T*)(sm + 16 + off0);                         // s[r * nc + c]; 16-byte aligned exactly where the output is
-  const int G = (TT + R - 1) / R;
-  T* tot = (T*)(sm + 16 + 16 + (((size_t)TT * nc * sizeof(T) + 15) & ~(size_t)15));   // tot[g * nc + c]
-  const T* x = in + cd.elem_off;
-  const int groups = (rows + R - 1) / R;
-  // ---- load + running sums inside every run of R rows
-  for (int it = threadIdx.x; it < groups * nc; it += blockDim.x) {
-    const int g = it / nc, c = it - g * nc;
-    const int r0 = g * R, nr = min(R, rows - r0);
-    const T* p = x + (long long)c * ns + t0 + r0;
-    T v[R];
-    if (nr == R && ((uintptr_t)p & 15) == 0) {
-      uint4 q[2];
-      q[0] = ((const uint4*)p)[0]; q[1] = ((const uint4*)p)[1];
-      memcpy(v, q, 32);
-    } else {
+  const T* x = in + cd.elem_off + t0;
+  const size_t n_cells = (size_t)n_chunks * max_tiles * nc;
+  const size_t cell0 = ((size_t)ci * max_tiles + tl) * nc;           // this tile's cells; the predecessor's are nc below
+  // ---- the predecessor's cells are requested first, then the thread's runs -> registers
+  T pv[J];
+  unsigned pk[J];
 #pragma unroll
-      for (int r = 0; r < R; r++) v[r] = r < nr ? p[r] : (T)0;
-    }
-    T run = 0;
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      if (td) { run = (T)(run + v[r]); v[r] = run; }
-      if (r < nr) s[(r0 + r) * nc + c] = v[r];
-    }
-    tot[g * nc + c] = run;
+  for (int j = 0; j < J; j++) {
+    const int c = threadIdx.x + j * blockDim.x;
+    pv[j] = 0; pk[j] = 0;
+    if (td && tl > 0 && c < nc) pk[j] = InvCell<T>::get(cells, n_cells, cell0 - nc + c, epoch, pv[j]);
   }
-  __syncthreads();
-  if (td) {
-    T* my_agg = agg + ((long long)ci * max_tiles + tl) * nc;
-    T* my_incl = incl + ((long long)ci * max_tiles + tl) * nc;
-    unsigned* st = state + (long long)ci * max_tiles;
-    // ---- aggregate of the tile, published at once
-    for (int c = threadIdx.x; c < nc; c += blockDim.x) {
-      T a = 0;
-      for (int g = 0; g < groups; g++) a = (T)(a + tot[g * nc + c]);
-      my_agg[c] = a;
+  uint4 q[J][G][2];
+#pragma unroll
+  for (int j = 0; j < J; j++) {
+    const int c = threadIdx.x + j * blockDim.x;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      const int nr = min(R, rows - g * R);
+      if (c < nc && nr > 0) load_run<T>(q[j][g], x + (long long)c * ns + g * R, nr);
+      else q[j][g][0] = q[j][g][1] = make_uint4(0, 0, 0, 0);
     }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) *(volatile unsigned*)&st[tl] = 1u;
-    // ---- look-back + carries into the tile
-    for (int c = threadIdx.x; c < nc; c += blockDim.x) {
-      T carry = 0;
+  }
+  // ---- aggregate, look-back, running sums in registers, one shared-memory store per element (the transposition)
+#pragma unroll
+  for (int j = 0; j < J; j++) {
+    const int c = threadIdx.x + j * blockDim.x;
+    if (c >= nc) continue;
+    T a = 0;
+    if (td) {
+      const bool publish = (long long)(tl + 1) * TT < ns;            // somebody comes after this tile
+      T total = 0;
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        T v[R];
+        memcpy(v, q[j][g], 32);
+#pragma unroll
+        for (int r = 0; r < R; r++) total = (T)(total + v[r]);
+      }
+      if (publish && pk[j] != 2 && tl > 0) InvCell<T>::put(cells, n_cells, cell0 + c, epoch, 1, total);
+      T cy = 0;
       for (int i = tl - 1; i >= 0; i--) {
-        unsigned f;
-        while ((f = *(volatile unsigned*)&st[i]) == 0u) {
+        T v = pv[j];
+        unsigned kind = pk[j];
+        pk[j] = 0;                                                   // (the prefetched answer serves the first step only)
+        while (kind == 0) {
+          kind = InvCell<T>::get(cells, n_cells, ((size_t)ci * max_tiles + i) * nc + c, epoch, v);
 #ifdef MTSCOMP_EMU
-          emu::yield();
+          if (kind == 0) emu::yield();
 #endif
         }
-        __threadfence();
-        if (f == 2u) { carry = (T)(carry + ((volatile T*)(incl + ((long long)ci * max_tiles + i) * nc))[c]); break; }
-        carry = (T)(carry + ((volatile T*)(agg + ((long long)ci * max_tiles + i) * nc))[c]);
+        cy = (T)(cy + v);
+        if (kind == 2) break;
       }
-      T a = carry;
-      for (int g = 0; g < groups; g++) {
-        const T t = tot[g * nc + c];
-        const int r1 = min(g * R + R, rows);
-        for (int r = g * R; r < r1; r++) s[r * nc + c] = (T)(s[r * nc + c] + a);
-        a = (T)(a + t);
-      }
-      my_incl[c] = a;
+      if (publish) InvCell<T>::put(cells, n_cells, cell0 + c, epoch, 2, (T)(cy + total));
+      a = cy;
     }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) *(volatile unsigned*)&st[tl] = 2u;
+    T* sp = s + c;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      T v[R];
+      memcpy(v, q[j][g], 32);
+      if (rows == TT) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          if (td) { a = (T)(a + v[r]); v[r] = a; }
+          sp[(long long)(g * R + r) * nc] = v[r];
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          if (td) { a = (T)(a + v[r]); v[r] = a; }
+          if (g * R + r < rows) sp[(long long)(g * R + r) * nc] = v[r];
+        }
+      }
+    }
   }
+  __syncthreads();
   if (sd) {
     // per-row running sum over the channels (after the time sums: the two commute in modular arithmetic)
     const int nw = blockDim.x >> 5;
     for (int r = warp_id(); r < rows; r += nw) {
-      T carry = 0;
+      T cy = 0;
       for (int c0 = 0; c0 < nc; c0 += 32) {
         const int c = c0 + lane_id();
         T v = (c < nc) ? s[r * nc + c] : (T)0;
-        v = (T)(warp_incl_scan(v) + carry);
+        v = (T)(warp_incl_scan(v) + cy);
         if (c < nc) s[r * nc + c] = v;
-        carry = __shfl_sync(0xffffffffu, v, 31);
+        cy = __shfl_sync(0xffffffffu, v, 31);
       }
     }
     __syncthreads();

@@ -154,3 +154,46 @@ def test_emulated_float_golden(emu, name):
     assert zlib.decompress(bytes(comp[offs[0]:offs[1]])) == (GOLDEN / (name + '.tr')).read_bytes()
     out2, st2 = emu.decompress(comp, offs, b, ch['n_channels'], raw.dtype, fl)
     assert not st2.any() and out2.tobytes() == dec.tobytes()
+
+
+@pytest.mark.parametrize('nc,dtype', [(1, 'int16'), (31, 'uint8'), (447, 'int16'), (449, 'int16'), (449, 'int64'),
+                                      (900, 'int32'), (1800, 'int16'), (2100, 'int16'), (450, 'uint8')])
+def test_emulated_tile_kernels_channel_counts(emu, nc, dtype):
+    """The channel-major tile kernels give a thread 1, 2 or 4 channels depending on n_channels and fall back to the
+    generic kernels beyond that: every regime, ragged chunk lengths, all four difference settings."""
+    from mtscomp_b200 import _native
+    rng = np.random.default_rng(nc)
+    ns = [70, 33, 5, 129]
+    x = np.cumsum(rng.integers(-3, 4, (sum(ns), nc)), axis=0).astype(dtype)
+    rows = np.concatenate(([0], np.cumsum(ns)))
+    for td, sd in ((True, False), (True, True), (False, True), (False, False)):
+        fl = _native.flags_of(td, sd, 'F')
+        kw = dict(do_time_diff=td, do_spatial_diff=sd, chunk_order='F')
+        for i in range(len(ns)):
+            assert emu.delta_transform(x[rows[i]:rows[i + 1]], fl).tobytes() == ora.transform_chunk(x[rows[i]:rows[i + 1]], **kw)
+        comp = [ora.encode_chunk(x[rows[i]:rows[i + 1]], **kw) for i in range(len(ns))]
+        offs = np.concatenate(([0], np.cumsum([len(c) for c in comp])))
+        out, st = emu.decompress(b''.join(comp), offs, rows, nc, dtype, fl)
+        assert not st.any() and np.array_equal(out, x), (td, sd)
+
+
+def test_emulated_inverse_lookback_epochs(emu):
+    """inv_tile_kernel tags its look-back cells with a launch epoch instead of clearing them: repeated launches over the
+    same cells, other shapes in between, and the wrap of the epoch counter."""
+    from mtscomp_b200 import _native
+    rng = np.random.default_rng(5)
+    cases = []
+    for nc, dt, ns in ((40, 'int16', [300, 300, 77]), (40, 'int32', [500]), (7, 'int64', [260, 90]), (40, 'uint8', [333, 20])):
+        x = np.cumsum(rng.integers(-3, 4, (sum(ns), nc)), axis=0).astype(dt)
+        rows = np.concatenate(([0], np.cumsum(ns)))
+        comp = [ora.encode_chunk(x[rows[i]:rows[i + 1]]) for i in range(len(ns))]
+        cases.append((x, rows, b''.join(comp), np.concatenate(([0], np.cumsum([len(c) for c in comp]))), nc, dt))
+    seen = []
+    for rep in range(4):
+        if rep == 1:
+            emu.set_param('inv_epoch', 0x3ffc)              # (the first round sized the buffer, which restarts the epochs)
+        for x, rows, comp, offs, nc, dt in cases:
+            out, st = emu.decompress(comp, offs, rows, nc, dt, _native.TIME_DIFF)
+            assert not st.any() and np.array_equal(out, x)
+            seen.append(emu.get_param('inv_epoch'))
+    assert min(seen) == 1 and max(seen) == 0x3fff           # wrapped once, cells cleared
