@@ -70,6 +70,7 @@ struct mtsb_ctx {
   bool ignore_index = false;    // (internal) decode every chunk as a plain zlib stream: the retry of chunks whose index misled
   Buf d_raw, d_raw2, d_out2, d_comp2, d_T, d_tok, d_hist, d_codes, d_hdrs, d_tab, d_so, d_seg_adler, d_chunk_adler, d_chunk_off, d_out,
       d_partial, d_comp, d_status, d_tadler, d_gather, d_subabs, d_subtok, d_invstate, d_invcells;
+  int inv_cells_isz = 0;           // element size of the launch that last wrote the look-back cells
   unsigned inv_epoch = 0;          // epoch of the last inv_tile_kernel launch (tags its look-back cells)
   long long inv_order_block = 2;   // inv_tile_kernel: consecutive tiles of a chunk that get consecutive tickets
   long long inv_single_pass = 1;   // channel-major inverse transform in one pass (inv_tile_kernel); 0: tile sums + apply
@@ -261,9 +262,11 @@ int launch_inv_t(mtsb_ctx* c, const void* tbuf, void* out, const ChunkDesc* d_cd
     const size_t cells_bytes = td ? n_tiles * nc * inv_state_bytes<T>() + 256 : 256;
     const void* before = c->d_invcells.p;
     NEED(c->d_invcells, cells_bytes);
-    if (c->d_invcells.p != before || c->inv_epoch >= INV_EPOCH_MAX) {
+    // (a word of one element size can read as a valid one of another, and the 64-bit layout depends on the cell count)
+    if (c->d_invcells.p != before || c->inv_epoch >= INV_EPOCH_MAX || c->inv_cells_isz != (int)sizeof(T) || sizeof(T) == 8) {
       CK(cudaMemsetAsync(c->d_invcells.p, 0, c->d_invcells.cap, c->stream));
       c->inv_epoch = 0;
+      c->inv_cells_isz = (int)sizeof(T);
     }
     const unsigned epoch = ++c->inv_epoch;
     NEED(c->d_invstate, 64);

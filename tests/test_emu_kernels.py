@@ -188,12 +188,16 @@ def test_emulated_inverse_lookback_epochs(emu):
         rows = np.concatenate(([0], np.cumsum(ns)))
         comp = [ora.encode_chunk(x[rows[i]:rows[i + 1]]) for i in range(len(ns))]
         cases.append((x, rows, b''.join(comp), np.concatenate(([0], np.cumsum([len(c) for c in comp]))), nc, dt))
-    seen = []
-    for rep in range(4):
-        if rep == 1:
-            emu.set_param('inv_epoch', 0x3ffc)              # (the first round sized the buffer, which restarts the epochs)
+    for rep in range(3):                                    # element sizes alternate: the cells are cleared in between
         for x, rows, comp, offs, nc, dt in cases:
             out, st = emu.decompress(comp, offs, rows, nc, dt, _native.TIME_DIFF)
             assert not st.any() and np.array_equal(out, x)
-            seen.append(emu.get_param('inv_epoch'))
-    assert min(seen) == 1 and max(seen) == 0x3fff           # wrapped once, cells cleared
+    x, rows, comp, offs, nc, dt = cases[0]
+    seen = []
+    for rep in range(8):                                    # same element size: epochs count up and wrap
+        if rep == 2:
+            emu.set_param('inv_epoch', 0x3ffc)
+        out, st = emu.decompress(comp, offs, rows, nc, dt, _native.TIME_DIFF)
+        assert not st.any() and np.array_equal(out, x)
+        seen.append(emu.get_param('inv_epoch'))
+    assert seen[1] == seen[0] + 1 and min(seen) == 1 and max(seen) == 0x3fff
