@@ -55,14 +55,18 @@ const char* mtsb_last_error(mtsb_ctx* ctx);
 int mtsb_sync(mtsb_ctx* ctx);
 
 /* Tunables (by name): "seg_bytes" target encoder segment size (default 262144), "lz_ctas_per_sm" (resident
- * match-finder CTAs per SM, 2), "write_index" (append the segment index after each chunk's zlib stream, 1),
+ * match-finder CTAs per SM, 2), "write_index" (append the in-band index of segments and sub-blocks after each chunk's
+ * zlib stream, 1; with 0 the output is exactly one zlib stream per chunk, as the reference writes it),
  * "batch_bytes" (raw bytes processed per internal sub-batch), "host_batch_bytes" (the same when a host buffer is
  * involved: copies of one sub-batch overlap the kernels of the next), "par_batch_bytes" (host-buffer sub-batch of
  * index-less chunks on the decode side), "par_inflate" (1: block-parallel decoder; 0: serial warp per stream),
- * "par_indexed" (1: indexed segments go through the block kernels as well), "par_lz_wide" (-1 auto / 0 / 1: shape of
- * the token-resolve kernel), "par_cells" (-1 auto / 0 / 1: resolve the blocks of an index-less stream in parallel —
- * the low-latency path for few streams).  Read-only: "par_survivors", "par_candidates", "par_chained", "par_resumed" (what the
- * block-parallel decoder did in the last call).  Returns MTSB_E_ARG for unknown names. */
+ * "par_indexed" (1: indexed segments that the step kernels do not take go through the block kernels), "seg_v2" (1: indexed
+ * segments of the second index format are decoded by seg_tokens_kernel / seg_resolve_kernel), "par_lz_wide"
+ * (-1 auto / 0 / 1: shape of the token-resolve kernel), "par_cells" (-1 auto / 0 / 1: resolve the blocks of an
+ * index-less stream in parallel — the low-latency path for few streams), "inv_single_pass" (1: channel-major inverse
+ * transform in one pass with look-back carries; 0: tile sums + scan + apply), "inv_order_block" (consecutive tiles of a
+ * chunk that run together in the single-pass inverse, 2).  Read-only: "par_survivors", "par_candidates", "par_chained",
+ * "par_resumed" (what the parallel decoders did in the last call), "sm_count".  Returns MTSB_E_ARG for unknown names. */
 int mtsb_set_param(mtsb_ctx* ctx, const char* name, long long value);
 long long mtsb_get_param(mtsb_ctx* ctx, const char* name);
 
@@ -95,8 +99,11 @@ int mtsb_compress_chunks(mtsb_ctx* ctx, const void* src, int src_is_device, int 
 /* Batched decoder — replaces Reader.decompress_chunks / Reader.read_chunk after the pread (mtscomp.py:618-650): chunk i
  * is the zlib stream comp[comp_offsets[i] : comp_offsets[i+1]] (host int64 offsets, any origin) and decodes to rows
  * [chunk_rows[i], chunk_rows[i+1]) of the row-major (chunk_rows[n_chunks], nc) array at `dst`.  Streams written by
- * mtsb_compress_chunks with write_index=1 are decoded segment-parallel; any other valid zlib stream (e.g. written by
- * the reference) is decoded serially by one warp.  chunk_status (n_chunks host ints, may be NULL) receives
+ * mtsb_compress_chunks with write_index=1 are decoded through their index (a lane per 8 KB sub-block, all tokens of a
+ * step at once); any other valid zlib stream (e.g. written by the reference) by the block-parallel decoder, which
+ * finds the deflate blocks itself; what neither takes is decoded serially by one warp, which also decides what is
+ * corrupt.  A chunk whose trailing bytes look like an index but do not decode with it is decoded again as a plain
+ * stream (zlib ignores what follows a stream, so such a chunk is valid).  chunk_status (n_chunks host ints, may be NULL) receives
  * MTSB_CHUNK_*; the call returns MTSB_E_CORRUPT if any is non-zero. */
 int mtsb_decompress_chunks(mtsb_ctx* ctx, const void* comp, int comp_is_device, const long long* comp_offsets,
                            int n_chunks, const long long* chunk_rows, int nc, int itemsize, int flags, void* dst,

@@ -15,6 +15,7 @@ ignores trailing bytes), which lets the GPU Reader decode a chunk's segments in 
 import bisect
 from collections import OrderedDict
 from functools import lru_cache
+import contextlib
 import hashlib
 import json
 from concurrent.futures import ThreadPoolExecutor
@@ -52,6 +53,20 @@ def _require_integer_dtype(dtype):
             "mtscomp_b200 implements the codec for int8..int64 and float32/float64; dtype %s is not "
             "supported and there is no CPU fallback." % dtype)
     return dtype
+
+
+@contextlib.contextmanager
+def _codec_param(codec, name, value):
+    """Set a codec tunable for the duration of a block (None: leave it alone)."""
+    if value is None:
+        yield
+        return
+    old = codec.get_param(name)
+    codec.set_param(name, int(bool(value)))
+    try:
+        yield
+    finally:
+        codec.set_param(name, old)
 
 
 def _codec_for(config):
@@ -124,7 +139,8 @@ class Writer:
 
     Options: chunk_duration, algorithm ('zlib'), comp_level (recorded only, as in the reference: SURVEY G1),
     do_time_diff, do_spatial_diff, chunk_order, n_threads (batch size attribute), check_after_compress,
-    before_check (callback), quiet; plus `device` (CUDA device index).
+    before_check (callback), quiet; plus `device` (CUDA device index) and `write_index` (False: no in-band index after
+    the chunks' zlib streams, i.e. the reference's exact .cbin layout; default: the codec's setting, on).
     """
 
     def __init__(self, before_check=None, **kwargs):
@@ -260,8 +276,12 @@ class Writer:
             fb.write(comp)
             self.sha1_compressed.update(comp)
 
-        with codec.stage_lock, open(out, 'wb') as fb, \
+        # write_index=False (Writer / compress() keyword, or "write_index" in ~/.mtscomp) gives exactly the reference's
+        # .cbin layout, one zlib stream per chunk and nothing else; the default appends the in-band index to each chunk.
+        with codec.stage_lock, _codec_param(codec, 'write_index', self.config.get('write_index')), open(out, 'wb') as fb, \
                 ThreadPoolExecutor(1) as raw_worker, ThreadPoolExecutor(1) as out_worker:
+            if self.config.get('write_index') is not None:
+                caps = [sum(codec.compress_bound(b[i + 1] - b[i], nc, isz, flags) for i in range(lo, hi)) for lo, hi in ranges]
             raw_bufs = [codec.host_buffer('w_raw%d' % i, max((b[hi] - b[lo]) * nc * isz for lo, hi in ranges)) for i in (0, 1)]
             comp_bufs = [codec.host_buffer('w_comp%d' % i, max(caps)) for i in (0, 1)]
             pending = [[], []]

@@ -40,6 +40,8 @@ enum { SEG_FIRST = 1, SEG_LAST = 2 };
 // the match itself starts in.  Files of the first format ("MTSB": k lengths | segment bytes, k, magic, sum) still decode.
 static const unsigned IDX_MAGIC_V1 = 0x4253544Du, IDX_MAGIC_V2 = 0x3253544Du;
 static const int IDX_SUB_BYTES = 8192;
+static const int IDX_MIN_RAW = 2048;       // a chunk of one segment shorter than this gets no index (it would dwarf the stream)
+__host__ __device__ inline bool idx_wanted(int n_seg, int first_seg_len) { return !(n_seg == 1 && first_seg_len < IDX_MIN_RAW); }
 __host__ __device__ inline int idx_n_sub(long long seg_len) {
   return (int)((seg_len + IDX_SUB_BYTES - 1) / IDX_SUB_BYTES) + (seg_len > IDX_SUB_BYTES / 2 ? 1 : 0);
 }
@@ -679,7 +681,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(const DeflateSeg* __restrict
       if ((fl & SEG_LAST) && write_index) {
         const ChunkDesc cd = chunks[segs[i].chunk];
         const unsigned subs = (unsigned)(segs[i].sub_first + idx_n_sub(segs[i].in_len) - segs[cd.first_seg].sub_first);
-        sz += 4ull * subs + 4ull * (unsigned)cd.n_seg + 24;
+        if (idx_wanted(cd.n_seg, segs[cd.first_seg].in_len)) sz += 4ull * subs + 4ull * (unsigned)cd.n_seg + 24;
       }
     }
     unsigned long long incl = warp_incl_scan(sz);
@@ -964,6 +966,7 @@ __global__ void __launch_bounds__(128) trailer_kernel(const DeflateSeg* __restri
   const ChunkDesc cd = chunks[blockIdx.x];
   const unsigned k = (unsigned)cd.n_seg;
   const DeflateSeg s0 = segs[cd.first_seg], s1 = segs[cd.first_seg + k - 1];
+  if (!idx_wanted(cd.n_seg, s0.in_len)) return;
   const unsigned n_subs = (unsigned)(s1.sub_first + idx_n_sub(s1.in_len) - s0.sub_first);
   unsigned char* ix = dst + chunk_off[blockIdx.x + 1] - (4ull * n_subs + 4ull * k + 24);
   for (unsigned q = threadIdx.x; q < k; q += blockDim.x) {

@@ -314,4 +314,33 @@ def case_load_raw_data(tmp_path):   # reference tests.py:161-180
     assert load_raw_data(tmp_path / 'empty.bin', n_channels=3, dtype=np.int16).shape == (0, 3)
 
 
+def case_write_index_option(tmp_path):   # (no reference counterpart: the in-band index is this package's superset)
+    """Default: every chunk is a zlib stream followed by the index (zlib ignores it); write_index=False: the
+    reference's exact layout, nothing after the streams.  Both decode here and with CPython zlib."""
+    import zlib
+    _use_tmp_config(tmp_path)
+    arr = _arr16(5)
+    arr.tofile(tmp_path / 'data.bin')
+    sizes = {}
+    for name, kw in (('idx', {}), ('plain', dict(write_index=False))):
+        compress(tmp_path / 'data.bin', tmp_path / (name + '.cbin'), tmp_path / (name + '.ch'), sample_rate=sample_rate,
+                 n_channels=n_channels, dtype=np.int16, quiet=True, **kw)
+        meta = json.loads((tmp_path / (name + '.ch')).read_text())
+        blob = (tmp_path / (name + '.cbin')).read_bytes()
+        o = meta['chunk_offsets']
+        unused = 0
+        for i in range(len(o) - 1):
+            d = zlib.decompressobj()
+            d.decompress(blob[o[i]:o[i + 1]])
+            assert d.eof
+            unused += len(d.unused_data)
+        sizes[name] = (len(blob), unused)
+        r = decompress(tmp_path / (name + '.cbin'), tmp_path / (name + '.ch'))
+        assert np.array_equal(r[:], arr)
+        r.close()
+    assert sizes['plain'][1] == 0 and sizes['idx'][1] > 0
+    assert sizes['idx'][0] - sizes['idx'][1] == sizes['plain'][0]          # the same streams, plus the index
+    assert M._native.default_codec().get_param('write_index') == 1         # the option does not stick to the codec
+
+
 ALL_CASES = [v for k, v in sorted(globals().items()) if k.startswith('case_')]
