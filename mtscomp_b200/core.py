@@ -697,22 +697,32 @@ class Reader:
         codec = _codec_for(self.config)
         row_bytes = self.n_channels * dtype.itemsize
         ranges = list(_batch_ranges(self.chunk_bounds, row_bytes, 0, self.n_chunks))
-        # two pinned output buffers: the GPU decodes batch k+1 into one while a worker writes batch k from the other
-        with codec.stage_lock, open(out, 'wb') as fb, ThreadPoolExecutor(1) as writer:
+        # two pinned output buffers: the GPU decodes batch k+1 into one while workers write batch k from the other, in
+        # four pieces at their file offsets (a single write() of the page cache's memcpy was the ceiling: 3.4 GB/s)
+        def _pwrite_piece(fd, mv, lo, hi, base):
+            done = lo
+            while done < hi:
+                done += os.pwrite(fd, mv[done:hi], base + done)
+
+        with codec.stage_lock, open(out, 'wb') as fb, ThreadPoolExecutor(4) as writer:
             n_max = max((self.chunk_bounds[hi] - self.chunk_bounds[lo]) * row_bytes for lo, hi in ranges)
             bufs = [codec.host_buffer('r_out%d' % i, n_max) for i in (0, 1)]
-            pending = [None, None]
+            pending = [[], []]
+            fd, dsize = fb.fileno(), 0
             for k, (lo, hi) in enumerate(tqdm(ranges, desc='Decompressing', disable=self.quiet)):
                 slot = k & 1
-                if pending[slot] is not None:
-                    pending[slot].result()
+                for f in pending[slot]:
+                    f.result()
                 ids = list(range(lo, hi))
                 rows = self._decode_into(ids, [self._span(i) for i in ids], bufs[slot].ptr, False)
-                pending[slot] = writer.submit(fb.write, bufs[slot].array[:int(rows[-1]) * row_bytes])
-            for f in pending:
-                if f is not None:
+                n = int(rows[-1]) * row_bytes
+                mv = memoryview(bufs[slot].array[:n])
+                step = max(-(-n // 4), 1 << 20)
+                pending[slot] = [writer.submit(_pwrite_piece, fd, mv, a, min(a + step, n), dsize) for a in range(0, n, step)]
+                dsize += n
+            for fs in pending:
+                for f in fs:
                     f.result()
-            dsize = fb.tell()
         assert dsize == self.chunk_bounds[-1] * self.n_channels * self.dtype.itemsize
         logger.info("Wrote %s (%.1f GB).", out, dsize / 1024 ** 3)
         if self.check_after_decompress:

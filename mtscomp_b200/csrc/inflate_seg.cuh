@@ -34,7 +34,10 @@ static const int SEG_BATCHES = SEG_TOK_STRIDE / 32;
 static const int SEG_MAX_SPS = IDX_SUB_BYTES / 256;      // steps per sub-block at the smallest step
 static const int SEG_RING = 32768;
 static const int SEG_MAX_STEPS = 1024;                   // steps per segment the resolve kernel keeps in shared memory
-static const int SEG_RES_WARPS = 8;
+#ifndef MTS_SEG_RES_WARPS
+#define MTS_SEG_RES_WARPS 8
+#endif
+static const int SEG_RES_WARPS = MTS_SEG_RES_WARPS;
 static const unsigned TOK_MATCH = 0x80000000u;
 
 // ---------------------------------------------------------------------------------------------- seg_tokens_kernel
