@@ -107,7 +107,7 @@ template <int STRIDE, int NT> struct LzSmem {
   static const int SEG = NT * STRIDE;         // bytes per step
 #ifndef MTS_HL_BITS
 #define MTS_HL_BITS 13
-#define MTS_HS_BITS 12
+#define MTS_HS_BITS 13
 #endif
   static const int HL_BITS = MTS_HL_BITS;     // buckets of table L (u32 each)
   static const int HS_BITS = MTS_HS_BITS;     // buckets of table S

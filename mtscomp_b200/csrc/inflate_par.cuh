@@ -138,6 +138,7 @@ struct SBits {
     ring = lane_ring; rw = (const unsigned*)lane_ring;
     bmax = (mis + max(in_len, 1u) - 1) >> 4;
     const unsigned ab = bit + 8 * mis, w0 = ab >> 5, b0 = w0 >> 2;
+    cp_async_wait<0>();          // copies a previous pass left in flight must not land on top of the new ones
     fetch(b0); fetch(b0 + 1); fetch(b0 + 2);
     cp_async_wait<0>();
     lo = word(w0); hi = word(w0 + 1); ahead = word(w0 + 2);
@@ -162,6 +163,7 @@ struct SBits {
   __device__ __forceinline__ unsigned window() const { return __funnelshift_r(lo, hi, pos); }
   __device__ __forceinline__ void drop(unsigned n) { pos += n; }
   __device__ __forceinline__ unsigned bit_pos() const { return base_bit + pos; }
+  __device__ __forceinline__ void finish() { cp_async_wait<0>(); }      // nothing in flight when the ring is given up
 };
 
 // ---------------------------------------------------------------------------------------------- header parse
@@ -496,6 +498,7 @@ __device__ __forceinline__ void blk_span(bool run, const unsigned char* in, unsi
     ntok++;
     nout += isl ? len : 1u;
   }
+  br.finish();
   if (!run) return;
   if (br.bit_pos() > in_bits) flags |= 2;
   r.end = br.bit_pos(); r.ntok = ntok; r.nout = nout; r.flags = flags;

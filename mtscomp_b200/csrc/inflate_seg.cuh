@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(32) seg_tokens_kernel(const unsigned char* __r
         }
       }
     }
+    br.finish();
     if (act && good) {
       if (have) sink.put(pend, ppos);
       sink.close(((last ? out_len : idx_bound(j + 1)) - idx_bound(j) + sg.step_bytes - 1) >> step_shift);

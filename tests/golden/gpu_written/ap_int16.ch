@@ -8,9 +8,9 @@
   ],
   "chunk_offsets": [
     0,
-    38448,
-    77341,
-    101138
+    38335,
+    77099,
+    100829
   ],
   "chunk_order": "F",
   "comp_level": -1,
@@ -19,7 +19,7 @@
   "dtype": "int16",
   "n_channels": 50,
   "sample_rate": 1000.0,
-  "sha1_compressed": "d8f972542bfe07a0e455f736104a3415991c01e0",
+  "sha1_compressed": "02fd8abf584743e623735aa96045c23d79f0899a",
   "sha1_uncompressed": "5aa54da682e5042a4671d3e040a0967d68a38d0f",
   "shape": [
     2600,

@@ -9,10 +9,10 @@
   ],
   "chunk_offsets": [
     0,
-    7030,
-    14059,
-    21093,
-    26454
+    7033,
+    14063,
+    21102,
+    26466
   ],
   "chunk_order": "C",
   "comp_level": -1,
@@ -21,7 +21,7 @@
   "dtype": "int16",
   "n_channels": 20,
   "sample_rate": 1000.0,
-  "sha1_compressed": "0427b69c3a7abbc96481cbf59d2fbdd33928f88d",
+  "sha1_compressed": "244db4627716038e2125cc0d53049a1a599b79e7",
   "sha1_uncompressed": "36b9d0a72f5f9e6c2d71ede3e82a200ee6bbfb44",
   "shape": [
     1500,

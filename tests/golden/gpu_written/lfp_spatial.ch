@@ -8,9 +8,9 @@
   ],
   "chunk_offsets": [
     0,
-    38929,
-    77785,
-    97707
+    38196,
+    76292,
+    95887
   ],
   "chunk_order": "F",
   "comp_level": -1,
@@ -19,7 +19,7 @@
   "dtype": "int16",
   "n_channels": 40,
   "sample_rate": 1000.0,
-  "sha1_compressed": "546e6c3449f0eccc07c8c006500968f05e2bcc43",
+  "sha1_compressed": "11bdccd57327fda9046c2f70d733ad185dd1a76c",
   "sha1_uncompressed": "3e219b584766b271cc7b4da961d9d4f7a296cddb",
   "shape": [
     2500,

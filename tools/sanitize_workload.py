@@ -36,6 +36,10 @@ roundtrip(synth.ap_chunk(1500, 33, seed=3), [0, 1500], order='C', label='order C
 roundtrip((synth.ap_chunk(20000, 8, seed=4) & 0xff).astype(np.uint8), [0, 20000], label='uint8')
 roundtrip(synth.ap_chunk(4000, 16, seed=5).astype(np.int32), [0, 4000], label='int32')
 roundtrip(synth.ap_chunk(30000, 24, seed=6), [0, 30000], label='ap long channels (multi-block streams)')
+roundtrip(synth.ap_chunk(900, 7, seed=8).astype(np.int64), [0, 500, 900], label='int64 (look-back with value / tag arrays)')
+roundtrip(synth.ap_chunk(400, 900, seed=9), [0, 150, 400], label='900 channels (two per thread)')
+roundtrip(synth.ap_chunk(300, 1800, seed=10), [0, 300], sd=True, label='1800 channels (four per thread), spatial')
+roundtrip(synth.ap_chunk(200, 2100, seed=11), [0, 200], label='2100 channels (generic transform kernels)')
 for cells in (1, 0):
     cd.set_param('par_cells', cells)
     roundtrip(synth.ap_chunk(30000, 16, seed=7), [0, 30000], label='reference streams, par_cells=%d' % cells)
