@@ -569,7 +569,10 @@ __device__ bool blk_parse_header(const unsigned char* in, unsigned in_len, unsig
   return true;
 }
 
-static const int PAR_BLK_WARPS = 4;
+#ifndef MTS_PAR_BLK_WARPS
+#define MTS_PAR_BLK_WARPS 4
+#endif
+static const int PAR_BLK_WARPS = MTS_PAR_BLK_WARPS;   // (tables 4.1 KB + bit-reader ring 2 KB per warp, static shared memory)
 static const unsigned PAR_PREROLL_BITS = 768;       // see par_block_kernel
 static const unsigned PAR_RUN_ON_BITS = 1u << 20;   // how far past the next candidate the last lane may look for the end-of-block code
 __global__ void __launch_bounds__(PAR_BLK_WARPS * 32) par_block_kernel(const unsigned char* __restrict__ comp,

@@ -184,7 +184,7 @@ def file_leg(n_chunks=128):
 
 
 # ---------------------------------------------------------------------------------------------------- configs[2]: one file, N ranks
-def sharded_leg(rank, world, chunks_per_rank, group=None, zlib_sample=4):
+def sharded_leg(rank, world, chunks_per_rank, group=None, zlib_sample=4, warm_chunks_per_rank=None):
     """A synthetic AP recording of world x chunks_per_rank one-second chunks on tmpfs, compressed by all ranks into ONE
     .cbin/.ch (sharding.write_sharded), then verified: every rank decodes its chunk range with the GPU Reader and
     compares it with the source; rank 0 inflates a sample of chunks with CPython zlib against the oracle's transform.
@@ -216,9 +216,24 @@ def sharded_leg(rank, world, chunks_per_rank, group=None, zlib_sample=4):
         os.pwrite(fd, base[i % 4].tobytes(), i * cb)
     os.close(fd)
     sharding._barrier(group)
-    # (first call: context and pinned staging buffers; the second one is timed)
-    sharding.write_sharded(raw_path, d / 'warm.cbin', d / 'warm.ch', rank, world, sample_rate=sr, n_channels=nc, dtype=np.int16,
-                           group=group, hash_raw=False)
+    # (first call: context and pinned staging buffers; the second one is timed.  For a large recording the warm-up
+    # runs on a short recording of its own.)
+    if warm_chunks_per_rank is None or warm_chunks_per_rank >= chunks_per_rank:
+        sharding.write_sharded(raw_path, d / 'warm.cbin', d / 'warm.ch', rank, world, sample_rate=sr, n_channels=nc,
+                               dtype=np.int16, group=group, hash_raw=False)
+    else:
+        wn = world * warm_chunks_per_rank
+        if rank == 0:
+            with open(d / 'warm.bin', 'wb') as f:
+                for i in range(wn):
+                    f.write(base[i % 4].tobytes())
+        sharding._barrier(group)
+        sharding.write_sharded(d / 'warm.bin', d / 'warm.cbin', d / 'warm.ch', rank, world, sample_rate=sr, n_channels=nc,
+                               dtype=np.int16, group=group, hash_raw=False)
+        sharding._barrier(group)
+        if rank == 0:
+            for name in ('warm.bin', 'warm.cbin', 'warm.ch'):
+                os.unlink(d / name)
     sharding._barrier(group)
     t = time.perf_counter()
     offsets, secs = sharding.write_sharded(raw_path, d / 'rec.cbin', d / 'rec.ch', rank, world, sample_rate=sr,
