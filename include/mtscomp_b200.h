@@ -60,7 +60,8 @@ int mtsb_sync(mtsb_ctx* ctx);
  * "batch_bytes" (raw bytes processed per internal sub-batch), "host_batch_bytes" (the same when a host buffer is
  * involved: copies of one sub-batch overlap the kernels of the next), "par_batch_bytes" (host-buffer sub-batch of
  * index-less chunks on the decode side), "par_inflate" (1: block-parallel decoder; 0: serial warp per stream),
- * "par_indexed" (1: indexed segments that the step kernels do not take go through the block kernels), "seg_v2" (1: indexed
+ * "par_indexed" (1: indexed segments that the step kernels do not take go through the block kernels), "par_single_pass"
+ * (1: the block decoder keeps the tokens of its counting pass instead of decoding every block twice), "seg_v2" (1: indexed
  * segments of the second index format are decoded by seg_tokens_kernel / seg_resolve_kernel), "par_lz_wide"
  * (-1 auto / 0 / 1: shape of the token-resolve kernel), "par_cells" (-1 auto / 0 / 1: resolve the blocks of an
  * index-less stream in parallel — the low-latency path for few streams), "inv_single_pass" (1: channel-major inverse

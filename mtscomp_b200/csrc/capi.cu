@@ -65,6 +65,8 @@ struct mtsb_ctx {
   int lz_ctas_per_sm = 2;
   // device scratch
   Buf d_pstreams, d_surv, d_cand, d_pcount, d_tokens, d_cells, d_ptab, d_plist, d_pbad;   // block-parallel inflate scratch
+  Buf d_pieces;
+  long long par_single_pass = 1;   // par_block_kernel keeps the tokens of its counting pass (see par_decode)
   Buf d_segv2, d_btab, d_subout;                                                          // indexed (second format) segments
   long long seg_v2 = 1;         // indexed segments of the second format go through seg_tokens / seg_resolve
   bool ignore_index = false;    // (internal) decode every chunk as a plain zlib stream: the retry of chunks whose index misled
@@ -415,7 +417,7 @@ void mtsb_destroy(mtsb_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   Buf* bufs[] = {&c->d_pstreams, &c->d_surv, &c->d_cand, &c->d_pcount, &c->d_tokens, &c->d_cells, &c->d_ptab, &c->d_plist, &c->d_pbad,
-                 &c->d_segv2, &c->d_btab, &c->d_subout,
+                 &c->d_segv2, &c->d_btab, &c->d_subout, &c->d_pieces,
                  &c->d_raw, &c->d_raw2, &c->d_out2, &c->d_comp2, &c->d_T, &c->d_tok, &c->d_hist, &c->d_codes, &c->d_hdrs, &c->d_tab, &c->d_so,
                  &c->d_seg_adler, &c->d_chunk_adler, &c->d_chunk_off, &c->d_out, &c->d_partial, &c->d_comp,
                  &c->d_status, &c->d_tadler, &c->d_gather, &c->d_subabs, &c->d_subtok, &c->d_invstate, &c->d_invcells, &c->h_tab, &c->h_small};
@@ -446,6 +448,7 @@ int mtsb_set_param(mtsb_ctx* c, const char* name, long long v) {
   else if (s == "write_index") c->write_index = v ? 1 : 0;
   else if (s == "par_inflate") c->par_inflate = v ? 1 : 0;
   else if (s == "par_indexed") c->par_indexed = v ? 1 : 0;
+  else if (s == "par_single_pass") c->par_single_pass = v ? 1 : 0;
   else if (s == "seg_v2") c->seg_v2 = v ? 1 : 0;
   else if (s == "inv_single_pass") c->inv_single_pass = v ? 1 : 0;
   else if (s == "inv_epoch") c->inv_epoch = (unsigned)v;          // (tests: the wrap of the look-back epochs)
@@ -469,6 +472,7 @@ long long mtsb_get_param(mtsb_ctx* c, const char* name) {
   if (s == "par_lz_wide") return c->par_lz_wide;
   if (s == "par_cells") return c->par_cells;
   if (s == "par_indexed") return c->par_indexed;
+  if (s == "par_single_pass") return c->par_single_pass;
   if (s == "seg_v2") return c->seg_v2;
   if (s == "inv_single_pass") return c->inv_single_pass;
   if (s == "inv_order_block") return c->inv_order_block;
@@ -878,6 +882,15 @@ static int par_decode(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Infla
   NEED(c->d_pbad, (size_t)ns * sizeof(ParRes) + 64);
   NEED(c->d_plist, n_slots * sizeof(ParBlk));
   NEED(c->d_tokens, (size_t)tok_total * 4 + 64);
+  // plain streams: the counting pass of par_block_kernel leaves its tokens in a scratch area with one slot per
+  // PAR_PIECE_BITS input bits (addressed by the bit's offset in the buffer), from where they are copied instead of decoded again
+  unsigned* d_pieces = nullptr;
+  if (!blks && c->par_single_pass) {
+    long long span = 0;
+    for (int i = 0; i < ns; i++) span = std::max(span, ps[i].in_off + ps[i].in_len);
+    NEED(c->d_pieces, ((size_t)span * 8 / PAR_PIECE_BITS + 64) * 4);
+    d_pieces = (unsigned*)c->d_pieces.p;
+  }
   const size_t o_blk = ((size_t)ns * sizeof(ParStream) + 255) & ~(size_t)255;   // host staging: [streams | blocks]
   NEED(c->h_tab, o_blk + (blks ? n_slots * sizeof(ParBlk) : 0) + 64);
   NEED(c->h_small, 4096 + (size_t)ns * (sizeof(ParRes) + 4) + 64);
@@ -908,7 +921,7 @@ static int par_decode(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Infla
   }
   MTS_LAUNCH(par_block_kernel, dim3((unsigned)((n_slots + PAR_BLK_WARPS - 1) / PAR_BLK_WARPS)), dim3(PAR_BLK_WARPS * 32), 0, c->stream,
              dcomp, d_ps, (ParBlk*)c->d_plist.p, (unsigned)n_slots, (unsigned*)c->d_tokens.p,
-             (unsigned long long*)((char*)c->d_pcount.p + 16), (unsigned long long)tok_total);
+             (unsigned long long*)((char*)c->d_pcount.p + 16), (unsigned long long)tok_total, d_pieces);
   CKL();
   // measured (ms of inflate, chain of tiles / cells): 1 stream 23.4 / 4.1, 8 streams 25.4 / 9.6, 64 streams 35 / 48,
   // 600 streams 180 / 415 -> the cells path is the low-latency path for a handful of streams only

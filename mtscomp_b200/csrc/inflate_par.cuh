@@ -454,7 +454,8 @@ struct SpanRes { unsigned end, ntok, nout, flags; };   // flags: 1 end-of-block 
 template <bool EMIT>
 __device__ __forceinline__ void blk_span(bool run, const unsigned char* in, unsigned in_len, unsigned start,
                                          unsigned bound, const BlkTabs& T, const unsigned short* lenx,
-                                         const unsigned* distx, unsigned* tok, SpanRes& r, uint4* lane_ring) {
+                                         const unsigned* distx, unsigned* tok, SpanRes& r, uint4* lane_ring,
+                                         unsigned cap = 0xffffffffu) {
   const unsigned in_bits = in_len * 8;
   SBits br;
   br.init(in, in_len, run ? start : 0u, lane_ring);
@@ -494,7 +495,7 @@ __device__ __forceinline__ void blk_span(bool run, const unsigned char* in, unsi
     const unsigned xb2 = dx >> 16;
     const unsigned dist = (dx & 0xffffu) + ((win2 >> cl2) & ((1u << xb2) - 1));
     br.drop(isl ? cl2 + xb2 : 0u);
-    if (EMIT) tok[ntok] = isl ? (0x80000000u | (len << 16) | (dist - 1)) : val;
+    if (EMIT && ntok < cap) tok[ntok] = isl ? (0x80000000u | (len << 16) | (dist - 1)) : val;
     ntok++;
     nout += isl ? len : 1u;
   }
@@ -574,13 +575,18 @@ __device__ bool blk_parse_header(const unsigned char* in, unsigned in_len, unsig
 #endif
 static const int PAR_BLK_WARPS = MTS_PAR_BLK_WARPS;   // (tables 4.1 KB + bit-reader ring 2 KB per warp, static shared memory)
 static const unsigned PAR_PREROLL_BITS = 768;       // see par_block_kernel
+#ifndef MTS_PAR_PIECE_BITS
+#define MTS_PAR_PIECE_BITS 8
+#endif
+static const unsigned PAR_PIECE_BITS = MTS_PAR_PIECE_BITS;   // input bits per token slot of the speculative token area
 static const unsigned PAR_RUN_ON_BITS = 1u << 20;   // how far past the next candidate the last lane may look for the end-of-block code
 __global__ void __launch_bounds__(PAR_BLK_WARPS * 32) par_block_kernel(const unsigned char* __restrict__ comp,
                                                                        const ParStream* __restrict__ streams,
                                                                        ParBlk* __restrict__ blks, unsigned n,
                                                                        unsigned* __restrict__ tokens,
                                                                        unsigned long long* __restrict__ tok_cursor,
-                                                                       unsigned long long tok_capacity) {
+                                                                       unsigned long long tok_capacity,
+                                                                       unsigned* __restrict__ pieces) {
   __shared__ BlkTabs tabs[PAR_BLK_WARPS];
   __shared__ uint4 rings[PAR_BLK_WARPS][4 * 32];              // SBits: four 16-byte slots per lane
   __shared__ unsigned short lenx[32];
@@ -633,7 +639,19 @@ __global__ void __launch_bounds__(PAR_BLK_WARPS * 32) par_block_kernel(const uns
       blk_span<false>(lane > 0 && back > 0, in, in_len, guess - back, guess, T, lenx, distx, nullptr, pr, lane_ring);
       if (lane > 0 && pr.flags == 0 && pr.end >= guess && pr.end < bound) start = pr.end;
     }
-    blk_span<false>(true, in, in_len, start, bound, T, lenx, distx, nullptr, r, lane_ring);
+    // The counting pass already writes its tokens, into the lane's PIECE of a scratch area (piece = the slots of the bits of the
+    // lane's sub-chunk: typical streams spend 9..15 bits per token); if every lane's tokens fit its piece, the tokens are then COPIED to their final place instead of being
+    // decoded a second time.  (One slot per PAR_PIECE_BITS input bits, addressed by the bit's offset in the buffer.)
+    unsigned* piece = nullptr;
+    unsigned pcap = 0;
+    if (pieces) {
+      const unsigned long long b0 = ((unsigned long long)st.in_off * 8 + hdr_end + lane * sc) / PAR_PIECE_BITS;
+      const unsigned long long b1 = ((unsigned long long)st.in_off * 8 + min(hdr_end + (lane + 1) * sc, limit)) / PAR_PIECE_BITS;
+      piece = pieces + b0;
+      pcap = b1 > b0 ? (unsigned)(b1 - b0) : 0u;
+    }
+    if (pieces) blk_span<true>(true, in, in_len, start, bound, T, lenx, distx, piece, r, lane_ring, pcap);
+    else blk_span<false>(true, in, in_len, start, bound, T, lenx, distx, nullptr, r, lane_ring);
     for (int it = 0; it < 34; it++) {
       const unsigned pe = __shfl_up_sync(0xffffffffu, r.end, 1), pf = __shfl_up_sync(0xffffffffu, r.flags, 1);
       bool ch = false, rerun = false;
@@ -646,7 +664,10 @@ __global__ void __launch_bounds__(PAR_BLK_WARPS * 32) par_block_kernel(const uns
           ch = true;
         }
       }
-      if (__any_sync(0xffffffffu, rerun)) blk_span<false>(rerun, in, in_len, start, bound, T, lenx, distx, nullptr, r, lane_ring);
+      if (__any_sync(0xffffffffu, rerun)) {
+        if (pieces) blk_span<true>(rerun, in, in_len, start, bound, T, lenx, distx, piece, r, lane_ring, pcap);
+        else blk_span<false>(rerun, in, in_len, start, bound, T, lenx, distx, nullptr, r, lane_ring);
+      }
       if (!__any_sync(0xffffffffu, ch)) break;
     }
     // ---- totals and token offsets
@@ -667,7 +688,17 @@ __global__ void __launch_bounds__(PAR_BLK_WARPS * 32) par_block_kernel(const uns
     toff = __shfl_sync(0xffffffffu, toff, 0);
     if (toff + total_tok > tok_capacity) ok = false;
     blk.tok_off = (long long)toff;
-    {
+    const bool in_pieces = pieces && __all_sync(0xffffffffu, (r.flags & 4) || r.ntok <= pcap);
+    if (ok && in_pieces) {
+      for (int l = 0; l < 32; l++) {
+        const unsigned n = __shfl_sync(0xffffffffu, (r.flags & 4) ? 0u : r.ntok, l);
+        const unsigned off = __shfl_sync(0xffffffffu, pre - r.ntok, l);
+        const unsigned long long pb = __shfl_sync(0xffffffffu, (unsigned long long)(piece - pieces), l);
+        const unsigned* src = pieces + pb;
+        unsigned* dst = tokens + blk.tok_off + off;
+        for (unsigned i = lane; i < n; i += 32) dst[i] = src[i];
+      }
+    } else {
       const bool emit = ok && !(r.flags & 4) && r.ntok;
       if (__any_sync(0xffffffffu, emit)) {
         SpanRes r2 = r;
