@@ -158,6 +158,8 @@ int set_attrs(mtsb_ctx* c) {
   CK(cudaFuncSetAttribute(fwd_transform_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
   CK(cudaFuncSetAttribute(fwd_transform_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
   CK(cudaFuncSetAttribute(fwd_transform_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+  CK(cudaFuncSetAttribute((par_lz_kernel<1024, 16384>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAR_LZ_MIRROR));
+  CK(cudaFuncSetAttribute((par_lz_kernel<256, 4096>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAR_LZ_MIRROR));
 #define MTS_INV_ATTR(T) \
   CK(cudaFuncSetAttribute((inv_tile_kernel<T, 4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 73728)); \
   CK(cudaFuncSetAttribute((inv_tile_kernel<T, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 73728)); \
@@ -944,13 +946,13 @@ static int par_decode(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Infla
     c->launches += 3;
   } else if (c->par_lz_wide < 0 ? ns <= 2 * c->sm_count : c->par_lz_wide == 1) {
     auto k = par_lz_kernel<1024, 16384>;
-    MTS_LAUNCH(k, dim3(ns), dim3(1024), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p, bcap, (const unsigned*)c->d_tokens.p, dT,
+    MTS_LAUNCH(k, dim3(ns), dim3(1024), PAR_LZ_MIRROR, c->stream, d_ps, (const ParBlk*)c->d_plist.p, bcap, (const unsigned*)c->d_tokens.p, dT,
                (ParRes*)c->d_pbad.p);
     CKL();
     c->launches++;
   } else {
     auto k = par_lz_kernel<256, 4096>;
-    MTS_LAUNCH(k, dim3(ns), dim3(256), 0, c->stream, d_ps, (const ParBlk*)c->d_plist.p, bcap, (const unsigned*)c->d_tokens.p, dT,
+    MTS_LAUNCH(k, dim3(ns), dim3(256), PAR_LZ_MIRROR, c->stream, d_ps, (const ParBlk*)c->d_plist.p, bcap, (const unsigned*)c->d_tokens.p, dT,
                (ParRes*)c->d_pbad.p);
     CKL();
     c->launches++;

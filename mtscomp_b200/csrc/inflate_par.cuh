@@ -752,6 +752,7 @@ __device__ __forceinline__ bool par_range(unsigned* bm, unsigned a, unsigned b) 
   }
   return hit;
 }
+static const unsigned PAR_LZ_MIRROR = 32768;          // dynamic shared memory of par_lz_kernel
 template <int PAR_LZ_THREADS, int PAR_LZ_CAP>
 __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream* __restrict__ streams,
                                                                 const ParBlk* __restrict__ blks,
@@ -759,6 +760,12 @@ __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream*
                                                                 const unsigned* __restrict__ tokens,
                                                                 unsigned char* out_base, ParRes* __restrict__ res) {
   const int NT = PAR_LZ_THREADS;
+  // The last 32 KB of the stream's finished output are mirrored in (dynamic) shared memory: what a match copies from
+  // before the tile comes from there instead of from global memory, whose round trip (stores of the previous tile,
+  // then dependent loads) was on the critical path of every tile (600 reference chunks: 178 -> 167 ms of inflate).
+  const bool MIRROR = true;
+  const unsigned MR = PAR_LZ_MIRROR;
+  MTS_DYN_SMEM(mirror);
   __shared__ unsigned ob_w[PAR_LZ_CAP / 4 + 1];
   __shared__ unsigned pend_w[PAR_LZ_CAP / 32 + 1];
   __shared__ unsigned wsum[NT / 32];
@@ -815,11 +822,15 @@ __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream*
       if (n_old < L) {                                              // has an in-tile part: its bytes are pending
         par_range<0>(pend_w, rel, rel + L);
       }
+      if (MIRROR) {
+        const unsigned m0 = obase + (unsigned)srel;                 // (srel < 0 here whenever n_old > 0; wraps as intended)
+        for (unsigned j = 0; j < n_old; j++) ob[rel + j] = mirror[(m0 + j) & (MR - 1)];
+      }
       // bytes from before the tile: aligned 32-bit loads (the output buffer is 4-byte aligned and padded), 8 bytes a turn
       const unsigned char* sp = out + obase + srel;
       const unsigned mis = (unsigned)((uintptr_t)sp & 3);
       const unsigned* sw = (const unsigned*)(sp - mis);
-      for (unsigned j0 = 0; j0 < n_old; j0 += 8) {
+      for (unsigned j0 = 0; !MIRROR && j0 < n_old; j0 += 8) {
         const unsigned w0 = sw[0], w1 = (mis + n_old - j0 > 4) ? sw[1] : 0u, w2 = (mis + n_old - j0 > 8) ? sw[2] : 0u;
         unsigned v0 = __funnelshift_r(w0, w1, mis * 8), v1 = __funnelshift_r(w1, w2, mis * 8);
         unsigned char* dp = ob + rel + j0;
@@ -866,6 +877,7 @@ __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream*
       }
       const unsigned rest = head + nvec * 16;
       if (rest + tid < total) gp[rest + tid] = ob[rest + tid];
+      if (MIRROR) for (unsigned i = tid; i < total; i += NT) mirror[(obase + i) & (MR - 1)] = ob[i];
     }
     obase += total;
     t0 += ncut;
