@@ -1174,12 +1174,14 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
   const long long sb_limit = host_io ? std::min(c->batch_bytes, c->host_batch_bytes) : hard_limit;
   // index-less chunks with host buffers: equal sub-batches of about par_batch_bytes
   long long par_limit = std::max(sb_limit, c->par_batch_bytes);
+  bool small_first = false;                 // several sub-batches of index-less chunks: start with a small one
   {
     long long total_par = 0, max_cb = 0;
     for (int i = 0; i < n_chunks; i++)
       if (!nseg[i]) { long long cb = (chunk_rows[i + 1] - chunk_rows[i]) * row_bytes; total_par += cb; max_cb = std::max(max_cb, cb); }
     const long long n_par = std::max<long long>(1, (total_par + par_limit / 2) / par_limit);
     par_limit = (total_par + n_par - 1) / n_par + max_cb;
+    small_first = n_par > 1;
   }
   std::vector<int> sb_first;
   long long max_sb_bytes = 0, max_sb_comp = 0;
@@ -1193,7 +1195,8 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
       // index-less chunks decoded block-parallel have thousands of independent blocks: with host buffers they are
       // batched by bytes so that copies overlap the decode of the neighbouring sub-batches
       const bool par_b = host_io && c->par_inflate && !nseg[b];
-      if (b > a && par_b && bb + cb > par_limit) break;
+      // (the first sub-batch is a quarter of the others: its decode is the one thing the download cannot overlap)
+      if (b > a && par_b && bb + cb > ((a == 0 && small_first) ? par_limit / 4 : par_limit)) break;
       if (b > a && !par_b && bb + cb > sb_limit && streams >= min_streams) break;
       bb += cb; streams += nseg[b] ? nseg[b] : 1; b++;
     }

@@ -90,12 +90,15 @@ def test_port_reader_equals_reference_reader(ref, tmp_path):
 def test_reference_suite_subset_against_this_package(tmp_path):
     """The reference's OWN tests (unmodified /root/reference/tests.py) with `import mtscomp` aliased to this package
     and the kernels emulated on the host: a subset here to keep the CPU suite short; tools/run_reference_tests.py runs
-    all 192 (result per round in profiles/)."""
+    all 192 (result per round in profiles/).  (test_check_fail[zeros] is left out here: the reference test overwrites
+    8 bytes of an all-zero float file with os.urandom and asserts `not np.allclose`, which fails by itself whenever the
+    random bytes happen to be tiny floats — about one run in six, with the reference's own codec too.)"""
     import subprocess
     import sys
     root = Path(__file__).resolve().parents[1]
     r = subprocess.run([sys.executable, str(root / 'tools' / 'run_reference_tests.py'), '-x', '-k',
-                        'test_low or test_high or test_chop or test_check_fail or test_comp_decomp or test_3d'],
+                        '(test_low or test_high or test_chop or test_check_fail or test_comp_decomp or test_3d) and not '
+                        '(test_check_fail and zeros)'],
                        cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
