@@ -201,3 +201,59 @@ def test_emulated_inverse_lookback_epochs(emu):
         assert not st.any() and np.array_equal(out, x)
         seen.append(emu.get_param('inv_epoch'))
     assert seen[1] == seen[0] + 1 and min(seen) == 1 and max(seen) == 0x3fff
+
+
+def test_emulated_false_index_is_not_trusted(emu):
+    """The host logic around the in-band index, without a GPU (the B200 version is in test_gpu_parity_holes.py): bytes
+    behind a reference-written stream that pass every check of both index formats must not change what the chunk
+    decodes to — zlib ignores them — while a damaged stream under a genuine index is still reported."""
+    import struct
+    from mtscomp_b200 import _native, synth
+    ns, nc = 6000, 24
+    x = synth.ap_chunk(ns, nc, seed=77)
+    z = ora.encode_chunk(x)
+    raw, seg = x.nbytes, 252000                                   # 21 channel runs of 12000 bytes
+    k = (raw + seg - 1) // seg
+    body = len(z) - 8
+    lens = [body // k] * k
+    lens[-1] += body - sum(lens)
+    v1 = z + b''.join(struct.pack('<I', v) for v in lens) + struct.pack('<IIII', seg, k, 0x4253544D, sum(lens))
+    n_sub = sum((min(seg, raw - j * seg) + 8191) // 8192 + (1 if min(seg, raw - j * seg) > 4096 else 0) for j in range(k))
+    table = b''.join(struct.pack('<I', 20000 | (3 << 17)) for _ in range(n_sub))
+    v2 = z + table + b''.join(struct.pack('<I', v) for v in lens) + struct.pack('<II', 8192, 1024) + \
+        struct.pack('<IIII', seg, k, 0x3253544D, sum(lens))
+    fl = _native.TIME_DIFF
+    for forged in (v1, v2):
+        assert zlib.decompress(forged) == ora.transform_chunk(x)
+        out, st = emu.decompress(forged, [0, len(forged)], [0, ns], nc, np.int16, fl)
+        assert not st.any() and np.array_equal(out, x)
+    comp, offs = emu.compress(x, [0, ns], fl)
+    bad = bytearray(comp)
+    bad[len(bad) // 3] ^= 0x40
+    try:
+        _, st = emu.decompress(bytes(bad), offs, [0, ns], nc, np.int16, fl)
+    except _native.NativeError:
+        st = [1]
+    assert st[0] != 0
+
+
+def test_emulated_fuzz_of_valid_zlib_streams(emu):
+    """A reduced form of the B200 fuzz (test_gpu_parity_holes.py): whatever zlib writes must decode — levels, strategies,
+    window sizes, memLevels, on data with long runs (length-258 matches), far matches (distance 32768), periodic,
+    low-entropy and incompressible content — through the block-parallel path (streams of 64 KB and more) and the
+    serial decoder."""
+    rng = np.random.default_rng(99)
+    n = 90_000
+    far = rng.integers(0, 256, 32768, dtype=np.uint8)
+    inputs = [rng.integers(0, 256, n, dtype=np.uint8), rng.integers(0, 4, n, dtype=np.uint8),
+              np.tile(np.arange(7, dtype=np.uint8), n // 7 + 1)[:n],
+              np.repeat(rng.integers(0, 256, n // 300 + 1, dtype=np.uint8), 300)[:n],
+              np.concatenate([far, far, far[:1000], rng.integers(0, 256, 5000, dtype=np.uint8), far])[:n]]
+    strategies = [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]
+    for data in inputs:
+        for level, strat, wbits, mem in [(0, 0, 15, 8), (6, 0, 15, 8), (9, 0, 15, 9), (6, 2, 15, 8), (6, 3, 15, 8), (6, 4, 15, 8),
+                                         (9, 0, 9, 1), (2, 3, 10, 5)]:
+            co = zlib.compressobj(level, zlib.DEFLATED, wbits, mem, strategies[strat])
+            z = co.compress(data.tobytes()) + co.flush()
+            out, st = emu.decompress(z, [0, len(z)], [0, len(data)], 1, np.uint8, 0)
+            assert not st.any() and np.array_equal(out[:, 0], data), (level, strat, wbits, mem)
