@@ -65,6 +65,8 @@ struct mtsb_ctx {
   int lz_ctas_per_sm = 2;
   // device scratch
   Buf d_pstreams, d_surv, d_cand, d_pcount, d_tokens, d_cells, d_ptab, d_plist, d_pbad;   // block-parallel inflate scratch
+  std::vector<uint32_t> lz_adler;   // per segment of the current sub-batch: adler32 left by par_lz_kernel ...
+  std::vector<char> lz_adler_have;  // ... where it produced the whole stream
   Buf d_pieces;
   long long par_single_pass = 1;   // par_block_kernel keeps the tokens of its counting pass (see par_decode)
   Buf d_segv2, d_btab, d_subout;                                                          // indexed (second format) segments
@@ -978,6 +980,10 @@ static int par_decode(mtsb_ctx* c, const unsigned char* dcomp, std::vector<Infla
     s.start_bit = r.tail_bit;
     s.opos0 = r.tail_out;
     c->par_stats[3]++;
+    if ((r.flags & 4) && zflag && r.tail_out == (unsigned)s.out_len && (size_t)ids[sidx] < c->lz_adler.size()) {
+      c->lz_adler[ids[sidx]] = r.adler;          // the whole stream went through par_lz_kernel: its adler32 is known
+      c->lz_adler_have[ids[sidx]] = 1;
+    }
   }
   return 0;
 }
@@ -1288,6 +1294,8 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
     }
     c->end();
     c->begin(2);
+    c->lz_adler.assign(n_segs, 0);
+    c->lz_adler_have.assign(n_segs, 0);
     // (the block kernels address bits with 32-bit offsets: streams of 256 MB and more stay with the serial decoder)
     const int PAR_MAX_IN = 1 << 28;
     if (c->par_inflate && !whole.empty()) {
@@ -1328,6 +1336,9 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
             const unsigned long long t = (unsigned long long)(len2 % ADLER_BASE) * ((s1a + ADLER_BASE - 1) % ADLER_BASE);
             a = ((uint32_t)((s2a + s2b + t) % ADLER_BASE) << 16) | s1;
           } else { all = false; break; }
+        }
+        if (!nseg[c0 + i] && first_inf[i + 1] == first_inf[i] + 1 && c->lz_adler_have[first_inf[i]]) {
+          all = true; a = c->lz_adler[first_inf[i]];          // a plain stream that par_lz_kernel produced completely
         }
         if (all) { have_adler[i] = 1; host_adler[i] = a; }
         const long long raw = (long long)cds[i].ns * row_bytes, tbase = cds[i].elem_off * itemsize;

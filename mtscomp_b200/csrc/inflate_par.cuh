@@ -44,7 +44,9 @@ struct ParRes {          // per stream, written by par_lz_kernel
   unsigned tail_bit;     // bit offset where the serial decoder has to resume
   unsigned tail_out;     // output bytes produced so far
   unsigned n_done;       // blocks resolved
-  unsigned flags;        // 1 = the last resolved block was final, 2 = inconsistent tokens (decode the stream serially)
+  unsigned flags;        // 1 = the last resolved block was final, 2 = inconsistent tokens (decode the stream serially),
+                         // 4 = `adler` is the adler32 of out[0, tail_out) (par_lz_kernel; not the cells path)
+  unsigned adler;
 };
 
 // Decoding tables of one block, in SHARED memory, owned by the warp that decodes the block.  Entries are 16 bits:
@@ -770,6 +772,7 @@ __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream*
   __shared__ unsigned pend_w[PAR_LZ_CAP / 32 + 1];
   __shared__ unsigned wsum[NT / 32];
   __shared__ unsigned s_total;
+  __shared__ unsigned long long s_ad[2 * (NT / 32)];
   unsigned char* ob = (unsigned char*)ob_w;
   const ParStream st = streams[blockIdx.x];
   unsigned char* out = out_base + st.out_off;
@@ -778,6 +781,9 @@ __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream*
   for (unsigned i = tid; i < PAR_LZ_CAP / 32 + 1; i += NT) pend_w[i] = 0;
   unsigned obase = 0;
   bool fail = false;
+  // adler32 of the stream, from the bytes that pass through the storing threads' registers (as seg_resolve_kernel):
+  // ad_a = sum of bytes, ad_b = sum of (out_cap - position) * byte
+  unsigned long long ad_a = 0, ad_b = 0;
   // ---- walk the chain of blocks: the first block starts right after the zlib header, every next one where its
   //      predecessor ended; the walk stops at the first block that is missing or was not decoded cleanly
   unsigned cur_bit = st.first_bit, n_done = 0, fin = 0;
@@ -863,7 +869,7 @@ __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream*
       // staging words, whose alignment differs), bytes of the rest
       unsigned char* gp = out + obase;
       const unsigned head = min(total, (unsigned)((16 - ((uintptr_t)gp & 15)) & 15));
-      if (tid < head) gp[tid] = ob[tid];
+      if (tid < head) { const unsigned v = ob[tid]; gp[tid] = (unsigned char)v; ad_a += v; ad_b += (unsigned long long)(out_cap - (obase + tid)) * v; }
       const unsigned nvec = (total - head) >> 4;
       for (unsigned v = tid; v < nvec; v += NT) {
         const unsigned o = head + v * 16;
@@ -874,9 +880,21 @@ __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream*
         val.x = __funnelshift_r(a0, a1, sh); val.y = __funnelshift_r(a1, a2, sh);
         val.z = __funnelshift_r(a2, a3, sh); val.w = __funnelshift_r(a3, a4, sh);
         *(uint4*)(gp + o) = val;
+        const unsigned wv[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const unsigned w = wv[q];
+          const unsigned sum = (w & 0xffu) + ((w >> 8) & 0xffu) + ((w >> 16) & 0xffu) + (w >> 24);
+          ad_a += sum;
+          ad_b += (unsigned long long)(out_cap - (obase + o + 4 * q)) * sum - (((w >> 8) & 0xffu) + 2 * ((w >> 16) & 0xffu) + 3 * (w >> 24));
+        }
       }
       const unsigned rest = head + nvec * 16;
-      if (rest + tid < total) gp[rest + tid] = ob[rest + tid];
+      if (rest + tid < total) {
+        const unsigned v = ob[rest + tid];
+        gp[rest + tid] = (unsigned char)v;
+        ad_a += v; ad_b += (unsigned long long)(out_cap - (obase + rest + tid)) * v;
+      }
       if (MIRROR) for (unsigned i = tid; i < total; i += NT) mirror[(obase + i) & (MR - 1)] = ob[i];
     }
     obase += total;
@@ -890,9 +908,20 @@ __global__ void __launch_bounds__(PAR_LZ_THREADS) par_lz_kernel(const ParStream*
     bj++;
     if (fin) break;
   }
+  {
+    unsigned long long a = warp_sum(ad_a), b2 = warp_sum(ad_b % ADLER_BASE);
+    if (lane == 0) { s_ad[2 * wid] = a; s_ad[2 * wid + 1] = b2; }
+  }
+  __syncthreads();
   if (tid == 0) {
+    unsigned long long ta = 0, tb = 0;
+    for (int w = 0; w < NT / 32; w++) { ta += s_ad[2 * w]; tb += s_ad[2 * w + 1]; }
     ParRes r;
-    r.tail_bit = cur_bit; r.tail_out = obase; r.n_done = n_done; r.flags = fin | (fail ? 2u : 0u);
+    r.tail_bit = cur_bit; r.tail_out = obase; r.n_done = n_done; r.flags = fin | (fail ? 2u : 0u) | 4u;
+    // (ad_b weighs a byte at position p with out_cap - p; for a prefix of obase bytes the weight is obase - p)
+    const unsigned long long short_by = (unsigned long long)(out_cap - obase) % ADLER_BASE * (ta % ADLER_BASE) % ADLER_BASE;
+    const unsigned long long s2 = (tb + ADLER_BASE - short_by + obase % ADLER_BASE) % ADLER_BASE;
+    r.adler = ((unsigned)s2 << 16) | (unsigned)((1 + ta) % ADLER_BASE);
     res[blockIdx.x] = r;
   }
 }

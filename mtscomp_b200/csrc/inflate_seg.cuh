@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(32) seg_tokens_kernel(const unsigned char* __r
   const unsigned char* in = comp + sg.in_off;
   const unsigned in_len = (unsigned)sg.in_len, in_bits = in_len * 8, out_len = (unsigned)sg.out_len;
   ParRes r0;
-  r0.tail_bit = 0; r0.tail_out = 0; r0.n_done = 0; r0.flags = 2;              // until proven good
+  r0.tail_bit = 0; r0.tail_out = 0; r0.n_done = 0; r0.flags = 2; r0.adler = 0;   // until proven good
   int nl = 0, nd = 0, hok = 0;
   unsigned fin = 0, hdr_end = 0;
   if (lane == 0) hok = blk_parse_header(in, in_len, 0, T.lens, (unsigned char*)T.dtab, nl, nd, fin, hdr_end) ? 1 : 0;
