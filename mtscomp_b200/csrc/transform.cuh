@@ -387,8 +387,8 @@ template <class T> struct InvCell {
   }
 };
 
-template <class T, int G, int J>
-__global__ void __launch_bounds__(INV_TILE_MAXT, 2) inv_tile_kernel(const T* __restrict__ in, T* __restrict__ out,
+template <class T, int G, int J, int MINB = 2>
+__global__ void __launch_bounds__(INV_TILE_MAXT, MINB) inv_tile_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                                     const ChunkDesc* __restrict__ chunks, int n_chunks,
                                                                     int nc, int max_tiles, int flags, int order_block,
                                                                     void* cells, unsigned epoch, unsigned* ticket) {

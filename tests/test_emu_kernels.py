@@ -177,6 +177,28 @@ def test_emulated_tile_kernels_channel_counts(emu, nc, dtype):
         assert not st.any() and np.array_equal(out, x), (td, sd)
 
 
+@pytest.mark.parametrize('half', [1, 2])
+def test_emulated_inverse_half_tiles(emu, half):
+    """inv_tile_kernel with tiles of 2 runs per channel (the inv_half_tile setting): twice the tiles in every look-back
+    chain, ragged last tiles, the 64-bit cells, spatial sums on top."""
+    from mtscomp_b200 import _native
+    rng = np.random.default_rng(half)
+    emu.set_param('inv_half_tile', half)
+    try:
+        for nc, dt, ns in ((40, 'int16', [300, 77, 31]), (385, 'int16', [210]), (9, 'int64', [130, 8]), (33, 'uint8', [333])):
+            x = np.cumsum(rng.integers(-3, 4, (sum(ns), nc)), axis=0).astype(dt)
+            rows = np.concatenate(([0], np.cumsum(ns)))
+            for td, sd in ((True, False), (True, True), (False, True)):
+                kw = dict(do_time_diff=td, do_spatial_diff=sd, chunk_order='F')
+                comp = [ora.encode_chunk(x[rows[i]:rows[i + 1]], **kw) for i in range(len(ns))]
+                offs = np.concatenate(([0], np.cumsum([len(c) for c in comp])))
+                out, st = emu.decompress(b''.join(comp), offs, rows, nc, dt, _native.flags_of(td, sd, 'F'))
+                assert not st.any() and np.array_equal(out, x), (nc, dt, td, sd)
+        assert emu.get_param('inv_half_tile') == half
+    finally:
+        emu.set_param('inv_half_tile', 0)
+
+
 def test_emulated_inverse_lookback_epochs(emu):
     """inv_tile_kernel tags its look-back cells with a launch epoch instead of clearing them: repeated launches over the
     same cells, other shapes in between, and the wrap of the epoch counter."""

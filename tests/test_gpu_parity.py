@@ -152,6 +152,29 @@ def test_many_chunks_batch_properties(codec):
         assert np.array_equal(out[k * 3000:(k + 1) * 3000], x[i * 3000:(i + 1) * 3000])
 
 
+@pytest.mark.parametrize('half', [0, 1, 2])
+def test_inverse_tile_shapes(codec, half):
+    """K4's single-pass kernel with tiles of 4 and of 2 runs per channel (`inv_half_tile`): long look-back chains over
+    many chunks at once, ragged last tiles, time and spatial sums, 2- and 8-byte elements."""
+    from mtscomp_b200 import synth
+    rng = np.random.default_rng(40 + half)
+    before = codec.get_param('inv_half_tile')
+    codec.set_param('inv_half_tile', half)
+    try:
+        x = np.concatenate([synth.ap_chunk(ns=30000 - 7 * i, nc=385, seed=90 + i) for i in range(6)])
+        rows = np.concatenate(([0], np.cumsum([30000 - 7 * i for i in range(6)])))
+        for td, sd in ((True, False), (True, True)):
+            comp, offs = codec.compress(x, rows, F(td, sd))
+            out, st = codec.decompress(comp, offs, rows, 385, np.int16, F(td, sd))
+            assert not st.any() and np.array_equal(out, x), (td, sd)
+        y = np.cumsum(rng.integers(-9, 10, (5000, 100)), axis=0).astype(np.int64)
+        comp, offs = codec.compress(y, [0, 3333, 5000], F())
+        out, st = codec.decompress(comp, offs, [0, 3333, 5000], 100, np.int64, F())
+        assert not st.any() and np.array_equal(out, y)
+    finally:
+        codec.set_param('inv_half_tile', before)
+
+
 def test_incompressible_and_runs(codec):
     rng = np.random.default_rng(9)
     x = rng.integers(-32768, 32767, (5000, 64), dtype=np.int64).astype(np.int16)
