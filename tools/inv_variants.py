@@ -3,7 +3,7 @@
 
     python tools/inv_variants.py [n_chunks] [n_distinct]
 
-Compresses n_chunks AP chunks once on the GPU, then decodes them with inv_half_tile = 0 / 1 / 2 and a few
+Compresses n_chunks AP chunks once on the GPU, then decodes them with inv_persistent = 0 / 1 and a few
 inv_order_block values and prints the `inverse` stage time of each (CUDA events inside the library) next to the HBM
 fraction it amounts to (2 bytes moved per raw byte)."""
 import json
@@ -41,8 +41,8 @@ def main():
     lib.mtsb_memcpy(cd.ctx, d_raw, x.ctypes.data, raw_bytes, 1)
     offs = cd.compress_ptr(d_raw, 1, rows, nc, 2, fl, d_comp, 1, cap)
     back = np.empty_like(x)
-    for half, ob in ((0, 2), (1, 2), (2, 2), (1, 4), (2, 4), (1, 1), (0, 2)):
-        cd.set_param('inv_half_tile', half)
+    for half, ob in ((0, 2), (1, 2), (1, 1), (1, 4), (0, 1), (1, 2), (0, 2)):
+        cd.set_param('inv_persistent', half)
         cd.set_param('inv_order_block', ob)
         best = None
         for it in range(3):
@@ -53,7 +53,7 @@ def main():
             if best is None or tm[4] < best[0]:
                 best = (tm[4], tm[7], dt)
         assert not st.any()
-        print('inv_half_tile=%d inv_order_block=%d  inverse %.3f ms = %.3f of HBM peak  (decode total %.2f ms, %.1f GB/s)' % (
+        print('inv_persistent=%d inv_order_block=%d  inverse %.3f ms = %.3f of HBM peak  (decode total %.2f ms, %.1f GB/s)' % (
             half, ob, best[0], 2 * raw_bytes / (best[0] * 1e-3) / 1e9 / peak, best[1], raw_bytes / (best[1] * 1e-3) / 1e9),
             flush=True)
         if half:
