@@ -66,8 +66,7 @@ int mtsb_sync(mtsb_ctx* ctx);
  * (-1 auto / 0 / 1: shape of the token-resolve kernel), "par_cells" (-1 auto / 0 / 1: resolve the blocks of an
  * index-less stream in parallel — the low-latency path for few streams), "inv_single_pass" (1: channel-major inverse
  * transform in one pass with look-back carries; 0: tile sums + scan + apply), "inv_order_block" (consecutive tiles of a
- * chunk that run together in the single-pass inverse, 2), "inv_persistent" (1: the single-pass inverse runs as persistent
- * CTAs with two staging buffers each instead of one CTA per tile).  Read-only: "par_survivors", "par_candidates", "par_chained",
+ * chunk that run together in the single-pass inverse, 2).  Read-only: "par_survivors", "par_candidates", "par_chained",
  * "par_resumed" (what the parallel decoders did in the last call), "sm_count".  Returns MTSB_E_ARG for unknown names. */
 int mtsb_set_param(mtsb_ctx* ctx, const char* name, long long value);
 long long mtsb_get_param(mtsb_ctx* ctx, const char* name);

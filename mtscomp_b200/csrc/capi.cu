@@ -77,7 +77,6 @@ struct mtsb_ctx {
   int inv_cells_isz = 0;           // element size of the launch that last wrote the look-back cells
   unsigned inv_epoch = 0;          // epoch of the last inv_tile_kernel launch (tags its look-back cells)
   long long inv_order_block = 2;   // inv_tile_kernel: consecutive tiles of a chunk that get consecutive tickets
-  long long inv_persistent = 0;    // single-pass inverse by persistent CTAs with two staging buffers (inv_tile_pers_kernel)
   long long inv_single_pass = 1;   // channel-major inverse transform in one pass (inv_tile_kernel); 0: tile sums + apply
   Buf h_tab, h_small;
   // timings
@@ -166,10 +165,7 @@ int set_attrs(mtsb_ctx* c) {
 #define MTS_INV_ATTR(T) \
   CK(cudaFuncSetAttribute((inv_tile_kernel<T, 4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 73728)); \
   CK(cudaFuncSetAttribute((inv_tile_kernel<T, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 73728)); \
-  CK(cudaFuncSetAttribute((inv_tile_kernel<T, 1, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, 73728)); \
-  CK(cudaFuncSetAttribute((inv_tile_pers_kernel<T, 4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 73728)); \
-  CK(cudaFuncSetAttribute((inv_tile_pers_kernel<T, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 73728)); \
-  CK(cudaFuncSetAttribute((inv_tile_pers_kernel<T, 1, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 73728));
+  CK(cudaFuncSetAttribute((inv_tile_kernel<T, 1, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, 73728));
   MTS_INV_ATTR(uint8_t) MTS_INV_ATTR(uint16_t) MTS_INV_ATTR(uint32_t) MTS_INV_ATTR(uint64_t)
 #undef MTS_INV_ATTR
 #define MTS_FWD_ATTR(T) \
@@ -281,18 +277,6 @@ int launch_inv_t(mtsb_ctx* c, const void* tbuf, void* out, const ChunkDesc* d_cd
     const unsigned epoch = ++c->inv_epoch;
     NEED(c->d_invstate, 64);
     CK(cudaMemsetAsync(c->d_invstate.p, 0, 64, c->stream));
-    if (c->inv_persistent && n_tiles < (1u << 31)) {
-      // persistent CTAs, two staging buffers each: as many as stay resident (two per SM while their buffers fit)
-      auto kp = J == 1 ? inv_tile_pers_kernel<T, 4, 1> : J == 2 ? inv_tile_pers_kernel<T, 2, 2> : inv_tile_pers_kernel<T, 1, 4>;
-      const size_t buf = (smem + 15) & ~(size_t)15;
-      const int per_sm = 2 * (2 * buf + 2048) <= (size_t)233472 ? 2 : 1;
-      const unsigned grid = (unsigned)std::min<size_t>(n_tiles, (size_t)c->sm_count * per_sm);
-      MTS_LAUNCH(kp, dim3(grid), dim3(threads), 2 * buf, c->stream, (const T*)tbuf, (T*)out, d_cd, n_chunks, nc,
-                 max_tiles, flags, ob, c->d_invcells.p, epoch, (unsigned*)c->d_invstate.p, (unsigned)n_tiles, (unsigned)buf);
-      c->launches++;
-      CKL();
-      return 0;
-    }
     auto k = J == 1 ? inv_tile_kernel<T, 4, 1> : J == 2 ? inv_tile_kernel<T, 2, 2> : inv_tile_kernel<T, 1, 4>;
     MTS_LAUNCH(k, dim3((unsigned)n_tiles), dim3(threads), smem, c->stream, (const T*)tbuf, (T*)out, d_cd, n_chunks, nc,
                max_tiles, flags, ob, c->d_invcells.p, epoch, (unsigned*)c->d_invstate.p);
@@ -471,7 +455,6 @@ int mtsb_set_param(mtsb_ctx* c, const char* name, long long v) {
   else if (s == "par_single_pass") c->par_single_pass = v ? 1 : 0;
   else if (s == "seg_v2") c->seg_v2 = v ? 1 : 0;
   else if (s == "inv_single_pass") c->inv_single_pass = v ? 1 : 0;
-  else if (s == "inv_persistent") c->inv_persistent = v ? 1 : 0;
   else if (s == "inv_epoch") c->inv_epoch = (unsigned)v;          // (tests: the wrap of the look-back epochs)
   else if (s == "inv_order_block") c->inv_order_block = std::min<long long>(std::max<long long>(v, 1), 64);
   else if (s == "par_cells") c->par_cells = v < 0 ? -1 : (v ? 1 : 0);
@@ -497,7 +480,6 @@ long long mtsb_get_param(mtsb_ctx* c, const char* name) {
   if (s == "seg_v2") return c->seg_v2;
   if (s == "inv_single_pass") return c->inv_single_pass;
   if (s == "inv_order_block") return c->inv_order_block;
-  if (s == "inv_persistent") return c->inv_persistent;
   if (s == "inv_epoch") return c->inv_epoch;
   if (s == "par_batch_bytes") return c->par_batch_bytes;
   if (s == "par_survivors") return c->par_stats[0];

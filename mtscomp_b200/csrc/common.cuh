@@ -56,7 +56,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 __device__ __forceinline__ void mbar_wait(mbar_t, unsigned) {}
 __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) { memcpy(dst, src, bytes); }
 __device__ __forceinline__ void bulk_s2g_wait() {}
-template <int N> __device__ __forceinline__ void bulk_s2g_wait_but() {}
 __device__ __forceinline__ void fence_async_smem() {}
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
 __device__ __forceinline__ void cp_async_commit() {}
@@ -95,8 +94,6 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned by
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_s2g_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-// ... all but the thread's N most recent bulk groups
-template <int N> __device__ __forceinline__ void bulk_s2g_wait_but() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // Per-thread asynchronous copies of 16 bytes global -> shared (no destination register, so nothing in the issuing warp
 // waits for the load until cp_async_wait<N>: all but the thread's N most recent groups are complete).

@@ -517,153 +517,6 @@ __global__ void __launch_bounds__(INV_TILE_MAXT, 2) inv_tile_kernel(const T* __r
   }
 }
 
-// The same tile algorithm with PERSISTENT CTAs: a CTA keeps taking tickets until they run out, so what a one-tile CTA pays
-// serially in front of and behind its tile is overlapped with a neighbouring tile: the next ticket is drawn (one atomic)
-// while this tile's data is in flight, and the tile leaves through one of TWO staging buffers, so the TMA store of tile i
-// drains while tile i + 1 is loaded and transposed into the other buffer (thread 0 only waits for the store before the
-// last one).  Tickets are still handed out in look-back order and only to running CTAs, so the waiting argument above
-// holds unchanged.  buf_bytes: size of one staging buffer (a multiple of 16).
-template <class T, int G, int J>
-__global__ void __launch_bounds__(INV_TILE_MAXT, 2) inv_tile_pers_kernel(const T* __restrict__ in, T* __restrict__ out,
-                                                                         const ChunkDesc* __restrict__ chunks, int n_chunks,
-                                                                         int nc, int max_tiles, int flags, int order_block,
-                                                                         void* cells, unsigned epoch, unsigned* ticket,
-                                                                         unsigned n_tickets, unsigned buf_bytes) {
-  const int R = ColRun<T>::R, TT = G * R;
-  MTS_DYN_SMEM(sm);                                    // 2 x [16 bytes][tile: data at offset off0, rows x nc]
-  __shared__ unsigned s_ticket[2];
-  if (threadIdx.x == 0) s_ticket[0] = atomicAdd(ticket, 1u);
-  const bool td = (flags & FLAG_TIME_DIFF) != 0, sd = (flags & FLAG_SPATIAL_DIFF) != 0;
-  const unsigned per = (unsigned)order_block * (unsigned)n_chunks;
-  const size_t n_cells = (size_t)n_chunks * max_tiles * nc;
-  unsigned bufi = 0;                                   // staging buffer of the current tile (flips per tile that has rows)
-  for (unsigned it = 0;; it++) {
-    __syncthreads();                                   // the ticket is there; the buffer of two tiles ago is free
-    const unsigned tk = s_ticket[it & 1];
-    if (tk >= n_tickets) break;
-    unsigned next_tk = 0;
-    if (threadIdx.x == 0) next_tk = atomicAdd(ticket, 1u);            // (stored below, when its latency is long over)
-    const unsigned rem = tk % per;
-    const int ci = (int)(rem / (unsigned)order_block), tl = (int)(tk / per) * order_block + (int)(rem % (unsigned)order_block);
-    const ChunkDesc cd = chunks[ci];
-    const int ns = cd.ns;
-    const int t0 = tl * TT;
-    if (t0 >= ns) {                                                   // (a tile beyond the end of a short chunk)
-      if (threadIdx.x == 0) s_ticket[(it + 1) & 1] = next_tk;
-      continue;
-    }
-    const int rows = min(TT, ns - t0);
-    unsigned char* gout = (unsigned char*)(out + cd.elem_off + (long long)t0 * nc);
-    const unsigned off0 = (unsigned)((uintptr_t)gout & 15);
-    T* s = (T*)(sm + (size_t)bufi * buf_bytes + 16 + off0);
-    bufi ^= 1;
-    const T* x = in + cd.elem_off + t0;
-    const size_t cell0 = ((size_t)ci * max_tiles + tl) * nc;
-    T pv[J];
-    unsigned pk[J];
-#pragma unroll
-    for (int j = 0; j < J; j++) {
-      const int c = threadIdx.x + j * blockDim.x;
-      pv[j] = 0; pk[j] = 0;
-      if (td && tl > 0 && c < nc) pk[j] = InvCell<T>::get(cells, n_cells, cell0 - nc + c, epoch, pv[j]);
-    }
-    uint4 q[J][G][2];
-#pragma unroll
-    for (int j = 0; j < J; j++) {
-      const int c = threadIdx.x + j * blockDim.x;
-#pragma unroll
-      for (int g = 0; g < G; g++) {
-        const int nr = min(R, rows - g * R);
-        if (c < nc && nr > 0) load_run<T>(q[j][g], x + (long long)c * ns + g * R, nr);
-        else q[j][g][0] = q[j][g][1] = make_uint4(0, 0, 0, 0);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < J; j++) {
-      const int c = threadIdx.x + j * blockDim.x;
-      if (c >= nc) continue;
-      T a = 0;
-      if (td) {
-        const bool publish = (long long)(tl + 1) * TT < ns;
-        T total = 0;
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-          T v[R];
-          memcpy(v, q[j][g], 32);
-#pragma unroll
-          for (int r = 0; r < R; r++) total = (T)(total + v[r]);
-        }
-        if (publish && pk[j] != 2 && tl > 0) InvCell<T>::put(cells, n_cells, cell0 + c, epoch, 1, total);
-        T cy = 0;
-        for (int i = tl - 1; i >= 0; i--) {
-          T v = pv[j];
-          unsigned kind = pk[j];
-          pk[j] = 0;
-          while (kind == 0) {
-            kind = InvCell<T>::get(cells, n_cells, ((size_t)ci * max_tiles + i) * nc + c, epoch, v);
-#ifdef MTSCOMP_EMU
-            if (kind == 0) emu::yield();
-#endif
-          }
-          cy = (T)(cy + v);
-          if (kind == 2) break;
-        }
-        if (publish) InvCell<T>::put(cells, n_cells, cell0 + c, epoch, 2, (T)(cy + total));
-        a = cy;
-      }
-      T* sp = s + c;
-#pragma unroll
-      for (int g = 0; g < G; g++) {
-        T v[R];
-        memcpy(v, q[j][g], 32);
-        if (rows == TT) {
-#pragma unroll
-          for (int r = 0; r < R; r++) {
-            if (td) { a = (T)(a + v[r]); v[r] = a; }
-            sp[(long long)(g * R + r) * nc] = v[r];
-          }
-        } else {
-#pragma unroll
-          for (int r = 0; r < R; r++) {
-            if (td) { a = (T)(a + v[r]); v[r] = a; }
-            if (g * R + r < rows) sp[(long long)(g * R + r) * nc] = v[r];
-          }
-        }
-      }
-    }
-    if (threadIdx.x == 0) s_ticket[(it + 1) & 1] = next_tk;
-    __syncthreads();
-    if (sd) {
-      const int nw = blockDim.x >> 5;
-      for (int r = warp_id(); r < rows; r += nw) {
-        T cy = 0;
-        for (int c0 = 0; c0 < nc; c0 += 32) {
-          const int c = c0 + lane_id();
-          T v = (c < nc) ? s[r * nc + c] : (T)0;
-          v = (T)(warp_incl_scan(v) + cy);
-          if (c < nc) s[r * nc + c] = v;
-          cy = __shfl_sync(0xffffffffu, v, 31);
-        }
-      }
-      __syncthreads();
-    }
-    const unsigned span = (unsigned)(rows * nc) * (unsigned)sizeof(T);
-    const unsigned head = min(span, (16 - off0) & 15), mid = (span - head) & ~15u;
-    const unsigned char* sb = (const unsigned char*)s;
-    for (unsigned i = threadIdx.x; i < head; i += blockDim.x) gout[i] = sb[i];
-    for (unsigned i = head + mid + threadIdx.x; i < span; i += blockDim.x) gout[i] = sb[i];
-    if (mid) {
-      fence_async_smem();
-      __syncthreads();
-      // (the other buffer, which the next tile fills, must have been read by ITS store: all but the newest group)
-      if (threadIdx.x == 0) { bulk_s2g(gout + head, sb + head, mid); bulk_s2g_wait_but<1>(); }
-    } else if (threadIdx.x == 0) {
-      bulk_s2g_wait_but<0>();                          // no store from this buffer: the other one is the newest group
-    }
-  }
-  if (threadIdx.x == 0) bulk_s2g_wait();
-}
-
 // Inverse of the above: per-channel running sum seeded by the scanned tile sums (tile = TT rows, TT % R == 0).
 template <class T>
 __global__ void __launch_bounds__(128) inv_cols_kernel(const T* __restrict__ in, T* __restrict__ out,

@@ -177,30 +177,23 @@ def test_emulated_tile_kernels_channel_counts(emu, nc, dtype):
         assert not st.any() and np.array_equal(out, x), (td, sd)
 
 
-@pytest.mark.parametrize('pers', [0, 1])
-def test_emulated_inverse_persistent_ctas(emu, pers):
-    """The single-pass inverse as persistent CTAs with two staging buffers (`inv_persistent`) and as one CTA per tile:
-    chunks of very different lengths (tickets of tiles past the end of a short chunk), ragged last tiles, tiles too small
-    for a bulk store, every thread-per-channel regime, the 64-bit cells, spatial sums on top."""
+def test_emulated_inverse_ragged_batches(emu):
+    """The single-pass inverse over chunks of very different lengths in one launch (tickets of tiles past the end of a
+    short chunk), ragged last tiles, tiles too small for a bulk store, every thread-per-channel regime, the 64-bit cells,
+    spatial sums on top, the same cells used twice."""
     from mtscomp_b200 import _native
     rng = np.random.default_rng(3)
-    before = emu.get_param('inv_persistent')
-    emu.set_param('inv_persistent', pers)
-    try:
-        for nc, dt, ns in ((40, 'int16', [300, 77, 31, 1, 1500]), (385, 'int16', [210, 64]), (9, 'int64', [130, 8]),
-                           (33, 'uint8', [333, 2]), (3, 'int16', [1, 2, 700]), (900, 'int32', [50, 9]), (1800, 'int16', [70])):
-            x = np.cumsum(rng.integers(-3, 4, (sum(ns), nc)), axis=0).astype(dt)
-            rows = np.concatenate(([0], np.cumsum(ns)))
-            for td, sd in ((True, False), (True, True), (False, True)):
-                kw = dict(do_time_diff=td, do_spatial_diff=sd, chunk_order='F')
-                comp = [ora.encode_chunk(x[rows[i]:rows[i + 1]], **kw) for i in range(len(ns))]
-                offs = np.concatenate(([0], np.cumsum([len(c) for c in comp])))
-                for rep in range(2):
-                    out, st = emu.decompress(b''.join(comp), offs, rows, nc, dt, _native.flags_of(td, sd, 'F'))
-                    assert not st.any() and np.array_equal(out, x), (nc, dt, td, sd)
-        assert emu.get_param('inv_persistent') == pers
-    finally:
-        emu.set_param('inv_persistent', before)
+    for nc, dt, ns in ((40, 'int16', [300, 77, 31, 1, 1500]), (385, 'int16', [210, 64]), (9, 'int64', [130, 8]),
+                       (33, 'uint8', [333, 2]), (3, 'int16', [1, 2, 700]), (900, 'int32', [50, 9]), (1800, 'int16', [70])):
+        x = np.cumsum(rng.integers(-3, 4, (sum(ns), nc)), axis=0).astype(dt)
+        rows = np.concatenate(([0], np.cumsum(ns)))
+        for td, sd in ((True, False), (True, True), (False, True)):
+            kw = dict(do_time_diff=td, do_spatial_diff=sd, chunk_order='F')
+            comp = [ora.encode_chunk(x[rows[i]:rows[i + 1]], **kw) for i in range(len(ns))]
+            offs = np.concatenate(([0], np.cumsum([len(c) for c in comp])))
+            for rep in range(2):
+                out, st = emu.decompress(b''.join(comp), offs, rows, nc, dt, _native.flags_of(td, sd, 'F'))
+                assert not st.any() and np.array_equal(out, x), (nc, dt, td, sd)
 
 
 def test_emulated_inverse_lookback_epochs(emu):

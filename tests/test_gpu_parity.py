@@ -152,34 +152,28 @@ def test_many_chunks_batch_properties(codec):
         assert np.array_equal(out[k * 3000:(k + 1) * 3000], x[i * 3000:(i + 1) * 3000])
 
 
-@pytest.mark.parametrize('pers', [0, 1])
-def test_inverse_single_pass_both_launch_shapes(codec, pers):
-    """K4's single-pass kernel as one CTA per tile and as persistent CTAs with two staging buffers (`inv_persistent`): long
-    look-back chains over many chunks at once, chunks of different lengths, ragged last tiles, time and spatial sums,
-    2- and 8-byte elements, repeated launches over the same cells."""
+def test_inverse_single_pass_ragged_batches(codec):
+    """K4's single-pass kernel: long look-back chains over many chunks at once, chunks of very different lengths in one
+    launch, ragged last tiles, time and spatial sums, 2- and 8-byte elements, more channels than threads, repeated
+    launches over the same cells."""
     from mtscomp_b200 import synth
-    rng = np.random.default_rng(40 + pers)
-    before = codec.get_param('inv_persistent')
-    codec.set_param('inv_persistent', pers)
-    try:
-        lens = [30000 - 7 * i for i in range(6)] + [50, 1]
-        x = np.concatenate([synth.ap_chunk(ns=n, nc=385, seed=90 + i) for i, n in enumerate(lens)])
-        rows = np.concatenate(([0], np.cumsum(lens)))
-        for td, sd in ((True, False), (True, True)):
-            comp, offs = codec.compress(x, rows, F(td, sd))
-            for rep in range(2):
-                out, st = codec.decompress(comp, offs, rows, 385, np.int16, F(td, sd))
-                assert not st.any() and np.array_equal(out, x), (td, sd)
-        y = np.cumsum(rng.integers(-9, 10, (5000, 100)), axis=0).astype(np.int64)
-        comp, offs = codec.compress(y, [0, 3333, 5000], F())
-        out, st = codec.decompress(comp, offs, [0, 3333, 5000], 100, np.int64, F())
-        assert not st.any() and np.array_equal(out, y)
-        z = np.cumsum(rng.integers(-9, 10, (4000, 1500)), axis=0).astype(np.int16)
-        comp, offs = codec.compress(z, [0, 1000, 4000], F())
-        out, st = codec.decompress(comp, offs, [0, 1000, 4000], 1500, np.int16, F())
-        assert not st.any() and np.array_equal(out, z)
-    finally:
-        codec.set_param('inv_persistent', before)
+    rng = np.random.default_rng(40)
+    lens = [30000 - 7 * i for i in range(6)] + [50, 1]
+    x = np.concatenate([synth.ap_chunk(ns=n, nc=385, seed=90 + i) for i, n in enumerate(lens)])
+    rows = np.concatenate(([0], np.cumsum(lens)))
+    for td, sd in ((True, False), (True, True)):
+        comp, offs = codec.compress(x, rows, F(td, sd))
+        for rep in range(2):
+            out, st = codec.decompress(comp, offs, rows, 385, np.int16, F(td, sd))
+            assert not st.any() and np.array_equal(out, x), (td, sd)
+    y = np.cumsum(rng.integers(-9, 10, (5000, 100)), axis=0).astype(np.int64)
+    comp, offs = codec.compress(y, [0, 3333, 5000], F())
+    out, st = codec.decompress(comp, offs, [0, 3333, 5000], 100, np.int64, F())
+    assert not st.any() and np.array_equal(out, y)
+    z = np.cumsum(rng.integers(-9, 10, (4000, 1500)), axis=0).astype(np.int16)
+    comp, offs = codec.compress(z, [0, 1000, 4000], F())
+    out, st = codec.decompress(comp, offs, [0, 1000, 4000], 1500, np.int16, F())
+    assert not st.any() and np.array_equal(out, z)
 
 
 def test_incompressible_and_runs(codec):
