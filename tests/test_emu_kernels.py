@@ -276,3 +276,39 @@ def test_emulated_fuzz_of_valid_zlib_streams(emu):
             z = co.compress(data.tobytes()) + co.flush()
             out, st = emu.decompress(z, [0, len(z)], [0, len(data)], 1, np.uint8, 0)
             assert not st.any() and np.array_equal(out[:, 0], data), (level, strat, wbits, mem)
+
+
+@pytest.mark.parametrize('shared', [False, True])
+def test_emulated_contexts_from_several_threads(shared):
+    """The reference calls its codec seam from n_threads pool threads at once (mtscomp.py:422, 648).  Here a context is
+    one stream plus its scratch: callers either share one (calls are serialised by the binding's lock) or own one each
+    (nothing is shared between contexts: no device globals, per-context scratch, staging and look-back cells)."""
+    import threading
+    from mtscomp_b200 import _native, build, synth
+    lib = _native.load_library(build.build_emulation())
+    codecs = [_native.Codec(0, lib=lib) for _ in range(1 if shared else 4)]
+    res = {}
+
+    def work(k):
+        try:
+            cd = codecs[0 if shared else k]
+            x = synth.ap_chunk(2000, 40, seed=300 + k)
+            rows = [0, 700, 2000]
+            for rep in range(2):
+                comp, offs = cd.compress(x, rows, _native.TIME_DIFF)
+                for i in range(2):
+                    assert zlib.decompress(bytes(comp[offs[i]:offs[i + 1]])) == ora.transform_chunk(x[rows[i]:rows[i + 1]])
+                out, st = cd.decompress(comp, offs, rows, 40, np.int16, _native.TIME_DIFF)
+                assert not st.any() and np.array_equal(out, x)
+            res[k] = True
+        except Exception as e:                      # noqa: BLE001 (reported below, from the main thread)
+            res[k] = repr(e)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for cd in codecs:
+        cd.close()
+    assert res == {k: True for k in range(4)}, res
