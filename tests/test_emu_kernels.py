@@ -312,3 +312,35 @@ def test_emulated_contexts_from_several_threads(shared):
     for cd in codecs:
         cd.close()
     assert res == {k: True for k in range(4)}, res
+
+
+def test_emulated_plain_stream_checksum_from_the_resolve_kernel(emu):
+    """For a reference-written (index-less) stream that par_lz_kernel produces completely, the adler32 compared with the
+    stream's trailer is the one that kernel sums from the bytes it stores: a wrong trailer, and any bit flipped in the
+    body that zlib objects to, must still be reported — per chunk, the neighbours untouched."""
+    from mtscomp_b200 import _native, synth
+    fl = _native.TIME_DIFF
+    xs = [synth.ap_chunk(3000, 40, seed=s) for s in range(4)]
+    zs = [ora.encode_chunk(x) for x in xs]
+    rows = np.arange(5) * 3000
+    for pos, bit in ((-1, 1), (-4, 0x80), (-2, 4)):
+        b = bytearray(zs[2])
+        b[pos] ^= bit
+        parts = [zs[0], zs[1], bytes(b), zs[3]]
+        offs = np.concatenate(([0], np.cumsum([len(c) for c in parts])))
+        out, st = emu.decompress(b''.join(parts), offs, rows, 40, np.int16, fl)
+        assert st[2] != 0 and not st[[0, 1, 3]].any()
+        for k in (0, 1, 3):
+            assert np.array_equal(out[rows[k]:rows[k + 1]], xs[k])
+    rng = np.random.default_rng(0)
+    z = zs[0]
+    for t in range(12):
+        b = bytearray(z)
+        b[int(rng.integers(2, len(z) - 4))] ^= 1 << int(rng.integers(0, 8))
+        try:
+            zlib.decompress(bytes(b))
+            accepted = True
+        except zlib.error:
+            accepted = False
+        out, st = emu.decompress(bytes(b), [0, len(b)], [0, 3000], 40, np.int16, fl)
+        assert (st[0] == 0) == accepted
