@@ -124,3 +124,56 @@ def test_files_written_on_the_b200_open_in_the_reference_reader(ref, tmp_path, n
     assert (tmp_path / 'back.bin').read_bytes() == raw
     assert meta['sha1_uncompressed'] == hashlib.sha1(raw).hexdigest()
     assert meta['sha1_compressed'] == hashlib.sha1((GPU_WRITTEN / (name + '.cbin')).read_bytes()).hexdigest()
+
+
+def test_reader_indexing_differential_against_the_reference(ref, emulated_default_codec, tmp_path):
+    """Random index expressions (slices with steps, negative and out-of-range bounds, integers, column selections) on the
+    same file through this package's Reader — device-side LRU of decoded chunks, batched decode of the misses — and
+    through the reference Reader: same result or same exception type, for several cache sizes, on a reference-written
+    and on a file written here.  (reference mtscomp.py:652-684, 798-856)"""
+    import mtscomp_b200 as M
+    from mtscomp_b200 import synth
+    M.CONFIG_PATH = tmp_path / '.mtscomp'
+    arr = synth.ap_chunk(ns=2300, nc=9, sample_rate=30000., seed=21)
+    raw = tmp_path / 'data.bin'
+    arr.tofile(raw)
+    kw = dict(sample_rate=1000., n_channels=9, dtype='int16', quiet=True, chunk_duration=0.1)
+    ref.compress(raw, tmp_path / 'r.cbin', tmp_path / 'r.ch', n_threads=1, **kw)
+    M.compress(raw, tmp_path / 'g.cbin', tmp_path / 'g.ch', **kw)
+    rng = np.random.default_rng(8)
+
+    def bound():
+        return [None, int(rng.integers(-2600, 2600)), int(rng.integers(0, 2300)), int(rng.integers(-300, 0))][int(rng.integers(0, 4))]
+
+    def draw():
+        k = int(rng.integers(0, 10))
+        step = [None, 1, 2, 7, 150][int(rng.integers(0, 5))]
+        if k < 5:
+            return slice(bound(), bound(), step)
+        if k < 7:
+            return int(rng.integers(-2300, 2300))
+        cols = [slice(None), slice(2, 7), slice(None, None, 3), 4, -1][int(rng.integers(0, 5))]
+        if k < 9:
+            return (slice(bound(), bound(), step), cols)
+        return (int(rng.integers(-2300, 2300)), cols)
+
+    items = [draw() for _ in range(150)]
+    for name in ('r', 'g'):
+        for cache_size in (1, 4, 64):
+            a = ref.Reader(cache_size=cache_size)
+            a.open(tmp_path / (name + '.cbin'), tmp_path / (name + '.ch'))
+            b = M.Reader(cache_size=cache_size)
+            b.open(tmp_path / (name + '.cbin'), tmp_path / (name + '.ch'))
+            for item in items:
+                try:
+                    want = a[item]
+                except Exception as e:          # noqa: BLE001 (whatever the reference raises is the contract)
+                    with pytest.raises(type(e)):
+                        b[item]
+                    continue
+                got = b[item]
+                assert np.asarray(got).shape == np.asarray(want).shape, item
+                assert np.asarray(got).dtype == np.asarray(want).dtype, item
+                assert np.array_equal(got, want), item
+            a.close()
+            b.close()
