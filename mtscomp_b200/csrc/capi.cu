@@ -1319,7 +1319,8 @@ int mtsb_decompress_chunks(mtsb_ctx* c, const void* comp_, int comp_is_device, c
       if (r) return r;
     }
     // adler32 of each chunk's transformed bytes: folded on the host from the segments' sums where the second-format
-    // kernels produced every segment of the chunk, computed by the adler kernels otherwise
+    // kernels produced every segment of the chunk, taken from par_lz_kernel where it produced a plain stream completely,
+    // computed by the adler kernels otherwise
     std::vector<uint32_t> host_adler(nb, 0);
     std::vector<char> have_adler(nb, 0);
     {
